@@ -1,0 +1,90 @@
+"""ctypes binding of ``libfreegaussian_b200.so`` (the C ABI declared in include/fg_api.h).
+
+There is no CPU fallback: if the library is missing or a call fails, this raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libfreegaussian_b200.so"
+
+ABI_VERSION = 1
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_pi = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); mirrors include/fg_api.h one to one
+SIGNATURES = {
+    "fg_last_error": (C.c_char_p, []),
+    "fg_abi_version": (_i32, []),
+    "fg_launch_count": (C.c_longlong, []),
+    "fg_project_fwd": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _i32,
+                              _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fg_project_bwd": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32,
+                              _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_scan_workspace_bytes": (_i64, [_i64]),
+    "fg_exclusive_scan_i32": (_i32, [_i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "fg_isect_emit": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fg_radix_sort_workspace_bytes": (_i64, [_i64]),
+    "fg_radix_sort_pairs_u64_u32": (_i32, [_i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _pi, _vp]),
+    "fg_radix_sort_pairs_u32_u32": (_i32, [_i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _pi, _vp]),
+    "fg_isect_offsets": (_i32, [_i64, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "fg_rasterize_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                                _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "fg_rasterize_bwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                                _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_knn_workspace_bytes": (_i64, [_i64]),
+    "fg_knn_f32": (_i32, [_i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
+}
+
+
+class FgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the library once.  Raises (never falls back) if it is not built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FgError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the render path)"
+            )
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if L.fg_abi_version() != ABI_VERSION:
+            raise FgError(f"ABI mismatch: library {L.fg_abi_version()} vs binding {ABI_VERSION}; rebuild")
+        _lib = L
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        msg = lib().fg_last_error().decode()
+        if code == 1:
+            raise AssertionError(msg)  # gsplat convention: bad arguments are assertion failures
+        raise FgError(f"fg error {code}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Tensor must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "internal: non-contiguous tensor handed to the C ABI"
+    return t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(lib().fg_launch_count())

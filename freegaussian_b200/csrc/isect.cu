@@ -1,0 +1,239 @@
+// (2a) Tile-intersection bookkeeping: exclusive scan of per-splat tile counts, emission
+// of (camera|tile|depth) keys, and per-tile offsets into the sorted list.
+// Replaces gsplat isect_tiles (+torch.cumsum) and isect_offset_encode
+// (tile_size=16 at freegaussian_model.py:806).
+//
+// Roofline: HBM.  Scan: 8 B read + 4 B written per (c,n).  Emission: 20 B read per (c,n),
+// 12 B written per intersection.  Offsets: 8 B read per intersection + 4 B per tile.
+#include "common.cuh"
+#include "splat_math.h"
+
+namespace fg {
+
+// ------------------------------------------------------------------ exclusive scan (int32)
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 4096 counts per block
+
+__device__ __forceinline__ long long warp_incl_scan(long long v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        long long o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one int64 per thread; returns exclusive prefix, total via *total
+__device__ __forceinline__ long long block_excl_scan(long long v, long long* total, long long* warp_sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long incl = warp_incl_scan(v);
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = lane < (SCAN_THREADS / 32) ? warp_sums[lane] : 0;
+        long long wi = warp_incl_scan(w);
+        if (lane < (SCAN_THREADS / 32)) warp_sums[lane] = wi - w;
+        if (lane == 31) warp_sums[32] = wi;
+    }
+    __syncthreads();
+    long long excl = incl - v + warp_sums[warp];
+    *total = warp_sums[32];
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(long long n, const int32_t* __restrict__ counts,
+                                                                   long long* __restrict__ block_sums) {
+    __shared__ long long warp_sums[33];
+    const long long base = (long long)blockIdx.x * SCAN_TILE;
+    long long s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        long long idx = base + i * SCAN_THREADS + threadIdx.x;
+        if (idx < n) s += counts[idx];
+    }
+    long long total;
+    block_excl_scan(s, &total, warp_sums);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block_sums in place, grand total -> *total
+__global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(int nblocks, long long* __restrict__ block_sums,
+                                                                  long long* __restrict__ total_out) {
+    __shared__ long long warp_sums[33];
+    long long carry = 0;
+    for (int base = 0; base < nblocks; base += SCAN_THREADS) {
+        int i = base + threadIdx.x;
+        long long v = i < nblocks ? block_sums[i] : 0;
+        long long total;
+        long long excl = block_excl_scan(v, &total, warp_sums);
+        if (i < nblocks) block_sums[i] = carry + excl;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(long long n, const int32_t* __restrict__ counts,
+                                                                  const long long* __restrict__ block_sums,
+                                                                  int32_t* __restrict__ offsets) {
+    __shared__ long long warp_sums[33];
+    // blocked arrangement: thread t owns items [t*ITEMS, (t+1)*ITEMS) of the tile
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    long long s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? counts[base + i] : 0;
+        s += v[i];
+    }
+    long long total;
+    long long run = block_excl_scan(s, &total, warp_sums) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) offsets[base + i] = (int32_t)run;
+        run += v[i];
+    }
+}
+
+// ------------------------------------------------------------------ emission
+// One thread per (c,n).  Splats touching many tiles are emitted cooperatively by their
+// whole warp so a single huge splat does not serialise one lane.
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_COOP_MIN = 32;  // tiles; at or above this the warp shares the work
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+    isect_emit_kernel(int C, int N, const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
+                      const float* __restrict__ depths, const int32_t* __restrict__ offsets, int tile_size,
+                      int tile_w, int tile_h, int tile_bits, int64_t* __restrict__ isect_ids,
+                      int32_t* __restrict__ flatten_ids) {
+    const long long total = (long long)C * N;
+    const long long idx = (long long)blockIdx.x * EMIT_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0, cnt = 0, off = 0;
+    int64_t key_base = 0;
+    if (idx < total) {
+        int r = radii[idx];
+        if (r > 0) {
+            float2 m = means2d[idx];
+            TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
+            x0 = t.x0; x1 = t.x1; y0 = t.y0; y1 = t.y1;
+            cnt = (x1 - x0) * (y1 - y0);
+            off = offsets[idx];
+            int64_t cam = idx / N;
+            key_base = (cam << (32 + tile_bits)) | (int64_t)(uint32_t)__float_as_int(depths[idx]);
+        }
+    }
+    // small splats: each lane writes its own
+    if (cnt > 0 && cnt < EMIT_COOP_MIN) {
+        int k = off;
+        for (int i = y0; i < y1; ++i)
+            for (int j = x0; j < x1; ++j) {
+                isect_ids[k] = key_base | ((int64_t)(i * tile_w + j) << 32);
+                flatten_ids[k] = (int32_t)idx;
+                ++k;
+            }
+    }
+    // large splats: whole warp cooperates, one splat at a time
+    unsigned big = __ballot_sync(0xffffffffu, cnt >= EMIT_COOP_MIN);
+    while (big) {
+        int src = __ffs(big) - 1;
+        big &= big - 1;
+        int bx0 = __shfl_sync(0xffffffffu, x0, src), bx1 = __shfl_sync(0xffffffffu, x1, src);
+        int by0 = __shfl_sync(0xffffffffu, y0, src);
+        int bcnt = __shfl_sync(0xffffffffu, cnt, src), boff = __shfl_sync(0xffffffffu, off, src);
+        long long bkey = __shfl_sync(0xffffffffu, (long long)key_base, src);
+        long long bidx = idx - lane + src;
+        int w = bx1 - bx0;
+        for (int t = lane; t < bcnt; t += 32) {
+            int i = by0 + t / w, j = bx0 + t % w;
+            isect_ids[boff + t] = (int64_t)bkey | ((int64_t)(i * tile_w + j) << 32);
+            flatten_ids[boff + t] = (int32_t)bidx;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ offsets
+// offsets[t] = first index whose (cam,tile) id is >= t.  Thread i compares id(i-1), id(i)
+// and fills every tile id in (id(i-1), id(i)]; the last thread also fills the tail.
+__global__ void __launch_bounds__(256)
+    isect_offsets_kernel(long long n_isects, const int64_t* __restrict__ sorted_ids, int n_tiles_per_cam,
+                         int tile_bits, long long n_tiles_total, int32_t* __restrict__ offsets) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_isects) return;
+    auto lin = [&](int64_t key) -> long long {
+        long long id = key >> 32;
+        long long cam = id >> tile_bits;
+        long long tile = id & ((1ll << tile_bits) - 1);
+        return cam * n_tiles_per_cam + tile;
+    };
+    const long long cur = lin(sorted_ids[i]);
+    const long long prev = (i == 0) ? -1 : lin(sorted_ids[i - 1]);
+    for (long long t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
+    if (i == n_isects - 1)
+        for (long long t = cur + 1; t < n_tiles_total; ++t) offsets[t] = (int32_t)n_isects;
+}
+
+__global__ void fill_i32_kernel(long long n, int32_t v, int32_t* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+}  // namespace fg
+
+using namespace fg;
+
+extern "C" int64_t fg_scan_workspace_bytes(int64_t n) {
+    int64_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+    return (nblocks + 1) * (int64_t)sizeof(long long);
+}
+
+extern "C" int fg_exclusive_scan_i32(int64_t n, const int32_t* counts, int32_t* offsets, int64_t* total,
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
+    FG_REQUIRE(n >= 0 && total, "n must be >= 0 and total must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        FG_CUDA(cudaMemsetAsync(total, 0, sizeof(int64_t), st));
+        return FG_OK;
+    }
+    FG_REQUIRE(counts && offsets && workspace, "counts/offsets/workspace must not be NULL");
+    FG_REQUIRE(workspace_bytes >= fg_scan_workspace_bytes(n), "scan workspace too small");
+    int nblocks = ceil_div(n, SCAN_TILE);
+    long long* block_sums = (long long*)workspace;
+    FG_LAUNCH(scan_reduce_kernel, nblocks, SCAN_THREADS, 0, st, (long long)n, counts, block_sums);
+    FG_LAUNCH(scan_spine_kernel, 1, SCAN_THREADS, 0, st, nblocks, block_sums, (long long*)total);
+    FG_LAUNCH(scan_apply_kernel, nblocks, SCAN_THREADS, 0, st, (long long)n, counts, block_sums, offsets);
+    return FG_OK;
+}
+
+extern "C" int fg_isect_emit(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
+                             const int32_t* offsets, int tile_size, int tile_w, int tile_h, int64_t* isect_ids,
+                             int32_t* flatten_ids, void* stream) {
+    FG_REQUIRE(C >= 1 && N >= 0 && (long long)C * N < (1ll << 31), "bad C/N");
+    FG_REQUIRE(tile_size > 0 && tile_w > 0 && tile_h > 0, "bad tile geometry");
+    if (N == 0) return FG_OK;
+    FG_REQUIRE(means2d && radii && depths && offsets && isect_ids && flatten_ids, "NULL pointer");
+    int tile_bits = tile_bits_of(tile_w * tile_h);
+    long long total = (long long)C * N;
+    FG_LAUNCH(isect_emit_kernel, ceil_div(total, EMIT_THREADS), EMIT_THREADS, 0, stream, C, N,
+              (const float2*)means2d, radii, depths, offsets, tile_size, tile_w, tile_h, tile_bits, isect_ids,
+              flatten_ids);
+    return FG_OK;
+}
+
+extern "C" int fg_isect_offsets(int64_t n_isects, const int64_t* sorted_isect_ids, int C, int tile_w, int tile_h,
+                                int32_t* offsets, void* stream) {
+    FG_REQUIRE(n_isects >= 0 && n_isects < (1ll << 31), "n_isects must be in [0, 2^31)");
+    FG_REQUIRE(C >= 1 && tile_w > 0 && tile_h > 0 && offsets, "bad arguments");
+    long long n_tiles = (long long)C * tile_w * tile_h;
+    if (n_isects == 0) {
+        FG_LAUNCH(fill_i32_kernel, ceil_div(n_tiles, 256), 256, 0, stream, n_tiles, 0, offsets);
+        return FG_OK;
+    }
+    FG_REQUIRE(sorted_isect_ids, "sorted_isect_ids must not be NULL");
+    int tile_bits = tile_bits_of(tile_w * tile_h);
+    FG_LAUNCH(isect_offsets_kernel, ceil_div(n_isects, 256), 256, 0, stream, (long long)n_isects,
+              sorted_isect_ids, tile_w * tile_h, tile_bits, n_tiles, offsets);
+    return FG_OK;
+}

@@ -1,0 +1,262 @@
+// (3b) Per-tile alpha compositing, backward (pixel-parallel variant).
+// Replaces gsplat rasterize_to_pixels_bwd behind the
+// loss.backward() of the training step that calls freegaussian_model.py:847-868.
+//
+// Each thread replays its pixel back-to-front from last_ids with T = T_final, recovering
+// T_i by division, and produces per-(pixel,Gaussian) partials for the CH feature channels,
+// the conic (3), the 2-D mean (2), |d/dmean| (2, absgrad) and the opacity (1).  Partials
+// are summed over the warp's 8x4 pixel patch with shuffles and added to the per-Gaussian
+// accumulators with one atomic per value per warp; a warp whose 32 pixels all skip a
+// Gaussian skips the whole reduction (the common case for splats smaller than a tile).
+//
+// Roofline: FP32 pipe + shuffle/atomic throughput; ~70 flop per evaluated pair at 6
+// channels.
+#include "rasterize_common.cuh"
+
+namespace fg {
+
+struct RasterBwdParams {
+    int C, N, width, height, tile_w, tile_h;
+    const float2* means2d;
+    const float* conics;
+    const float* feat;
+    const float* opacities;
+    const float* backgrounds;
+    const float4* flow_affine;
+    int flow_ch0;
+    const int32_t* isect_offsets;
+    const int32_t* flatten_ids;
+    long long n_isects;
+    const float* alphas;
+    const int32_t* last_ids;
+    const float* v_render;
+    const float* v_alphas;
+    float* v_means2d;
+    float* v_means2d_abs;
+    float* v_conics;
+    float* v_feat;
+    float* v_opacities;
+    float* v_flow_affine;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int CH, bool AFF>
+__global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams p) {
+    constexpr int FV = (CH + 3) / 4;
+    __shared__ float4 sA[BATCH];
+    __shared__ float4 sB[BATCH];
+    __shared__ float4 sF[FV][BATCH];
+    __shared__ float4 sM[AFF ? BATCH : 1];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cam = blockIdx.z;
+    const int tile_id = (cam * p.tile_h + blockIdx.y) * p.tile_w + blockIdx.x;
+    int lx, ly;
+    tile_pixel(tid, lx, ly);
+    const int ix = blockIdx.x * TILE + lx, iy = blockIdx.y * TILE + ly;
+    const float px = ix + 0.5f, py = iy + 0.5f;
+    const bool inside = ix < p.width && iy < p.height;
+    const size_t pix = ((size_t)cam * p.height + min(iy, p.height - 1)) * p.width + min(ix, p.width - 1);
+
+    const int range_start = p.isect_offsets[tile_id];
+    const int range_end = (tile_id == p.C * p.tile_h * p.tile_w - 1) ? (int)p.n_isects : p.isect_offsets[tile_id + 1];
+    const int nb = (range_end - range_start + BATCH - 1) / BATCH;
+    if (nb == 0) return;
+
+    const float T_final = 1.f - p.alphas[pix];
+    float T = T_final;
+    float buffer[CH];
+    float v_out[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        buffer[k] = 0.f;
+        v_out[k] = inside ? p.v_render[pix * CH + k] : 0.f;
+    }
+    const float v_alpha_out = (inside && p.v_alphas) ? p.v_alphas[pix] : 0.f;
+    float bg_dot = 0.f;
+    if (p.backgrounds) {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) bg_dot += p.backgrounds[cam * CH + k] * v_out[k];
+    }
+    const int bin_final = inside ? p.last_ids[pix] : -1;
+    const int warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
+
+    for (int b = 0; b < nb; ++b) {
+        __syncthreads();
+        // batches run back to front; within a batch, smem slot t holds sorted index batch_end - t
+        const int batch_end = range_end - 1 - BATCH * b;
+        const int bs = min(BATCH, batch_end + 1 - range_start);
+        const int idx = batch_end - tid;
+        if (idx >= range_start) {
+            const int g = p.flatten_ids[idx];
+            const float2 m = p.means2d[g];
+            const float ca = p.conics[3 * (size_t)g], cb = p.conics[3 * (size_t)g + 1], cc = p.conics[3 * (size_t)g + 2];
+            sA[tid] = make_float4(m.x, m.y, p.opacities[g], 0.5f * LOG2E * ca);
+            sB[tid] = make_float4(LOG2E * cb, 0.5f * LOG2E * cc, __int_as_float(g), 0.f);
+            float f[FV * 4];
+#pragma unroll
+            for (int k = 0; k < FV * 4; ++k) f[k] = (k < CH) ? p.feat[(size_t)g * CH + k] : 0.f;
+#pragma unroll
+            for (int j = 0; j < FV; ++j) sF[j][tid] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (AFF) sM[tid] = p.flow_affine[g];
+        }
+        __syncthreads();
+        for (int t = max(0, batch_end - warp_bin_final); t < bs; ++t) {
+            const float4 a4 = sA[t], b4 = sB[t];
+            const GeomA ga = {a4.x, a4.y, a4.z, a4.w};
+            const GeomB gb = {b4.x, b4.y, 0, 0.f};
+            float dx, dy, vis, alpha;
+            bool valid = eval_alpha(ga, gb, px, py, dx, dy, vis, alpha);
+            valid = valid && (batch_end - t <= bin_final);
+            if (!__any_sync(0xffffffffu, valid)) continue;
+
+            float v_f[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) v_f[k] = 0.f;
+            float v_ca = 0.f, v_cb = 0.f, v_cc = 0.f, v_x = 0.f, v_y = 0.f, v_ax = 0.f, v_ay = 0.f, v_op = 0.f;
+            float v_m0 = 0.f, v_m1 = 0.f, v_m2 = 0.f, v_m3 = 0.f;
+            if (valid) {
+                float f[FV * 4];
+#pragma unroll
+                for (int j = 0; j < FV; ++j) {
+                    const float4 v = sF[j][t];
+                    f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+                }
+                float4 M = make_float4(0.f, 0.f, 0.f, 0.f);
+                float vo0 = 0.f, vo1 = 0.f;  // v_out of the two flow channels
+                if (AFF) {
+                    M = sM[t];
+                    const float e0 = M.x * dx + M.y * dy, e1 = M.z * dx + M.w * dy;
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) {
+                        if (k == p.flow_ch0) { f[k] -= e0; vo0 = v_out[k]; }
+                        if (k == p.flow_ch0 + 1) { f[k] -= e1; vo1 = v_out[k]; }
+                    }
+                }
+                const float ra = 1.f / (1.f - alpha);
+                T *= ra;
+                const float fac = alpha * T;
+                float v_alpha = 0.f;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    v_f[k] = fac * v_out[k];
+                    v_alpha += (f[k] * T - buffer[k] * ra) * v_out[k];
+                    buffer[k] += f[k] * fac;
+                }
+                v_alpha += T_final * ra * v_alpha_out;
+                if (p.backgrounds) v_alpha -= T_final * ra * bg_dot;
+                if (AFF) {
+                    // f_flow = feat - M delta: d/dM and d/ddelta of the composited flow
+                    v_m0 = -fac * vo0 * dx; v_m1 = -fac * vo0 * dy;
+                    v_m2 = -fac * vo1 * dx; v_m3 = -fac * vo1 * dy;
+                    v_x = -fac * (vo0 * M.x + vo1 * M.z);
+                    v_y = -fac * (vo0 * M.y + vo1 * M.w);
+                }
+                if (a4.z * vis <= ALPHA_MAX) {
+                    const float v_sigma = -a4.z * vis * v_alpha;
+                    v_ca = 0.5f * v_sigma * dx * dx;
+                    v_cb = v_sigma * dx * dy;
+                    v_cc = 0.5f * v_sigma * dy * dy;
+                    // unscaled conic: A = 2 qa / log2e, B = qb / log2e, C = 2 qc / log2e
+                    const float vs = v_sigma * LN2;
+                    const float gx = vs * (2.f * a4.w * dx + b4.x * dy);
+                    const float gy = vs * (b4.x * dx + 2.f * b4.y * dy);
+                    v_ax = fabsf(gx);
+                    v_ay = fabsf(gy);
+                    v_x += gx;
+                    v_y += gy;
+                    v_op = vis * v_alpha;
+                }
+            }
+            // warp reduction, then one atomic per value
+#pragma unroll
+            for (int k = 0; k < CH; ++k) v_f[k] = warp_sum(v_f[k]);
+            v_ca = warp_sum(v_ca); v_cb = warp_sum(v_cb); v_cc = warp_sum(v_cc);
+            v_x = warp_sum(v_x); v_y = warp_sum(v_y);
+            v_op = warp_sum(v_op);
+            if (p.v_means2d_abs) { v_ax = warp_sum(v_ax); v_ay = warp_sum(v_ay); }
+            if (AFF) { v_m0 = warp_sum(v_m0); v_m1 = warp_sum(v_m1); v_m2 = warp_sum(v_m2); v_m3 = warp_sum(v_m3); }
+            if (lane == 0) {
+                const size_t g = (size_t)__float_as_int(b4.z);
+#pragma unroll
+                for (int k = 0; k < CH; ++k) atomicAdd(p.v_feat + g * CH + k, v_f[k]);
+                atomicAdd(p.v_conics + 3 * g, v_ca);
+                atomicAdd(p.v_conics + 3 * g + 1, v_cb);
+                atomicAdd(p.v_conics + 3 * g + 2, v_cc);
+                atomicAdd(p.v_means2d + 2 * g, v_x);
+                atomicAdd(p.v_means2d + 2 * g + 1, v_y);
+                if (p.v_means2d_abs) {
+                    atomicAdd(p.v_means2d_abs + 2 * g, v_ax);
+                    atomicAdd(p.v_means2d_abs + 2 * g + 1, v_ay);
+                }
+                atomicAdd(p.v_opacities + g, v_op);
+                if (AFF) {
+                    atomicAdd(p.v_flow_affine + 4 * g, v_m0);
+                    atomicAdd(p.v_flow_affine + 4 * g + 1, v_m1);
+                    atomicAdd(p.v_flow_affine + 4 * g + 2, v_m2);
+                    atomicAdd(p.v_flow_affine + 4 * g + 3, v_m3);
+                }
+            }
+        }
+    }
+}
+
+template <int CH>
+static int launch_raster_bwd(const RasterBwdParams& p, cudaStream_t st) {
+    dim3 grid(p.tile_w, p.tile_h, p.C);
+    if (p.flow_affine) {
+        if (CH >= 2) {
+            FG_LAUNCH((rasterize_bwd_kernel<(CH >= 2 ? CH : 2), true>), grid, TILE_PIX, 0, st, p);
+        }
+    } else {
+        FG_LAUNCH((rasterize_bwd_kernel<CH, false>), grid, TILE_PIX, 0, st, p);
+    }
+    return FG_OK;
+}
+
+}  // namespace fg
+
+using namespace fg;
+
+extern "C" int fg_rasterize_bwd(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
+                                const float* conics, const float* feat, const float* opacities,
+                                const float* backgrounds, const float* flow_affine, int flow_ch0,
+                                const int32_t* isect_offsets, const int32_t* flatten_ids, int64_t n_isects,
+                                const float* alphas, const int32_t* last_ids, const float* v_render,
+                                const float* v_alphas, float* v_means2d, float* v_means2d_abs, float* v_conics,
+                                float* v_feat, float* v_opacities, float* v_flow_affine, void* stream) {
+    FG_REQUIRE(tile_size == TILE, "only tile_size=16 is supported (freegaussian_model.py:806)");
+    FG_REQUIRE(C >= 1 && N >= 0 && width > 0 && height > 0, "bad C/N/width/height");
+    FG_REQUIRE(CH >= 1 && CH <= FG_MAX_CHANNELS, "CH must be in 1..FG_MAX_CHANNELS");
+    FG_REQUIRE(n_isects >= 0 && n_isects < (1ll << 31), "n_isects out of range");
+    if (n_isects == 0) return FG_OK;
+    FG_REQUIRE(means2d && conics && feat && opacities && isect_offsets && flatten_ids && alphas && last_ids && v_render,
+               "NULL input pointer");
+    FG_REQUIRE(v_means2d && v_conics && v_feat && v_opacities, "NULL gradient output pointer");
+    FG_REQUIRE(!flow_affine || (flow_ch0 >= 0 && flow_ch0 + 1 < CH && v_flow_affine), "bad flow_affine arguments");
+    RasterBwdParams p;
+    p.C = C; p.N = N; p.width = width; p.height = height;
+    p.tile_w = (width + TILE - 1) / TILE; p.tile_h = (height + TILE - 1) / TILE;
+    p.means2d = (const float2*)means2d; p.conics = conics; p.feat = feat; p.opacities = opacities;
+    p.backgrounds = backgrounds; p.flow_affine = (const float4*)flow_affine; p.flow_ch0 = flow_ch0;
+    p.isect_offsets = isect_offsets; p.flatten_ids = flatten_ids; p.n_isects = n_isects;
+    p.alphas = alphas; p.last_ids = last_ids; p.v_render = v_render; p.v_alphas = v_alphas;
+    p.v_means2d = v_means2d; p.v_means2d_abs = v_means2d_abs; p.v_conics = v_conics; p.v_feat = v_feat;
+    p.v_opacities = v_opacities; p.v_flow_affine = v_flow_affine;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (CH) {
+        case 1: return launch_raster_bwd<1>(p, st);
+        case 2: return launch_raster_bwd<2>(p, st);
+        case 3: return launch_raster_bwd<3>(p, st);
+        case 4: return launch_raster_bwd<4>(p, st);
+        case 5: return launch_raster_bwd<5>(p, st);
+        case 6: return launch_raster_bwd<6>(p, st);
+        case 7: return launch_raster_bwd<7>(p, st);
+        default: return launch_raster_bwd<8>(p, st);
+    }
+}

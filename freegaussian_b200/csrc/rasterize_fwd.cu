@@ -1,0 +1,178 @@
+// (3a) Per-tile front-to-back alpha compositing, forward: RGB + depth + flow (all CH
+// channels) in one pass.  Replaces gsplat rasterize_to_pixels_fwd
+// behind freegaussian_model.py:847-868.
+//
+// Roofline: FP32 pipe / shared memory.  Unit = one evaluated (pixel, Gaussian) pair:
+// ~12 flop for delta/sigma/alpha/T + 2 flop per channel + one MUFU.EX2 (24 flop at 6
+// channels).  HBM floor: 32-56 B gathered per intersection + the images.
+//
+// One CTA per 16x16 tile, one pixel per thread, warps own 8x4 patches.  The tile's sorted
+// list is consumed in batches of 256 Gaussians staged in shared memory as float4 records
+// (every inner-loop read is a broadcast LDS.128).
+#include "rasterize_common.cuh"
+
+namespace fg {
+
+struct RasterFwdParams {
+    int C, N, width, height, tile_w, tile_h;
+    const float2* means2d;
+    const float* conics;
+    const float* feat;
+    const float* opacities;
+    const float* backgrounds;
+    const float4* flow_affine;
+    int flow_ch0;
+    const int32_t* isect_offsets;
+    const int32_t* flatten_ids;
+    long long n_isects;
+    float* render;
+    float* alphas;
+    int32_t* last_ids;
+};
+
+template <int CH, bool AFF>
+__global__ void __launch_bounds__(TILE_PIX) rasterize_fwd_kernel(RasterFwdParams p) {
+    constexpr int FV = (CH + 3) / 4;  // float4 per Gaussian for the features
+    __shared__ float4 sA[BATCH];
+    __shared__ float4 sB[BATCH];
+    __shared__ float4 sF[FV][BATCH];
+    __shared__ float4 sM[AFF ? BATCH : 1];
+
+    const int tid = threadIdx.x;
+    const int cam = blockIdx.z;
+    const int tile_id = (cam * p.tile_h + blockIdx.y) * p.tile_w + blockIdx.x;
+    int lx, ly;
+    tile_pixel(tid, lx, ly);
+    const int ix = blockIdx.x * TILE + lx, iy = blockIdx.y * TILE + ly;
+    const float px = ix + 0.5f, py = iy + 0.5f;
+    const bool inside = ix < p.width && iy < p.height;
+    bool done = !inside;
+
+    const int range_start = p.isect_offsets[tile_id];
+    const int range_end = (tile_id == p.C * p.tile_h * p.tile_w - 1) ? (int)p.n_isects : p.isect_offsets[tile_id + 1];
+    const int nb = (range_end - range_start + BATCH - 1) / BATCH;
+
+    float T = 1.f;
+    int cur_idx = 0;
+    float acc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[k] = 0.f;
+
+    for (int b = 0; b < nb; ++b) {
+        // barrier (previous batch fully consumed) + early exit when every pixel is finished
+        if (__syncthreads_count(done) >= TILE_PIX) break;
+        const int batch_start = range_start + b * BATCH;
+        const int idx = batch_start + tid;
+        if (idx < range_end) {
+            const int g = p.flatten_ids[idx];
+            const float2 m = p.means2d[g];
+            const float ca = p.conics[3 * (size_t)g], cb = p.conics[3 * (size_t)g + 1], cc = p.conics[3 * (size_t)g + 2];
+            sA[tid] = make_float4(m.x, m.y, p.opacities[g], 0.5f * LOG2E * ca);
+            sB[tid] = make_float4(LOG2E * cb, 0.5f * LOG2E * cc, __int_as_float(g), 0.f);
+            float f[FV * 4];
+#pragma unroll
+            for (int k = 0; k < FV * 4; ++k) f[k] = (k < CH) ? p.feat[(size_t)g * CH + k] : 0.f;
+#pragma unroll
+            for (int j = 0; j < FV; ++j) sF[j][tid] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (AFF) sM[tid] = p.flow_affine[g];
+        }
+        __syncthreads();
+        const int bs = min(BATCH, range_end - batch_start);
+        for (int t = 0; t < bs && !done; ++t) {
+            const float4 a4 = sA[t], b4 = sB[t];
+            const GeomA ga = {a4.x, a4.y, a4.z, a4.w};
+            const GeomB gb = {b4.x, b4.y, 0, 0.f};
+            float dx, dy, vis, alpha;
+            if (!eval_alpha(ga, gb, px, py, dx, dy, vis, alpha)) continue;
+            const float next_T = T * (1.f - alpha);
+            if (next_T <= T_STOP) {  // this Gaussian is not composited
+                done = true;
+                break;
+            }
+            const float w = alpha * T;
+            float f[FV * 4];
+#pragma unroll
+            for (int j = 0; j < FV; ++j) {
+                const float4 v = sF[j][t];
+                f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+            }
+            float e0 = 0.f, e1 = 0.f;
+            if (AFF) {  // flow channels get + A (p - mu) = -A delta
+                const float4 M = sM[t];
+                e0 = M.x * dx + M.y * dy;
+                e1 = M.z * dx + M.w * dy;
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                float fk = f[k];
+                if (AFF) {
+                    if (k == p.flow_ch0) fk -= e0;
+                    if (k == p.flow_ch0 + 1) fk -= e1;
+                }
+                acc[k] = fmaf(fk, w, acc[k]);
+            }
+            cur_idx = batch_start + t;
+            T = next_T;
+        }
+    }
+    if (inside) {
+        const size_t pix = ((size_t)cam * p.height + iy) * p.width + ix;
+        p.alphas[pix] = 1.f - T;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            float v = acc[k];
+            if (p.backgrounds) v = fmaf(T, p.backgrounds[cam * CH + k], v);
+            p.render[pix * CH + k] = v;
+        }
+        p.last_ids[pix] = cur_idx;
+    }
+}
+
+template <int CH>
+static int launch_raster_fwd(const RasterFwdParams& p, cudaStream_t st) {
+    dim3 grid(p.tile_w, p.tile_h, p.C);
+    if (p.flow_affine) {
+        if (CH >= 2) {
+            FG_LAUNCH((rasterize_fwd_kernel<(CH >= 2 ? CH : 2), true>), grid, TILE_PIX, 0, st, p);
+        }
+    } else {
+        FG_LAUNCH((rasterize_fwd_kernel<CH, false>), grid, TILE_PIX, 0, st, p);
+    }
+    return FG_OK;
+}
+
+}  // namespace fg
+
+using namespace fg;
+
+extern "C" int fg_rasterize_fwd(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
+                                const float* conics, const float* feat, const float* opacities,
+                                const float* backgrounds, const float* flow_affine, int flow_ch0,
+                                const int32_t* isect_offsets, const int32_t* flatten_ids, int64_t n_isects,
+                                float* render, float* alphas, int32_t* last_ids, void* stream) {
+    FG_REQUIRE(tile_size == TILE, "only tile_size=16 is supported (freegaussian_model.py:806)");
+    FG_REQUIRE(C >= 1 && N >= 0 && width > 0 && height > 0, "bad C/N/width/height");
+    FG_REQUIRE(CH >= 1 && CH <= FG_MAX_CHANNELS, "CH must be in 1..FG_MAX_CHANNELS");
+    FG_REQUIRE(n_isects >= 0 && n_isects < (1ll << 31), "n_isects out of range");
+    FG_REQUIRE(isect_offsets && render && alphas && last_ids, "NULL output/offset pointer");
+    FG_REQUIRE(n_isects == 0 || (means2d && conics && feat && opacities && flatten_ids), "NULL input pointer");
+    FG_REQUIRE(!flow_affine || (flow_ch0 >= 0 && flow_ch0 + 1 < CH), "flow_ch0 out of range");
+    RasterFwdParams p;
+    p.C = C; p.N = N; p.width = width; p.height = height;
+    p.tile_w = (width + TILE - 1) / TILE; p.tile_h = (height + TILE - 1) / TILE;
+    p.means2d = (const float2*)means2d; p.conics = conics; p.feat = feat; p.opacities = opacities;
+    p.backgrounds = backgrounds; p.flow_affine = (const float4*)flow_affine; p.flow_ch0 = flow_ch0;
+    p.isect_offsets = isect_offsets; p.flatten_ids = flatten_ids; p.n_isects = n_isects;
+    p.render = render; p.alphas = alphas; p.last_ids = last_ids;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (CH) {
+        case 1: return launch_raster_fwd<1>(p, st);
+        case 2: return launch_raster_fwd<2>(p, st);
+        case 3: return launch_raster_fwd<3>(p, st);
+        case 4: return launch_raster_fwd<4>(p, st);
+        case 5: return launch_raster_fwd<5>(p, st);
+        case 6: return launch_raster_fwd<6>(p, st);
+        case 7: return launch_raster_fwd<7>(p, st);
+        default: return launch_raster_fwd<8>(p, st);
+    }
+}

@@ -1,0 +1,399 @@
+"""``rasterization(...)`` -- the drop-in boundary of the B200-native splat renderer.
+
+Same call signature, return tuple and ``meta`` keys as ``gsplat.rendering.rasterization``
+(gsplat 1.4 semantics) as FreeGaussian calls it at
+``freegaussian/freegaussian_model.py:847-868``, ``freegaussian_control_model.py:158-179``
+and (``packed=True``, ``"ED"``) ``preprocess/knn_gaussian.py:93-113``.  Host logic only:
+every arithmetic step runs in the hand-written sm_100a kernels behind the C ABI of
+``include/fg_api.h`` (``libfreegaussian_b200.so``), on ``torch.cuda.current_stream()``.
+There is no CPU path: non-CUDA inputs raise.
+
+Extension (BASELINE.json north_star): pass ``means_next`` (frame t+1
+means; optionally ``quats_next`` / ``scales_next`` with ``flow_mode="cov"``) and the rendered
+Gaussian flow ``sum_i T_i alpha_i (mu2d_i(t+1) - mu2d_i(t))`` (``docs/index.html:286-299``)
+comes back as ``meta["flow"]`` ``[C,H,W,2]``, composited in the same pass as RGB and depth.
+Without these kwargs the behaviour is exactly the reference call's.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, ptr
+
+MAX_CH = 8  # FG_MAX_CHANNELS
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Workspace:
+    """Per-device scratch buffers reused across calls (safe to drop at any time)."""
+
+    def __init__(self):
+        self.bufs: Dict[Tuple[str, int], Tensor] = {}
+
+    def get(self, name: str, nbytes: int, device) -> Tensor:
+        key = (name, torch.device(device).index or 0)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1024), dtype=torch.uint8, device=device)
+            self.bufs[key] = buf
+        return buf
+
+
+_ws = _Workspace()
+
+
+def _require_cuda(**tensors) -> None:
+    for name, t in tensors.items():
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                f"freegaussian_b200.rasterization: `{name}` is on {t.device}; the renderer has no CPU path "
+                "(the CUDA kernels are the only implementation)"
+            )
+        assert t.dtype == torch.float32, f"{name} must be float32, got {t.dtype}"
+
+
+# --------------------------------------------------------------------------- projection
+class _Project(torch.autograd.Function):
+    """fg_project_fwd / fg_project_bwd.  Outputs: radii, means2d, depths, conics, comps, feat, tiles."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, colors, means_next, viewmats, Ks, cfg):
+        L = _lib.lib()
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        means, quats, scales = means.contiguous(), quats.contiguous(), scales.contiguous()
+        viewmats, Ks = viewmats.contiguous(), Ks.contiguous()
+        sh_degree = cfg["sh_degree"]
+        use_sh = sh_degree is not None
+        if use_sh:
+            colors = colors.contiguous()
+            sh_bases = colors.shape[-2]
+            n_col = 3
+        else:
+            sh_bases = 0
+            n_col = 0 if colors is None else colors.shape[-1]
+        want_depth, want_flow = cfg["want_depth"], means_next is not None
+        if means_next is not None:
+            means_next = means_next.contiguous()
+        CH = n_col + (1 if want_depth else 0) + (2 if want_flow else 0)
+        rgb_off = 0 if use_sh else -1
+        depth_off = n_col if want_depth else -1
+        flow_off = n_col + (1 if want_depth else 0) if want_flow else -1
+
+        radii = torch.empty(C, N, dtype=torch.int32, device=dev)
+        means2d = torch.empty(C, N, 2, device=dev)
+        depths = torch.empty(C, N, device=dev)
+        conics = torch.empty(C, N, 3, device=dev)
+        comps = torch.empty(C, N, device=dev) if cfg["antialiased"] else None
+        feat = torch.empty(C, N, CH, device=dev)
+        tiles = torch.empty(C, N, dtype=torch.int32, device=dev)
+        check(L.fg_project_fwd(
+            C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
+            cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"], cfg["tile_size"],
+            sh_degree if use_sh else -1, sh_bases, ptr(colors) if use_sh else None, ptr(means_next), None, None, 0,
+            ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(feat), CH, rgb_off, depth_off,
+            flow_off, None, ptr(tiles), _stream()))
+        if not use_sh and colors is not None:
+            feat[..., :n_col] = colors if colors.dim() == 3 else colors[None]
+        ctx.save_for_backward(means, quats, scales, colors if use_sh else None, means_next, viewmats, Ks, radii)
+        ctx.cfg = cfg
+        ctx.layout = (CH, n_col, rgb_off, depth_off, flow_off, sh_bases, use_sh,
+                      None if colors is None else colors.dim())
+        ctx.mark_non_differentiable(radii, tiles)
+        if comps is None:
+            comps = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(comps)
+        return radii, means2d, depths, conics, comps, feat, tiles
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_feat, _v_tiles):
+        L = _lib.lib()
+        means, quats, scales, sh, means_next, viewmats, Ks, radii = ctx.saved_tensors
+        cfg = ctx.cfg
+        CH, n_col, rgb_off, depth_off, flow_off, sh_bases, use_sh, col_dim = ctx.layout
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+
+        def c(t):
+            return None if t is None else t.contiguous()
+
+        v_means2d, v_depths, v_conics, v_feat = c(v_means2d), c(v_depths), c(v_conics), c(v_feat)
+        v_comps = c(v_comps) if cfg["antialiased"] else None
+        v_means = torch.empty(N, 3, device=dev)
+        v_quats = torch.empty(N, 4, device=dev)
+        v_scales = torch.empty(N, 3, device=dev)
+        v_sh = torch.empty(N, sh_bases, 3, device=dev) if use_sh else None
+        v_means_next = torch.empty(N, 3, device=dev) if means_next is not None else None
+        check(L.fg_project_bwd(
+            C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
+            cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"],
+            cfg["sh_degree"] if use_sh else -1, sh_bases, ptr(sh), ptr(means_next), None, None, 0, ptr(radii),
+            ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_feat), CH, rgb_off, depth_off,
+            flow_off, None, ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_sh), ptr(v_means_next), None, None,
+            _stream()))
+        v_colors = None
+        if use_sh:
+            v_colors = v_sh
+        elif col_dim is not None and v_feat is not None:
+            v_colors = v_feat[..., :n_col]
+            if col_dim == 2:
+                v_colors = v_colors.sum(0)
+        return v_means, v_quats, v_scales, v_colors, v_means_next, None, None, None
+
+
+# --------------------------------------------------------------------------- tile intersection
+@torch.no_grad()
+def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
+                tile_w: int, tile_h: int):
+    """scan -> emit -> 64-bit (camera|tile|depth) radix sort -> per-tile offsets.
+
+    Returns isect_ids [M] int64 (sorted), flatten_ids [M] int32 (sorted), isect_offsets
+    [C,tile_h,tile_w] int32.  One host sync (reading M), like gsplat.
+    """
+    L = _lib.lib()
+    C, N = radii.shape
+    dev = radii.device
+    st = _stream()
+    total = C * N
+    offsets = torch.empty(total, dtype=torch.int32, device=dev)
+    n_dev = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = _ws.get("scan", L.fg_scan_workspace_bytes(total), dev)
+    check(L.fg_exclusive_scan_i32(total, ptr(tiles_per_gauss), ptr(offsets), ptr(n_dev), ptr(ws), ws.numel(), st))
+    M = int(n_dev.item())  # host sync: sizes the intersection buffers
+    assert M < 2**31, "too many tile intersections"
+    ids_a = torch.empty(M, dtype=torch.int64, device=dev)
+    ids_b = torch.empty(M, dtype=torch.int64, device=dev)
+    val_a = torch.empty(M, dtype=torch.int32, device=dev)
+    val_b = torch.empty(M, dtype=torch.int32, device=dev)
+    isect_offsets = torch.empty(C, tile_h, tile_w, dtype=torch.int32, device=dev)
+    if M > 0:
+        check(L.fg_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(offsets), tile_size, tile_w, tile_h,
+                              ptr(ids_a), ptr(val_a), st))
+        tile_bits = int(math.floor(math.log2(tile_w * tile_h))) + 1
+        cam_bits = int(math.floor(math.log2(C))) + 1
+        ws = _ws.get("sort", L.fg_radix_sort_workspace_bytes(M), dev)
+        sel = ctypes.c_int(0)
+        check(L.fg_radix_sort_pairs_u64_u32(M, ptr(ids_a), ptr(val_a), ptr(ids_b), ptr(val_b),
+                                            32 + tile_bits + cam_bits, ptr(ws), ws.numel(), ctypes.byref(sel), st))
+        if sel.value == 1:
+            ids_a, val_a = ids_b, val_b
+    check(L.fg_isect_offsets(M, ptr(ids_a), C, tile_w, tile_h, ptr(isect_offsets), st))
+    return ids_a, val_a, isect_offsets
+
+
+# --------------------------------------------------------------------------- compositing
+class _Rasterize(torch.autograd.Function):
+    """fg_rasterize_fwd / fg_rasterize_bwd over one chunk of <= 8 channels."""
+
+    @staticmethod
+    def forward(ctx, means2d, conics, feat, opacities, backgrounds, isect_offsets, flatten_ids, width, height,
+                tile_size, absgrad, chunked=False):
+        L = _lib.lib()
+        ctx.chunked = chunked
+        C = isect_offsets.shape[0]
+        CH = feat.shape[-1]
+        NN = feat.numel() // CH  # C*N (or nnz when packed)
+        dev = feat.device
+        means2d_c, conics_c, feat_c, opac_c = (t.contiguous() for t in (means2d, conics, feat, opacities))
+        bg = None if backgrounds is None else backgrounds.contiguous()
+        render = torch.empty(C, height, width, CH, device=dev)
+        alphas = torch.empty(C, height, width, 1, device=dev)
+        last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
+        M = flatten_ids.shape[0]
+        check(L.fg_rasterize_fwd(C, NN, CH, width, height, tile_size, ptr(means2d_c),
+                                 ptr(conics_c), ptr(feat_c), ptr(opac_c), ptr(bg), None, 0, ptr(isect_offsets),
+                                 ptr(flatten_ids), M, ptr(render), ptr(alphas), ptr(last_ids), _stream()))
+        ctx.save_for_backward(means2d_c, conics_c, feat_c, opac_c, bg, isect_offsets, flatten_ids, alphas, last_ids)
+        ctx.dims = (C, NN, CH, width, height, tile_size, absgrad)
+        ctx.means2d_obj = means2d  # the very tensor the caller holds as meta["means2d"] (model.py:869-871)
+        return render, alphas
+
+    @staticmethod
+    def backward(ctx, v_render, v_alphas):
+        L = _lib.lib()
+        means2d, conics, feat, opac, bg, isect_offsets, flatten_ids, alphas, last_ids = ctx.saved_tensors
+        C, NN, CH, width, height, tile_size, absgrad = ctx.dims
+        dev = feat.device
+        v_render = v_render.contiguous()
+        v_alphas = v_alphas.contiguous()
+        v_means2d = torch.zeros_like(means2d)
+        v_abs = torch.zeros_like(means2d) if absgrad else None
+        v_conics = torch.zeros_like(conics)
+        v_feat = torch.zeros_like(feat)
+        v_opac = torch.zeros_like(opac)
+        M = flatten_ids.shape[0]
+        check(L.fg_rasterize_bwd(C, NN, CH, width, height, tile_size, ptr(means2d),
+                                 ptr(conics), ptr(feat), ptr(opac), ptr(bg), None, 0, ptr(isect_offsets),
+                                 ptr(flatten_ids), M, ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas),
+                                 ptr(v_means2d), ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), None,
+                                 _stream()))
+        if absgrad:
+            obj = ctx.means2d_obj
+            prev = getattr(obj, "absgrad", None) if ctx.chunked else None
+            obj.absgrad = v_abs if prev is None else prev + v_abs
+        v_bg = None
+        if bg is not None and ctx.needs_input_grad[4]:
+            v_bg = (v_render * (1.0 - alphas)).sum(dim=(1, 2))
+        return v_means2d, v_conics, v_feat, v_opac, v_bg, None, None, None, None, None, None, None
+
+
+def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets,
+                        flatten_ids, backgrounds=None, absgrad=False):
+    """Composite ``colors [.., D]`` (any D; chunks of 8 channels per pass).  gsplat-compatible helper."""
+    D = colors.shape[-1]
+    outs, alphas = [], None
+    for s in range(0, D, MAX_CH):
+        e = min(D, s + MAX_CH)
+        bg = None if backgrounds is None else backgrounds[..., s:e]
+        r, a = _Rasterize.apply(means2d, conics, colors[..., s:e], opacities, bg, isect_offsets, flatten_ids,
+                                image_width, image_height, tile_size, absgrad, D > MAX_CH)
+        outs.append(r)
+        alphas = a if alphas is None else alphas
+    return (outs[0] if len(outs) == 1 else torch.cat(outs, -1)), alphas
+
+
+# --------------------------------------------------------------------------- boundary
+def rasterization(
+    means: Tensor,  # [N, 3]
+    quats: Tensor,  # [N, 4]
+    scales: Tensor,  # [N, 3]
+    opacities: Tensor,  # [N]
+    colors: Tensor,  # [(C,) N, D] or [N, K, 3]
+    viewmats: Tensor,  # [C, 4, 4]
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = True,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: str = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: str = "classic",
+    channel_chunk: int = 32,
+    distributed: bool = False,
+    camera_model: str = "pinhole",
+    covars: Optional[Tensor] = None,
+    # ---- rendered Gaussian flow (north_star extension)
+    means_next: Optional[Tensor] = None,
+    quats_next: Optional[Tensor] = None,
+    scales_next: Optional[Tensor] = None,
+    flow_mode: str = "mean",
+) -> Tuple[Tensor, Tensor, Dict]:
+    """Render N Gaussians into C cameras; returns ``(render [C,H,W,X], alpha [C,H,W,1], meta)``.
+
+    X = 3 ("RGB"), 4 ("RGB+D"/"RGB+ED", depth last) or 1 ("D"/"ED"); with ``sh_degree=None``
+    the D colour channels are rendered as given.  ``meta["means2d"]`` is a graph tensor
+    (``retain_grad()`` works) that carries ``.absgrad`` after backward when ``absgrad=True``.
+    """
+    N = means.shape[0]
+    C = viewmats.shape[0]
+    assert means.shape == (N, 3), means.shape
+    assert quats.shape == (N, 4), quats.shape
+    assert scales.shape == (N, 3), scales.shape
+    assert opacities.shape == (N,), opacities.shape
+    assert viewmats.shape == (C, 4, 4), viewmats.shape
+    assert Ks.shape == (C, 3, 3), Ks.shape
+    assert render_mode in ["RGB", "D", "ED", "RGB+D", "RGB+ED"], render_mode
+    assert rasterize_mode in ["classic", "antialiased"], rasterize_mode
+    assert flow_mode in ["mean", "cov"], flow_mode
+    assert tile_size == 16, "tile_size must be 16 (freegaussian_model.py:806)"
+    if sh_degree is None:
+        assert (colors.dim() == 2 and colors.shape[0] == N) or (
+            colors.dim() == 3 and colors.shape[:2] == (C, N)
+        ), colors.shape
+    else:
+        assert colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3, colors.shape
+        assert (sh_degree + 1) ** 2 <= colors.shape[1], colors.shape
+        assert 0 <= sh_degree <= 3, "sh_degree must be in 0..3"
+    if backgrounds is not None:
+        assert backgrounds.shape[0] == C, backgrounds.shape
+    if covars is not None or distributed or camera_model != "pinhole" or sparse_grad:
+        raise NotImplementedError(
+            "covars / distributed / non-pinhole cameras / sparse_grad are never used by the reference "
+            "(freegaussian_model.py:847-868) and are not implemented"
+        )
+    if flow_mode == "cov":
+        raise NotImplementedError("flow_mode='cov' is not built yet")
+    if viewmats.requires_grad or Ks.requires_grad:
+        raise NotImplementedError("camera gradients: the reference's camera optimizer is 'off' (model.py:120)")
+    _require_cuda(means=means, quats=quats, scales=scales, opacities=opacities, colors=colors, viewmats=viewmats,
+                  Ks=Ks, backgrounds=backgrounds, means_next=means_next)
+    if means_next is not None:
+        assert means_next.shape == (N, 3), means_next.shape
+
+    want_depth = render_mode in ("D", "ED", "RGB+D", "RGB+ED")
+    only_depth = render_mode in ("D", "ED")
+    cfg = dict(width=int(width), height=int(height), eps2d=float(eps2d), near_plane=float(near_plane),
+               far_plane=float(far_plane), radius_clip=float(radius_clip), tile_size=int(tile_size),
+               sh_degree=None if only_depth else sh_degree, want_depth=want_depth,
+               antialiased=rasterize_mode == "antialiased")
+    proj_colors = None if only_depth else colors
+    radii, means2d, depths, conics, comps, feat, tiles = _Project.apply(
+        means, quats, scales, proj_colors, means_next, viewmats, Ks, cfg)
+    n_user = feat.shape[-1] - (2 if means_next is not None else 0)
+
+    opac = opacities[None].expand(C, N)
+    if rasterize_mode == "antialiased":
+        opac = opac * comps
+
+    if backgrounds is not None:
+        if only_depth:
+            backgrounds = torch.zeros(C, 1, device=means.device)
+        elif want_depth:
+            backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=means.device)], -1)
+        if means_next is not None:
+            backgrounds = torch.cat([backgrounds, torch.zeros(C, 2, device=means.device)], -1)
+
+    tile_w = math.ceil(width / tile_size)
+    tile_h = math.ceil(height / tile_size)
+    isect_ids, flatten_ids, isect_offsets = isect_tiles(means2d, radii, depths, tiles, tile_size, tile_w, tile_h)
+
+    meta = {}
+    if packed:
+        # compact per-Gaussian tensors to the visible (c,n) pairs in ascending order (Appendix A.8)
+        vis = (radii > 0).reshape(-1)
+        idx = torch.nonzero(vis).squeeze(-1)
+        remap = (torch.cumsum(vis, 0, dtype=torch.int32) - 1).to(torch.int32)
+        flatten_ids = remap[flatten_ids.long()].contiguous()
+        means2d = means2d.reshape(C * N, 2)[idx]
+        depths = depths.reshape(C * N)[idx]
+        conics = conics.reshape(C * N, 3)[idx]
+        feat = feat.reshape(C * N, -1)[idx]
+        opac = opac.reshape(C * N)[idx]
+        radii = radii.reshape(C * N)[idx]
+        meta["camera_ids"] = idx // N
+        meta["gaussian_ids"] = idx % N
+
+    render_all, alphas = rasterize_to_pixels(means2d, conics, feat, opac, width, height, tile_size, isect_offsets,
+                                             flatten_ids, backgrounds=backgrounds, absgrad=absgrad)
+    render = render_all[..., :n_user]
+    if render_mode in ("ED", "RGB+ED"):
+        render = torch.cat([render[..., :-1], render[..., -1:] / alphas.clamp(min=1e-10)], -1)
+
+    meta.update({
+        "radii": radii, "means2d": means2d, "depths": depths, "conics": conics, "opacities": opac,
+        "tile_width": tile_w, "tile_height": tile_h, "tiles_per_gauss": tiles, "isect_ids": isect_ids,
+        "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width, "height": height,
+        "tile_size": tile_size, "n_cameras": C,
+    })
+    if means_next is not None:
+        meta["flow"] = render_all[..., n_user:]
+    return render, alphas, meta

@@ -1,0 +1,160 @@
+/* freegaussian_b200 -- C ABI of the B200-native splat-render hot path.
+ *
+ * This is the drop-in boundary below the Python `rasterization(...)` call that
+ * FreeGaussian makes at freegaussian/freegaussian_model.py:847-868 and
+ * freegaussian/freegaussian_control_model.py:158-179.  The
+ * reference binds that call to the un-vendored gsplat package; each entry point below
+ * names the gsplat stage and the reference line it stands behind.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and no
+ *     entry point synchronises the host unless it says so.
+ *   - every function returns 0 on success or an FG_ERR_* code; the message of the last
+ *     failure on the calling thread is returned by fg_last_error().  Nothing throws.
+ *   - arrays are dense row-major float32 / int32 / int64 with the shapes given.
+ *   - C = cameras, N = Gaussians, CH = composited channels, M = tile intersections.
+ */
+#ifndef FG_API_H_
+#define FG_API_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FG_OK 0
+#define FG_ERR_INVALID 1   /* bad argument (shape, range, null) */
+#define FG_ERR_CUDA 2      /* a CUDA runtime call or launch failed */
+#define FG_ERR_WORKSPACE 3 /* workspace too small */
+
+#define FG_MAX_CHANNELS 8 /* channels composited in one pass; wider inputs are chunked by the host */
+
+const char* fg_last_error(void);
+/* ABI version; bumped on any signature change. */
+int fg_abi_version(void);
+/* Number of kernels launched by this library in this process so far (bench.py `gpu_launches`). */
+long long fg_launch_count(void);
+
+/* ---- (1) fused projection + EWA covariance + culling + SH->RGB (+ flow features) -------
+ * Replaces gsplat `fully_fused_projection` + `spherical_harmonics` + the depth/flow
+ * channel concatenation inside `rasterization` as called at freegaussian_model.py:847-868
+ * (arguments: near_plane=0.01, far_plane=1e10, eps2d=0.3, radius_clip=0, :859-867).
+ *
+ * Inputs   means[N,3] quats[N,4] (w,x,y,z, any norm) scales[N,3] (linear)
+ *          viewmats[C,4,4] rigid world->camera (utils.py:162-179)  Ks[C,3,3]
+ *          sh_coeffs[N,sh_bases,3] with sh_degree in 0..3 evaluated, or sh_degree=-1 (none)
+ *          means_next[N,3] (frame t+1; NULL = no flow).  flow_cov!=0 additionally uses
+ *          quats_next/scales_next (NULL = reuse frame t) and writes flow_affine.
+ * Outputs  radii[C,N] int32 (0 = culled)  means2d[C,N,2]  depths[C,N]  conics[C,N,3]
+ *          compensations[C,N] (NULL unless rasterize_mode="antialiased")
+ *          feat[C,N,feat_stride]: rgb at channel rgb_off (if sh_degree>=0), depth at
+ *          depth_off (if >=0), flow (mu2d(t+1)-mu2d(t)) at flow_off (if >=0).
+ *          flow_affine[C,N,4] = B(t+1) B(t)^-1 - I, row-major (covariance flow mode).
+ *          tiles_per_gauss[C,N] int32 = number of 16x16 tiles each splat touches.
+ */
+int fg_project_fwd(int C, int N, const float* means, const float* quats, const float* scales,
+                   const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                   float near_plane, float far_plane, float radius_clip, int tile_size,
+                   int sh_degree, int sh_bases, const float* sh_coeffs, const float* means_next,
+                   const float* quats_next, const float* scales_next, int flow_cov, int32_t* radii,
+                   float* means2d, float* depths, float* conics, float* compensations, float* feat,
+                   int feat_stride, int rgb_off, int depth_off, int flow_off, float* flow_affine,
+                   int32_t* tiles_per_gauss, void* stream);
+
+/* VJP of fg_project_fwd (gsplat `fully_fused_projection_bwd` + `spherical_harmonics` bwd).
+ * Any of v_means2d / v_depths / v_conics / v_compensations / v_feat / v_flow_affine may be
+ * NULL (= zero).  Outputs are fully overwritten (no pre-zeroing needed):
+ *   v_means[N,3] v_quats[N,4] v_scales[N,3] v_sh[N,sh_bases,3] (if sh_degree>=0)
+ *   v_means_next[N,3] (if means_next) v_quats_next[N,4] v_scales_next[N,3] (if flow_cov and given)
+ * Gradients of the C cameras are summed inside one thread per Gaussian (deterministic).
+ */
+int fg_project_bwd(int C, int N, const float* means, const float* quats, const float* scales,
+                   const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                   float near_plane, float far_plane, float radius_clip, int sh_degree,
+                   int sh_bases, const float* sh_coeffs, const float* means_next,
+                   const float* quats_next, const float* scales_next, int flow_cov,
+                   const int32_t* radii, const float* v_means2d, const float* v_depths,
+                   const float* v_conics, const float* v_compensations, const float* v_feat,
+                   int feat_stride, int rgb_off, int depth_off, int flow_off,
+                   const float* v_flow_affine, float* v_means, float* v_quats, float* v_scales,
+                   float* v_sh, float* v_means_next, float* v_quats_next, float* v_scales_next,
+                   void* stream);
+
+/* ---- (2) tile intersection: scan, emission, sort, offsets ------------------------------
+ * Replaces gsplat `isect_tiles` (+cumsum), `cub::DeviceRadixSort::SortPairs`, and
+ * `isect_offset_encode` (tile_size=16 from freegaussian_model.py:806).
+ */
+
+/* Exclusive prefix sum of counts[n] -> offsets[n] (int32), total -> *total (int64, device).
+ * workspace: fg_scan_workspace_bytes(n) bytes. */
+int64_t fg_scan_workspace_bytes(int64_t n);
+int fg_exclusive_scan_i32(int64_t n, const int32_t* counts, int32_t* offsets, int64_t* total,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Emit (key64, flatten_id) for every (splat, tile) pair in flattened (c*N+n) order:
+ *   key = c << (32+tile_bits) | (ty*tile_w+tx) << 32 | float_bits(depth),
+ *   tile_bits = floor(log2(tile_w*tile_h)) + 1, value = c*N+n.
+ * `offsets` is the exclusive scan of tiles_per_gauss. */
+int fg_isect_emit(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
+                  const int32_t* offsets, int tile_size, int tile_w, int tile_h, int64_t* isect_ids,
+                  int32_t* flatten_ids, void* stream);
+
+/* Stable LSD radix sort of (uint64 key, uint32 value) pairs on key bits [0, end_bit).
+ * Hand-written onesweep (chained-scan, decoupled look-back); the result is the unique
+ * stable order, bit-identical to cub::DeviceRadixSort::SortPairs.  The two buffer pairs are
+ * used as ping-pong storage (both are clobbered); *result_in_out (host int) is set to 1 if
+ * the sorted data ended in keys_out/vals_out, 0 if it ended in keys_in/vals_in. */
+int64_t fg_radix_sort_workspace_bytes(int64_t n);
+int fg_radix_sort_pairs_u64_u32(int64_t n, uint64_t* keys_in, uint32_t* vals_in, uint64_t* keys_out,
+                                uint32_t* vals_out, int end_bit, void* workspace,
+                                int64_t workspace_bytes, int* result_in_out, void* stream);
+/* Same for 32-bit keys (depth-only and tile-only sorts of the two-level path). */
+int fg_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out,
+                                uint32_t* vals_out, int end_bit, void* workspace,
+                                int64_t workspace_bytes, int* result_in_out, void* stream);
+
+/* offsets[c,ty,tx] (int32, C*tile_h*tile_w entries) = lower bound of that tile in the sorted keys. */
+int fg_isect_offsets(int64_t n_isects, const int64_t* sorted_isect_ids, int C, int tile_w, int tile_h,
+                     int32_t* offsets, void* stream);
+
+/* ---- (3) per-tile front-to-back alpha compositing, forward and backward ----------------
+ * Replaces gsplat `rasterize_to_pixels` fwd/bwd.  One pass composites all CH channels
+ * (RGB + depth + flow).  alpha = min(0.999, opacity*exp(-sigma)); skip alpha < 1/255;
+ * stop when T(1-alpha) <= 1e-4.
+ *   feat[C*N,CH]  opacities[C*N]  backgrounds[C,CH] or NULL
+ *   flow_affine[C*N,4] or NULL: channels flow_ch0, flow_ch0+1 get + A_g (p - mu_g) per pixel.
+ *   render[C,H,W,CH]  alphas[C,H,W]  last_ids[C,H,W] int32 (index into the sorted list)
+ */
+int fg_rasterize_fwd(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
+                     const float* conics, const float* feat, const float* opacities,
+                     const float* backgrounds, const float* flow_affine, int flow_ch0,
+                     const int32_t* isect_offsets, const int32_t* flatten_ids, int64_t n_isects,
+                     float* render, float* alphas, int32_t* last_ids, void* stream);
+
+/* Backward.  v_* outputs must be zero-initialised by the caller (they are accumulated with
+ * atomics); v_means2d_abs may be NULL (absgrad=False).  v_flow_affine NULL unless flow_affine. */
+int fg_rasterize_bwd(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
+                     const float* conics, const float* feat, const float* opacities,
+                     const float* backgrounds, const float* flow_affine, int flow_ch0,
+                     const int32_t* isect_offsets, const int32_t* flatten_ids, int64_t n_isects,
+                     const float* alphas, const int32_t* last_ids, const float* v_render,
+                     const float* v_alphas, float* v_means2d, float* v_means2d_abs, float* v_conics,
+                     float* v_feat, float* v_opacities, float* v_flow_affine, void* stream);
+
+/* ---- (4) exact k-nearest neighbours ----------------------------------------------------
+ * Replaces FreeGaussianModel.k_nearest_sklearn (freegaussian_model.py:293-311):
+ * sklearn NearestNeighbors(n_neighbors=k+1, metric="euclidean") of the set against itself
+ * with the self column dropped.  Distances are float64 sqrt(dx^2+dy^2+dz^2) in x,y,z order
+ * (bit-identical to sklearn's kd-tree), returned as float32; indices int32; ascending
+ * (distance, index) order.  workspace: fg_knn_workspace_bytes(n). */
+int64_t fg_knn_workspace_bytes(int64_t n);
+int fg_knn_f32(int64_t n, const float* points /*[n,3]*/, int k, float* out_dist /*[n,k]*/,
+               int32_t* out_idx /*[n,k]*/, void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FG_API_H_ */
