@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd MPix/s (RGB+depth+flow) of the splat-render hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+Workload (config.workload = "cfg3"): 1 M Gaussians, 1920x1080, SH degree 3, render_mode
+"RGB+ED" + rendered flow (6 composited channels), one view per GPU per step (view-sharded,
+weak scaling), scalar loss = sum(render * w_rgbd) + sum(flow * w_flow), backward to all
+Gaussian parameters; at N>1 the step ends with the NCCL all-reduce of the parameter gradients
+and the densification statistics (freegaussian_b200/dist.py).  Synthetic "trained-like" scene
+(SURVEY.md 8(d)); working set (236 MB of parameters + ~0.5 GB of intersection buffers) is far
+larger than the 126 MB L2, so no explicit L2 flush is needed between iterations.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_gaussians, width, height)
+    "cfg1": (10_000, 128, 128),
+    "cfg2": (300_000, 960, 540),
+    "cfg3": (1_000_000, 1920, 1080),
+    "cfg4": (3_000_000, 2704, 2028),
+}
+N_VIEW_POOL = 8  # distinct cameras cycled through per rank
+CPU_CROP = 128   # the CPU arm renders a CPU_CROP x CPU_CROP centre crop of the same frame
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--recipe", default="trained_like", choices=["trained_like", "init_like"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ workload
+def build_scene(workload: str, recipe: str, device, n_views: int):
+    from freegaussian_b200.knn import k_nearest
+    from freegaussian_b200.scenes import make_scene
+    n, w, h = WORKLOADS[workload]
+    knn3 = lambda m: k_nearest(m.to(device), 3)[0].cpu()  # the product KNN kernel seeds the scales (model.py:158)
+    sc = make_scene(n, w, h, n_views=n_views, recipe=recipe, seed=0, knn3=knn3)
+    return sc
+
+
+def loss_weights(h: int, w: int, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(1, h, w, 4, generator=g), torch.rand(1, h, w, 2, generator=g) * 0.1
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from freegaussian_b200 import _lib
+    from freegaussian_b200 import rendering
+    from freegaussian_b200.dist import DensificationStats
+    from freegaussian_b200.rendering import rasterization
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from freegaussian_b200 import _build
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+    L = _lib.lib()
+
+    n, W, H = WORKLOADS[args.workload]
+    sc = build_scene(args.workload, args.recipe, dev, N_VIEW_POOL * world)
+    d = sc.to(dev)
+    params = [d.means, d.quats, d.scales, d.opacities, d.sh, d.means_next]
+    for p in params:
+        p.requires_grad_(True)
+    my_views = list(range(rank, N_VIEW_POOL * world, world))  # dist.shard_views
+    # per-step host inputs (pinned): camera + the loss weight images standing in for GT rgb/depth/flow
+    host_vm = [sc.viewmats[v:v + 1].clone().pin_memory() for v in my_views]
+    host_K = [sc.Ks[v:v + 1].clone().pin_memory() for v in my_views]
+    w_rgbd_h, w_flow_h = loss_weights(H, W, 1 + rank)
+    w_rgbd_h, w_flow_h = w_rgbd_h.pin_memory(), w_flow_h.pin_memory()
+    w_rgbd, w_flow = w_rgbd_h.to(dev), w_flow_h.to(dev)
+    dev_vm = [v.to(dev) for v in host_vm]
+    dev_K = [k.to(dev) for k in host_K]
+    stats = DensificationStats(n, dev)
+    info = {}
+
+    def step(i: int, e2e: bool):
+        j = i % len(my_views)
+        if e2e:
+            vm = host_vm[j].to(dev, non_blocking=True)
+            K = host_K[j].to(dev, non_blocking=True)
+            wr = w_rgbd_h.to(dev, non_blocking=True)
+            wf = w_flow_h.to(dev, non_blocking=True)
+        else:
+            vm, K, wr, wf = dev_vm[j], dev_K[j], w_rgbd, w_flow
+        for p in params:
+            p.grad = None
+        render, alpha, meta = rasterization(d.means, d.quats, d.scales, d.opacities, d.sh, vm, K, W, H,
+                                            packed=False, near_plane=0.01, far_plane=1e10, render_mode="RGB+ED",
+                                            sh_degree=3, sparse_grad=False, absgrad=True, rasterize_mode="classic",
+                                            means_next=d.means_next)
+        meta["means2d"].retain_grad()
+        loss = (render * wr).sum() + (meta["flow"] * wf).sum()
+        loss.backward()
+        stats.accumulate_local(meta["radii"], meta["means2d"].absgrad, H, W)
+        if world > 1:
+            works = [dist.all_reduce(p.grad, async_op=True) for p in params]
+            stats.reduce()
+            for wk in works:
+                wk.wait()
+        else:
+            stats.reduce()
+        info["meta"] = meta
+        if e2e:
+            return float(loss.item())  # D2H read of the step's result
+        return None
+
+    def timed(k: int, e2e: bool):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            step(i, e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(max(args.warmup, 3)):
+        step(i, False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_dev = timed(args.steps, False)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    step(0, True)
+    ms_e2e = timed(args.steps, True)
+
+    # ---- per-kernel timing + roofline (rank 0, after the headline timing)
+    out = None
+    if rank == 0:
+        rendering.stage_timer.enabled = True
+        rendering.stage_timer.reset()
+        for i in range(min(args.steps, 8)):
+            step(i, False)
+        stage_ms = {k: statistics.mean(v) for k, v in rendering.stage_timer.summary().items()}
+        rendering.stage_timer.enabled = False
+        meta = info["meta"]
+        M = int(meta["flatten_ids"].numel())
+        n_vis = int((meta["radii"] > 0).sum())
+        # evaluated (pixel, Gaussian) pairs a pixel must visit: from its tile's list start to its last contributor
+        offs = meta["isect_offsets"][0]
+        start_px = offs.repeat_interleave(16, 0).repeat_interleave(16, 1)[:H, :W]
+        contributed = meta["last_ids"][0] >= start_px
+        pairs = int(((meta["last_ids"][0] - start_px + 1).clamp(min=0) * contributed).sum())
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        import ctypes
+        tf = ctypes.c_double(0)
+        L.fg_measure_fp32_tflops(ctypes.byref(tf), torch.cuda.current_stream().cuda_stream)
+        fp32_peak = tf.value
+        cam_bits, tile_bits = 1, int(math.floor(math.log2(math.ceil(W / 16) * math.ceil(H / 16)))) + 1
+        passes = (32 + tile_bits + cam_bits + 7) // 8
+        algo = {  # algorithmic bytes / flops per launch (DESIGN.md "Kernels")
+            "project_fwd": ("hbm", n_vis * 276 + (n - n_vis) * 44),
+            "project_bwd": ("hbm", n_vis * 548 + (n - n_vis) * (44 + 4 + 236)),
+            "sort": ("hbm", M * (8 + passes * 24)),
+            "emit": ("hbm", n * 20 + M * 12),
+            "rasterize_fwd": ("fp32", pairs * 24),
+            "rasterize_bwd": ("fp32", pairs * 70),
+        }
+        kernels = {}
+        for name, (bound, work) in algo.items():
+            if name not in stage_ms:
+                continue
+            t = stage_ms[name] * 1e-3
+            if bound == "hbm":
+                ach = work / t / 1e9
+                kernels[name] = {"bound": "hbm", "ms": stage_ms[name], "achieved": ach, "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": ach / hbm_peak}
+            else:
+                ach = work / t / 1e12
+                kernels[name] = {"bound": "fp32", "ms": stage_ms[name], "achieved": ach, "peak": fp32_peak,
+                                 "unit": "TFLOP/s", "frac": ach / fp32_peak if fp32_peak else None}
+        dominant = max(stage_ms, key=stage_ms.get)
+        roof = dict(kernels.get(dominant, {}))
+        roof.update({"kernel": dominant, "traffic": None,
+                     "peak_source": "fg_measure_fp32_tflops (FFMA microbenchmark, this run)" if roof.get("bound") == "fp32" else hbm_src})
+        hbm_kernels = {k: v for k, v in kernels.items() if v["bound"] == "hbm"}
+        dom_hbm = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms"]) if hbm_kernels else None
+
+        pix = world * W * H
+        out = {
+            "metric": "fwd+bwd MPix/s (RGB+depth+flow) at 1M Gaussians",
+            "value": pix * args.steps / (ms_dev * 1e-3) / 1e6,
+            "unit": "MPix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n} Gaussians, {W}x{H}, 1 view/GPU/step, SH3, RGB+ED+flow (6 ch), "
+                                   f"{args.recipe} scene", "views_per_step": world, "l2": "inputs larger than L2 (no flush)",
+                       "n_isects": M, "visible": n_vis, "pairs_per_pixel": pairs / (W * H),
+                       "parallelism": f"view-sharded dp{world}" if world > 1 else "single GPU"},
+            "e2e": {"value": pix * args.steps / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s",
+                    "h2d_bytes_per_step": int(host_vm[0].numel() * 4 + host_K[0].numel() * 4 + w_rgbd_h.numel() * 4 + w_flow_h.numel() * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "roofline_hbm": dict(hbm_kernels[dom_hbm], kernel=dom_hbm, peak_source=hbm_src) if dom_hbm else None,
+            "kernels": kernels,
+            "stage_ms": stage_ms,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            out["cpu_baseline"] = cpu_arm(args, steps=args.cpu_steps, warmup=0)["cpu_baseline"]
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_arm(args, steps: int, warmup: int):
+    """The reference algorithm (oracle restatement of the gsplat path -- gsplat itself cannot be
+    installed here) on the host cores, bounded sample: the SAME scene and camera,
+    all Gaussians projected, CPU_CROP x CPU_CROP centre crop of the frame composited, fwd+bwd."""
+    from oracle import knn as oknn
+    from oracle import render as oracle
+    from freegaussian_b200.scenes import make_scene
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n, W, H = WORKLOADS[args.workload]
+    if torch.cuda.is_available():
+        from freegaussian_b200.knn import k_nearest
+        knn3 = lambda m: k_nearest(m.cuda(), 3)[0].cpu()  # scene construction only (untimed)
+    else:
+        knn3 = lambda m: torch.from_numpy(oknn.reference_knn(m.numpy(), 3)[0])
+    sc = make_scene(n, W, H, n_views=N_VIEW_POOL, recipe=args.recipe, seed=0, knn3=knn3)
+    cw, ch = min(CPU_CROP, W), min(CPU_CROP, H)
+    K = sc.Ks[:1].clone()
+    K[:, 0, 2] -= (W - cw) / 2
+    K[:, 1, 2] -= (H - ch) / 2
+    w_rgbd, w_flow = loss_weights(ch, cw, 1)
+    params = [sc.means, sc.quats, sc.scales, sc.opacities, sc.sh, sc.means_next]
+    for p in params:
+        p.requires_grad_(True)
+    times = []
+    for i in range(warmup + steps):
+        for p in params:
+            p.grad = None
+        t0 = time.perf_counter()
+        r, a, m = oracle.rasterization(sc.means, sc.quats, sc.scales, sc.opacities, sc.sh, sc.viewmats[:1], K, cw, ch,
+                                       near_plane=0.01, far_plane=1e10, render_mode="RGB+ED", sh_degree=3,
+                                       means_next=sc.means_next)
+        loss = (r * w_rgbd).sum() + (m["flow"] * w_flow).sum()
+        loss.backward()
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    t = sum(times) / len(times)
+    val = cw * ch / t / 1e6
+    sample = (f"{steps} step(s) of fwd+bwd on a {cw}x{ch} centre crop of the {W}x{H} frame, all {n} Gaussians "
+              f"projected, {m['flatten_ids'].numel()} intersections in the crop; {t:.2f} s/step")
+    base = {"value": val, "unit": "MPix/s", "cores": cores, "kind": "port", "sample": sample}
+    return {"cpu_baseline": base, "ms_per_step": t * 1e3, "config_workload": f"{args.workload}: {n} Gaussians, {W}x{H}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_arm(args, steps=args.steps, warmup=min(args.warmup, 1))
+    n, W, H = WORKLOADS[args.workload]
+    val = res["cpu_baseline"]["value"]
+    out = {
+        "impl": "reference",
+        "metric": "fwd+bwd MPix/s (RGB+depth+flow) at 1M Gaussians",
+        "value": val, "unit": "MPix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n} Gaussians, {W}x{H}, 1 view/step, SH3, RGB+ED+flow (6 ch), "
+                               f"{args.recipe} scene", "note": "CPU arm: bounded sample, see cpu_baseline.sample"},
+        "cpu_baseline": res["cpu_baseline"],
+        "e2e": {"value": val, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

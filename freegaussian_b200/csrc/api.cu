@@ -31,3 +31,51 @@ int fg_abi_version(void) { return 1; }
 long long fg_launch_count(void) { return fg::g_launch_count.load(); }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// FP32 FMA peak microbenchmark: the denominator for the FP32-pipe-bound compositing kernels
+// (MEASURED_PEAKS.json has only the HBM copy and the bf16 GEMM figures).  8 independent FFMA
+// chains per thread, 1024 threads per SM-resident CTA, 2 CTAs per SM.
+namespace fg {
+__global__ void __launch_bounds__(1024) fp32_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456f) out[0] = s;  // keep the chains alive
+}
+}  // namespace fg
+
+extern "C" int fg_measure_fp32_tflops(double* tflops_host, void* stream) {
+    FG_REQUIRE(tflops_host, "tflops_host must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d = nullptr;
+    FG_CUDA(cudaMalloc(&d, 4));
+    cudaEvent_t e0, e1;
+    FG_CUDA(cudaEventCreate(&e0));
+    FG_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = fg::kNumSMs * 2;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        FG_CUDA(cudaEventRecord(e0, st));
+        FG_LAUNCH(fg::fp32_peak_kernel, blocks, 1024, 0, st, d, iters, 1.0000001f, 1e-9f);
+        FG_CUDA(cudaEventRecord(e1, st));
+        FG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        FG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * iters * 1024.0 * blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops_host = best;
+    return FG_OK;
+}

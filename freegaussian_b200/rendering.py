@@ -52,6 +52,46 @@ class _Workspace:
 _ws = _Workspace()
 
 
+class StageTimer:
+    """Optional CUDA-event timing of each C-ABI stage (bench.py's per-kernel roofline).
+    Disabled by default: ``with _stage(name)`` then costs one attribute test."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = []  # (name, start, end)
+
+    def reset(self):
+        self.events = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out: Dict[str, list] = {}
+        for name, s, e in self.events:
+            out.setdefault(name, []).append(s.elapsed_time(e))
+        return out
+
+
+stage_timer = StageTimer()
+
+
+class _stage:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if stage_timer.enabled:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if stage_timer.enabled:
+            self.e.record()
+            stage_timer.events.append((self.name, self.s, self.e))
+        return False
+
+
 def _require_cuda(**tensors) -> None:
     for name, t in tensors.items():
         if t is None:
@@ -99,7 +139,8 @@ class _Project(torch.autograd.Function):
         comps = torch.empty(C, N, device=dev) if cfg["antialiased"] else None
         feat = torch.empty(C, N, CH, device=dev)
         tiles = torch.empty(C, N, dtype=torch.int32, device=dev)
-        check(L.fg_project_fwd(
+        with _stage("project_fwd"):
+          check(L.fg_project_fwd(
             C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
             cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"], cfg["tile_size"],
             sh_degree if use_sh else -1, sh_bases, ptr(colors) if use_sh else None, ptr(means_next), None, None, 0,
@@ -136,7 +177,8 @@ class _Project(torch.autograd.Function):
         v_scales = torch.empty(N, 3, device=dev)
         v_sh = torch.empty(N, sh_bases, 3, device=dev) if use_sh else None
         v_means_next = torch.empty(N, 3, device=dev) if means_next is not None else None
-        check(L.fg_project_bwd(
+        with _stage("project_bwd"):
+          check(L.fg_project_bwd(
             C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
             cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"],
             cfg["sh_degree"] if use_sh else -1, sh_bases, ptr(sh), ptr(means_next), None, None, 0, ptr(radii),
@@ -170,7 +212,8 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
     offsets = torch.empty(total, dtype=torch.int32, device=dev)
     n_dev = torch.empty(1, dtype=torch.int64, device=dev)
     ws = _ws.get("scan", L.fg_scan_workspace_bytes(total), dev)
-    check(L.fg_exclusive_scan_i32(total, ptr(tiles_per_gauss), ptr(offsets), ptr(n_dev), ptr(ws), ws.numel(), st))
+    with _stage("scan"):
+      check(L.fg_exclusive_scan_i32(total, ptr(tiles_per_gauss), ptr(offsets), ptr(n_dev), ptr(ws), ws.numel(), st))
     M = int(n_dev.item())  # host sync: sizes the intersection buffers
     assert M < 2**31, "too many tile intersections"
     ids_a = torch.empty(M, dtype=torch.int64, device=dev)
@@ -179,17 +222,20 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
     val_b = torch.empty(M, dtype=torch.int32, device=dev)
     isect_offsets = torch.empty(C, tile_h, tile_w, dtype=torch.int32, device=dev)
     if M > 0:
-        check(L.fg_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(offsets), tile_size, tile_w, tile_h,
+        with _stage("emit"):
+          check(L.fg_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(offsets), tile_size, tile_w, tile_h,
                               ptr(ids_a), ptr(val_a), st))
         tile_bits = int(math.floor(math.log2(tile_w * tile_h))) + 1
         cam_bits = int(math.floor(math.log2(C))) + 1
         ws = _ws.get("sort", L.fg_radix_sort_workspace_bytes(M), dev)
         sel = ctypes.c_int(0)
-        check(L.fg_radix_sort_pairs_u64_u32(M, ptr(ids_a), ptr(val_a), ptr(ids_b), ptr(val_b),
+        with _stage("sort"):
+          check(L.fg_radix_sort_pairs_u64_u32(M, ptr(ids_a), ptr(val_a), ptr(ids_b), ptr(val_b),
                                             32 + tile_bits + cam_bits, ptr(ws), ws.numel(), ctypes.byref(sel), st))
         if sel.value == 1:
             ids_a, val_a = ids_b, val_b
-    check(L.fg_isect_offsets(M, ptr(ids_a), C, tile_w, tile_h, ptr(isect_offsets), st))
+    with _stage("offsets"):
+      check(L.fg_isect_offsets(M, ptr(ids_a), C, tile_w, tile_h, ptr(isect_offsets), st))
     return ids_a, val_a, isect_offsets
 
 
@@ -212,16 +258,18 @@ class _Rasterize(torch.autograd.Function):
         alphas = torch.empty(C, height, width, 1, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
         M = flatten_ids.shape[0]
-        check(L.fg_rasterize_fwd(C, NN, CH, width, height, tile_size, ptr(means2d_c),
+        with _stage("rasterize_fwd"):
+          check(L.fg_rasterize_fwd(C, NN, CH, width, height, tile_size, ptr(means2d_c),
                                  ptr(conics_c), ptr(feat_c), ptr(opac_c), ptr(bg), None, 0, ptr(isect_offsets),
                                  ptr(flatten_ids), M, ptr(render), ptr(alphas), ptr(last_ids), _stream()))
         ctx.save_for_backward(means2d_c, conics_c, feat_c, opac_c, bg, isect_offsets, flatten_ids, alphas, last_ids)
         ctx.dims = (C, NN, CH, width, height, tile_size, absgrad)
         ctx.means2d_obj = means2d  # the very tensor the caller holds as meta["means2d"] (model.py:869-871)
-        return render, alphas
+        ctx.mark_non_differentiable(last_ids)
+        return render, alphas, last_ids
 
     @staticmethod
-    def backward(ctx, v_render, v_alphas):
+    def backward(ctx, v_render, v_alphas, _v_last):
         L = _lib.lib()
         means2d, conics, feat, opac, bg, isect_offsets, flatten_ids, alphas, last_ids = ctx.saved_tensors
         C, NN, CH, width, height, tile_size, absgrad = ctx.dims
@@ -234,7 +282,8 @@ class _Rasterize(torch.autograd.Function):
         v_feat = torch.zeros_like(feat)
         v_opac = torch.zeros_like(opac)
         M = flatten_ids.shape[0]
-        check(L.fg_rasterize_bwd(C, NN, CH, width, height, tile_size, ptr(means2d),
+        with _stage("rasterize_bwd"):
+          check(L.fg_rasterize_bwd(C, NN, CH, width, height, tile_size, ptr(means2d),
                                  ptr(conics), ptr(feat), ptr(opac), ptr(bg), None, 0, ptr(isect_offsets),
                                  ptr(flatten_ids), M, ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas),
                                  ptr(v_means2d), ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), None,
@@ -250,18 +299,19 @@ class _Rasterize(torch.autograd.Function):
 
 
 def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets,
-                        flatten_ids, backgrounds=None, absgrad=False):
+                        flatten_ids, backgrounds=None, absgrad=False, return_last_ids=False):
     """Composite ``colors [.., D]`` (any D; chunks of 8 channels per pass).  gsplat-compatible helper."""
     D = colors.shape[-1]
-    outs, alphas = [], None
+    outs, alphas, last_ids = [], None, None
     for s in range(0, D, MAX_CH):
         e = min(D, s + MAX_CH)
         bg = None if backgrounds is None else backgrounds[..., s:e]
-        r, a = _Rasterize.apply(means2d, conics, colors[..., s:e], opacities, bg, isect_offsets, flatten_ids,
-                                image_width, image_height, tile_size, absgrad, D > MAX_CH)
+        r, a, last_ids = _Rasterize.apply(means2d, conics, colors[..., s:e], opacities, bg, isect_offsets,
+                                          flatten_ids, image_width, image_height, tile_size, absgrad, D > MAX_CH)
         outs.append(r)
         alphas = a if alphas is None else alphas
-    return (outs[0] if len(outs) == 1 else torch.cat(outs, -1)), alphas
+    render = outs[0] if len(outs) == 1 else torch.cat(outs, -1)
+    return (render, alphas, last_ids) if return_last_ids else (render, alphas)
 
 
 # --------------------------------------------------------------------------- boundary
@@ -382,8 +432,9 @@ def rasterization(
         meta["camera_ids"] = idx // N
         meta["gaussian_ids"] = idx % N
 
-    render_all, alphas = rasterize_to_pixels(means2d, conics, feat, opac, width, height, tile_size, isect_offsets,
-                                             flatten_ids, backgrounds=backgrounds, absgrad=absgrad)
+    render_all, alphas, last_ids = rasterize_to_pixels(means2d, conics, feat, opac, width, height, tile_size,
+                                                       isect_offsets, flatten_ids, backgrounds=backgrounds,
+                                                       absgrad=absgrad, return_last_ids=True)
     render = render_all[..., :n_user]
     if render_mode in ("ED", "RGB+ED"):
         render = torch.cat([render[..., :-1], render[..., -1:] / alphas.clamp(min=1e-10)], -1)
@@ -392,7 +443,7 @@ def rasterization(
         "radii": radii, "means2d": means2d, "depths": depths, "conics": conics, "opacities": opac,
         "tile_width": tile_w, "tile_height": tile_h, "tiles_per_gauss": tiles, "isect_ids": isect_ids,
         "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width, "height": height,
-        "tile_size": tile_size, "n_cameras": C,
+        "tile_size": tile_size, "n_cameras": C, "last_ids": last_ids,
     })
     if means_next is not None:
         meta["flow"] = render_all[..., n_user:]

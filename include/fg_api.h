@@ -38,6 +38,10 @@ int fg_abi_version(void);
 /* Number of kernels launched by this library in this process so far (bench.py `gpu_launches`). */
 long long fg_launch_count(void);
 
+/* Measured FP32 FMA peak of this GPU in TFLOP/s (a short FFMA microbenchmark; synchronises).
+ * Denominator for the FP32-pipe-bound compositing kernels' roofline in bench.py. */
+int fg_measure_fp32_tflops(double* tflops_host, void* stream);
+
 /* ---- (1) fused projection + EWA covariance + culling + SH->RGB (+ flow features) -------
  * Replaces gsplat `fully_fused_projection` + `spherical_harmonics` + the depth/flow
  * channel concatenation inside `rasterization` as called at freegaussian_model.py:847-868
