@@ -254,13 +254,20 @@ def run_ours(args):
         tf = ctypes.c_double(0)
         L.fg_measure_fp32_tflops(ctypes.byref(tf), torch.cuda.current_stream().cuda_stream)
         fp32_peak = tf.value
-        cam_bits, tile_bits = 1, int(math.floor(math.log2(math.ceil(W / 16) * math.ceil(H / 16)))) + 1
-        passes = (32 + tile_bits + cam_bits + 7) // 8
+        n_tiles = math.ceil(W / 16) * math.ceil(H / 16)
+        if rendering.SORT_MODE == "key64":
+            cam_bits, tile_bits = 1, int(math.floor(math.log2(n_tiles))) + 1
+            passes = (32 + tile_bits + cam_bits + 7) // 8
+            sort_bytes, emit_bytes = M * (8 + passes * 24), n * 20 + M * 12
+        else:  # two-level: 32-bit tile keys, ceil(log2(tiles)/8) passes; depth sort of the n splats separately
+            passes = (max(1, math.ceil(math.log2(n_tiles))) + 7) // 8
+            sort_bytes, emit_bytes = M * (4 + passes * 16), n * 24 + M * 8
         algo = {  # algorithmic bytes / flops per launch (DESIGN.md "Kernels")
             "project_fwd": ("hbm", n_vis * 276 + (n - n_vis) * 44),
             "project_bwd": ("hbm", n_vis * 548 + (n - n_vis) * (44 + 4 + 236)),
-            "sort": ("hbm", M * (8 + passes * 24)),
-            "emit": ("hbm", n * 20 + M * 12),
+            "sort": ("hbm", sort_bytes),
+            "depth_sort": ("hbm", n * (8 + 8) + n * (4 + 4 * 16)),
+            "emit": ("hbm", emit_bytes),
             "rasterize_fwd": ("fp32", pairs * 24),
             "rasterize_bwd": ("fp32", pairs * 70),
         }
@@ -295,7 +302,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {n} Gaussians, {W}x{H}, 1 view/GPU/step, SH3, RGB+ED+flow (6 ch), "
                                    f"{args.recipe} scene", "views_per_step": world, "l2": "inputs larger than L2 (no flush)",
-                       "n_isects": M, "visible": n_vis, "pairs_per_pixel": pairs / (W * H),
+                       "n_isects": M, "visible": n_vis, "sort_mode": rendering.SORT_MODE, "pairs_per_pixel": pairs / (W * H),
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single GPU"},
             "e2e": {"value": pix * args.steps / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s",
                     "h2d_bytes_per_step": int(host_vm[0].numel() * 4 + host_K[0].numel() * 4 + w_rgbd_h.numel() * 4 + w_flow_h.numel() * 4),

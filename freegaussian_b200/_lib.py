@@ -35,6 +35,11 @@ SIGNATURES = {
     "fg_radix_sort_pairs_u64_u32": (_i32, [_i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _pi, _vp]),
     "fg_radix_sort_pairs_u32_u32": (_i32, [_i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _pi, _vp]),
     "fg_isect_offsets": (_i32, [_i64, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "fg_isect_depth_keys": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "fg_gather_i32": (_i32, [_i64, _vp, _vp, _vp, _vp]),
+    "fg_isect_emit_tiles": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fg_isect_offsets_tiles": (_i32, [_i64, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "fg_isect_ids_from_tiles": (_i32, [_i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "fg_rasterize_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
                                 _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "fg_rasterize_bwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,

@@ -103,26 +103,33 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(long long n, c
 constexpr int EMIT_THREADS = 256;
 constexpr int EMIT_COOP_MIN = 32;  // tiles; at or above this the warp shares the work
 
+// KEY64: key = cam << (32+tile_bits) | tile << 32 | depth bits (the reference layout), splats
+// visited in flattened (c*N+n) order.  !KEY64 (two-level path): splats visited in the order
+// given by `order` (depth-sorted flat ids) and key = cam*tiles_per_cam + tile (uint32).
+template <bool KEY64>
 __global__ void __launch_bounds__(EMIT_THREADS)
-    isect_emit_kernel(int C, int N, const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
+    isect_emit_kernel(int C, int N, long long total, const int32_t* __restrict__ order,
+                      const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
                       const float* __restrict__ depths, const int32_t* __restrict__ offsets, int tile_size,
                       int tile_w, int tile_h, int tile_bits, int64_t* __restrict__ isect_ids,
-                      int32_t* __restrict__ flatten_ids) {
-    const long long total = (long long)C * N;
-    const long long idx = (long long)blockIdx.x * EMIT_THREADS + threadIdx.x;
+                      uint32_t* __restrict__ tile_keys, int32_t* __restrict__ flatten_ids) {
+    const long long slot = (long long)blockIdx.x * EMIT_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0, cnt = 0, off = 0;
     int64_t key_base = 0;
-    if (idx < total) {
+    long long idx = -1;
+    if (slot < total) {
+        idx = KEY64 ? slot : (long long)order[slot];
         int r = radii[idx];
         if (r > 0) {
             float2 m = means2d[idx];
             TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
             x0 = t.x0; x1 = t.x1; y0 = t.y0; y1 = t.y1;
             cnt = (x1 - x0) * (y1 - y0);
-            off = offsets[idx];
+            off = offsets[slot];
             int64_t cam = idx / N;
-            key_base = (cam << (32 + tile_bits)) | (int64_t)(uint32_t)__float_as_int(depths[idx]);
+            if (KEY64) key_base = (cam << (32 + tile_bits)) | (int64_t)(uint32_t)__float_as_int(depths[idx]);
+            else key_base = cam * (int64_t)(tile_w * tile_h);
         }
     }
     // small splats: each lane writes its own
@@ -130,7 +137,8 @@ __global__ void __launch_bounds__(EMIT_THREADS)
         int k = off;
         for (int i = y0; i < y1; ++i)
             for (int j = x0; j < x1; ++j) {
-                isect_ids[k] = key_base | ((int64_t)(i * tile_w + j) << 32);
+                if (KEY64) isect_ids[k] = key_base | ((int64_t)(i * tile_w + j) << 32);
+                else tile_keys[k] = (uint32_t)(key_base + i * tile_w + j);
                 flatten_ids[k] = (int32_t)idx;
                 ++k;
             }
@@ -144,11 +152,12 @@ __global__ void __launch_bounds__(EMIT_THREADS)
         int by0 = __shfl_sync(0xffffffffu, y0, src);
         int bcnt = __shfl_sync(0xffffffffu, cnt, src), boff = __shfl_sync(0xffffffffu, off, src);
         long long bkey = __shfl_sync(0xffffffffu, (long long)key_base, src);
-        long long bidx = idx - lane + src;
+        long long bidx = __shfl_sync(0xffffffffu, idx, src);
         int w = bx1 - bx0;
         for (int t = lane; t < bcnt; t += 32) {
             int i = by0 + t / w, j = bx0 + t % w;
-            isect_ids[boff + t] = (int64_t)bkey | ((int64_t)(i * tile_w + j) << 32);
+            if (KEY64) isect_ids[boff + t] = (int64_t)bkey | ((int64_t)(i * tile_w + j) << 32);
+            else tile_keys[boff + t] = (uint32_t)(bkey + i * tile_w + j);
             flatten_ids[boff + t] = (int32_t)bidx;
         }
     }
@@ -157,22 +166,52 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 // ------------------------------------------------------------------ offsets
 // offsets[t] = first index whose (cam,tile) id is >= t.  Thread i compares id(i-1), id(i)
 // and fills every tile id in (id(i-1), id(i)]; the last thread also fills the tail.
+template <bool KEY64>
 __global__ void __launch_bounds__(256)
-    isect_offsets_kernel(long long n_isects, const int64_t* __restrict__ sorted_ids, int n_tiles_per_cam,
-                         int tile_bits, long long n_tiles_total, int32_t* __restrict__ offsets) {
+    isect_offsets_kernel(long long n_isects, const int64_t* __restrict__ sorted_ids,
+                         const uint32_t* __restrict__ sorted_tile_keys, int n_tiles_per_cam, int tile_bits,
+                         long long n_tiles_total, int32_t* __restrict__ offsets) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_isects) return;
-    auto lin = [&](int64_t key) -> long long {
-        long long id = key >> 32;
+    auto lin = [&](long long j) -> long long {
+        if (!KEY64) return (long long)sorted_tile_keys[j];
+        long long id = sorted_ids[j] >> 32;
         long long cam = id >> tile_bits;
         long long tile = id & ((1ll << tile_bits) - 1);
         return cam * n_tiles_per_cam + tile;
     };
-    const long long cur = lin(sorted_ids[i]);
-    const long long prev = (i == 0) ? -1 : lin(sorted_ids[i - 1]);
+    const long long cur = lin(i);
+    const long long prev = (i == 0) ? -1 : lin(i - 1);
     for (long long t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
     if (i == n_isects - 1)
         for (long long t = cur + 1; t < n_tiles_total; ++t) offsets[t] = (int32_t)n_isects;
+}
+
+// two-level path helpers ------------------------------------------------------------------
+// depth key of every (c,n): float bits of the depth (positive, so integer order = float order);
+// splats that touch no tile sort to the end.
+__global__ void depth_keys_kernel(long long total, const float* __restrict__ depths,
+                                  const int32_t* __restrict__ tiles_per_gauss, uint32_t* __restrict__ keys,
+                                  uint32_t* __restrict__ vals) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    keys[i] = tiles_per_gauss[i] > 0 ? (uint32_t)__float_as_int(depths[i]) : 0xffffffffu;
+    vals[i] = (uint32_t)i;
+}
+__global__ void gather_i32_kernel(long long n, const int32_t* __restrict__ src, const int32_t* __restrict__ idx,
+                                  int32_t* __restrict__ dst) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+// rebuild the reference's 64-bit keys from the two-level result (meta["isect_ids"], on demand)
+__global__ void isect_ids_kernel(long long n, const uint32_t* __restrict__ tile_keys,
+                                 const int32_t* __restrict__ flatten_ids, const float* __restrict__ depths,
+                                 int n_tiles_per_cam, int tile_bits, int64_t* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long lin = tile_keys[i];
+    long long cam = lin / n_tiles_per_cam, tile = lin - cam * n_tiles_per_cam;
+    out[i] = (cam << (32 + tile_bits)) | (tile << 32) | (long long)(uint32_t)__float_as_int(depths[flatten_ids[i]]);
 }
 
 __global__ void fill_i32_kernel(long long n, int32_t v, int32_t* out) {
@@ -216,9 +255,68 @@ extern "C" int fg_isect_emit(int C, int N, const float* means2d, const int32_t* 
     FG_REQUIRE(means2d && radii && depths && offsets && isect_ids && flatten_ids, "NULL pointer");
     int tile_bits = tile_bits_of(tile_w * tile_h);
     long long total = (long long)C * N;
-    FG_LAUNCH(isect_emit_kernel, ceil_div(total, EMIT_THREADS), EMIT_THREADS, 0, stream, C, N,
-              (const float2*)means2d, radii, depths, offsets, tile_size, tile_w, tile_h, tile_bits, isect_ids,
-              flatten_ids);
+    FG_LAUNCH((isect_emit_kernel<true>), ceil_div(total, EMIT_THREADS), EMIT_THREADS, 0, stream, C, N, total,
+              (const int32_t*)nullptr, (const float2*)means2d, radii, depths, offsets, tile_size, tile_w, tile_h,
+              tile_bits, isect_ids, (uint32_t*)nullptr, flatten_ids);
+    return FG_OK;
+}
+
+extern "C" int fg_isect_depth_keys(int64_t total, const float* depths, const int32_t* tiles_per_gauss,
+                                   uint32_t* keys, uint32_t* vals, void* stream) {
+    FG_REQUIRE(total >= 0 && total < (1ll << 31), "total out of range");
+    if (total == 0) return FG_OK;
+    FG_REQUIRE(depths && tiles_per_gauss && keys && vals, "NULL pointer");
+    FG_LAUNCH(depth_keys_kernel, ceil_div(total, 256), 256, 0, stream, (long long)total, depths, tiles_per_gauss,
+              keys, vals);
+    return FG_OK;
+}
+
+extern "C" int fg_gather_i32(int64_t n, const int32_t* src, const int32_t* idx, int32_t* dst, void* stream) {
+    FG_REQUIRE(n >= 0, "n must be >= 0");
+    if (n == 0) return FG_OK;
+    FG_REQUIRE(src && idx && dst, "NULL pointer");
+    FG_LAUNCH(gather_i32_kernel, ceil_div(n, 256), 256, 0, stream, (long long)n, src, idx, dst);
+    return FG_OK;
+}
+
+extern "C" int fg_isect_emit_tiles(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
+                                   const int32_t* offsets, int tile_size, int tile_w, int tile_h,
+                                   uint32_t* tile_keys, int32_t* flatten_ids, void* stream) {
+    FG_REQUIRE(C >= 1 && N >= 0 && (long long)C * N < (1ll << 31), "bad C/N");
+    FG_REQUIRE(tile_size > 0 && tile_w > 0 && tile_h > 0, "bad tile geometry");
+    FG_REQUIRE((long long)C * tile_w * tile_h < (1ll << 32), "too many tiles for 32-bit tile keys");
+    if (N == 0) return FG_OK;
+    FG_REQUIRE(order && means2d && radii && offsets && tile_keys && flatten_ids, "NULL pointer");
+    long long total = (long long)C * N;
+    FG_LAUNCH((isect_emit_kernel<false>), ceil_div(total, EMIT_THREADS), EMIT_THREADS, 0, stream, C, N, total, order,
+              (const float2*)means2d, radii, (const float*)nullptr, offsets, tile_size, tile_w, tile_h, 0,
+              (int64_t*)nullptr, tile_keys, flatten_ids);
+    return FG_OK;
+}
+
+extern "C" int fg_isect_offsets_tiles(int64_t n_isects, const uint32_t* sorted_tile_keys, int C, int tile_w,
+                                      int tile_h, int32_t* offsets, void* stream) {
+    FG_REQUIRE(n_isects >= 0 && n_isects < (1ll << 31), "n_isects must be in [0, 2^31)");
+    FG_REQUIRE(C >= 1 && tile_w > 0 && tile_h > 0 && offsets, "bad arguments");
+    long long n_tiles = (long long)C * tile_w * tile_h;
+    if (n_isects == 0) {
+        FG_LAUNCH(fill_i32_kernel, ceil_div(n_tiles, 256), 256, 0, stream, n_tiles, 0, offsets);
+        return FG_OK;
+    }
+    FG_REQUIRE(sorted_tile_keys, "sorted_tile_keys must not be NULL");
+    FG_LAUNCH((isect_offsets_kernel<false>), ceil_div(n_isects, 256), 256, 0, stream, (long long)n_isects,
+              (const int64_t*)nullptr, sorted_tile_keys, tile_w * tile_h, 0, n_tiles, offsets);
+    return FG_OK;
+}
+
+extern "C" int fg_isect_ids_from_tiles(int64_t n_isects, const uint32_t* sorted_tile_keys,
+                                       const int32_t* flatten_ids, const float* depths, int tile_w, int tile_h,
+                                       int64_t* isect_ids, void* stream) {
+    FG_REQUIRE(n_isects >= 0, "n_isects must be >= 0");
+    if (n_isects == 0) return FG_OK;
+    FG_REQUIRE(sorted_tile_keys && flatten_ids && depths && isect_ids, "NULL pointer");
+    FG_LAUNCH(isect_ids_kernel, ceil_div(n_isects, 256), 256, 0, stream, (long long)n_isects, sorted_tile_keys,
+              flatten_ids, depths, tile_w * tile_h, tile_bits_of(tile_w * tile_h), isect_ids);
     return FG_OK;
 }
 
@@ -233,7 +331,7 @@ extern "C" int fg_isect_offsets(int64_t n_isects, const int64_t* sorted_isect_id
     }
     FG_REQUIRE(sorted_isect_ids, "sorted_isect_ids must not be NULL");
     int tile_bits = tile_bits_of(tile_w * tile_h);
-    FG_LAUNCH(isect_offsets_kernel, ceil_div(n_isects, 256), 256, 0, stream, (long long)n_isects,
-              sorted_isect_ids, tile_w * tile_h, tile_bits, n_tiles, offsets);
+    FG_LAUNCH((isect_offsets_kernel<true>), ceil_div(n_isects, 256), 256, 0, stream, (long long)n_isects,
+              sorted_isect_ids, (const uint32_t*)nullptr, tile_w * tile_h, tile_bits, n_tiles, offsets);
     return FG_OK;
 }

@@ -124,6 +124,24 @@ int fg_radix_sort_pairs_u32_u32(int64_t n, uint32_t* keys_in, uint32_t* vals_in,
 int fg_isect_offsets(int64_t n_isects, const int64_t* sorted_isect_ids, int C, int tile_w, int tile_h,
                      int32_t* offsets, void* stream);
 
+/* Two-level variant of the same sort (identical resulting order, ~4x less sort traffic):
+ * (a) stable-sort the (c,n) splats once by depth bits (fg_isect_depth_keys + the u32 radix
+ * sort; splats touching no tile get key 0xffffffff), (b) emit their tiles in that order with
+ * 32-bit keys cam*tile_w*tile_h + tile (fg_gather_i32 of the counts, scan, fg_isect_emit_tiles),
+ * (c) stable-sort by tile key (2 radix passes instead of 6).  Ties at equal (camera, tile,
+ * depth) keep ascending c*N+n, exactly like the stable 64-bit sort. */
+int fg_isect_depth_keys(int64_t total, const float* depths, const int32_t* tiles_per_gauss,
+                        uint32_t* keys, uint32_t* vals, void* stream);
+int fg_gather_i32(int64_t n, const int32_t* src, const int32_t* idx, int32_t* dst, void* stream);
+int fg_isect_emit_tiles(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
+                        const int32_t* offsets, int tile_size, int tile_w, int tile_h, uint32_t* tile_keys,
+                        int32_t* flatten_ids, void* stream);
+int fg_isect_offsets_tiles(int64_t n_isects, const uint32_t* sorted_tile_keys, int C, int tile_w, int tile_h,
+                           int32_t* offsets, void* stream);
+/* Rebuild the reference's sorted 64-bit keys (gsplat meta["isect_ids"]) from the two-level result. */
+int fg_isect_ids_from_tiles(int64_t n_isects, const uint32_t* sorted_tile_keys, const int32_t* flatten_ids,
+                            const float* depths, int tile_w, int tile_h, int64_t* isect_ids, void* stream);
+
 /* ---- (3) per-tile front-to-back alpha compositing, forward and backward ----------------
  * Replaces gsplat `rasterize_to_pixels` fwd/bwd.  One pass composites all CH channels
  * (RGB + depth + flow).  alpha = min(0.999, opacity*exp(-sigma)); skip alpha < 1/255;

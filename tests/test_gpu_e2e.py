@@ -39,6 +39,10 @@ def test_render_and_grads_match_oracle(built_lib, render_mode, sh_degree, raster
                                                absgrad=True, rasterize_mode=rasterize_mode)
     assert torch.equal(m["radii"].cpu(), rm["radii"]), "borderline radius: pick another seed"
     assert torch.equal(m["flatten_ids"].cpu(), rm["flatten_ids"])  # sort order bit-exact end to end
+    # (lazily rebuilt) 64-bit keys: camera|tile fields identical; the depth field carries the kernel's own
+    # float32 depth, which may differ from the oracle's in the last ulp (bit-exact keys on identical
+    # projected inputs are checked in test_gpu_stages.py)
+    assert torch.equal(m["isect_ids"].cpu() >> 32, rm["isect_ids"] >> 32)
     assert torch.equal(m["isect_offsets"].cpu(), rm["isect_offsets"])
     assert r.shape == rr.shape and a.shape == ra.shape and m["flow"].shape == rm["flow"].shape
     assert rel_err(r, rr) < IMG_TOL, rel_err(r, rr)

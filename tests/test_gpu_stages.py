@@ -60,20 +60,23 @@ def test_projection_matches_oracle(L, sh_degree, recipe):
 
 def test_isect_sort_offsets_bit_exact(L):
     """Same projected tensors into both implementations: keys, order and tile ranges must be identical."""
-    from freegaussian_b200.rendering import isect_tiles
+    from freegaussian_b200.rendering import isect_tiles, isect_ids_from_tiles
     W, H = 200, 120
     tw, th = math.ceil(W / 16), math.ceil(H / 16)
     for seed, views, mul in [(0, 1, 1.0), (1, 3, 1.0), (2, 5, 4.0)]:
         sc = small_scene(4000, W, H, views=views, seed=seed, scale_mul=mul)
         radii, m2d, dep, con, comp, feat, tiles = project_gpu(sc, W, H, 0)
-        ids, flat, offs = isect_tiles(m2d.cuda(), radii.cuda(), dep.cuda(), tiles.cuda(), 16, tw, th)
         tpg, r_ids, r_flat = O.isect_tiles(m2d, radii, dep, 16, tw, th)
+        r_offs = O.isect_offset_encode(r_ids, views, tw, th)
         assert torch.equal(tpg, tiles)
         assert r_ids.numel() > 1000
-        assert torch.equal(ids.cpu(), r_ids), "sorted 64-bit keys differ"
-        assert torch.equal(flat.cpu(), r_flat), "sort order differs"
-        r_offs = O.isect_offset_encode(r_ids, views, tw, th)
-        assert torch.equal(offs.cpu(), r_offs)
+        for mode in ("key64", "two_level"):
+            ids, flat, offs, tk = isect_tiles(m2d.cuda(), radii.cuda(), dep.cuda(), tiles.cuda(), 16, tw, th, mode=mode)
+            if ids is None:
+                ids = isect_ids_from_tiles(tk, flat, dep.cuda(), tw, th)
+            assert torch.equal(ids.cpu(), r_ids), f"{mode}: sorted 64-bit keys differ"
+            assert torch.equal(flat.cpu(), r_flat), f"{mode}: sort order differs"
+            assert torch.equal(offs.cpu(), r_offs), f"{mode}: tile ranges differ"
 
 
 @pytest.mark.parametrize("n,end_bit", [(1, 64), (5, 13), (4096, 40), (4097, 64), (100_003, 46), (3_000_000, 53)])
@@ -138,7 +141,7 @@ def test_rasterize_fwd_bwd_matches_oracle(L, ch):
     tw, th = math.ceil(W / 16), math.ceil(H / 16)
     sc = small_scene(3000, W, H, views=2, seed=11 + ch)
     radii, m2d, dep, con, comp, feat, tiles = project_gpu(sc, W, H, 3)
-    ids, flat, offs = isect_tiles(m2d.cuda(), radii.cuda(), dep.cuda(), tiles.cuda(), 16, tw, th)
+    ids, flat, offs, _ = isect_tiles(m2d.cuda(), radii.cuda(), dep.cuda(), tiles.cuda(), 16, tw, th)
     g = torch.Generator().manual_seed(ch)
     cols = torch.rand(2, 3000, ch, generator=g)
     opac = sc.opacities[None].expand(2, -1).contiguous()
