@@ -4,10 +4,14 @@
 //
 // Each thread replays its pixel back-to-front from last_ids with T = T_final, recovering
 // T_i by division, and produces per-(pixel,Gaussian) partials for the CH feature channels,
-// the conic (3), the 2-D mean (2), |d/dmean| (2, absgrad) and the opacity (1).  Partials
-// are summed over the warp's 8x4 pixel patch with shuffles and added to the per-Gaussian
-// accumulators with one atomic per value per warp; a warp whose 32 pixels all skip a
-// Gaussian skips the whole reduction (the common case for splats smaller than a tile).
+// the conic (3), the 2-D mean (2), |d/dmean| (2, absgrad) and the opacity (1).  The only
+// per-pixel state is (T_i, S_i) with S_i = sum_{j>i} w_j A_j, A_j = sum_k c_jk v_k: the
+// gradient w.r.t. alpha_i is T_i A_i + (G - S_i)/(1 - alpha_i), so no per-channel buffer.
+// The 8+CH partials are summed over the warp's 8x4 pixel patch with a TRANSPOSING butterfly
+// (each stage halves the values a lane holds: 15 shuffles for 16 values instead of 80; ncu
+// r1a showed the plain butterfly at ~2/3 of all instructions), after which 16 lanes hold one
+// fully reduced value each and issue ONE atomic instruction per warp.  A warp whose 32 pixels
+// all skip a Gaussian skips the whole reduction (the common case for small splats).
 //
 // Roofline: FP32 pipe + shuffle/atomic throughput; ~70 flop per evaluated pair at 6
 // channels.
@@ -39,15 +43,42 @@ struct RasterBwdParams {
     float* v_flow_affine;
 };
 
-__device__ __forceinline__ float warp_sum(float v) {
+// Transposing butterfly: on entry every lane holds NV partials val[0..NV); on exit val[0] of
+// lane l is the warp-wide sum of partial number slot_of_lane(l) (lanes 2j and 2j+1 hold the same).
+template <int NV>
+__device__ __forceinline__ void transpose_reduce(float (&val)[NV], int lane) {
+    static_assert(NV == 16 || NV == 32, "NV must be 16 or 32");
+    if (NV == 32) {  // first fold 32 -> 16 values per lane pair (xor 1 twice is avoided: use xor 16 later)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+        for (int i = 0; i < 16; ++i) {
+            const bool up = lane & 1;
+            const float send = up ? val[i] : val[i + 16];
+            const float keep = up ? val[i + 16] : val[i];
+            val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+    }
+#pragma unroll
+    for (int half = 8, m = 16; half >= 1; half >>= 1, m >>= 1) {
+        const bool up = lane & m;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? val[i] : val[i + half];
+            const float keep = up ? val[i + half] : val[i];
+            val[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    if (NV == 16) val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
+}
+// which of the 16 partials lane l ends up holding (NV == 16); for NV == 32 add 16 * (l & 1)
+__device__ __forceinline__ int slot_of_lane(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
 template <int CH, bool AFF>
 __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams p) {
     constexpr int FV = (CH + 3) / 4;
+    constexpr int NVAL = CH + 8 + (AFF ? 4 : 0);  // partials per (pixel, Gaussian)
+    constexpr int NV = NVAL <= 16 ? 16 : 32;
     __shared__ float4 sA[BATCH];
     __shared__ float4 sB[BATCH];
     __shared__ float4 sF[FV][BATCH];
@@ -65,32 +96,48 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
 
     const int range_start = p.isect_offsets[tile_id];
     const int range_end = (tile_id == p.C * p.tile_h * p.tile_w - 1) ? (int)p.n_isects : p.isect_offsets[tile_id + 1];
-    const int nb = (range_end - range_start + BATCH - 1) / BATCH;
-    if (nb == 0) return;
+    if (range_end <= range_start) return;
+
+    // where this lane's reduced value goes: slot -> (array, elements per Gaussian, offset)
+    //   [0,CH) v_feat | CH..CH+2 v_conics | CH+3,4 v_means2d | CH+5,6 v_means2d_abs | CH+7 v_opacities | CH+8.. v_flow_affine
+    float* out_base = nullptr;
+    int out_stride = 0;
+    {
+        const int slot = slot_of_lane(lane) + (NV == 32 ? 16 * (lane & 1) : 0);
+        const bool owner = (NV == 32) ? true : ((lane & 1) == 0);
+        if (owner) {
+            if (slot < CH) { out_base = p.v_feat + slot; out_stride = CH; }
+            else if (slot < CH + 3) { out_base = p.v_conics + (slot - CH); out_stride = 3; }
+            else if (slot < CH + 5) { out_base = p.v_means2d + (slot - CH - 3); out_stride = 2; }
+            else if (slot < CH + 7) { if (p.v_means2d_abs) { out_base = p.v_means2d_abs + (slot - CH - 5); out_stride = 2; } }
+            else if (slot < CH + 8) { out_base = p.v_opacities; out_stride = 1; }
+            else if (AFF && slot < CH + 12) { out_base = p.v_flow_affine + (slot - CH - 8); out_stride = 4; }
+        }
+    }
 
     const float T_final = 1.f - p.alphas[pix];
     float T = T_final;
-    float buffer[CH];
+    float S = 0.f;  // sum over later list entries of w_j * A_j
     float v_out[CH];
 #pragma unroll
-    for (int k = 0; k < CH; ++k) {
-        buffer[k] = 0.f;
-        v_out[k] = inside ? p.v_render[pix * CH + k] : 0.f;
-    }
-    const float v_alpha_out = (inside && p.v_alphas) ? p.v_alphas[pix] : 0.f;
+    for (int k = 0; k < CH; ++k) v_out[k] = inside ? p.v_render[pix * CH + k] : 0.f;
     float bg_dot = 0.f;
     if (p.backgrounds) {
 #pragma unroll
         for (int k = 0; k < CH; ++k) bg_dot += p.backgrounds[cam * CH + k] * v_out[k];
     }
+    const float G = (((inside && p.v_alphas) ? p.v_alphas[pix] : 0.f) - bg_dot) * T_final;
     const int bin_final = inside ? p.last_ids[pix] : -1;
     const int warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
+    const int nb_all = (range_end - range_start + BATCH - 1) / BATCH;
 
-    for (int b = 0; b < nb; ++b) {
-        __syncthreads();
+    for (int b = 0; b < nb_all; ++b) {
         // batches run back to front; within a batch, smem slot t holds sorted index batch_end - t
         const int batch_end = range_end - 1 - BATCH * b;
         const int bs = min(BATCH, batch_end + 1 - range_start);
+        // skip (uniformly) batches that lie entirely behind every pixel's last contributor
+        const int need = __syncthreads_or(batch_end - bs + 1 <= warp_bin_final);
+        if (!need) continue;
         const int idx = batch_end - tid;
         if (idx >= range_start) {
             const int g = p.flatten_ids[idx];
@@ -115,11 +162,9 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
             valid = valid && (batch_end - t <= bin_final);
             if (!__any_sync(0xffffffffu, valid)) continue;
 
-            float v_f[CH];
+            float val[NV];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) v_f[k] = 0.f;
-            float v_ca = 0.f, v_cb = 0.f, v_cc = 0.f, v_x = 0.f, v_y = 0.f, v_ax = 0.f, v_ay = 0.f, v_op = 0.f;
-            float v_m0 = 0.f, v_m1 = 0.f, v_m2 = 0.f, v_m3 = 0.f;
+            for (int k = 0; k < NV; ++k) val[k] = 0.f;
             if (valid) {
                 float f[FV * 4];
 #pragma unroll
@@ -138,70 +183,46 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
                         if (k == p.flow_ch0 + 1) { f[k] -= e1; vo1 = v_out[k]; }
                     }
                 }
-                const float ra = 1.f / (1.f - alpha);
-                T *= ra;
+                float ra;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.f - alpha));
+                T *= ra;  // T_i, the transmittance in front of this Gaussian
                 const float fac = alpha * T;
-                float v_alpha = 0.f;
+                float A = 0.f;
 #pragma unroll
                 for (int k = 0; k < CH; ++k) {
-                    v_f[k] = fac * v_out[k];
-                    v_alpha += (f[k] * T - buffer[k] * ra) * v_out[k];
-                    buffer[k] += f[k] * fac;
+                    A = fmaf(f[k], v_out[k], A);
+                    val[k] = fac * v_out[k];
                 }
-                v_alpha += T_final * ra * v_alpha_out;
-                if (p.backgrounds) v_alpha -= T_final * ra * bg_dot;
+                const float v_alpha = fmaf(T, A, (G - S) * ra);
+                S = fmaf(fac, A, S);
+                float gx = 0.f, gy = 0.f;
                 if (AFF) {
                     // f_flow = feat - M delta: d/dM and d/ddelta of the composited flow
-                    v_m0 = -fac * vo0 * dx; v_m1 = -fac * vo0 * dy;
-                    v_m2 = -fac * vo1 * dx; v_m3 = -fac * vo1 * dy;
-                    v_x = -fac * (vo0 * M.x + vo1 * M.z);
-                    v_y = -fac * (vo0 * M.y + vo1 * M.w);
+                    val[CH + 8] = -fac * vo0 * dx; val[CH + 9] = -fac * vo0 * dy;
+                    val[CH + 10] = -fac * vo1 * dx; val[CH + 11] = -fac * vo1 * dy;
+                    gx = -fac * (vo0 * M.x + vo1 * M.z);
+                    gy = -fac * (vo0 * M.y + vo1 * M.w);
                 }
                 if (a4.z * vis <= ALPHA_MAX) {
                     const float v_sigma = -a4.z * vis * v_alpha;
-                    v_ca = 0.5f * v_sigma * dx * dx;
-                    v_cb = v_sigma * dx * dy;
-                    v_cc = 0.5f * v_sigma * dy * dy;
+                    val[CH] = 0.5f * v_sigma * dx * dx;
+                    val[CH + 1] = v_sigma * dx * dy;
+                    val[CH + 2] = 0.5f * v_sigma * dy * dy;
                     // unscaled conic: A = 2 qa / log2e, B = qb / log2e, C = 2 qc / log2e
                     const float vs = v_sigma * LN2;
-                    const float gx = vs * (2.f * a4.w * dx + b4.x * dy);
-                    const float gy = vs * (b4.x * dx + 2.f * b4.y * dy);
-                    v_ax = fabsf(gx);
-                    v_ay = fabsf(gy);
-                    v_x += gx;
-                    v_y += gy;
-                    v_op = vis * v_alpha;
+                    const float hx = vs * (2.f * a4.w * dx + b4.x * dy);
+                    const float hy = vs * (b4.x * dx + 2.f * b4.y * dy);
+                    val[CH + 5] = fabsf(hx);
+                    val[CH + 6] = fabsf(hy);
+                    gx += hx;
+                    gy += hy;
+                    val[CH + 7] = vis * v_alpha;
                 }
+                val[CH + 3] = gx;
+                val[CH + 4] = gy;
             }
-            // warp reduction, then one atomic per value
-#pragma unroll
-            for (int k = 0; k < CH; ++k) v_f[k] = warp_sum(v_f[k]);
-            v_ca = warp_sum(v_ca); v_cb = warp_sum(v_cb); v_cc = warp_sum(v_cc);
-            v_x = warp_sum(v_x); v_y = warp_sum(v_y);
-            v_op = warp_sum(v_op);
-            if (p.v_means2d_abs) { v_ax = warp_sum(v_ax); v_ay = warp_sum(v_ay); }
-            if (AFF) { v_m0 = warp_sum(v_m0); v_m1 = warp_sum(v_m1); v_m2 = warp_sum(v_m2); v_m3 = warp_sum(v_m3); }
-            if (lane == 0) {
-                const size_t g = (size_t)__float_as_int(b4.z);
-#pragma unroll
-                for (int k = 0; k < CH; ++k) atomicAdd(p.v_feat + g * CH + k, v_f[k]);
-                atomicAdd(p.v_conics + 3 * g, v_ca);
-                atomicAdd(p.v_conics + 3 * g + 1, v_cb);
-                atomicAdd(p.v_conics + 3 * g + 2, v_cc);
-                atomicAdd(p.v_means2d + 2 * g, v_x);
-                atomicAdd(p.v_means2d + 2 * g + 1, v_y);
-                if (p.v_means2d_abs) {
-                    atomicAdd(p.v_means2d_abs + 2 * g, v_ax);
-                    atomicAdd(p.v_means2d_abs + 2 * g + 1, v_ay);
-                }
-                atomicAdd(p.v_opacities + g, v_op);
-                if (AFF) {
-                    atomicAdd(p.v_flow_affine + 4 * g, v_m0);
-                    atomicAdd(p.v_flow_affine + 4 * g + 1, v_m1);
-                    atomicAdd(p.v_flow_affine + 4 * g + 2, v_m2);
-                    atomicAdd(p.v_flow_affine + 4 * g + 3, v_m3);
-                }
-            }
+            transpose_reduce<NV>(val, lane);
+            if (out_base) atomicAdd(out_base + (size_t)__float_as_int(b4.z) * out_stride, val[0]);
         }
     }
 }

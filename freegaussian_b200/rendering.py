@@ -28,6 +28,7 @@ from . import _lib
 from ._lib import check, ptr
 
 MAX_CH = 8  # FG_MAX_CHANNELS
+BWD_MODE = "pp"  # compositing backward: "pp" pixel-parallel (default) or "gp" Gaussian-parallel
 SORT_MODE = "two_level"  # or "key64": the reference's literal 64-bit key sort (same resulting order)
 
 
@@ -332,7 +333,8 @@ class _Rasterize(torch.autograd.Function):
           check(L.fg_rasterize_fwd(C, NN, CH, width, height, tile_size, ptr(means2d_c),
                                  ptr(conics_c), ptr(feat_c), ptr(opac_c), ptr(bg), None, 0, ptr(isect_offsets),
                                  ptr(flatten_ids), M, ptr(render), ptr(alphas), ptr(last_ids), _stream()))
-        ctx.save_for_backward(means2d_c, conics_c, feat_c, opac_c, bg, isect_offsets, flatten_ids, alphas, last_ids)
+        ctx.save_for_backward(means2d_c, conics_c, feat_c, opac_c, bg, isect_offsets, flatten_ids, alphas, last_ids,
+                              render)
         ctx.dims = (C, NN, CH, width, height, tile_size, absgrad)
         ctx.means2d_obj = means2d  # the very tensor the caller holds as meta["means2d"] (model.py:869-871)
         ctx.mark_non_differentiable(last_ids)
@@ -341,7 +343,7 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_render, v_alphas, _v_last):
         L = _lib.lib()
-        means2d, conics, feat, opac, bg, isect_offsets, flatten_ids, alphas, last_ids = ctx.saved_tensors
+        means2d, conics, feat, opac, bg, isect_offsets, flatten_ids, alphas, last_ids, render = ctx.saved_tensors
         C, NN, CH, width, height, tile_size, absgrad = ctx.dims
         dev = feat.device
         v_render = v_render.contiguous()
@@ -353,11 +355,16 @@ class _Rasterize(torch.autograd.Function):
         v_opac = torch.zeros_like(opac)
         M = flatten_ids.shape[0]
         with _stage("rasterize_bwd"):
-          check(L.fg_rasterize_bwd(C, NN, CH, width, height, tile_size, ptr(means2d),
-                                 ptr(conics), ptr(feat), ptr(opac), ptr(bg), None, 0, ptr(isect_offsets),
-                                 ptr(flatten_ids), M, ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas),
-                                 ptr(v_means2d), ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), None,
-                                 _stream()))
+            if BWD_MODE == "gp":
+                check(L.fg_rasterize_bwd_gp(C, NN, CH, width, height, tile_size, ptr(means2d), ptr(conics), ptr(feat),
+                                            ptr(opac), ptr(bg), ptr(isect_offsets), ptr(flatten_ids), M, ptr(render),
+                                            ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas), ptr(v_means2d),
+                                            ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), _stream()))
+            else:
+                check(L.fg_rasterize_bwd(C, NN, CH, width, height, tile_size, ptr(means2d), ptr(conics), ptr(feat),
+                                         ptr(opac), ptr(bg), None, 0, ptr(isect_offsets), ptr(flatten_ids), M,
+                                         ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas), ptr(v_means2d),
+                                         ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), None, _stream()))
         if absgrad:
             obj = ctx.means2d_obj
             prev = getattr(obj, "absgrad", None) if ctx.chunked else None

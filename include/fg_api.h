@@ -166,6 +166,19 @@ int fg_rasterize_bwd(int C, int N, int CH, int width, int height, int tile_size,
                      const float* v_alphas, float* v_means2d, float* v_means2d_abs, float* v_conics,
                      float* v_feat, float* v_opacities, float* v_flow_affine, void* stream);
 
+/* Same gradients, Gaussian-parallel mapping (default in rendering.py): per 256-entry batch the
+ * CTA replays the pixels front to back (checkpointing the per-pixel state every 32 entries),
+ * then each warp takes a 32-entry bucket with one lane per Gaussian and streams the tile's 256
+ * pixels through the warp, accumulating every Gaussian's gradients in registers: no
+ * per-pair warp reductions, one atomic per value per (tile, Gaussian).  Needs the forward's
+ * `render` output.  flow_affine is not supported by this variant. */
+int fg_rasterize_bwd_gp(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
+                        const float* conics, const float* feat, const float* opacities,
+                        const float* backgrounds, const int32_t* isect_offsets, const int32_t* flatten_ids,
+                        int64_t n_isects, const float* render, const float* alphas, const int32_t* last_ids,
+                        const float* v_render, const float* v_alphas, float* v_means2d, float* v_means2d_abs,
+                        float* v_conics, float* v_feat, float* v_opacities, void* stream);
+
 /* ---- (4) exact k-nearest neighbours ----------------------------------------------------
  * Replaces FreeGaussianModel.k_nearest_sklearn (freegaussian_model.py:293-311):
  * sklearn NearestNeighbors(n_neighbors=k+1, metric="euclidean") of the set against itself

@@ -133,10 +133,13 @@ def test_exclusive_scan(L):
         assert int(tot.item()) == int(c.long().sum())
 
 
+@pytest.mark.parametrize("bwd_mode", ["gp", "pp"])
 @pytest.mark.parametrize("ch", [1, 3, 4, 6, 8])
-def test_rasterize_fwd_bwd_matches_oracle(L, ch):
-    """Same projected tensors + same sorted lists into both compositors."""
+def test_rasterize_fwd_bwd_matches_oracle(L, ch, bwd_mode, monkeypatch):
+    """Same projected tensors + same sorted lists into both compositors (both backward mappings)."""
+    from freegaussian_b200 import rendering
     from freegaussian_b200.rendering import isect_tiles, rasterize_to_pixels
+    monkeypatch.setattr(rendering, "BWD_MODE", bwd_mode)
     W, H = 100, 70
     tw, th = math.ceil(W / 16), math.ceil(H / 16)
     sc = small_scene(3000, W, H, views=2, seed=11 + ch)
