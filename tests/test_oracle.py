@@ -1,0 +1,143 @@
+"""The oracle itself (CPU): golden fixtures, self-consistency in float64, analytic known answers,
+finite differences, and the structural properties of keys / sort / tile ranges."""
+import ast
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import render as O
+from util import small_scene, rel_err
+
+GOLD = Path(__file__).parent / "golden"
+
+
+@pytest.mark.parametrize("name", ["rgbed_sh3", "rgb_sh0_aa"])
+def test_render_golden(name):
+    z = np.load(GOLD / f"render_{name}.npz")
+    kw = ast.literal_eval(str(z["kwargs"]))
+    t = lambda k: torch.from_numpy(z[k])
+    r, a, m = O.rasterization(t("means"), t("quats"), t("scales"), t("opacities"), t("sh"), t("viewmats"), t("Ks"),
+                              int(z["width"]), int(z["height"]), means_next=t("means_next"), **kw)
+    assert np.array_equal(m["radii"].numpy(), z["radii"])
+    assert np.array_equal(m["flatten_ids"].numpy(), z["flatten_ids"])
+    assert np.array_equal(m["isect_ids"].numpy(), z["isect_ids"])
+    assert np.array_equal(m["isect_offsets"].numpy(), z["isect_offsets"])
+    assert np.array_equal(m["tiles_per_gauss"].numpy(), z["tiles_per_gauss"])
+    assert rel_err(r, t("render")) < 1e-6 and rel_err(a, t("alpha")) < 1e-6 and rel_err(m["flow"], t("flow")) < 1e-6
+
+
+def test_float32_vs_float64():
+    W, H = 64, 48
+    sc = small_scene(500, W, H, views=1, seed=31)
+    a32 = O.rasterization(sc.means, sc.quats, sc.scales, sc.opacities, sc.sh, sc.viewmats, sc.Ks, W, H, sh_degree=3,
+                          render_mode="RGB+ED", means_next=sc.means_next)
+    d = lambda x: x.double()
+    a64 = O.rasterization(d(sc.means), d(sc.quats), d(sc.scales), d(sc.opacities), d(sc.sh), d(sc.viewmats), d(sc.Ks),
+                          W, H, sh_degree=3, render_mode="RGB+ED", means_next=d(sc.means_next))
+    assert torch.equal(a32[2]["radii"], a64[2]["radii"])
+    assert rel_err(a32[0], a64[0]) < 1e-4 and rel_err(a32[1], a64[1]) < 1e-4
+    assert rel_err(a32[2]["flow"], a64[2]["flow"]) < 1e-4
+
+
+def test_single_gaussian_known_answer():
+    """One isotropic Gaussian at the optical axis: alpha(p) = min(.999, o * exp(-|p-mu|^2 / (2 s2d))) with
+    s2d = (f s / z)^2 + 0.3 (EWA blur), colour = SH DC * 0.2820948 + 0.5 (Appendix A.2/A.3/A.6)."""
+    W = H = 32
+    f, z, s, o = 40.0, 4.0, 0.2, 0.8
+    means = torch.tensor([[0.0, 0.0, z]])
+    quats = torch.tensor([[1.0, 0.0, 0.0, 0.0]])
+    scales = torch.full((1, 3), s)
+    sh = torch.zeros(1, 16, 3)
+    sh[0, 0] = torch.tensor([1.0, -0.5, 0.25])
+    vm = torch.eye(4)[None]
+    K = torch.tensor([[[f, 0, W / 2], [0, f, H / 2], [0, 0, 1.0]]])
+    r, a, m = O.rasterization(means, quats, scales, torch.tensor([o]), sh, vm, K, W, H, sh_degree=0, render_mode="RGB+ED")
+    s2d = (f * s / z) ** 2 + 0.3
+    ys, xs = torch.meshgrid(torch.arange(H) + 0.5, torch.arange(W) + 0.5, indexing="ij")
+    d2 = (xs - W / 2) ** 2 + (ys - H / 2) ** 2
+    alpha = torch.clamp(o * torch.exp(-0.5 * d2 / s2d), max=0.999)
+    alpha = torch.where(alpha >= 1 / 255, alpha, torch.zeros(()))
+    radius = math.ceil(3 * math.sqrt(s2d))
+    assert int(m["radii"][0, 0]) == radius
+    assert rel_err(a[0, ..., 0], alpha) < 1e-6
+    col = torch.clamp_min(sh[0, 0] * 0.2820947917738781 + 0.5, 0)
+    assert rel_err(r[0, ..., :3], alpha[..., None] * col) < 1e-6
+    assert rel_err(r[0, ..., 3][alpha > 0], torch.full_like(alpha, z)[alpha > 0]) < 1e-5  # ED = depth where covered (fp32 divide)
+
+
+def test_gradients_match_finite_differences():
+    W, H = 24, 16
+    sc = small_scene(40, W, H, views=1, seed=5, scale_mul=1.5)
+    d = lambda x: x.double()
+    base = [d(sc.means), d(sc.quats), d(sc.scales), d(sc.opacities), d(sc.sh), d(sc.means_next)]
+    g = torch.Generator().manual_seed(0)
+    wr = torch.randn(1, H, W, 4, generator=g, dtype=torch.double)
+    wf = torch.randn(1, H, W, 2, generator=g, dtype=torch.double)
+
+    def loss(ps):
+        r, a, m = O.rasterization(ps[0], ps[1], ps[2], ps[3], ps[4], d(sc.viewmats), d(sc.Ks), W, H, sh_degree=3,
+                                  render_mode="RGB+ED", means_next=ps[5])
+        return (r * wr).sum() + (m["flow"] * wf).sum() + a.sum()
+
+    ps = [p.clone().requires_grad_(True) for p in base]
+    loss(ps).backward()
+    rng = np.random.default_rng(0)
+    for pi in range(6):
+        for _ in range(3):
+            idx = tuple(int(rng.integers(0, s)) for s in base[pi].shape)
+            eps = 1e-6
+            plus = [p.clone() for p in base]; plus[pi][idx] += eps
+            minus = [p.clone() for p in base]; minus[pi][idx] -= eps
+            fd = float(loss(plus) - loss(minus)) / (2 * eps)
+            an = float(ps[pi].grad[idx])
+            assert abs(fd - an) <= 1e-4 * max(1.0, abs(an), abs(fd)), (pi, idx, fd, an)
+
+
+def test_keys_sort_and_offsets_properties():
+    W, H = 120, 72
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    sc = small_scene(1500, W, H, views=3, seed=8)
+    radii, m2d, dep, con, comp, _ = O.fully_fused_projection(sc.means, sc.quats, sc.scales, sc.viewmats, sc.Ks, W, H)
+    tpg, ids, flat = O.isect_tiles(m2d, radii, dep, 16, tw, th)
+    offs = O.isect_offset_encode(ids, 3, tw, th)
+    ids_n, flat_n = ids.numpy(), flat.numpy()
+    assert (np.diff(ids_n) >= 0).all()  # sortedness
+    same = np.diff(ids_n) == 0
+    assert (np.diff(flat_n)[same] > 0).all()  # stability: ties keep ascending c*N+n
+    tile_bits = int(math.floor(math.log2(tw * th))) + 1
+    cam = ids_n >> (32 + tile_bits)
+    assert np.array_equal(cam, flat_n // 1500)  # camera field agrees with the value
+    depth_bits = (ids_n & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+    assert np.array_equal(depth_bits, dep.reshape(-1).numpy()[flat_n])
+    assert int(tpg.sum()) == ids.numel()
+    o = offs.reshape(-1).numpy()
+    assert (np.diff(o) >= 0).all() and o[0] == 0 and o[-1] <= ids.numel()
+    # every (c,n) appears exactly tiles_per_gauss times
+    assert np.array_equal(np.bincount(flat_n, minlength=3 * 1500), tpg.reshape(-1).numpy())
+
+
+def test_flow_equals_extra_colour_channels():
+    W, H = 64, 48
+    sc = small_scene(400, W, H, views=1, seed=12)
+    r, a, m = O.rasterization(sc.means, sc.quats, sc.scales, sc.opacities, sc.sh, sc.viewmats, sc.Ks, W, H, sh_degree=3,
+                              means_next=sc.means_next)
+    uv, z = O.project_points(sc.means_next, sc.viewmats, sc.Ks)
+    f = torch.where(((m["radii"] > 0) & (z >= 0.01))[..., None], uv - m["means2d"], torch.zeros(()))
+    r2, _, _ = O.rasterization(sc.means, sc.quats, sc.scales, sc.opacities, f[0], sc.viewmats, sc.Ks, W, H, sh_degree=None)
+    assert rel_err(m["flow"], r2) < 1e-6
+
+
+def test_packed_meta_layout():
+    W, H = 48, 32
+    sc = small_scene(300, W, H, views=2, seed=2)
+    r0, a0, m0 = O.rasterization(sc.means, sc.quats, sc.scales, sc.opacities, sc.sh, sc.viewmats, sc.Ks, W, H, sh_degree=3,
+                                 render_mode="ED", packed=False)
+    r1, a1, m1 = O.rasterization(sc.means, sc.quats, sc.scales, sc.opacities, sc.sh, sc.viewmats, sc.Ks, W, H, sh_degree=3,
+                                 render_mode="ED", packed=True)
+    assert torch.equal(r0, r1)
+    nnz = int((m0["radii"] > 0).sum())
+    assert m1["means2d"].shape == (nnz, 2) and m1["gaussian_ids"].shape == (nnz,)
+    assert (np.diff((m1["camera_ids"] * 300 + m1["gaussian_ids"]).numpy()) > 0).all()
