@@ -40,6 +40,11 @@ SIGNATURES = {
     "fg_isect_emit_tiles": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fg_isect_offsets_tiles": (_i32, [_i64, _vp, _i32, _i32, _i32, _vp, _vp]),
     "fg_isect_ids_from_tiles": (_i32, [_i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "fg_bin_coarse_dims": (_i32, [_i32, _i32, _pi, _pi]),
+    "fg_bin_count": (_i32, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fg_bin_tile_scan": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "fg_bin_coarse_emit": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fg_bin_fine": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fg_rasterize_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
                                 _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "fg_rasterize_bwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,

@@ -1,0 +1,298 @@
+// (2c) Hierarchical tile binning: builds the per-tile depth-sorted lists WITHOUT sorting the
+// tile intersections.  Same output (flatten_ids, isect_offsets) as the reference's 64-bit key
+// sort: inside a tile, entries are ordered by (depth bits, c*N+n).
+//
+//   1. the (c,n) splats are stably sorted by depth once (radix_sort.cu, 32-bit keys)   [N items]
+//   2. bin_count: per splat, +1/-1 at the four corners of its tile rectangle in a 2-D
+//      difference grid, and the number of COARSE cells (4x4 tiles) it overlaps
+//   3. tile_scan: 2-D prefix sum of the grid = exact intersections per tile; their exclusive
+//      scan = isect_offsets; the grand total M sizes flatten_ids
+//   4. the (splat, coarse cell) pairs are emitted in depth order and stably sorted by cell
+//      (isect.cu emit + radix sort on ~0.1 M items: an order of magnitude fewer than M)
+//   5. fine_bin: one CTA per coarse cell streams the cell's list in order and appends each
+//      splat to the lists of the (up to 16) tiles it overlaps with ballot-ranked, coalesced
+//      stores.  Order inside a tile = order of the stream = depth order: stable by construction.
+//
+// Roofline: HBM.  Algorithmic bytes: 20 B per splat (count) + 28 B per coarse pair + 4 B per
+// tile intersection written once -- against 36 B (two-level sort) or 152 B (64-bit sort) per
+// intersection.
+#include "common.cuh"
+#include "splat_math.h"
+
+namespace fg {
+
+constexpr int CK = 4;        // coarse cell = CK x CK tiles
+constexpr int CK_SHIFT = 2;
+
+// ---- step 2 -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    bin_count_kernel(int C, int N, long long total, const int32_t* __restrict__ order,
+                     const float2* __restrict__ means2d, const int32_t* __restrict__ radii, int tile_size, int tile_w,
+                     int tile_h, int32_t* __restrict__ diff /*[C][tile_h+1][tile_w+1]*/,
+                     int32_t* __restrict__ coarse_cnt /*[total], in `order`*/) {
+    const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (slot >= total) return;
+    const long long idx = order[slot];
+    const int r = radii[idx];
+    int cnt = 0;
+    if (r > 0) {
+        const float2 m = means2d[idx];
+        const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
+        if (t.x1 > t.x0 && t.y1 > t.y0) {
+            int32_t* g = diff + (idx / N) * (long long)(tile_h + 1) * (tile_w + 1);
+            const int W1 = tile_w + 1;
+            atomicAdd(g + t.y0 * W1 + t.x0, 1);
+            atomicAdd(g + t.y0 * W1 + t.x1, -1);
+            atomicAdd(g + t.y1 * W1 + t.x0, -1);
+            atomicAdd(g + t.y1 * W1 + t.x1, 1);
+            cnt = (((t.x1 + CK - 1) >> CK_SHIFT) - (t.x0 >> CK_SHIFT)) * (((t.y1 + CK - 1) >> CK_SHIFT) - (t.y0 >> CK_SHIFT));
+        }
+    }
+    coarse_cnt[slot] = cnt;
+}
+
+// ---- step 3: one CTA; grids are small (<= ~100k tiles) ---------------------------------------
+__global__ void __launch_bounds__(1024)
+    tile_scan_kernel(int C, int tile_w, int tile_h, int32_t* __restrict__ diff, int32_t* __restrict__ offsets,
+                     long long* __restrict__ total_out) {
+    const int W1 = tile_w + 1, H1 = tile_h + 1;
+    __shared__ long long warp_sums[33];
+    __shared__ long long carry_s;
+    // row-wise prefix (warp per row, coalesced), then column-wise prefix (thread per column,
+    // next row prefetched): the difference grid becomes the per-tile counts, in place
+    const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int c = 0; c < C; ++c) {
+        int32_t* g = diff + (long long)c * H1 * W1;
+        for (int y = warp_; y < H1; y += nwarps) {
+            int carry = 0;
+            for (int x0 = 0; x0 < W1; x0 += 32) {
+                const int x = x0 + lane_;
+                int v = x < W1 ? g[y * W1 + x] : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int o = __shfl_up_sync(0xffffffffu, v, d);
+                    if (lane_ >= d) v += o;
+                }
+                v += carry;
+                if (x < W1) g[y * W1 + x] = v;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x < W1; x += blockDim.x) {
+            int run = 0;
+            int next = g[x];
+            for (int y = 0; y < H1; ++y) {
+                const int cur = next;
+                if (y + 1 < H1) next = g[(y + 1) * W1 + x];
+                run += cur;
+                g[y * W1 + x] = run;
+            }
+        }
+        __syncthreads();
+    }
+    // exclusive scan of counts over (c, y, x) in tile order
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const long long n_tiles = (long long)C * tile_w * tile_h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < n_tiles; base += blockDim.x) {
+        const long long t = base + threadIdx.x;
+        long long v = 0;
+        if (t < n_tiles) {
+            const int c = (int)(t / (tile_w * tile_h));
+            const int rem = (int)(t - (long long)c * tile_w * tile_h);
+            const int y = rem / tile_w, x = rem - y * tile_w;
+            v = diff[((long long)c * H1 + y) * W1 + x];
+        }
+        long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            long long o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = warp_sums[lane];
+            long long wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                long long o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            warp_sums[lane] = wi - w;
+            if (lane == 31) warp_sums[32] = wi;
+        }
+        __syncthreads();
+        const long long carry = carry_s;
+        if (t < n_tiles) offsets[t] = (int32_t)(carry + warp_sums[warp] + incl - v);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_sums[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+// ---- step 4: emit (splat, coarse cell) pairs in depth order --------------------------------
+__global__ void __launch_bounds__(256)
+    coarse_emit_kernel(int C, int N, long long total, const int32_t* __restrict__ order,
+                       const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
+                       const int32_t* __restrict__ coarse_off, int tile_size, int tile_w, int tile_h, int cw, int chh,
+                       uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (slot >= total) return;
+    const long long idx = order[slot];
+    const int r = radii[idx];
+    if (r <= 0) return;
+    const float2 m = means2d[idx];
+    const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
+    if (!(t.x1 > t.x0 && t.y1 > t.y0)) return;
+    const int cx0 = t.x0 >> CK_SHIFT, cx1 = (t.x1 + CK - 1) >> CK_SHIFT;
+    const int cy0 = t.y0 >> CK_SHIFT, cy1 = (t.y1 + CK - 1) >> CK_SHIFT;
+    const uint32_t cam_base = (uint32_t)((idx / N) * (long long)cw * chh);
+    int k = coarse_off[slot];
+    for (int y = cy0; y < cy1; ++y)
+        for (int x = cx0; x < cx1; ++x) {
+            keys[k] = cam_base + (uint32_t)(y * cw + x);
+            vals[k] = (int32_t)idx;
+            ++k;
+        }
+}
+
+// ---- step 5 -------------------------------------------------------------------------------
+// CTA = coarse cell.  Chunks of 256 list entries (thread = entry); for each of the cell's 16
+// tiles the entries that overlap it are ranked with a ballot + per-warp prefix and appended to
+// the tile's list.  Running per-tile cursors live in shared memory.
+__global__ void __launch_bounds__(256)
+    fine_bin_kernel(int N, const int32_t* __restrict__ coarse_offsets /*[n_cells]*/, long long n_coarse,
+                    int n_cells_total, const int32_t* __restrict__ coarse_vals, const float2* __restrict__ means2d,
+                    const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
+                    const int32_t* __restrict__ isect_offsets, int32_t* __restrict__ flatten_ids) {
+    constexpr int NT = CK * CK;
+    __shared__ int s_cursor[NT];       // entries already written per tile
+    __shared__ int s_warp_cnt[8][NT];  // per chunk: entries per (warp, tile)
+    __shared__ int s_tile_off[NT];     // isect_offsets of the cell's tiles (-1 = outside the image)
+    const int cell = blockIdx.x;
+    const int cam = cell / (cw * chh);
+    const int crem = cell - cam * cw * chh;
+    const int cy = crem / cw, cx = crem - cy * cw;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int start = coarse_offsets[cell];
+    const int end = (cell == n_cells_total - 1) ? (int)n_coarse : coarse_offsets[cell + 1];
+    if (end <= start) return;
+    if (tid < NT) {
+        const int tx = cx * CK + (tid & (CK - 1)), ty = cy * CK + (tid >> CK_SHIFT);
+        s_cursor[tid] = 0;
+        s_tile_off[tid] = (tx < tile_w && ty < tile_h) ? isect_offsets[(cam * tile_h + ty) * tile_w + tx] : -1;
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1;
+    for (int base = start; base < end; base += 256) {
+        const int e = base + tid;
+        unsigned mask = 0;  // bit (iy*CK + ix) set if the splat overlaps tile (cx*CK+ix, cy*CK+iy)
+        int id = 0;
+        if (e < end) {
+            id = coarse_vals[e];
+            const float2 m = means2d[id];
+            const TileRect t = tile_rect(m.x, m.y, radii[id], tile_size, tile_w, tile_h);
+            const int x0 = max(t.x0 - cx * CK, 0), x1 = min(t.x1 - cx * CK, CK);
+            const int y0 = max(t.y0 - cy * CK, 0), y1 = min(t.y1 - cy * CK, CK);
+            if (x1 > x0 && y1 > y0) {
+                const unsigned cols = ((1u << x1) - 1) & ~((1u << x0) - 1);  // CK bits
+                unsigned rows = 0;
+                for (int y = y0; y < y1; ++y) rows |= cols << (y * CK);
+                mask = rows;
+            }
+        }
+        // per-warp counts per tile
+        unsigned bal[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            bal[t] = __ballot_sync(0xffffffffu, (mask >> t) & 1u);
+            if (lane == 0) s_warp_cnt[warp][t] = __popc(bal[t]);
+        }
+        __syncthreads();
+        // exclusive prefix over warps (threads 0..NT-1), advance the cursors
+        if (tid < NT) {
+            int run = s_cursor[tid];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int c = s_warp_cnt[w][tid];
+                s_warp_cnt[w][tid] = run;
+                run += c;
+            }
+            s_cursor[tid] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if ((mask >> t) & 1u) {
+                const int pos = s_tile_off[t] + s_warp_cnt[warp][t] + __popc(bal[t] & lt);
+                flatten_ids[pos] = id;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace fg
+
+using namespace fg;
+
+extern "C" int fg_bin_coarse_dims(int tile_w, int tile_h, int* cw, int* chh) {
+    FG_REQUIRE(cw && chh, "NULL pointer");
+    *cw = (tile_w + CK - 1) / CK;
+    *chh = (tile_h + CK - 1) / CK;
+    return FG_OK;
+}
+
+extern "C" int fg_bin_count(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
+                            int tile_size, int tile_w, int tile_h, int32_t* diff_grid, int32_t* coarse_cnt,
+                            void* stream) {
+    FG_REQUIRE(C >= 1 && N >= 0 && (long long)C * N < (1ll << 31), "bad C/N");
+    FG_REQUIRE(diff_grid, "diff_grid must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    FG_CUDA(cudaMemsetAsync(diff_grid, 0, sizeof(int32_t) * (size_t)C * (tile_h + 1) * (tile_w + 1), st));
+    if (N == 0) return FG_OK;
+    FG_REQUIRE(order && means2d && radii && coarse_cnt, "NULL pointer");
+    const long long total = (long long)C * N;
+    FG_LAUNCH(bin_count_kernel, ceil_div(total, 256), 256, 0, st, C, N, total, order, (const float2*)means2d, radii,
+              tile_size, tile_w, tile_h, diff_grid, coarse_cnt);
+    return FG_OK;
+}
+
+extern "C" int fg_bin_tile_scan(int C, int tile_w, int tile_h, int32_t* diff_grid, int32_t* isect_offsets,
+                                int64_t* total, void* stream) {
+    FG_REQUIRE(C >= 1 && tile_w > 0 && tile_h > 0 && diff_grid && isect_offsets && total, "bad arguments");
+    FG_LAUNCH(tile_scan_kernel, 1, 1024, 0, stream, C, tile_w, tile_h, diff_grid, isect_offsets, (long long*)total);
+    return FG_OK;
+}
+
+extern "C" int fg_bin_coarse_emit(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
+                                  const int32_t* coarse_off, int tile_size, int tile_w, int tile_h,
+                                  uint32_t* coarse_keys, int32_t* coarse_vals, void* stream) {
+    FG_REQUIRE(C >= 1 && N >= 0 && (long long)C * N < (1ll << 31), "bad C/N");
+    if (N == 0) return FG_OK;
+    FG_REQUIRE(order && means2d && radii && coarse_off && coarse_keys && coarse_vals, "NULL pointer");
+    const long long total = (long long)C * N;
+    const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
+    FG_LAUNCH(coarse_emit_kernel, ceil_div(total, 256), 256, 0, stream, C, N, total, order, (const float2*)means2d,
+              radii, coarse_off, tile_size, tile_w, tile_h, cw, chh, coarse_keys, coarse_vals);
+    return FG_OK;
+}
+
+extern "C" int fg_bin_fine(int C, int N, int64_t n_coarse, const int32_t* coarse_offsets,
+                           const int32_t* coarse_vals_sorted, const float* means2d, const int32_t* radii,
+                           int tile_size, int tile_w, int tile_h, const int32_t* isect_offsets,
+                           int32_t* flatten_ids, void* stream) {
+    FG_REQUIRE(C >= 1 && n_coarse >= 0 && n_coarse < (1ll << 31), "bad arguments");
+    if (n_coarse == 0) return FG_OK;
+    FG_REQUIRE(coarse_offsets && coarse_vals_sorted && means2d && radii && isect_offsets && flatten_ids, "NULL pointer");
+    const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
+    const int n_cells = C * cw * chh;
+    FG_LAUNCH(fine_bin_kernel, n_cells, 256, 0, stream, N, coarse_offsets, (long long)n_coarse, n_cells,
+              coarse_vals_sorted, (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, isect_offsets,
+              flatten_ids);
+    return FG_OK;
+}

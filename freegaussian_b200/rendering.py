@@ -29,7 +29,7 @@ from ._lib import check, ptr
 
 MAX_CH = 8  # FG_MAX_CHANNELS
 BWD_MODE = "pp"  # compositing backward: "pp" pixel-parallel (default) or "gp" Gaussian-parallel
-SORT_MODE = "two_level"  # or "key64": the reference's literal 64-bit key sort (same resulting order)
+SORT_MODE = "binned"  # "binned" | "two_level" | "key64" (the reference's literal 64-bit key sort); same lists
 
 
 def _stream() -> int:
@@ -212,6 +212,9 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
     """Tile intersections sorted by (camera, tile, depth), ties in ascending c*N+n -- the order
     gsplat's 64-bit stable radix sort produces.
 
+    ``mode="binned"`` (default): no sort over the intersections at all -- splats are sorted by depth
+    once, exact per-tile counts come from a 2-D difference grid, and each 4x4-tile cell appends
+    its depth-ordered splats to its tiles' lists (csrc/binning.cu).
     ``mode="key64"``: the reference layout literally -- emit 64-bit (camera|tile|depth) keys in
     (c,n) order and radix-sort them (6-7 passes).  ``mode="two_level"`` (default): sort the
     splats once by depth, emit their tiles in that order with 32-bit tile keys and stable-sort
@@ -220,7 +223,7 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
     Returns ``(isect_ids | None, flatten_ids [M] int32, isect_offsets [C,tile_h,tile_w] int32,
     tile_keys | None)``; one host sync (reading M), like gsplat.
     """
-    assert mode in ("two_level", "key64"), mode
+    assert mode in ("binned", "two_level", "key64"), mode
     L = _lib.lib()
     C, N = radii.shape
     dev = radii.device
@@ -252,11 +255,43 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
             check(L.fg_isect_offsets(M, ptr(ids_a), C, tile_w, tile_h, ptr(isect_offsets), st))
         return ids_a, val_a, isect_offsets, None
 
-    # ---- two-level
+    # ---- both remaining modes start from the splats sorted by depth
     with _stage("depth_sort"):
         dk, dv = torch.empty(total, **i32), torch.empty(total, **i32)
         check(L.fg_isect_depth_keys(total, ptr(depths), ptr(tiles_per_gauss), ptr(dk), ptr(dv), st))
         _, order = _sort_pairs(L, total, dk, dv, torch.empty_like(dk), torch.empty_like(dv), 32, dev, st, False)
+
+    if mode == "binned":
+        cw_, ch_ = ctypes.c_int(0), ctypes.c_int(0)
+        check(L.fg_bin_coarse_dims(tile_w, tile_h, ctypes.byref(cw_), ctypes.byref(ch_)))
+        cw, chh = cw_.value, ch_.value
+        n2 = torch.empty(2, dtype=torch.int64, device=dev)
+        with _stage("bin_count"):
+            diff = torch.empty(C * (tile_h + 1) * (tile_w + 1), **i32)
+            coarse_cnt = torch.empty(total, **i32)
+            check(L.fg_bin_count(C, N, ptr(order), ptr(means2d), ptr(radii), tile_size, tile_w, tile_h, ptr(diff),
+                                 ptr(coarse_cnt), st))
+            check(L.fg_bin_tile_scan(C, tile_w, tile_h, ptr(diff), ptr(isect_offsets), n2[0:1].data_ptr(), st))
+            check(L.fg_exclusive_scan_i32(total, ptr(coarse_cnt), ptr(offsets), n2[1:2].data_ptr(), ptr(ws),
+                                          ws.numel(), st))
+        M, Mc = (int(v) for v in n2.tolist())  # the one host sync: sizes the list buffers
+        assert M < 2**31, "too many tile intersections"
+        fl = torch.empty(M, **i32)
+        if M > 0:
+            with _stage("coarse_sort"):
+                ck, cv = torch.empty(Mc, **i32), torch.empty(Mc, **i32)
+                check(L.fg_bin_coarse_emit(C, N, ptr(order), ptr(means2d), ptr(radii), ptr(offsets), tile_size,
+                                           tile_w, tile_h, ptr(ck), ptr(cv), st))
+                bits = max(1, int(math.ceil(math.log2(C * cw * chh))))
+                ck, cv = _sort_pairs(L, Mc, ck, cv, torch.empty_like(ck), torch.empty_like(cv), bits, dev, st, False)
+                coarse_offsets = torch.empty(C * cw * chh, **i32)
+                check(L.fg_isect_offsets_tiles(Mc, ptr(ck), C, cw, chh, ptr(coarse_offsets), st))
+            with _stage("fine_bin"):
+                check(L.fg_bin_fine(C, N, Mc, ptr(coarse_offsets), ptr(cv), ptr(means2d), ptr(radii), tile_size,
+                                    tile_w, tile_h, ptr(isect_offsets), ptr(fl), st))
+        return None, fl, isect_offsets, None
+
+    # ---- two-level
     with _stage("scan"):
         cnt_sorted = torch.empty(total, **i32)
         check(L.fg_gather_i32(total, ptr(tiles_per_gauss), ptr(order), ptr(cnt_sorted), st))
@@ -497,7 +532,16 @@ def rasterization(
     meta = _Meta()
     if isect_ids is None:
         flat_unpacked, depths_unpacked = flatten_ids, depths.detach()
-        meta.lazy("isect_ids", lambda: isect_ids_from_tiles(tile_keys, flat_unpacked, depths_unpacked, tile_w, tile_h))
+
+        def _rebuild_ids():
+            tk = tile_keys
+            if tk is None:  # binned mode: the tile of every list entry follows from the offsets
+                o = isect_offsets.reshape(-1).long()
+                counts = torch.diff(o, append=o.new_tensor([flat_unpacked.numel()]))
+                tk = torch.repeat_interleave(torch.arange(o.numel(), device=o.device), counts).to(torch.int32)
+            return isect_ids_from_tiles(tk, flat_unpacked, depths_unpacked, tile_w, tile_h)
+
+        meta.lazy("isect_ids", _rebuild_ids)
     else:
         meta["isect_ids"] = isect_ids
     if packed:

@@ -142,6 +142,28 @@ int fg_isect_offsets_tiles(int64_t n_isects, const uint32_t* sorted_tile_keys, i
 int fg_isect_ids_from_tiles(int64_t n_isects, const uint32_t* sorted_tile_keys, const int32_t* flatten_ids,
                             const float* depths, int tile_w, int tile_h, int64_t* isect_ids, void* stream);
 
+/* Hierarchical binning: the same per-tile lists and offsets with no sort over the M tile
+ * intersections at all (default path of rendering.py; csrc/binning.cu explains the steps).
+ *   order[C*N]       flat ids (c*N+n) stably sorted by depth (fg_isect_depth_keys + u32 sort)
+ *   fg_bin_count     corner increments of every splat's tile rectangle into diff_grid
+ *                    [C,tile_h+1,tile_w+1] (zeroed inside) + coarse-cell count per splat (in `order`)
+ *   fg_bin_tile_scan diff_grid -> per-tile counts (in place) -> isect_offsets, *total = M (device)
+ *   fg_bin_coarse_emit  (cell key, flat id) pairs in depth order; coarse_off = exclusive scan of the counts;
+ *                    cells are 4x4 tiles, key = cam*cw*ch + cy*cw + cx (fg_bin_coarse_dims gives cw, ch)
+ *   fg_bin_fine      after a stable sort of those pairs by key and fg_isect_offsets_tiles-style
+ *                    offsets per cell: append every splat to the lists of the tiles it overlaps */
+int fg_bin_coarse_dims(int tile_w, int tile_h, int* cw, int* ch);
+int fg_bin_count(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
+                 int tile_size, int tile_w, int tile_h, int32_t* diff_grid, int32_t* coarse_cnt, void* stream);
+int fg_bin_tile_scan(int C, int tile_w, int tile_h, int32_t* diff_grid, int32_t* isect_offsets,
+                     int64_t* total, void* stream);
+int fg_bin_coarse_emit(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
+                       const int32_t* coarse_off, int tile_size, int tile_w, int tile_h,
+                       uint32_t* coarse_keys, int32_t* coarse_vals, void* stream);
+int fg_bin_fine(int C, int N, int64_t n_coarse, const int32_t* coarse_offsets,
+                const int32_t* coarse_vals_sorted, const float* means2d, const int32_t* radii, int tile_size,
+                int tile_w, int tile_h, const int32_t* isect_offsets, int32_t* flatten_ids, void* stream);
+
 /* ---- (3) per-tile front-to-back alpha compositing, forward and backward ----------------
  * Replaces gsplat `rasterize_to_pixels` fwd/bwd.  One pass composites all CH channels
  * (RGB + depth + flow).  alpha = min(0.999, opacity*exp(-sigma)); skip alpha < 1/255;
