@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfreegaussian_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pi = C.POINTER(C.c_int)
@@ -45,12 +45,11 @@ SIGNATURES = {
     "fg_bin_tile_scan": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "fg_bin_coarse_emit": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fg_bin_fine": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "fg_rasterize_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
-                                _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
-    "fg_rasterize_bwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
-                                _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "fg_rasterize_bwd_gp": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
-                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_rasterize_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+                                _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "fg_rasterize_bwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+                                _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_densify_stats": (_i32, [_i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
     "fg_knn_workspace_bytes": (_i64, [_i64]),
     "fg_knn_f32": (_i32, [_i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
 }

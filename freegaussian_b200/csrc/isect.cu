@@ -214,6 +214,31 @@ __global__ void isect_ids_kernel(long long n, const uint32_t* __restrict__ tile_
     out[i] = (cam << (32 + tile_bits)) | (tile << 32) | (long long)(uint32_t)__float_as_int(depths[flatten_ids[i]]);
 }
 
+// densification statistics (freegaussian_model.py:369-392), all of this rank's views in one pass
+__global__ void densify_stats_kernel(int C, int N, const int32_t* __restrict__ radii, const float2* __restrict__ absgrad,
+                                     float inv_max_hw, float* __restrict__ grad_norm, float* __restrict__ vis_count,
+                                     float* __restrict__ max_size) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float g = 0.f, cnt = 0.f;
+    int rmax = 0;
+    for (int c = 0; c < C; ++c) {
+        const size_t i = (size_t)c * N + n;
+        const int r = radii[i];
+        if (r > 0) {
+            const float2 a = absgrad[i];
+            g += sqrtf(a.x * a.x + a.y * a.y);
+            cnt += 1.f;
+            rmax = max(rmax, r);
+        }
+    }
+    if (cnt > 0.f) {
+        grad_norm[n] += g;
+        vis_count[n] += cnt;
+        max_size[n] = fmaxf(max_size[n], (float)rmax * inv_max_hw);
+    }
+}
+
 __global__ void fill_i32_kernel(long long n, int32_t v, int32_t* out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = v;
@@ -333,5 +358,15 @@ extern "C" int fg_isect_offsets(int64_t n_isects, const int64_t* sorted_isect_id
     int tile_bits = tile_bits_of(tile_w * tile_h);
     FG_LAUNCH((isect_offsets_kernel<true>), ceil_div(n_isects, 256), 256, 0, stream, (long long)n_isects,
               sorted_isect_ids, (const uint32_t*)nullptr, tile_w * tile_h, tile_bits, n_tiles, offsets);
+    return FG_OK;
+}
+
+extern "C" int fg_densify_stats(int C, int N, const int32_t* radii, const float* absgrad, float inv_max_hw,
+                                float* grad_norm, float* vis_count, float* max_size, void* stream) {
+    FG_REQUIRE(C >= 1 && N >= 0, "bad C/N");
+    if (N == 0) return FG_OK;
+    FG_REQUIRE(radii && absgrad && grad_norm && vis_count && max_size, "NULL pointer");
+    FG_LAUNCH(densify_stats_kernel, ceil_div(N, 256), 256, 0, stream, C, N, radii, (const float2*)absgrad, inv_max_hw,
+              grad_norm, vis_count, max_size);
     return FG_OK;
 }

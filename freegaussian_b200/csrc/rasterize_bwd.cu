@@ -28,12 +28,17 @@ struct RasterBwdParams {
     const float* backgrounds;
     const float4* flow_affine;
     int flow_ch0;
+    int split;       // v_render holds channels [0,split), v_render2 channels [split,CH)
+    int ed_channel;  // "ED" channel (needs `render`), -1 = none
+    int opac_shared; // opacities / v_opacities are [N] (index g % N)
     const int32_t* isect_offsets;
     const int32_t* flatten_ids;
     long long n_isects;
+    const float* render;
     const float* alphas;
     const int32_t* last_ids;
     const float* v_render;
+    const float* v_render2;
     const float* v_alphas;
     float* v_means2d;
     float* v_means2d_abs;
@@ -102,6 +107,7 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
     //   [0,CH) v_feat | CH..CH+2 v_conics | CH+3,4 v_means2d | CH+5,6 v_means2d_abs | CH+7 v_opacities | CH+8.. v_flow_affine
     float* out_base = nullptr;
     int out_stride = 0;
+    bool out_is_opac = false;
     {
         const int slot = slot_of_lane(lane) + (NV == 32 ? 16 * (lane & 1) : 0);
         const bool owner = (NV == 32) ? true : ((lane & 1) == 0);
@@ -110,23 +116,39 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
             else if (slot < CH + 3) { out_base = p.v_conics + (slot - CH); out_stride = 3; }
             else if (slot < CH + 5) { out_base = p.v_means2d + (slot - CH - 3); out_stride = 2; }
             else if (slot < CH + 7) { if (p.v_means2d_abs) { out_base = p.v_means2d_abs + (slot - CH - 5); out_stride = 2; } }
-            else if (slot < CH + 8) { out_base = p.v_opacities; out_stride = 1; }
+            else if (slot < CH + 8) { out_base = p.v_opacities; out_stride = 1; out_is_opac = true; }
             else if (AFF && slot < CH + 12) { out_base = p.v_flow_affine + (slot - CH - 8); out_stride = 4; }
         }
     }
 
-    const float T_final = 1.f - p.alphas[pix];
+    const float a_out = p.alphas[pix];
+    const float T_final = 1.f - a_out;
     float T = T_final;
     float S = 0.f;  // sum over later list entries of w_j * A_j
     float v_out[CH];
+    float v_alpha_out = (inside && p.v_alphas) ? p.v_alphas[pix] : 0.f;
+    const int n2 = CH - p.split;
 #pragma unroll
-    for (int k = 0; k < CH; ++k) v_out[k] = inside ? p.v_render[pix * CH + k] : 0.f;
+    for (int k = 0; k < CH; ++k) {
+        float v = 0.f;
+        if (inside) {
+            if (k < p.split) v = p.v_render ? p.v_render[pix * p.split + k] : 0.f;
+            else v = p.v_render2 ? p.v_render2[pix * n2 + (k - p.split)] : 0.f;
+        }
+        if (k == p.ed_channel) {
+            // out = acc / max(alpha, 1e-10):  d/dacc = 1/alpha^,  d/dalpha = -out/alpha^ (0 under the clamp)
+            const float inv = 1.f / fmaxf(a_out, 1e-10f);
+            if (inside && a_out >= 1e-10f) v_alpha_out -= v * p.render[pix * p.split + k] * inv;
+            v *= inv;
+        }
+        v_out[k] = v;
+    }
     float bg_dot = 0.f;
     if (p.backgrounds) {
 #pragma unroll
         for (int k = 0; k < CH; ++k) bg_dot += p.backgrounds[cam * CH + k] * v_out[k];
     }
-    const float G = (((inside && p.v_alphas) ? p.v_alphas[pix] : 0.f) - bg_dot) * T_final;
+    const float G = (v_alpha_out - bg_dot) * T_final;
     const int bin_final = inside ? p.last_ids[pix] : -1;
     const int warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
     const int nb_all = (range_end - range_start + BATCH - 1) / BATCH;
@@ -143,8 +165,11 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
             const int g = p.flatten_ids[idx];
             const float2 m = p.means2d[g];
             const float ca = p.conics[3 * (size_t)g], cb = p.conics[3 * (size_t)g + 1], cc = p.conics[3 * (size_t)g + 2];
-            sA[tid] = make_float4(m.x, m.y, p.opacities[g], 0.5f * LOG2E * ca);
-            sB[tid] = make_float4(LOG2E * cb, 0.5f * LOG2E * cc, __int_as_float(g), 0.f);
+            const int go = p.opac_shared ? g % p.N : g;
+            sA[tid] = make_float4(m.x, m.y, p.opacities[go], 0.5f * LOG2E * ca);
+            // .w: row of the opacity gradient (g, or g % N when one opacity is shared by all cameras)
+            sB[tid] = make_float4(LOG2E * cb, 0.5f * LOG2E * cc, __int_as_float(g),
+                                  __int_as_float(go));
             float f[FV * 4];
 #pragma unroll
             for (int k = 0; k < FV * 4; ++k) f[k] = (k < CH) ? p.feat[(size_t)g * CH + k] : 0.f;
@@ -222,7 +247,10 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
                 val[CH + 4] = gy;
             }
             transpose_reduce<NV>(val, lane);
-            if (out_base) atomicAdd(out_base + (size_t)__float_as_int(b4.z) * out_stride, val[0]);
+            if (out_base) {
+                const int row = __float_as_int(out_is_opac ? b4.w : b4.z);
+                atomicAdd(out_base + (size_t)row * out_stride, val[0]);
+            }
         }
     }
 }
@@ -246,18 +274,22 @@ using namespace fg;
 
 extern "C" int fg_rasterize_bwd(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
                                 const float* conics, const float* feat, const float* opacities,
-                                const float* backgrounds, const float* flow_affine, int flow_ch0,
-                                const int32_t* isect_offsets, const int32_t* flatten_ids, int64_t n_isects,
+                                const float* backgrounds, const float* flow_affine, int flow_ch0, int split,
+                                int ed_channel, int opac_shared, const int32_t* isect_offsets,
+                                const int32_t* flatten_ids, int64_t n_isects, const float* render,
                                 const float* alphas, const int32_t* last_ids, const float* v_render,
-                                const float* v_alphas, float* v_means2d, float* v_means2d_abs, float* v_conics,
-                                float* v_feat, float* v_opacities, float* v_flow_affine, void* stream) {
+                                const float* v_render2, const float* v_alphas, float* v_means2d,
+                                float* v_means2d_abs, float* v_conics, float* v_feat, float* v_opacities,
+                                float* v_flow_affine, void* stream) {
     FG_REQUIRE(tile_size == TILE, "only tile_size=16 is supported (freegaussian_model.py:806)");
     FG_REQUIRE(C >= 1 && N >= 0 && width > 0 && height > 0, "bad C/N/width/height");
     FG_REQUIRE(CH >= 1 && CH <= FG_MAX_CHANNELS, "CH must be in 1..FG_MAX_CHANNELS");
     FG_REQUIRE(n_isects >= 0 && n_isects < (1ll << 31), "n_isects out of range");
     if (n_isects == 0) return FG_OK;
-    FG_REQUIRE(means2d && conics && feat && opacities && isect_offsets && flatten_ids && alphas && last_ids && v_render,
+    FG_REQUIRE(means2d && conics && feat && opacities && isect_offsets && flatten_ids && alphas && last_ids,
                "NULL input pointer");
+    FG_REQUIRE(split >= 1 && split <= CH, "bad split");
+    FG_REQUIRE(ed_channel >= -1 && ed_channel < split && (ed_channel < 0 || render), "ed_channel needs render and must be < split");
     FG_REQUIRE(v_means2d && v_conics && v_feat && v_opacities, "NULL gradient output pointer");
     FG_REQUIRE(!flow_affine || (flow_ch0 >= 0 && flow_ch0 + 1 < CH && v_flow_affine), "bad flow_affine arguments");
     RasterBwdParams p;
@@ -267,6 +299,7 @@ extern "C" int fg_rasterize_bwd(int C, int N, int CH, int width, int height, int
     p.backgrounds = backgrounds; p.flow_affine = (const float4*)flow_affine; p.flow_ch0 = flow_ch0;
     p.isect_offsets = isect_offsets; p.flatten_ids = flatten_ids; p.n_isects = n_isects;
     p.alphas = alphas; p.last_ids = last_ids; p.v_render = v_render; p.v_alphas = v_alphas;
+    p.split = split; p.ed_channel = ed_channel; p.opac_shared = opac_shared; p.render = render; p.v_render2 = v_render2;
     p.v_means2d = v_means2d; p.v_means2d_abs = v_means2d_abs; p.v_conics = v_conics; p.v_feat = v_feat;
     p.v_opacities = v_opacities; p.v_flow_affine = v_flow_affine;
     cudaStream_t st = (cudaStream_t)stream;

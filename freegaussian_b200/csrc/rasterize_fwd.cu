@@ -22,10 +22,14 @@ struct RasterFwdParams {
     const float* backgrounds;
     const float4* flow_affine;
     int flow_ch0;
+    int split;       // channels [0,split) -> render, [split,CH) -> render2
+    int ed_channel;  // this channel is divided by max(alpha, 1e-10) ("ED"), -1 = none
+    int opac_shared; // opacities is [N] shared by all cameras (index g % N) instead of [C*N]
     const int32_t* isect_offsets;
     const int32_t* flatten_ids;
     long long n_isects;
     float* render;
+    float* render2;
     float* alphas;
     int32_t* last_ids;
 };
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_fwd_kernel(RasterFwdParams
             const int g = p.flatten_ids[idx];
             const float2 m = p.means2d[g];
             const float ca = p.conics[3 * (size_t)g], cb = p.conics[3 * (size_t)g + 1], cc = p.conics[3 * (size_t)g + 2];
-            sA[tid] = make_float4(m.x, m.y, p.opacities[g], 0.5f * LOG2E * ca);
+            sA[tid] = make_float4(m.x, m.y, p.opacities[p.opac_shared ? g % p.N : g], 0.5f * LOG2E * ca);
             sB[tid] = make_float4(LOG2E * cb, 0.5f * LOG2E * cc, __int_as_float(g), 0.f);
             float f[FV * 4];
 #pragma unroll
@@ -117,12 +121,16 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_fwd_kernel(RasterFwdParams
     }
     if (inside) {
         const size_t pix = ((size_t)cam * p.height + iy) * p.width + ix;
-        p.alphas[pix] = 1.f - T;
+        const float a_out = 1.f - T;
+        p.alphas[pix] = a_out;
+        const int n2 = CH - p.split;
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
             float v = acc[k];
             if (p.backgrounds) v = fmaf(T, p.backgrounds[cam * CH + k], v);
-            p.render[pix * CH + k] = v;
+            if (k == p.ed_channel) v = v / fmaxf(a_out, 1e-10f);
+            if (k < p.split) p.render[pix * p.split + k] = v;
+            else p.render2[pix * n2 + (k - p.split)] = v;
         }
         p.last_ids[pix] = cur_idx;
     }
@@ -147,9 +155,10 @@ using namespace fg;
 
 extern "C" int fg_rasterize_fwd(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
                                 const float* conics, const float* feat, const float* opacities,
-                                const float* backgrounds, const float* flow_affine, int flow_ch0,
-                                const int32_t* isect_offsets, const int32_t* flatten_ids, int64_t n_isects,
-                                float* render, float* alphas, int32_t* last_ids, void* stream) {
+                                const float* backgrounds, const float* flow_affine, int flow_ch0, int split,
+                                int ed_channel, int opac_shared, const int32_t* isect_offsets,
+                                const int32_t* flatten_ids, int64_t n_isects, float* render, float* render2,
+                                float* alphas, int32_t* last_ids, void* stream) {
     FG_REQUIRE(tile_size == TILE, "only tile_size=16 is supported (freegaussian_model.py:806)");
     FG_REQUIRE(C >= 1 && N >= 0 && width > 0 && height > 0, "bad C/N/width/height");
     FG_REQUIRE(CH >= 1 && CH <= FG_MAX_CHANNELS, "CH must be in 1..FG_MAX_CHANNELS");
@@ -157,7 +166,10 @@ extern "C" int fg_rasterize_fwd(int C, int N, int CH, int width, int height, int
     FG_REQUIRE(isect_offsets && render && alphas && last_ids, "NULL output/offset pointer");
     FG_REQUIRE(n_isects == 0 || (means2d && conics && feat && opacities && flatten_ids), "NULL input pointer");
     FG_REQUIRE(!flow_affine || (flow_ch0 >= 0 && flow_ch0 + 1 < CH), "flow_ch0 out of range");
+    FG_REQUIRE(split >= 1 && split <= CH && (split == CH || render2), "bad split / render2");
+    FG_REQUIRE(ed_channel >= -1 && ed_channel < CH, "ed_channel out of range");
     RasterFwdParams p;
+    p.split = split; p.ed_channel = ed_channel; p.opac_shared = opac_shared; p.render2 = render2;
     p.C = C; p.N = N; p.width = width; p.height = height;
     p.tile_w = (width + TILE - 1) / TILE; p.tile_h = (height + TILE - 1) / TILE;
     p.means2d = (const float2*)means2d; p.conics = conics; p.feat = feat; p.opacities = opacities;

@@ -76,6 +76,15 @@ class DensificationStats:
     @torch.no_grad()
     def accumulate_local(self, radii: Tensor, absgrad: Tensor, height: int, width: int) -> None:
         """Fold this rank's views in: radii [C,N] int32, absgrad [C,N,2] (``meta["means2d"].absgrad``)."""
+        if radii.is_cuda:  # one fused kernel (fg_densify_stats) instead of ~10 elementwise launches
+            from . import _lib
+            C, N = radii.shape
+            _lib.check(_lib.lib().fg_densify_stats(
+                C, N, _lib.ptr(radii.contiguous()), _lib.ptr(absgrad.contiguous()), 1.0 / float(max(height, width)),
+                _lib.ptr(self._local_grad), _lib.ptr(self._local_vis), _lib.ptr(self._local_size),
+                torch.cuda.current_stream().cuda_stream))
+            return
+        # host tensors (gloo tests of the exchange logic): the same arithmetic in torch
         vis = radii > 0
         norms = absgrad.norm(dim=-1)
         self._local_grad += torch.where(vis, norms, torch.zeros_like(norms)).sum(0)

@@ -28,7 +28,6 @@ from . import _lib
 from ._lib import check, ptr
 
 MAX_CH = 8  # FG_MAX_CHANNELS
-BWD_MODE = "pp"  # compositing backward: "pp" pixel-parallel (default) or "gp" Gaussian-parallel
 SORT_MODE = "binned"  # "binned" | "two_level" | "key64" (the reference's literal 64-bit key sort); same lists
 
 
@@ -347,11 +346,15 @@ class _Meta(dict):
 
 # --------------------------------------------------------------------------- compositing
 class _Rasterize(torch.autograd.Function):
-    """fg_rasterize_fwd / fg_rasterize_bwd over one chunk of <= 8 channels."""
+    """fg_rasterize_fwd / fg_rasterize_bwd over <= 8 channels.
+
+    Channels [0,split) come back as ``render``, channels [split,CH) as ``render2`` (the flow image);
+    ``ed_channel`` is normalised by alpha inside the kernel.  ``opacities`` is ``[N]`` (shared by all
+    cameras) or ``[C,N]``."""
 
     @staticmethod
     def forward(ctx, means2d, conics, feat, opacities, backgrounds, isect_offsets, flatten_ids, width, height,
-                tile_size, absgrad, chunked=False):
+                tile_size, absgrad, split, ed_channel, chunked):
         L = _lib.lib()
         ctx.chunked = chunked
         C = isect_offsets.shape[0]
@@ -359,55 +362,70 @@ class _Rasterize(torch.autograd.Function):
         NN = feat.numel() // CH  # C*N (or nnz when packed)
         dev = feat.device
         means2d_c, conics_c, feat_c, opac_c = (t.contiguous() for t in (means2d, conics, feat, opacities))
+        opac_shared = int(opac_c.numel() != NN)
+        n_shared = opac_c.numel()
         bg = None if backgrounds is None else backgrounds.contiguous()
-        render = torch.empty(C, height, width, CH, device=dev)
+        render = torch.empty(C, height, width, split, device=dev)
+        render2 = torch.empty(C, height, width, CH - split, device=dev) if split < CH else None
         alphas = torch.empty(C, height, width, 1, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
         M = flatten_ids.shape[0]
         with _stage("rasterize_fwd"):
-          check(L.fg_rasterize_fwd(C, NN, CH, width, height, tile_size, ptr(means2d_c),
-                                 ptr(conics_c), ptr(feat_c), ptr(opac_c), ptr(bg), None, 0, ptr(isect_offsets),
-                                 ptr(flatten_ids), M, ptr(render), ptr(alphas), ptr(last_ids), _stream()))
+            check(L.fg_rasterize_fwd(C, n_shared if opac_shared else NN, CH, width, height, tile_size, ptr(means2d_c),
+                                     ptr(conics_c), ptr(feat_c), ptr(opac_c), ptr(bg), None, 0, split, ed_channel,
+                                     opac_shared, ptr(isect_offsets), ptr(flatten_ids), M, ptr(render), ptr(render2),
+                                     ptr(alphas), ptr(last_ids), _stream()))
         ctx.save_for_backward(means2d_c, conics_c, feat_c, opac_c, bg, isect_offsets, flatten_ids, alphas, last_ids,
-                              render)
-        ctx.dims = (C, NN, CH, width, height, tile_size, absgrad)
+                              render if ed_channel >= 0 else None)
+        ctx.dims = (C, NN, CH, width, height, tile_size, absgrad, split, ed_channel, opac_shared, n_shared)
         ctx.means2d_obj = means2d  # the very tensor the caller holds as meta["means2d"] (model.py:869-871)
         ctx.mark_non_differentiable(last_ids)
-        return render, alphas, last_ids
+        if render2 is None:
+            render2 = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(render2)
+        return render, render2, alphas, last_ids
 
     @staticmethod
-    def backward(ctx, v_render, v_alphas, _v_last):
+    def backward(ctx, v_render, v_render2, v_alphas, _v_last):
         L = _lib.lib()
         means2d, conics, feat, opac, bg, isect_offsets, flatten_ids, alphas, last_ids, render = ctx.saved_tensors
-        C, NN, CH, width, height, tile_size, absgrad = ctx.dims
+        C, NN, CH, width, height, tile_size, absgrad, split, ed_channel, opac_shared, n_shared = ctx.dims
         dev = feat.device
-        v_render = v_render.contiguous()
-        v_alphas = v_alphas.contiguous()
-        v_means2d = torch.zeros_like(means2d)
-        v_abs = torch.zeros_like(means2d) if absgrad else None
-        v_conics = torch.zeros_like(conics)
-        v_feat = torch.zeros_like(feat)
-        v_opac = torch.zeros_like(opac)
+
+        def c(t):
+            return None if t is None else t.contiguous()
+
+        v_render, v_alphas = c(v_render), c(v_alphas)
+        v_render2 = c(v_render2) if split < CH else None
+        # one zero-filled arena for the five atomically accumulated gradient tensors
+        sizes = [means2d.numel(), means2d.numel() if absgrad else 0, conics.numel(), feat.numel(), opac.numel()]
+        arena = torch.zeros(sum(sizes), device=dev)
+        parts = torch.split(arena, sizes)
+        v_means2d = parts[0].view_as(means2d)
+        v_abs = parts[1].view_as(means2d) if absgrad else None
+        v_conics, v_feat, v_opac = parts[2].view_as(conics), parts[3].view_as(feat), parts[4].view_as(opac)
         M = flatten_ids.shape[0]
         with _stage("rasterize_bwd"):
-            if BWD_MODE == "gp":
-                check(L.fg_rasterize_bwd_gp(C, NN, CH, width, height, tile_size, ptr(means2d), ptr(conics), ptr(feat),
-                                            ptr(opac), ptr(bg), ptr(isect_offsets), ptr(flatten_ids), M, ptr(render),
-                                            ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas), ptr(v_means2d),
-                                            ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), _stream()))
-            else:
-                check(L.fg_rasterize_bwd(C, NN, CH, width, height, tile_size, ptr(means2d), ptr(conics), ptr(feat),
-                                         ptr(opac), ptr(bg), None, 0, ptr(isect_offsets), ptr(flatten_ids), M,
-                                         ptr(alphas), ptr(last_ids), ptr(v_render), ptr(v_alphas), ptr(v_means2d),
-                                         ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), None, _stream()))
+            check(L.fg_rasterize_bwd(C, n_shared if opac_shared else NN, CH, width, height, tile_size, ptr(means2d),
+                                     ptr(conics), ptr(feat), ptr(opac), ptr(bg), None, 0, split, ed_channel,
+                                     opac_shared, ptr(isect_offsets), ptr(flatten_ids), M, ptr(render), ptr(alphas),
+                                     ptr(last_ids), ptr(v_render), ptr(v_render2), ptr(v_alphas), ptr(v_means2d),
+                                     ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), None, _stream()))
         if absgrad:
             obj = ctx.means2d_obj
             prev = getattr(obj, "absgrad", None) if ctx.chunked else None
             obj.absgrad = v_abs if prev is None else prev + v_abs
         v_bg = None
         if bg is not None and ctx.needs_input_grad[4]:
-            v_bg = (v_render * (1.0 - alphas)).sum(dim=(1, 2))
-        return v_means2d, v_conics, v_feat, v_opac, v_bg, None, None, None, None, None, None, None
+            vr = v_render if v_render is not None else torch.zeros(C, height, width, split, device=dev)
+            if split < CH:
+                vr2 = v_render2 if v_render2 is not None else torch.zeros(C, height, width, CH - split, device=dev)
+                vr = torch.cat([vr, vr2], -1)
+            if ed_channel >= 0:  # the ED channel's background is zero by construction
+                vr = vr.clone()
+                vr[..., ed_channel] = 0
+            v_bg = (vr * (1.0 - alphas)).sum(dim=(1, 2))
+        return (v_means2d, v_conics, v_feat, v_opac, v_bg) + (None,) * 9
 
 
 def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets,
@@ -418,8 +436,9 @@ def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_h
     for s in range(0, D, MAX_CH):
         e = min(D, s + MAX_CH)
         bg = None if backgrounds is None else backgrounds[..., s:e]
-        r, a, last_ids = _Rasterize.apply(means2d, conics, colors[..., s:e], opacities, bg, isect_offsets,
-                                          flatten_ids, image_width, image_height, tile_size, absgrad, D > MAX_CH)
+        r, _, a, last_ids = _Rasterize.apply(means2d, conics, colors[..., s:e], opacities, bg, isect_offsets,
+                                             flatten_ids, image_width, image_height, tile_size, absgrad, e - s, -1,
+                                             D > MAX_CH)
         outs.append(r)
         alphas = a if alphas is None else alphas
     render = outs[0] if len(outs) == 1 else torch.cat(outs, -1)
@@ -512,9 +531,8 @@ def rasterization(
         means, quats, scales, proj_colors, means_next, viewmats, Ks, cfg)
     n_user = feat.shape[-1] - (2 if means_next is not None else 0)
 
-    opac = opacities[None].expand(C, N)
-    if rasterize_mode == "antialiased":
-        opac = opac * comps
+    # classic: one opacity per Gaussian shared by all cameras ([N], no expand/copy); antialiased: per (c,n)
+    opac = opacities * comps if rasterize_mode == "antialiased" else opacities
 
     if backgrounds is not None:
         if only_depth:
@@ -554,17 +572,30 @@ def rasterization(
         depths = depths.reshape(C * N)[idx]
         conics = conics.reshape(C * N, 3)[idx]
         feat = feat.reshape(C * N, -1)[idx]
-        opac = opac.reshape(C * N)[idx]
+        opac = (opac if opac.dim() == 2 else opac[None].expand(C, N)).reshape(C * N)[idx]
         radii = radii.reshape(C * N)[idx]
         meta["camera_ids"] = idx // N
         meta["gaussian_ids"] = idx % N
 
-    render_all, alphas, last_ids = rasterize_to_pixels(means2d, conics, feat, opac, width, height, tile_size,
-                                                       isect_offsets, flatten_ids, backgrounds=backgrounds,
-                                                       absgrad=absgrad, return_last_ids=True)
-    render = render_all[..., :n_user]
-    if render_mode in ("ED", "RGB+ED"):
-        render = torch.cat([render[..., :-1], render[..., -1:] / alphas.clamp(min=1e-10)], -1)
+    CH = feat.shape[-1]
+    ed_channel = n_user - 1 if render_mode in ("ED", "RGB+ED") else -1
+    flow = None
+    if CH <= MAX_CH:
+        render, flow_img, alphas, last_ids = _Rasterize.apply(
+            means2d, conics, feat, opac, backgrounds, isect_offsets, flatten_ids, width, height, tile_size, absgrad,
+            n_user, ed_channel, False)
+        if means_next is not None:
+            flow = flow_img
+    else:  # many user colour channels: chunks of 8, normalisation / split done by torch
+        opac_full = opac if opac.dim() == 2 or packed else opac[None].expand(C, N)
+        render_all, alphas, last_ids = rasterize_to_pixels(means2d, conics, feat, opac_full, width, height, tile_size,
+                                                           isect_offsets, flatten_ids, backgrounds=backgrounds,
+                                                           absgrad=absgrad, return_last_ids=True)
+        render = render_all[..., :n_user]
+        if ed_channel >= 0:
+            render = torch.cat([render[..., :-1], render[..., -1:] / alphas.clamp(min=1e-10)], -1)
+        if means_next is not None:
+            flow = render_all[..., n_user:]
 
     meta.update({
         "radii": radii, "means2d": means2d, "depths": depths, "conics": conics, "opacities": opac,
@@ -573,5 +604,5 @@ def rasterization(
         "tile_size": tile_size, "n_cameras": C, "last_ids": last_ids,
     })
     if means_next is not None:
-        meta["flow"] = render_all[..., n_user:]
+        meta["flow"] = flow
     return render, alphas, meta

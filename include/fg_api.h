@@ -165,41 +165,43 @@ int fg_bin_fine(int C, int N, int64_t n_coarse, const int32_t* coarse_offsets,
                 int tile_w, int tile_h, const int32_t* isect_offsets, int32_t* flatten_ids, void* stream);
 
 /* ---- (3) per-tile front-to-back alpha compositing, forward and backward ----------------
- * Replaces gsplat `rasterize_to_pixels` fwd/bwd.  One pass composites all CH channels
- * (RGB + depth + flow).  alpha = min(0.999, opacity*exp(-sigma)); skip alpha < 1/255;
- * stop when T(1-alpha) <= 1e-4.
- *   feat[C*N,CH]  opacities[C*N]  backgrounds[C,CH] or NULL
- *   flow_affine[C*N,4] or NULL: channels flow_ch0, flow_ch0+1 get + A_g (p - mu_g) per pixel.
- *   render[C,H,W,CH]  alphas[C,H,W]  last_ids[C,H,W] int32 (index into the sorted list)
+ * Replaces gsplat `rasterize_to_pixels` fwd/bwd and the wrapper's "ED" normalisation.  One
+ * pass composites all CH channels (RGB + depth + flow).  alpha = min(0.999, opacity*exp(-sigma));
+ * skip alpha < 1/255; stop when T(1-alpha) <= 1e-4.
+ *   feat[C*N,CH]; opacities[C*N], or [N] shared by all cameras when opac_shared != 0
+ *   backgrounds[C,CH] or NULL (blended in the epilogue: out += T * bg)
+ *   flow_affine[C*N,4] or NULL: channels flow_ch0, flow_ch0+1 get + A_g (p - mu_g) per pixel
+ *   split: channels [0,split) are written to render[C,H,W,split], channels [split,CH) to
+ *          render2[C,H,W,CH-split] (split == CH: render2 unused) -- RGB(D) and flow come back as
+ *          two dense images without a slicing pass
+ *   ed_channel (< split, or -1): that channel is divided by max(alpha,1e-10) (render_mode "ED")
+ *   alphas[C,H,W]  last_ids[C,H,W] int32 (index into the sorted list of the last composited splat)
  */
 int fg_rasterize_fwd(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
                      const float* conics, const float* feat, const float* opacities,
-                     const float* backgrounds, const float* flow_affine, int flow_ch0,
-                     const int32_t* isect_offsets, const int32_t* flatten_ids, int64_t n_isects,
-                     float* render, float* alphas, int32_t* last_ids, void* stream);
+                     const float* backgrounds, const float* flow_affine, int flow_ch0, int split,
+                     int ed_channel, int opac_shared, const int32_t* isect_offsets,
+                     const int32_t* flatten_ids, int64_t n_isects, float* render, float* render2,
+                     float* alphas, int32_t* last_ids, void* stream);
 
 /* Backward.  v_* outputs must be zero-initialised by the caller (they are accumulated with
- * atomics); v_means2d_abs may be NULL (absgrad=False).  v_flow_affine NULL unless flow_affine. */
+ * atomics); v_opacities is [N] when opac_shared.  v_render / v_render2 / v_alphas may be NULL
+ * (= zero).  `render` (the forward output) is only read when ed_channel >= 0.  v_means2d_abs may
+ * be NULL (absgrad=False); v_flow_affine NULL unless flow_affine. */
 int fg_rasterize_bwd(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
                      const float* conics, const float* feat, const float* opacities,
-                     const float* backgrounds, const float* flow_affine, int flow_ch0,
-                     const int32_t* isect_offsets, const int32_t* flatten_ids, int64_t n_isects,
-                     const float* alphas, const int32_t* last_ids, const float* v_render,
+                     const float* backgrounds, const float* flow_affine, int flow_ch0, int split,
+                     int ed_channel, int opac_shared, const int32_t* isect_offsets,
+                     const int32_t* flatten_ids, int64_t n_isects, const float* render, const float* alphas,
+                     const int32_t* last_ids, const float* v_render, const float* v_render2,
                      const float* v_alphas, float* v_means2d, float* v_means2d_abs, float* v_conics,
                      float* v_feat, float* v_opacities, float* v_flow_affine, void* stream);
 
-/* Same gradients, Gaussian-parallel mapping (default in rendering.py): per 256-entry batch the
- * CTA replays the pixels front to back (checkpointing the per-pixel state every 32 entries),
- * then each warp takes a 32-entry bucket with one lane per Gaussian and streams the tile's 256
- * pixels through the warp, accumulating every Gaussian's gradients in registers: no
- * per-pair warp reductions, one atomic per value per (tile, Gaussian).  Needs the forward's
- * `render` output.  flow_affine is not supported by this variant. */
-int fg_rasterize_bwd_gp(int C, int N, int CH, int width, int height, int tile_size, const float* means2d,
-                        const float* conics, const float* feat, const float* opacities,
-                        const float* backgrounds, const int32_t* isect_offsets, const int32_t* flatten_ids,
-                        int64_t n_isects, const float* render, const float* alphas, const int32_t* last_ids,
-                        const float* v_render, const float* v_alphas, float* v_means2d, float* v_means2d_abs,
-                        float* v_conics, float* v_feat, float* v_opacities, void* stream);
+/* Densification statistics of freegaussian_model.py:369-392 folded over this rank's C views in
+ * one pass: grad_norm[n] += sum_c vis ? |absgrad[c,n]|_2 : 0; vis_count[n] += sum_c vis;
+ * max_size[n] = max(max_size[n], max_c radii[c,n] / max(H,W)). */
+int fg_densify_stats(int C, int N, const int32_t* radii, const float* absgrad, float inv_max_hw,
+                     float* grad_norm, float* vis_count, float* max_size, void* stream);
 
 /* ---- (4) exact k-nearest neighbours ----------------------------------------------------
  * Replaces FreeGaussianModel.k_nearest_sklearn (freegaussian_model.py:293-311):

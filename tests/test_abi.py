@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in declared_functions():
         assert hasattr(lib, name), f"{name} declared in fg_api.h but not exported"
     lib.fg_abi_version.restype = ctypes.c_int
-    assert lib.fg_abi_version() == 1
+    from freegaussian_b200 import _lib
+    assert lib.fg_abi_version() == _lib.ABI_VERSION
 
 
 def test_python_binding_matches_header(built_lib):
@@ -47,8 +48,8 @@ def test_library_is_sm100a_only(built_lib):
 def test_bad_arguments_return_error_codes_not_crashes(built_lib):
     from freegaussian_b200 import _lib
     L = _lib.lib()
-    rc = L.fg_rasterize_fwd(1, 10, 99, 64, 64, 16, None, None, None, None, None, None, 0, None, None, 0, None, None,
-                            None, None)
+    rc = L.fg_rasterize_fwd(1, 10, 99, 64, 64, 16, None, None, None, None, None, None, 0, 99, -1, 0, None, None, 0,
+                            None, None, None, None, None)
     assert rc == 1 and b"CH" in L.fg_last_error()
     rc = L.fg_project_fwd(0, 10, None, None, None, None, None, 64, 64, 0.3, 0.01, 1e10, 0.0, 16, -1, 0, None, None,
                           None, None, 0, None, None, None, None, None, None, 0, -1, -1, -1, None, None, None)
