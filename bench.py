@@ -226,13 +226,15 @@ def run_ours(args):
     step(0, True)
     ms_e2e = timed(args.steps, True)
 
-    # ---- per-kernel timing + roofline (rank 0, after the headline timing)
+    # ---- per-kernel timing + roofline (every rank runs the steps -- they contain collectives --
+    #      rank 0 records the CUDA-event time of each C-ABI stage)
     out = None
+    rendering.stage_timer.enabled = rank == 0
+    rendering.stage_timer.reset()
+    for i in range(min(args.steps, 8)):
+        step(i, False)
+    torch.cuda.synchronize()
     if rank == 0:
-        rendering.stage_timer.enabled = True
-        rendering.stage_timer.reset()
-        for i in range(min(args.steps, 8)):
-            step(i, False)
         stage_ms = {k: statistics.mean(v) for k, v in rendering.stage_timer.summary().items()}
         rendering.stage_timer.enabled = False
         meta = info["meta"]

@@ -88,8 +88,11 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
     __shared__ float4 sB[BATCH];
     __shared__ float4 sF[FV][BATCH];
     __shared__ float4 sM[AFF ? BATCH : 1];
+    __shared__ unsigned char sMask[BATCH];
+    __shared__ unsigned char sList[TILE_PIX / 32][BATCH];
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float tile_cx0 = (float)(blockIdx.x * TILE) + 0.5f, tile_cy0 = (float)(blockIdx.y * TILE) + 0.5f;
     const int cam = blockIdx.z;
     const int tile_id = (cam * p.tile_h + blockIdx.y) * p.tile_w + blockIdx.x;
     int lx, ly;
@@ -166,7 +169,10 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
             const float2 m = p.means2d[g];
             const float ca = p.conics[3 * (size_t)g], cb = p.conics[3 * (size_t)g + 1], cc = p.conics[3 * (size_t)g + 2];
             const int go = p.opac_shared ? g % p.N : g;
-            sA[tid] = make_float4(m.x, m.y, p.opacities[go], 0.5f * LOG2E * ca);
+            const float opac = p.opacities[go];
+            sA[tid] = make_float4(m.x, m.y, opac, 0.5f * LOG2E * ca);
+            sMask[tid] = (unsigned char)patch_mask(m.x, m.y, opac, 0.5f * LOG2E * ca, LOG2E * cb, 0.5f * LOG2E * cc,
+                                                   tile_cx0, tile_cy0);
             // .w: row of the opacity gradient (g, or g % N when one opacity is shared by all cameras)
             sB[tid] = make_float4(LOG2E * cb, 0.5f * LOG2E * cc, __int_as_float(g),
                                   __int_as_float(go));
@@ -178,7 +184,10 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
             if (AFF) sM[tid] = p.flow_affine[g];
         }
         __syncthreads();
-        for (int t = max(0, batch_end - warp_bin_final); t < bs; ++t) {
+        // this warp's 8x4 patch only walks the Gaussians that can reach it (slot t <-> index batch_end - t)
+        const int n_list = build_warp_list(sMask, sList[warp], warp, lane, max(0, batch_end - warp_bin_final), bs);
+        for (int li = 0; li < n_list; ++li) {
+            const int t = sList[warp][li];
             const float4 a4 = sA[t], b4 = sB[t];
             const GeomA ga = {a4.x, a4.y, a4.z, a4.w};
             const GeomB gb = {b4.x, b4.y, 0, 0.f};

@@ -52,4 +52,58 @@ __device__ __forceinline__ bool eval_alpha(const GeomA& a, const GeomB& b, float
     return (p >= 0.f) && (alpha >= ALPHA_MIN);
 }
 
+// ---- per-warp culling ---------------------------------------------------------------------
+// Which of the tile's eight 8x4 pixel patches (= warps) can a Gaussian touch at all, i.e. has a
+// pixel with alpha >= 1/255?  alpha >= 1/255  <=>  power <= log2(255 opac) (pre-scaled units), so
+// a patch is dropped when a lower bound of the power over the patch's rectangle of pixel
+// centres exceeds that threshold.  The bound is the exact minimum of the convex quadratic over
+// the continuous rectangle (zero if the mean lies inside, else the best of the four edge
+// minima), with a small safety margin: conservative, so compositing results are unchanged.
+// ncu r1g: 60 % of the (warp, Gaussian) steps had no valid pixel and cost ~25 instructions each.
+__device__ __forceinline__ float edge_min(float q_cc, float q_cv, float q_vv, float c, float vlo, float vhi) {
+    // minimise q_cc c^2 + q_cv c v + q_vv v^2 over v in [vlo, vhi]
+    const float v = fminf(fmaxf(-0.5f * q_cv * c / q_vv, vlo), vhi);
+    return fmaf(q_cc * c, c, fmaf(q_cv * c, v, q_vv * v * v));
+}
+
+__device__ __forceinline__ unsigned patch_mask(float mx, float my, float opac, float qa, float qb, float qc,
+                                               float tile_x0, float tile_y0) {
+    // tile_x0/tile_y0: centre of the tile's first pixel
+    const float thr = __log2f(255.f * opac) * 1.00002f + 2e-4f;
+    if (!(thr > 0.f) || !(qa > 0.f) || !(qc > 0.f)) return (thr > 0.f) ? 0xffu : 0u;  // degenerate conic: keep
+    unsigned mask = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const float x0 = tile_x0 + (float)((w & 1) << 3), y0 = tile_y0 + (float)((w >> 1) << 2);
+        // delta = mu - p, p in [x0, x0+7] x [y0, y0+3]
+        const float dxlo = mx - (x0 + 7.f), dxhi = mx - x0, dylo = my - (y0 + 3.f), dyhi = my - y0;
+        float pmin;
+        if (dxlo <= 0.f && dxhi >= 0.f && dylo <= 0.f && dyhi >= 0.f) {
+            pmin = 0.f;
+        } else {
+            pmin = fminf(fminf(edge_min(qa, qb, qc, dxlo, dylo, dyhi), edge_min(qa, qb, qc, dxhi, dylo, dyhi)),
+                         fminf(edge_min(qc, qb, qa, dylo, dxlo, dxhi), edge_min(qc, qb, qa, dyhi, dxlo, dxhi)));
+        }
+        if (pmin <= thr) mask |= 1u << w;
+    }
+    return mask;
+}
+
+// Compact, in order, the batch slots t in [t_min, bs) whose patch mask has this warp's bit set.
+__device__ __forceinline__ int build_warp_list(const unsigned char* sMask, unsigned char* list, int warp, int lane,
+                                               int t_min, int bs) {
+    int n = 0;
+    const unsigned lt = (1u << lane) - 1;
+#pragma unroll
+    for (int c = 0; c < BATCH / 32; ++c) {
+        const int t = c * 32 + lane;
+        const bool keep = t >= t_min && t < bs && ((sMask[t] >> warp) & 1u);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) list[n + __popc(m & lt)] = (unsigned char)t;
+        n += __popc(m);
+    }
+    __syncwarp();
+    return n;
+}
+
 }  // namespace fg

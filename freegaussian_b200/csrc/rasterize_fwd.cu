@@ -41,9 +41,12 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_fwd_kernel(RasterFwdParams
     __shared__ float4 sB[BATCH];
     __shared__ float4 sF[FV][BATCH];
     __shared__ float4 sM[AFF ? BATCH : 1];
+    __shared__ unsigned char sMask[BATCH];
+    __shared__ unsigned char sList[TILE_PIX / 32][BATCH];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cam = blockIdx.z;
+    const float tile_cx0 = (float)(blockIdx.x * TILE) + 0.5f, tile_cy0 = (float)(blockIdx.y * TILE) + 0.5f;
     const int tile_id = (cam * p.tile_h + blockIdx.y) * p.tile_w + blockIdx.x;
     int lx, ly;
     tile_pixel(tid, lx, ly);
@@ -71,8 +74,11 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_fwd_kernel(RasterFwdParams
             const int g = p.flatten_ids[idx];
             const float2 m = p.means2d[g];
             const float ca = p.conics[3 * (size_t)g], cb = p.conics[3 * (size_t)g + 1], cc = p.conics[3 * (size_t)g + 2];
-            sA[tid] = make_float4(m.x, m.y, p.opacities[p.opac_shared ? g % p.N : g], 0.5f * LOG2E * ca);
+            const float opac = p.opacities[p.opac_shared ? g % p.N : g];
+            sA[tid] = make_float4(m.x, m.y, opac, 0.5f * LOG2E * ca);
             sB[tid] = make_float4(LOG2E * cb, 0.5f * LOG2E * cc, __int_as_float(g), 0.f);
+            sMask[tid] = (unsigned char)patch_mask(m.x, m.y, opac, 0.5f * LOG2E * ca, LOG2E * cb, 0.5f * LOG2E * cc,
+                                                   tile_cx0, tile_cy0);
             float f[FV * 4];
 #pragma unroll
             for (int k = 0; k < FV * 4; ++k) f[k] = (k < CH) ? p.feat[(size_t)g * CH + k] : 0.f;
@@ -82,7 +88,10 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_fwd_kernel(RasterFwdParams
         }
         __syncthreads();
         const int bs = min(BATCH, range_end - batch_start);
-        for (int t = 0; t < bs && !done; ++t) {
+        // this warp's 8x4 patch only walks the Gaussians that can reach it
+        const int n_list = build_warp_list(sMask, sList[warp], warp, lane, 0, bs);
+        for (int li = 0; li < n_list && !done; ++li) {
+            const int t = sList[warp][li];
             const float4 a4 = sA[t], b4 = sB[t];
             const GeomA ga = {a4.x, a4.y, a4.z, a4.w};
             const GeomB gb = {b4.x, b4.y, 0, 0.f};
