@@ -33,6 +33,9 @@ struct ProjParams {
     int sh_row_floats;  // floats per Gaussian row of sh_coeffs (sh_bases*3)
     const float* sh;
     const float* means_next;
+    const float* quats_next;   // covariance flow mode: frame t+1 rotation / scale (NULL = frame t's)
+    const float* scales_next;
+    int flow_cov;
     int feat_stride, rgb_off, depth_off, flow_off;
     // forward outputs
     int32_t* radii;
@@ -41,6 +44,7 @@ struct ProjParams {
     float* conics;
     float* comps;
     float* feat;
+    float* flow_affine;
     int32_t* tiles_per_gauss;
     // backward inputs
     const int32_t* radii_in;
@@ -49,12 +53,15 @@ struct ProjParams {
     const float* v_conics;
     const float* v_comps;
     const float* v_feat;
+    const float* v_flow_affine;
     // backward outputs
     float* v_means;
     float* v_quats;
     float* v_scales;
     float* v_sh;
     float* v_means_next;
+    float* v_quats_next;
+    float* v_scales_next;
 };
 
 template <int DEG>
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(PB) project_fwd_kernel(ProjParams p) {
     const bool in_range = n < p.N;
 
     float m[3] = {0.f, 0.f, 0.f}, mn[3] = {0.f, 0.f, 0.f};
-    Sym3 cov = {};
+    Sym3 cov = {}, cov_next = {};
     if (in_range) {
         float q[4], s[3];
 #pragma unroll
@@ -124,6 +131,18 @@ __global__ void __launch_bounds__(PB) project_fwd_kernel(ProjParams p) {
         if (p.means_next) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) mn[i] = __ldg(p.means_next + 3 * (size_t)n + i);
+        }
+        if (p.flow_cov) {
+            float qn[4] = {q[0], q[1], q[2], q[3]}, sn[3] = {s[0], s[1], s[2]};
+            if (p.quats_next) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(p.quats_next) + n);
+                qn[0] = t.x; qn[1] = t.y; qn[2] = t.z; qn[3] = t.w;
+            }
+            if (p.scales_next) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sn[i] = __ldg(p.scales_next + 3 * (size_t)n + i);
+            }
+            cov_next = quat_scale_to_cov(qn, sn);
         }
     }
 
@@ -139,13 +158,21 @@ __global__ void __launch_bounds__(PB) project_fwd_kernel(ProjParams p) {
             const size_t i = (size_t)c * p.N + n;
             int ntiles = 0;
             float fu = 0.f, fv = 0.f;
+            float A[4] = {0.f, 0.f, 0.f, 0.f};
             if (ok) {
                 vis |= 1u << (c - c0);
                 TileRect r = tile_rect(o.mx, o.my, o.radius, p.tile_size, p.tile_w, p.tile_h);
                 ntiles = (r.x1 - r.x0) * (r.y1 - r.y0);
                 if (p.means_next) {
                     float u, v;
-                    if (project_point(mn, cam, p.pc.near_plane, u, v)) { fu = u - o.mx; fv = v - o.my; }
+                    if (p.flow_cov) {
+                        float cn[3];
+                        if (project_cov2d(mn, cov_next, cam, p.pc, cn[0], cn[1], cn[2], u, v)) {
+                            fu = u - o.mx; fv = v - o.my;
+                            const float ct[3] = {o.a, o.b, o.c};
+                            flow_affine(ct, cn, A);
+                        }
+                    } else if (project_point(mn, cam, p.pc.near_plane, u, v)) { fu = u - o.mx; fv = v - o.my; }
                 }
             } else {
                 o.mx = o.my = o.depth = o.ca = o.cb = o.cc = o.comp = 0.f;
@@ -159,6 +186,7 @@ __global__ void __launch_bounds__(PB) project_fwd_kernel(ProjParams p) {
             float* f = p.feat + i * p.feat_stride;
             if (p.depth_off >= 0) f[p.depth_off] = o.depth;
             if (p.flow_off >= 0) { f[p.flow_off] = fu; f[p.flow_off + 1] = fv; }
+            if (p.flow_affine) reinterpret_cast<float4*>(p.flow_affine)[i] = make_float4(A[0], A[1], A[2], A[3]);
         }
         if (DEG >= 0) {
             using S = ShShape<(DEG >= 0 ? DEG : 0)>;
@@ -208,7 +236,8 @@ __global__ void __launch_bounds__(PB) project_bwd_kernel(ProjParams p) {
     constexpr int NEED = (DEG >= 0) ? S::NEED : 1;
 
     float m[3] = {0.f, 0.f, 0.f}, mn[3] = {0.f, 0.f, 0.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, s[3] = {1.f, 1.f, 1.f};
-    Sym3 cov = {};
+    float qn[4] = {1.f, 0.f, 0.f, 0.f}, sn[3] = {1.f, 1.f, 1.f};
+    Sym3 cov = {}, cov_next = {};
     if (in_range) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) m[i] = __ldg(p.means + 3 * (size_t)n + i);
@@ -220,6 +249,21 @@ __global__ void __launch_bounds__(PB) project_bwd_kernel(ProjParams p) {
         if (p.means_next) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) mn[i] = __ldg(p.means_next + 3 * (size_t)n + i);
+        }
+        if (p.flow_cov) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qn[i] = q[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sn[i] = s[i];
+            if (p.quats_next) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(p.quats_next) + n);
+                qn[0] = t.x; qn[1] = t.y; qn[2] = t.z; qn[3] = t.w;
+            }
+            if (p.scales_next) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sn[i] = __ldg(p.scales_next + 3 * (size_t)n + i);
+            }
+            cov_next = quat_scale_to_cov(qn, sn);
         }
     }
     if (DEG >= 0) {
@@ -233,7 +277,7 @@ __global__ void __launch_bounds__(PB) project_bwd_kernel(ProjParams p) {
     if (DEG >= 0) read_sh_row<(DEG >= 0 ? DEG : 0), VEC4>(smem, coef);
 
     float v_mean[3] = {0.f, 0.f, 0.f}, v_mean_next[3] = {0.f, 0.f, 0.f};
-    Sym3 G = {};
+    Sym3 G = {}, G_next = {};
     for (int c = 0; c < p.C; ++c) {
         if (!in_range) break;
         const size_t i = (size_t)c * p.N + n;
@@ -248,7 +292,7 @@ __global__ void __launch_bounds__(PB) project_bwd_kernel(ProjParams p) {
         if (p.v_feat) {
             const float* vf = p.v_feat + i * p.feat_stride;
             if (p.depth_off >= 0) v_depth += vf[p.depth_off];
-            if (p.flow_off >= 0 && p.means_next) {
+            if (p.flow_off >= 0 && p.means_next && !p.flow_cov) {
                 float u, v;
                 if (project_point(mn, cam, p.pc.near_plane, u, v)) {
                     float vu = vf[p.flow_off], vv = vf[p.flow_off + 1];
@@ -284,11 +328,47 @@ __global__ void __launch_bounds__(PB) project_bwd_kernel(ProjParams p) {
                 v_mean[2] += (vd[2] - dot * z) * inorm;
             }
         }
-        project_gaussian_vjp(m, cov, cam, p.pc, v_m2d, v_depth, v_con, v_comp, v_mean, G);
+        float v_ct[3] = {0.f, 0.f, 0.f};
+        bool have_ct = false;
+        if (p.flow_cov && p.means_next) {
+            // covariance flow mode: the frame t+1 splat contributes through its mean AND its 2-D covariance
+            float ct[3], cn[3], ut, vt, un, vn;
+            if (project_cov2d(mn, cov_next, cam, p.pc, cn[0], cn[1], cn[2], un, vn) &&
+                project_cov2d(m, cov, cam, p.pc, ct[0], ct[1], ct[2], ut, vt)) {
+                float vuv[2] = {0.f, 0.f};
+                if (p.v_feat && p.flow_off >= 0) {
+                    const float* vf = p.v_feat + i * p.feat_stride;
+                    vuv[0] = vf[p.flow_off]; vuv[1] = vf[p.flow_off + 1];
+                    v_m2d[0] -= vuv[0]; v_m2d[1] -= vuv[1];
+                }
+                float v_cn[3] = {0.f, 0.f, 0.f};
+                if (p.v_flow_affine) {
+                    const float4 t = reinterpret_cast<const float4*>(p.v_flow_affine)[i];
+                    const float vA[4] = {t.x, t.y, t.z, t.w};
+                    flow_affine_vjp(ct, cn, vA, v_ct, v_cn);
+                    have_ct = true;
+                }
+                const float zero3[3] = {0.f, 0.f, 0.f};
+                project_gaussian_vjp(mn, cov_next, cam, p.pc, vuv, 0.f, zero3, 0.f, v_mean_next, G_next, v_cn);
+            }
+        }
+        project_gaussian_vjp(m, cov, cam, p.pc, v_m2d, v_depth, v_con, v_comp, v_mean, G, have_ct ? v_ct : nullptr);
     }
     if (in_range) {
         float v_q[4] = {0.f, 0.f, 0.f, 0.f}, v_s[3] = {0.f, 0.f, 0.f};
         quat_scale_to_cov_vjp(q, s, G, v_q, v_s);
+        if (p.flow_cov) {
+            // split G_next between rotation and scale of frame t+1; tensors that were not given
+            // separately are frame t's, so their share folds into v_q / v_s
+            float v_qn[4] = {0.f, 0.f, 0.f, 0.f}, v_sn[3] = {0.f, 0.f, 0.f};
+            quat_scale_to_cov_vjp(qn, sn, G_next, v_qn, v_sn);
+            if (p.v_quats_next) reinterpret_cast<float4*>(p.v_quats_next)[n] = make_float4(v_qn[0], v_qn[1], v_qn[2], v_qn[3]);
+            else { v_q[0] += v_qn[0]; v_q[1] += v_qn[1]; v_q[2] += v_qn[2]; v_q[3] += v_qn[3]; }
+            if (p.v_scales_next) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) p.v_scales_next[3 * (size_t)n + i] = v_sn[i];
+            } else { v_s[0] += v_sn[0]; v_s[1] += v_sn[1]; v_s[2] += v_sn[2]; }
+        }
 #pragma unroll
         for (int i = 0; i < 3; ++i) p.v_means[3 * (size_t)n + i] = v_mean[i];
         reinterpret_cast<float4*>(p.v_quats)[n] = make_float4(v_q[0], v_q[1], v_q[2], v_q[3]);
@@ -382,15 +462,15 @@ extern "C" int fg_project_fwd(int C, int N, const float* means, const float* qua
                               int32_t* tiles_per_gauss, void* stream) {
     if (int e = check_common(C, N, means, quats, scales, viewmats, Ks, sh_degree, sh_bases, sh_coeffs)) return e;
     FG_REQUIRE(width > 0 && height > 0 && tile_size > 0, "width/height/tile_size must be positive");
-    FG_REQUIRE(!flow_cov, "covariance flow mode is handled by fg_project_flow_cov (not in this entry point yet)");
+    FG_REQUIRE(!flow_cov || (means_next && flow_affine), "covariance flow mode needs means_next and flow_affine");
     FG_REQUIRE(radii && means2d && depths && conics && tiles_per_gauss, "output pointers must not be NULL");
     FG_REQUIRE(feat || (sh_degree < 0 && depth_off < 0 && flow_off < 0), "feat must not be NULL");
     FG_REQUIRE(flow_off < 0 || means_next, "flow_off given without means_next");
-    (void)quats_next; (void)scales_next; (void)flow_affine;
     if (N == 0) return FG_OK;
     ProjParams p = {};
     p.C = C; p.N = N; p.means = means; p.quats = quats; p.scales = scales; p.viewmats = viewmats; p.Ks = Ks;
     p.pc = {width, height, eps2d, near_plane, far_plane, radius_clip};
+    p.quats_next = quats_next; p.scales_next = scales_next; p.flow_cov = flow_cov; p.flow_affine = flow_cov ? flow_affine : nullptr;
     p.tile_size = tile_size;
     p.tile_w = (width + tile_size - 1) / tile_size;
     p.tile_h = (height + tile_size - 1) / tile_size;
@@ -421,14 +501,18 @@ extern "C" int fg_project_bwd(int C, int N, const float* means, const float* qua
                               float* v_sh, float* v_means_next, float* v_quats_next, float* v_scales_next,
                               void* stream) {
     if (int e = check_common(C, N, means, quats, scales, viewmats, Ks, sh_degree, sh_bases, sh_coeffs)) return e;
-    FG_REQUIRE(!flow_cov, "covariance flow mode is not handled by this entry point yet");
+    FG_REQUIRE(!flow_cov || means_next, "covariance flow mode needs means_next");
     FG_REQUIRE(radii && v_means && v_quats && v_scales, "radii and v_means/v_quats/v_scales must not be NULL");
     FG_REQUIRE(sh_degree < 0 || v_sh, "v_sh must not be NULL when sh_degree >= 0");
-    (void)quats_next; (void)scales_next; (void)v_flow_affine; (void)v_quats_next; (void)v_scales_next;
+    FG_REQUIRE((quats_next != nullptr) == (v_quats_next != nullptr) || !flow_cov, "v_quats_next must mirror quats_next");
+    FG_REQUIRE((scales_next != nullptr) == (v_scales_next != nullptr) || !flow_cov, "v_scales_next must mirror scales_next");
     if (N == 0) return FG_OK;
     ProjParams p = {};
     p.C = C; p.N = N; p.means = means; p.quats = quats; p.scales = scales; p.viewmats = viewmats; p.Ks = Ks;
     p.pc = {width, height, eps2d, near_plane, far_plane, radius_clip};
+    p.quats_next = quats_next; p.scales_next = scales_next; p.flow_cov = flow_cov;
+    p.v_flow_affine = flow_cov ? v_flow_affine : nullptr;
+    p.v_quats_next = flow_cov ? v_quats_next : nullptr; p.v_scales_next = flow_cov ? v_scales_next : nullptr;
     p.sh_row_floats = sh_bases * 3; p.sh = sh_coeffs; p.means_next = means_next;
     p.feat_stride = feat_stride; p.rgb_off = rgb_off; p.depth_off = depth_off; p.flow_off = flow_off;
     p.radii_in = radii; p.v_means2d = v_means2d; p.v_depths = v_depths; p.v_conics = v_conics;

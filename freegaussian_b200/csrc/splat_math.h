@@ -219,6 +219,67 @@ FG_HD bool project_gaussian(const float m[3], const Sym3& cov, const Camera& cam
     return true;
 }
 
+// Blurred 2-D covariance + projected mean with NO culling except the near plane (frame t+1 of the
+// covariance flow mode, Appendix A.7).  Returns false if behind the near plane.
+FG_HD bool project_cov2d(const float m[3], const Sym3& cov, const Camera& cam, const ProjConsts& pc, float& a,
+                         float& b, float& c, float& u, float& v) {
+    float p[3];
+    world_to_cam(cam, m, p);
+    if (!(p[2] >= pc.near_plane)) return false;
+    Sym3 cc = cov_world_to_cam(cam, cov);
+    PerspJ J = persp_jacobian(cam, p, pc.width, pc.height);
+    float u0 = J.j00 * cc.xx + J.j02 * cc.xz;
+    float u1 = J.j00 * cc.xy + J.j02 * cc.yz;
+    float u2 = J.j00 * cc.xz + J.j02 * cc.zz;
+    float w1 = J.j11 * cc.yy + J.j12 * cc.yz;
+    float w2 = J.j11 * cc.yz + J.j12 * cc.zz;
+    a = u0 * J.j00 + u2 * J.j02 + pc.eps2d;
+    b = u1 * J.j11 + u2 * J.j12;
+    c = w1 * J.j11 + w2 * J.j12 + pc.eps2d;
+    u = cam.fx * p[0] * J.rz + cam.cx;
+    v = cam.fy * p[1] * J.rz + cam.cy;
+    return true;
+}
+
+// ---------------------------------------------------------------- covariance flow (A.7)
+// A = B(t+1) B(t)^-1 - I with B the lower Cholesky factor of the blurred 2-D covariance;
+// row-major (A00, A01 = 0, A10, A11).  The flow of Gaussian g at pixel p is f_g + A (p - mu_g).
+FG_HD void flow_affine(const float ct[3], const float cn[3], float A[4]) {
+    float l00 = sqrtf(ct[0]), l10 = ct[1] / l00, l11 = sqrtf(ct[2] - l10 * l10);
+    float m00 = sqrtf(cn[0]), m10 = cn[1] / m00, m11 = sqrtf(cn[2] - m10 * m10);
+    float i00 = 1.f / l00, i11 = 1.f / l11;
+    A[0] = m00 * i00 - 1.f;
+    A[1] = 0.f;
+    A[2] = m10 * i00 - m11 * l10 * i00 * i11;
+    A[3] = m11 * i11 - 1.f;
+}
+// VJP: vA[4] -> v_ct[3], v_cn[3] (gradients w.r.t. the stored (a,b,c) of both covariances; accumulated)
+FG_HD void flow_affine_vjp(const float ct[3], const float cn[3], const float vA[4], float v_ct[3], float v_cn[3]) {
+    float l00 = sqrtf(ct[0]), l10 = ct[1] / l00, l11 = sqrtf(ct[2] - l10 * l10);
+    float m00 = sqrtf(cn[0]), m10 = cn[1] / m00, m11 = sqrtf(cn[2] - m10 * m10);
+    float i00 = 1.f / l00, i11 = 1.f / l11;
+    float v_m00 = vA[0] * i00;
+    float v_i00 = vA[0] * m00 + vA[2] * (m10 - m11 * l10 * i11);
+    float v_m10 = vA[2] * i00;
+    float v_m11 = -vA[2] * l10 * i00 * i11 + vA[3] * i11;
+    float v_l10 = -vA[2] * m11 * i00 * i11;
+    float v_i11 = -vA[2] * m11 * l10 * i00 + vA[3] * m11;
+    float v_l00 = -v_i00 * i00 * i00;
+    float v_l11 = -v_i11 * i11 * i11;
+    // Cholesky VJP, frame t: l00 = sqrt(a), l10 = b/l00, l11 = sqrt(c - l10^2)
+    v_ct[2] += v_l11 / (2.f * l11);
+    v_l10 += -v_l11 * l10 / l11;
+    v_ct[1] += v_l10 * i00;
+    v_l00 += -v_l10 * l10 * i00;
+    v_ct[0] += v_l00 / (2.f * l00);
+    // frame t+1
+    v_cn[2] += v_m11 / (2.f * m11);
+    v_m10 += -v_m11 * m10 / m11;
+    v_cn[1] += v_m10 / m00;
+    v_m00 += -v_m10 * m10 / m00;
+    v_cn[0] += v_m00 / (2.f * m00);
+}
+
 // Project a point only (frame t+1 mean for the flow channel, Appendix A.7).
 FG_HD bool project_point(const float m[3], const Camera& cam, float near_plane, float& u, float& v) {
     float p[3];
@@ -238,10 +299,11 @@ FG_HD void project_point_vjp(const float m[3], const Camera& cam, float v_u, flo
 }
 
 // VJP of project_gaussian for a non-culled Gaussian.
-//   v_m2d[2], v_depth, v_conic[3] (d/d(stored A,B,C)), v_comp  ->  accumulates v_mean[3], G (dL/dSigma, full-symmetric)
+//   v_m2d[2], v_depth, v_conic[3] (d/d(stored A,B,C)), v_comp, v_cov2d[3] (d/d(stored blurred a,b,c); may be null)
+//   ->  accumulates v_mean[3], G (dL/dSigma, full-symmetric)
 FG_HD void project_gaussian_vjp(const float m[3], const Sym3& cov, const Camera& cam, const ProjConsts& pc,
                                 const float v_m2d[2], float v_depth, const float v_conic[3], float v_comp,
-                                float v_mean[3], Sym3& G) {
+                                float v_mean[3], Sym3& G, const float* v_cov2d = nullptr) {
     float p[3];
     world_to_cam(cam, m, p);
     Sym3 cc = cov_world_to_cam(cam, cov);
@@ -266,6 +328,11 @@ FG_HD void project_gaussian_vjp(const float m[3], const Sym3& cov, const Camera&
     float V00 = -(A * X00 + B * X10);
     float V01 = -(A * X01 + B * X11);
     float V11 = -(B * X01 + C * X11);
+    if (v_cov2d) {  // stored b stands for both off-diagonal entries of the symmetric matrix
+        V00 += v_cov2d[0];
+        V01 += 0.5f * v_cov2d[1];
+        V11 += v_cov2d[2];
+    }
     if (v_comp != 0.f) {
         // comp = sqrt(max(0, det_orig/det)); d(comp^2)/dcov2d = (1-comp^2) Ci - eps2d det(Ci) I
         float det_orig = a0 * c0 - b0 * b0;

@@ -110,7 +110,7 @@ class _Project(torch.autograd.Function):
     """fg_project_fwd / fg_project_bwd.  Outputs: radii, means2d, depths, conics, comps, feat, tiles."""
 
     @staticmethod
-    def forward(ctx, means, quats, scales, colors, means_next, viewmats, Ks, cfg):
+    def forward(ctx, means, quats, scales, colors, means_next, quats_next, scales_next, viewmats, Ks, cfg):
         L = _lib.lib()
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
@@ -128,6 +128,9 @@ class _Project(torch.autograd.Function):
         want_depth, want_flow = cfg["want_depth"], means_next is not None
         if means_next is not None:
             means_next = means_next.contiguous()
+        flow_cov = bool(cfg.get("flow_cov")) and want_flow
+        quats_next = quats_next.contiguous() if (flow_cov and quats_next is not None) else None
+        scales_next = scales_next.contiguous() if (flow_cov and scales_next is not None) else None
         CH = n_col + (1 if want_depth else 0) + (2 if want_flow else 0)
         rgb_off = 0 if use_sh else -1
         depth_off = n_col if want_depth else -1
@@ -140,31 +143,36 @@ class _Project(torch.autograd.Function):
         comps = torch.empty(C, N, device=dev) if cfg["antialiased"] else None
         feat = torch.empty(C, N, CH, device=dev)
         tiles = torch.empty(C, N, dtype=torch.int32, device=dev)
+        flow_affine = torch.empty(C, N, 4, device=dev) if flow_cov else None
         with _stage("project_fwd"):
           check(L.fg_project_fwd(
             C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
             cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"], cfg["tile_size"],
-            sh_degree if use_sh else -1, sh_bases, ptr(colors) if use_sh else None, ptr(means_next), None, None, 0,
-            ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(feat), CH, rgb_off, depth_off,
-            flow_off, None, ptr(tiles), _stream()))
+            sh_degree if use_sh else -1, sh_bases, ptr(colors) if use_sh else None, ptr(means_next), ptr(quats_next),
+            ptr(scales_next), int(flow_cov), ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(feat),
+            CH, rgb_off, depth_off, flow_off, ptr(flow_affine), ptr(tiles), _stream()))
         if not use_sh and colors is not None:
             feat[..., :n_col] = colors if colors.dim() == 3 else colors[None]
-        ctx.save_for_backward(means, quats, scales, colors if use_sh else None, means_next, viewmats, Ks, radii)
+        ctx.save_for_backward(means, quats, scales, colors if use_sh else None, means_next, quats_next, scales_next,
+                              viewmats, Ks, radii)
         ctx.cfg = cfg
         ctx.layout = (CH, n_col, rgb_off, depth_off, flow_off, sh_bases, use_sh,
-                      None if colors is None else colors.dim())
+                      None if colors is None else colors.dim(), flow_cov)
         ctx.mark_non_differentiable(radii, tiles)
         if comps is None:
             comps = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(comps)
-        return radii, means2d, depths, conics, comps, feat, tiles
+        if flow_affine is None:
+            flow_affine = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(flow_affine)
+        return radii, means2d, depths, conics, comps, feat, tiles, flow_affine
 
     @staticmethod
-    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_feat, _v_tiles):
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_feat, _v_tiles, v_flow_affine):
         L = _lib.lib()
-        means, quats, scales, sh, means_next, viewmats, Ks, radii = ctx.saved_tensors
+        means, quats, scales, sh, means_next, quats_next, scales_next, viewmats, Ks, radii = ctx.saved_tensors
         cfg = ctx.cfg
-        CH, n_col, rgb_off, depth_off, flow_off, sh_bases, use_sh, col_dim = ctx.layout
+        CH, n_col, rgb_off, depth_off, flow_off, sh_bases, use_sh, col_dim, flow_cov = ctx.layout
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
 
@@ -178,14 +186,17 @@ class _Project(torch.autograd.Function):
         v_scales = torch.empty(N, 3, device=dev)
         v_sh = torch.empty(N, sh_bases, 3, device=dev) if use_sh else None
         v_means_next = torch.empty(N, 3, device=dev) if means_next is not None else None
+        v_quats_next = torch.empty(N, 4, device=dev) if quats_next is not None else None
+        v_scales_next = torch.empty(N, 3, device=dev) if scales_next is not None else None
+        v_flow_affine = c(v_flow_affine) if flow_cov else None
         with _stage("project_bwd"):
           check(L.fg_project_bwd(
             C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
             cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"],
-            cfg["sh_degree"] if use_sh else -1, sh_bases, ptr(sh), ptr(means_next), None, None, 0, ptr(radii),
-            ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_feat), CH, rgb_off, depth_off,
-            flow_off, None, ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_sh), ptr(v_means_next), None, None,
-            _stream()))
+            cfg["sh_degree"] if use_sh else -1, sh_bases, ptr(sh), ptr(means_next), ptr(quats_next), ptr(scales_next),
+            int(flow_cov), ptr(radii), ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_feat), CH,
+            rgb_off, depth_off, flow_off, ptr(v_flow_affine), ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_sh),
+            ptr(v_means_next), ptr(v_quats_next), ptr(v_scales_next), _stream()))
         v_colors = None
         if use_sh:
             v_colors = v_sh
@@ -193,7 +204,7 @@ class _Project(torch.autograd.Function):
             v_colors = v_feat[..., :n_col]
             if col_dim == 2:
                 v_colors = v_colors.sum(0)
-        return v_means, v_quats, v_scales, v_colors, v_means_next, None, None, None
+        return v_means, v_quats, v_scales, v_colors, v_means_next, v_quats_next, v_scales_next, None, None, None
 
 
 # --------------------------------------------------------------------------- tile intersection
@@ -354,7 +365,7 @@ class _Rasterize(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, feat, opacities, backgrounds, isect_offsets, flatten_ids, width, height,
-                tile_size, absgrad, split, ed_channel, chunked):
+                tile_size, absgrad, split, ed_channel, chunked, flow_affine=None):
         L = _lib.lib()
         ctx.chunked = chunked
         C = isect_offsets.shape[0]
@@ -365,6 +376,7 @@ class _Rasterize(torch.autograd.Function):
         opac_shared = int(opac_c.numel() != NN)
         n_shared = opac_c.numel()
         bg = None if backgrounds is None else backgrounds.contiguous()
+        aff = None if flow_affine is None else flow_affine.contiguous()
         render = torch.empty(C, height, width, split, device=dev)
         render2 = torch.empty(C, height, width, CH - split, device=dev) if split < CH else None
         alphas = torch.empty(C, height, width, 1, device=dev)
@@ -372,11 +384,11 @@ class _Rasterize(torch.autograd.Function):
         M = flatten_ids.shape[0]
         with _stage("rasterize_fwd"):
             check(L.fg_rasterize_fwd(C, n_shared if opac_shared else NN, CH, width, height, tile_size, ptr(means2d_c),
-                                     ptr(conics_c), ptr(feat_c), ptr(opac_c), ptr(bg), None, 0, split, ed_channel,
+                                     ptr(conics_c), ptr(feat_c), ptr(opac_c), ptr(bg), ptr(aff), split, split, ed_channel,
                                      opac_shared, ptr(isect_offsets), ptr(flatten_ids), M, ptr(render), ptr(render2),
                                      ptr(alphas), ptr(last_ids), _stream()))
         ctx.save_for_backward(means2d_c, conics_c, feat_c, opac_c, bg, isect_offsets, flatten_ids, alphas, last_ids,
-                              render if ed_channel >= 0 else None)
+                              render if ed_channel >= 0 else None, aff)
         ctx.dims = (C, NN, CH, width, height, tile_size, absgrad, split, ed_channel, opac_shared, n_shared)
         ctx.means2d_obj = means2d  # the very tensor the caller holds as meta["means2d"] (model.py:869-871)
         ctx.mark_non_differentiable(last_ids)
@@ -388,7 +400,8 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_render, v_render2, v_alphas, _v_last):
         L = _lib.lib()
-        means2d, conics, feat, opac, bg, isect_offsets, flatten_ids, alphas, last_ids, render = ctx.saved_tensors
+        (means2d, conics, feat, opac, bg, isect_offsets, flatten_ids, alphas, last_ids, render,
+         aff) = ctx.saved_tensors
         C, NN, CH, width, height, tile_size, absgrad, split, ed_channel, opac_shared, n_shared = ctx.dims
         dev = feat.device
 
@@ -398,19 +411,21 @@ class _Rasterize(torch.autograd.Function):
         v_render, v_alphas = c(v_render), c(v_alphas)
         v_render2 = c(v_render2) if split < CH else None
         # one zero-filled arena for the five atomically accumulated gradient tensors
-        sizes = [means2d.numel(), means2d.numel() if absgrad else 0, conics.numel(), feat.numel(), opac.numel()]
+        sizes = [means2d.numel(), means2d.numel() if absgrad else 0, conics.numel(), feat.numel(), opac.numel(),
+                 0 if aff is None else aff.numel()]
         arena = torch.zeros(sum(sizes), device=dev)
         parts = torch.split(arena, sizes)
+        v_aff = None if aff is None else parts[5].view_as(aff)
         v_means2d = parts[0].view_as(means2d)
         v_abs = parts[1].view_as(means2d) if absgrad else None
         v_conics, v_feat, v_opac = parts[2].view_as(conics), parts[3].view_as(feat), parts[4].view_as(opac)
         M = flatten_ids.shape[0]
         with _stage("rasterize_bwd"):
             check(L.fg_rasterize_bwd(C, n_shared if opac_shared else NN, CH, width, height, tile_size, ptr(means2d),
-                                     ptr(conics), ptr(feat), ptr(opac), ptr(bg), None, 0, split, ed_channel,
+                                     ptr(conics), ptr(feat), ptr(opac), ptr(bg), ptr(aff), split, split, ed_channel,
                                      opac_shared, ptr(isect_offsets), ptr(flatten_ids), M, ptr(render), ptr(alphas),
                                      ptr(last_ids), ptr(v_render), ptr(v_render2), ptr(v_alphas), ptr(v_means2d),
-                                     ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), None, _stream()))
+                                     ptr(v_abs), ptr(v_conics), ptr(v_feat), ptr(v_opac), ptr(v_aff), _stream()))
         if absgrad:
             obj = ctx.means2d_obj
             prev = getattr(obj, "absgrad", None) if ctx.chunked else None
@@ -425,7 +440,7 @@ class _Rasterize(torch.autograd.Function):
                 vr = vr.clone()
                 vr[..., ed_channel] = 0
             v_bg = (vr * (1.0 - alphas)).sum(dim=(1, 2))
-        return (v_means2d, v_conics, v_feat, v_opac, v_bg) + (None,) * 9
+        return (v_means2d, v_conics, v_feat, v_opac, v_bg) + (None,) * 9 + (v_aff,)
 
 
 def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets,
@@ -511,8 +526,6 @@ def rasterization(
             "covars / distributed / non-pinhole cameras / sparse_grad are never used by the reference "
             "(freegaussian_model.py:847-868) and are not implemented"
         )
-    if flow_mode == "cov":
-        raise NotImplementedError("flow_mode='cov' is not built yet")
     if viewmats.requires_grad or Ks.requires_grad:
         raise NotImplementedError("camera gradients: the reference's camera optimizer is 'off' (model.py:120)")
     _require_cuda(means=means, quats=quats, scales=scales, opacities=opacities, colors=colors, viewmats=viewmats,
@@ -525,10 +538,12 @@ def rasterization(
     cfg = dict(width=int(width), height=int(height), eps2d=float(eps2d), near_plane=float(near_plane),
                far_plane=float(far_plane), radius_clip=float(radius_clip), tile_size=int(tile_size),
                sh_degree=None if only_depth else sh_degree, want_depth=want_depth,
-               antialiased=rasterize_mode == "antialiased")
+               antialiased=rasterize_mode == "antialiased", flow_cov=flow_mode == "cov" and means_next is not None)
     proj_colors = None if only_depth else colors
-    radii, means2d, depths, conics, comps, feat, tiles = _Project.apply(
-        means, quats, scales, proj_colors, means_next, viewmats, Ks, cfg)
+    radii, means2d, depths, conics, comps, feat, tiles, flow_affine = _Project.apply(
+        means, quats, scales, proj_colors, means_next, quats_next, scales_next, viewmats, Ks, cfg)
+    if not cfg["flow_cov"]:
+        flow_affine = None
     n_user = feat.shape[-1] - (2 if means_next is not None else 0)
 
     # classic: one opacity per Gaussian shared by all cameras ([N], no expand/copy); antialiased: per (c,n)
@@ -573,6 +588,8 @@ def rasterization(
         conics = conics.reshape(C * N, 3)[idx]
         feat = feat.reshape(C * N, -1)[idx]
         opac = (opac if opac.dim() == 2 else opac[None].expand(C, N)).reshape(C * N)[idx]
+        if flow_affine is not None:
+            flow_affine = flow_affine.reshape(C * N, 4)[idx]
         radii = radii.reshape(C * N)[idx]
         meta["camera_ids"] = idx // N
         meta["gaussian_ids"] = idx % N
@@ -583,10 +600,12 @@ def rasterization(
     if CH <= MAX_CH:
         render, flow_img, alphas, last_ids = _Rasterize.apply(
             means2d, conics, feat, opac, backgrounds, isect_offsets, flatten_ids, width, height, tile_size, absgrad,
-            n_user, ed_channel, False)
+            n_user, ed_channel, False, flow_affine)
         if means_next is not None:
             flow = flow_img
     else:  # many user colour channels: chunks of 8, normalisation / split done by torch
+        if flow_affine is not None:
+            raise NotImplementedError("flow_mode='cov' with more than 8 composited channels")
         opac_full = opac if opac.dim() == 2 or packed else opac[None].expand(C, N)
         render_all, alphas, last_ids = rasterize_to_pixels(means2d, conics, feat, opac_full, width, height, tile_size,
                                                            isect_offsets, flatten_ids, backgrounds=backgrounds,

@@ -80,25 +80,8 @@ def project_points(means: Tensor, viewmats: Tensor, Ks: Tensor) -> Tuple[Tensor,
     return torch.stack([u, v], -1), z
 
 
-def fully_fused_projection(
-    means: Tensor,  # [N,3]
-    quats: Tensor,  # [N,4]
-    scales: Tensor,  # [N,3]
-    viewmats: Tensor,  # [C,4,4]
-    Ks: Tensor,  # [C,3,3]
-    width: int,
-    height: int,
-    eps2d: float = 0.3,
-    near_plane: float = 0.01,
-    far_plane: float = 1e10,
-    radius_clip: float = 0.0,
-) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """EWA projection with culling (Appendix A.2).
-
-    Returns radii [C,N] int32 (0 = culled), means2d [C,N,2], depths [C,N],
-    conics [C,N,3], compensations [C,N], cov2d (blurred) [C,N,3] = (a,b,c).
-    Values at culled entries are zeroed.
-    """
+def project_cov2d(means, quats, scales, viewmats, Ks, width, height):
+    """Un-blurred 2-D covariance [C,N,2,2], projected mean [C,N,2] and camera depth [C,N]; no culling."""
     C, N = viewmats.shape[0], means.shape[0]
     covars = quat_scale_to_covar(quats, scales)  # [N,3,3]
     R = viewmats[:, :3, :3]
@@ -122,6 +105,29 @@ def fully_fused_projection(
     J = torch.stack([fx * rz, O, -fx * tx * rz2, O, fy * rz, -fy * ty * rz2], -1).reshape(C, N, 2, 3)
     cov2d = J @ cov_c @ J.transpose(-1, -2)  # [C,N,2,2]
     means2d = torch.stack([fx * x * rz + cx, fy * y * rz + cy], -1)
+    return cov2d, means2d, z
+
+
+def fully_fused_projection(
+    means: Tensor,  # [N,3]
+    quats: Tensor,  # [N,4]
+    scales: Tensor,  # [N,3]
+    viewmats: Tensor,  # [C,4,4]
+    Ks: Tensor,  # [C,3,3]
+    width: int,
+    height: int,
+    eps2d: float = 0.3,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """EWA projection with culling (Appendix A.2).
+
+    Returns radii [C,N] int32 (0 = culled), means2d [C,N,2], depths [C,N],
+    conics [C,N,3], compensations [C,N], cov2d (blurred) [C,N,3] = (a,b,c).
+    Values at culled entries are zeroed.
+    """
+    cov2d, means2d, z = project_cov2d(means, quats, scales, viewmats, Ks, width, height)
 
     a0, b0, c0 = cov2d[..., 0, 0], cov2d[..., 0, 1], cov2d[..., 1, 1]
     det_orig = a0 * c0 - b0 * b0
@@ -484,12 +490,13 @@ def rasterization(
         if flow_mode == "cov":
             qn = quats if quats_next is None else quats_next
             sn = scales if scales_next is None else scales_next
-            _, _, _, _, _, cov2d_n = fully_fused_projection(
-                means_next, qn, sn, viewmats, Ks, width, height, eps2d, -1e30, 1e30, -1.0
-            )
+            c2n, _, _ = project_cov2d(means_next, qn, sn, viewmats, Ks, width, height)
+            eps = torch.tensor([eps2d, 0.0, eps2d], dtype=cols.dtype)
+            cov_n = torch.stack([c2n[..., 0, 0], c2n[..., 0, 1], c2n[..., 1, 1]], -1) + eps
             # outside the frame-t visible set, or behind the near plane at t+1: no term
-            safe_t = torch.where(vis[..., None], cov2d, torch.tensor([1.0, 0.0, 1.0], dtype=cols.dtype))
-            safe_n = torch.where(ok, cov2d_n, safe_t)
+            ident = torch.tensor([1.0, 0.0, 1.0], dtype=cols.dtype)
+            safe_t = torch.where(vis[..., None], cov2d, ident)
+            safe_n = torch.where(ok, cov_n, ident)
             flow_affine = flow_affine_from_cov(safe_t, safe_n)
             flow_affine = torch.where(ok, flow_affine, torch.zeros((), dtype=cols.dtype))
 

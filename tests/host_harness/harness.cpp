@@ -119,4 +119,15 @@ void h_project_bwd(int C, int N, const float* means, const float* quats, const f
     }
 }
 
+void h_flow_affine(int n, const float* ct, const float* cn, float* A) {
+    for (int i = 0; i < n; ++i) flow_affine(ct + 3 * i, cn + 3 * i, A + 4 * i);
+}
+void h_flow_affine_vjp(int n, const float* ct, const float* cn, const float* vA, float* v_ct, float* v_cn) {
+    for (int i = 0; i < n; ++i) {
+        v_ct[3 * i] = v_ct[3 * i + 1] = v_ct[3 * i + 2] = 0.f;
+        v_cn[3 * i] = v_cn[3 * i + 1] = v_cn[3 * i + 2] = 0.f;
+        flow_affine_vjp(ct + 3 * i, cn + 3 * i, vA + 4 * i, v_ct + 3 * i, v_cn + 3 * i);
+    }
+}
+
 }  // extern "C"

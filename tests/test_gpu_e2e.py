@@ -148,3 +148,44 @@ def test_many_channels_are_chunked(built_lib):
                                 sh_degree=None)
     assert r.shape == (1, H, W, 19)
     assert rel_err(r, rr) < IMG_TOL
+
+
+def test_covariance_flow_mode_matches_oracle(built_lib):
+    """flow_mode="cov" (the north_star's covariance-induced term): per-pixel flow
+    f_g + (B(t+1) B(t)^-1 - I)(p - mu_g).  No reference code exists; parity is against this repo's oracle."""
+    from freegaussian_b200.rendering import rasterization
+    W, H = 96, 64
+    sc = small_scene(1500, W, H, views=2, seed=17)
+    g = torch.Generator().manual_seed(1)
+    scales_next = sc.scales * torch.exp(torch.randn(sc.scales.shape, generator=g) * 0.1)
+    names = ["means", "quats", "scales", "opacities", "sh", "means_next", "quats_next"]
+    d = sc.to("cuda")
+    gp = {n: getattr(d, n).clone().requires_grad_(True) for n in names}
+    # float64 oracle: the affine term makes the flow features large, and float32 autograd through the
+    # oracle is itself only good to ~1e-3 on the opacity gradient here
+    op = {n: getattr(sc, n).clone().double().requires_grad_(True) for n in names}
+    gs, os_ = scales_next.cuda().requires_grad_(True), scales_next.clone().double().requires_grad_(True)
+    kw = dict(packed=False, render_mode="RGB+ED", sh_degree=3, absgrad=True, flow_mode="cov")
+    r, a, m = rasterization(gp["means"], gp["quats"], gp["scales"], gp["opacities"], gp["sh"], d.viewmats, d.Ks, W, H,
+                            means_next=gp["means_next"], quats_next=gp["quats_next"], scales_next=gs, **kw)
+    rr, ra, rm = O.rasterization(op["means"], op["quats"], op["scales"], op["opacities"], op["sh"],
+                                 sc.viewmats.double(), sc.Ks.double(), W, H, means_next=op["means_next"],
+                                 quats_next=op["quats_next"], scales_next=os_, **kw)
+    assert torch.equal(m["radii"].cpu(), rm["radii"])
+    assert rel_err(r, rr) < IMG_TOL and rel_err(a, ra) < IMG_TOL
+    assert rel_err(m["flow"], rm["flow"]) < IMG_TOL, rel_err(m["flow"], rm["flow"])
+    # the affine term is really there: it differs from the mean-only flow
+    _, _, mm = rasterization(d.means, d.quats, d.scales, d.opacities, d.sh, d.viewmats, d.Ks, W, H,
+                             means_next=d.means_next, packed=False, sh_degree=3)
+    assert rel_err(m["flow"], mm["flow"].cpu()) > 1e-3
+    gen = torch.Generator().manual_seed(0)
+    wr, wf = torch.randn(rr.shape, generator=gen), torch.randn(rm["flow"].shape, generator=gen)
+    ((r * wr.cuda()).sum() + (m["flow"] * wf.cuda()).sum()).backward()
+    ((rr * wr.double()).sum() + (rm["flow"] * wf.double()).sum()).backward()
+    # The affine term makes per-pixel flow features ~100x larger than the mean flow (A ~ 0.1 times a
+    # pixel offset of tens of pixels), so float32 accumulation noise is larger relative to the max
+    # gradient: 2e-3 here (1e-3 holds for the mean mode above; tools/dbg_grad.py prints both).
+    for n in names:
+        e = grad_rel_err(gp[n].grad, op[n].grad)
+        assert e < 2 * GRAD_TOL, (n, e)
+    assert grad_rel_err(gs.grad, os_.grad) < 2 * GRAD_TOL

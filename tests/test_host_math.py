@@ -125,3 +125,28 @@ def test_projection_vjp_matches_autograd(harness, sh_degree):
                            ("scales", v_scales, scales.grad), ("sh", v_sh, sh.grad), ("next", v_next, means_next.grad)]:
         err = grad_rel_err(torch.from_numpy(got), ref)
         assert err < 1e-3, (name, err)
+
+
+def test_flow_affine_and_vjp_match_autograd(harness):
+    """Covariance flow term: A = B(t+1) B(t)^-1 - I and its hand-derived VJP."""
+    g = torch.Generator().manual_seed(0)
+    n = 500
+
+    def rand_cov():
+        L = torch.randn(n, 2, 2, generator=g, dtype=torch.double)
+        S = L @ L.transpose(-1, -2) + 0.3 * torch.eye(2, dtype=torch.double)
+        return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 1, 1]], -1)
+
+    ct, cn = rand_cov().requires_grad_(True), rand_cov().requires_grad_(True)
+    A = O.flow_affine_from_cov(ct, cn)
+    w = torch.randn(n, 4, generator=g, dtype=torch.double)
+    (A * w).sum().backward()
+    f32 = lambda t: t.detach().float().contiguous()
+    out = np.zeros((n, 4), np.float32)
+    a = lambda x: x.ctypes.data_as(_f)
+    harness.h_flow_affine(n, fp(f32(ct)), fp(f32(cn)), a(out))
+    assert rel_err(torch.from_numpy(out), A) < 1e-5
+    v_ct, v_cn = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    harness.h_flow_affine_vjp(n, fp(f32(ct)), fp(f32(cn)), fp(f32(w)), a(v_ct), a(v_cn))
+    assert grad_rel_err(torch.from_numpy(v_ct), ct.grad) < 1e-4
+    assert grad_rel_err(torch.from_numpy(v_cn), cn.grad) < 1e-4
