@@ -111,7 +111,7 @@ __device__ __forceinline__ void read_sh_row(const float* smem, float* coef) {
 }
 
 template <int DEG, bool VEC4>
-__global__ void __launch_bounds__(PB) project_fwd_kernel(ProjParams p) {
+__global__ void __launch_bounds__(PB, 4) project_fwd_kernel(ProjParams p) {
     extern __shared__ __align__(16) float smem[];
     const int n0 = blockIdx.x * PB;
     const int n = n0 + threadIdx.x;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(PB) project_fwd_kernel(ProjParams p) {
 
 // ------------------------------------------------------------------------------ backward
 template <int DEG, bool VEC4>
-__global__ void __launch_bounds__(PB) project_bwd_kernel(ProjParams p) {
+__global__ void __launch_bounds__(PB, 3) project_bwd_kernel(ProjParams p) {
     extern __shared__ __align__(16) float smem[];
     using S = ShShape<(DEG >= 0 ? DEG : 0)>;
     const int n0 = blockIdx.x * PB;
