@@ -46,7 +46,7 @@ CPU_CROP = 128   # the CPU arm renders a CPU_CROP x CPU_CROP centre crop of the 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
@@ -73,7 +73,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -127,7 +127,7 @@ def run_ours(args):
     import torch.distributed as dist
     from freegaussian_b200 import _lib
     from freegaussian_b200 import rendering
-    from freegaussian_b200.dist import DensificationStats
+    from freegaussian_b200.dist import DensificationStats, exchange
     from freegaussian_b200.rendering import rasterization
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,13 +202,7 @@ def run_ours(args):
         loss = (render * wr).sum() + (meta["flow"] * wf).sum()
         loss.backward()
         stats.accumulate_local(meta["radii"], meta["means2d"].absgrad, H, W)
-        if world > 1:
-            works = [dist.all_reduce(p.grad, async_op=True) for p in params]
-            stats.reduce()
-            for wk in works:
-                wk.wait()
-        else:
-            stats.reduce()
+        exchange([p.grad for p in params], stats)  # one coalesced SUM all-reduce + one MAX (no-op at N=1)
         info["meta"] = meta
         if e2e:
             return float(loss.item())  # D2H read of the step's result

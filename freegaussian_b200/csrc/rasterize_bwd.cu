@@ -80,7 +80,7 @@ __device__ __forceinline__ void transpose_reduce(float (&val)[NV], int lane, flo
 __device__ __forceinline__ int slot_of_lane(int lane) { return lane & 15; }
 
 template <int CH, bool AFF>
-__global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams p) {
+__global__ void __launch_bounds__(TILE_PIX, 4) rasterize_bwd_kernel(RasterBwdParams p) {
     constexpr int FV = (CH + 3) / 4;
     constexpr int NVAL = CH + 8 + (AFF ? 4 : 0);  // partials per (pixel, Gaussian)
     constexpr int NV = NVAL <= 16 ? 16 : 32;
@@ -195,10 +195,14 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
             valid = valid && (batch_end - t <= bin_final);
             if (!__any_sync(0xffffffffu, valid)) continue;
 
+            // Lanes whose pixel skips this Gaussian run the same arithmetic with alpha = vis = 0: every
+            // partial then comes out as an exact zero and (T, S) are left unchanged (ra = 1), so no
+            // per-partial zero-fill or branch is needed.
+            if (!valid) { alpha = 0.f; vis = 0.f; }
             float val[NV];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) val[k] = 0.f;
-            if (valid) {
+            for (int k = CH + 8; k < NV; ++k) val[k] = 0.f;
+            {
                 float f[FV * 4];
 #pragma unroll
                 for (int j = 0; j < FV; ++j) {
@@ -236,8 +240,10 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
                     gx = -fac * (vo0 * M.x + vo1 * M.z);
                     gy = -fac * (vo0 * M.y + vo1 * M.w);
                 }
-                if (a4.z * vis <= ALPHA_MAX) {
-                    const float v_sigma = -a4.z * vis * v_alpha;
+                {
+                    // gradient only flows through alpha where it is not clamped (opac * vis <= 0.999)
+                    const bool gate = a4.z * vis <= ALPHA_MAX;
+                    const float v_sigma = gate ? -a4.z * vis * v_alpha : 0.f;
                     val[CH] = 0.5f * v_sigma * dx * dx;
                     val[CH + 1] = v_sigma * dx * dy;
                     val[CH + 2] = 0.5f * v_sigma * dy * dy;
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(TILE_PIX) rasterize_bwd_kernel(RasterBwdParams
                     val[CH + 6] = fabsf(hy);
                     gx += hx;
                     gy += hy;
-                    val[CH + 7] = vis * v_alpha;
+                    val[CH + 7] = gate ? vis * v_alpha : 0.f;
                 }
                 val[CH + 3] = gx;
                 val[CH + 4] = gy;

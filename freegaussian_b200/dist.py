@@ -92,10 +92,19 @@ class DensificationStats:
         size = radii.to(torch.float32) / float(max(height, width))
         self._local_size = torch.maximum(self._local_size, size.max(0).values)
 
+    def sum_tensors(self) -> List[Tensor]:
+        """Per-step buffers reduced with SUM (so they can ride in the gradients' coalesced all-reduce)."""
+        return [self._local_grad, self._local_vis]
+
+    def max_tensors(self) -> List[Tensor]:
+        return [self._local_size]
+
     @torch.no_grad()
-    def reduce(self, group=None) -> None:
-        """The exchange step: SUM, SUM, MAX across ranks, then fold into the running statistics."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    def reduce(self, group=None, already_reduced: bool = False) -> None:
+        """The exchange step: SUM, SUM, MAX across ranks, then fold into the running statistics.
+        ``already_reduced``: the buffers were reduced by :func:`exchange`; only fold."""
+        if (not already_reduced and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size(group) > 1):
             packed = torch.stack([self._local_grad, self._local_vis])
             dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
             self._local_grad, self._local_vis = packed[0], packed[1]
@@ -106,3 +115,31 @@ class DensificationStats:
         self._local_grad = torch.zeros_like(self._local_grad)
         self._local_vis = torch.zeros_like(self._local_vis)
         self._local_size = torch.zeros_like(self._local_size)
+
+
+def exchange(grads: Sequence[Tensor], stats: Optional[DensificationStats] = None, group=None) -> None:
+    """THE exchange step of a view-sharded training step: all-reduce(SUM) of every
+    parameter gradient and of the two summed statistics in ONE coalesced NCCL launch, plus one
+    all-reduce(MAX) for ``max_2Dsize``; then the statistics are folded.  Eight separate collectives
+    cost ~0.4 ms of launch latency per step on top of the 0.35 ms the 236 MB actually need on NVLink."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi:
+        sums = [g for g in grads if g is not None] + (stats.sum_tensors() if stats is not None else [])
+        if dist.get_backend(group) == "nccl":
+            from torch.distributed.distributed_c10d import _coalescing_manager
+            with _coalescing_manager(group=group, device=sums[0].device, async_ops=True) as cm:
+                for t in sums:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            work = cm
+        else:  # gloo (CPU tests of the host logic): no coalescing support, same arithmetic
+            work = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in sums]
+        if stats is not None:
+            for t in stats.max_tensors():
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        if isinstance(work, list):
+            for w in work:
+                w.wait()
+        else:
+            work.wait()
+    if stats is not None:
+        stats.reduce(group, already_reduced=multi)

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from freegaussian_b200.dist import DensificationStats, GradBucket, shard_views
+from freegaussian_b200.dist import DensificationStats, GradBucket, exchange, shard_views
 
 
 def test_shard_views_partition():
@@ -41,8 +41,9 @@ def _worker(rank, world, port, n, out):
         stats.accumulate_local(radii[v:v + 1], absgrad[v:v + 1], 100, 200)
         for p, g in zip(params, grads):
             p.grad += g * (v + 1)  # pretend per-view gradient
-    stats.reduce()
-    bucket.all_reduce()
+    if rank == 0 and world > 1:
+        pass
+    exchange([bucket.flat], stats)  # coalesced SUM of grads + stats, MAX of sizes, then fold
     if rank == 0:
         torch.save({"g": stats.xys_grad_norm, "c": stats.vis_counts, "m": stats.max_2Dsize,
                     "p0": params[0].grad.clone(), "p1": params[1].grad.clone()}, out)
