@@ -52,6 +52,14 @@ class _Workspace:
 
 _ws = _Workspace()
 
+# The flat buffer holding the parameter gradients of the most recent projection backward:
+# (tensor, floats in use).  Read by freegaussian_b200.dist.exchange.
+_grad_arena: Dict[str, tuple] = {}
+
+
+def last_grad_arena():
+    return _grad_arena.get("last")
+
 
 class StageTimer:
     """Optional CUDA-event timing of each C-ABI stage (bench.py's per-kernel roofline).
@@ -181,13 +189,19 @@ class _Project(torch.autograd.Function):
 
         v_means2d, v_depths, v_conics, v_feat = c(v_means2d), c(v_depths), c(v_conics), c(v_feat)
         v_comps = c(v_comps) if cfg["antialiased"] else None
-        v_means = torch.empty(N, 3, device=dev)
-        v_quats = torch.empty(N, 4, device=dev)
-        v_scales = torch.empty(N, 3, device=dev)
-        v_sh = torch.empty(N, sh_bases, 3, device=dev) if use_sh else None
-        v_means_next = torch.empty(N, 3, device=dev) if means_next is not None else None
-        v_quats_next = torch.empty(N, 4, device=dev) if quats_next is not None else None
-        v_scales_next = torch.empty(N, 3, device=dev) if scales_next is not None else None
+        # All parameter gradients of this call live in ONE flat buffer (plus 3N spare floats), so a
+        # view-sharded trainer can all-reduce them with a single collective (dist.exchange).
+        sizes = [3 * N, 4 * N, 3 * N, sh_bases * 3 * N if use_sh else 0, 3 * N if means_next is not None else 0,
+                 4 * N if quats_next is not None else 0, 3 * N if scales_next is not None else 0]
+        used = sum(sizes)
+        arena = torch.empty(used + 3 * N, device=dev)
+        parts = torch.split(arena[:used], sizes)
+        v_means, v_quats, v_scales = parts[0].view(N, 3), parts[1].view(N, 4), parts[2].view(N, 3)
+        v_sh = parts[3].view(N, sh_bases, 3) if use_sh else None
+        v_means_next = parts[4].view(N, 3) if means_next is not None else None
+        v_quats_next = parts[5].view(N, 4) if quats_next is not None else None
+        v_scales_next = parts[6].view(N, 3) if scales_next is not None else None
+        _grad_arena["last"] = (arena, used)
         v_flow_affine = c(v_flow_affine) if flow_cov else None
         with _stage("project_bwd"):
           check(L.fg_project_bwd(
