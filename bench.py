@@ -302,9 +302,17 @@ def run_ours(args):
                 ach = work / t / 1e12
                 kernels[name] = {"bound": "fp32", "ms": stage_ms[name], "achieved": ach, "peak": fp32_peak,
                                  "unit": "TFLOP/s", "frac": ach / fp32_peak if fp32_peak else None}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+        # captures (profiles/r1_final_*.txt); only valid for the configuration they were taken on
+        ncu_traffic = {}
+        if args.workload == "cfg3" and args.recipe == "trained_like":
+            ncu_traffic = {"rasterize_bwd": 128.3e6, "rasterize_fwd": 27.2e6, "project_bwd": 505.8e6,
+                           "project_fwd": 287.5e6, "fine_bin": 107.1e6}
+        for name, k in kernels.items():
+            k["traffic"] = ncu_traffic.get(name)
         dominant = max(stage_ms, key=stage_ms.get)
         roof = dict(kernels.get(dominant, {}))
-        roof.update({"kernel": dominant, "traffic": None,
+        roof.update({"kernel": dominant, "traffic": ncu_traffic.get(dominant),
                      "peak_source": "fg_measure_fp32_tflops (FFMA microbenchmark, this run)" if roof.get("bound") == "fp32" else hbm_src})
         hbm_kernels = {k: v for k, v in kernels.items() if v["bound"] == "hbm"}
         dom_hbm = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms"]) if hbm_kernels else None
