@@ -110,6 +110,25 @@ __device__ __forceinline__ void read_sh_row(const float* smem, float* coef) {
     }
 }
 
+// Sparse visibility: a thread fetches just its own row straight from global memory (no staging),
+// so rows of culled Gaussians are never read.
+template <int DEG, bool VEC4>
+__device__ __forceinline__ void read_sh_row_global(const float* __restrict__ sh, int row_floats, int n, float* coef) {
+    using S = ShShape<DEG>;
+    if (VEC4) {
+        const float4* r = reinterpret_cast<const float4*>(sh) + (size_t)n * (row_floats >> 2);
+#pragma unroll
+        for (int j = 0; j < S::NV; ++j) {
+            float4 v = __ldg(r + j);
+            coef[4 * j] = v.x; coef[4 * j + 1] = v.y; coef[4 * j + 2] = v.z; coef[4 * j + 3] = v.w;
+        }
+    } else {
+        const float* r = sh + (size_t)n * row_floats;
+#pragma unroll
+        for (int k = 0; k < S::NEED; ++k) coef[k] = __ldg(r + k);
+    }
+}
+
 template <int DEG, bool VEC4>
 __global__ void __launch_bounds__(PB, 4) project_fwd_kernel(ProjParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -146,7 +165,11 @@ __global__ void __launch_bounds__(PB, 4) project_fwd_kernel(ProjParams p) {
         }
     }
 
-    bool staged = false;
+    // SH rows: staged through shared memory (coalesced) when at least half of the block is visible,
+    // otherwise each visible thread reads its own row and culled rows are never touched
+    int sh_mode = 0;  // 0 undecided, 1 staged, 2 per-thread
+    bool have_coef = false;
+    float coef[ShShape<(DEG >= 0 ? DEG : 0)>::NEED];
     for (int c0 = 0; c0 < p.C; c0 += 32) {
         const int c1 = min(p.C, c0 + 32);
         uint32_t vis = 0;
@@ -190,16 +213,22 @@ __global__ void __launch_bounds__(PB, 4) project_fwd_kernel(ProjParams p) {
         }
         if (DEG >= 0) {
             using S = ShShape<(DEG >= 0 ? DEG : 0)>;
-            if (!staged) {
-                // uniform branch: `staged` only changes under a block-wide vote
-                if (__syncthreads_or(vis != 0)) {
+            if (sh_mode == 0) {
+                // uniform branch: sh_mode only changes under a block-wide vote
+                const int nvis = __syncthreads_count(vis != 0);
+                if (nvis * 2 >= PB) {
                     stage_sh_rows<(DEG >= 0 ? DEG : 0), VEC4>(p.sh, p.sh_row_floats, n0, p.N, smem);
                     __syncthreads();
-                    staged = true;
+                    sh_mode = 1;
+                } else if (nvis > 0) {
+                    sh_mode = 2;
                 }
             }
-            float coef[S::NEED];
-            if (vis) read_sh_row<(DEG >= 0 ? DEG : 0), VEC4>(smem, coef);
+            if (vis && !have_coef) {
+                if (sh_mode == 1) read_sh_row<(DEG >= 0 ? DEG : 0), VEC4>(smem, coef);
+                else read_sh_row_global<(DEG >= 0 ? DEG : 0), VEC4>(p.sh, p.sh_row_floats, n, coef);
+                have_coef = true;
+            }
             for (int c = c0; c < c1; ++c) {
                 if (!in_range) continue;
                 float rgb[3] = {0.f, 0.f, 0.f};
@@ -266,15 +295,24 @@ __global__ void __launch_bounds__(PB, 3) project_bwd_kernel(ProjParams p) {
             cov_next = quat_scale_to_cov(qn, sn);
         }
     }
-    if (DEG >= 0) {
-        stage_sh_rows<(DEG >= 0 ? DEG : 0), VEC4>(p.sh, p.sh_row_floats, n0, p.N, smem);
-        __syncthreads();
-    }
     float coef[NEED];
     float vcoef[NEED];
 #pragma unroll
     for (int k = 0; k < NEED; ++k) vcoef[k] = 0.f;
-    if (DEG >= 0) read_sh_row<(DEG >= 0 ? DEG : 0), VEC4>(smem, coef);
+    if (DEG >= 0) {
+        // same hybrid as the forward: staged when the block is mostly visible, per-thread otherwise
+        bool vis_any = false;
+        if (in_range)
+            for (int c = 0; c < p.C; ++c) vis_any |= p.radii_in[(size_t)c * p.N + n] > 0;
+        const int nvis = __syncthreads_count(vis_any);
+        if (nvis * 2 >= PB) {
+            stage_sh_rows<(DEG >= 0 ? DEG : 0), VEC4>(p.sh, p.sh_row_floats, n0, p.N, smem);
+            __syncthreads();
+            if (vis_any) read_sh_row<(DEG >= 0 ? DEG : 0), VEC4>(smem, coef);
+        } else if (vis_any) {
+            read_sh_row_global<(DEG >= 0 ? DEG : 0), VEC4>(p.sh, p.sh_row_floats, n, coef);
+        }
+    }
 
     float v_mean[3] = {0.f, 0.f, 0.f}, v_mean_next[3] = {0.f, 0.f, 0.f};
     Sym3 G = {}, G_next = {};

@@ -60,10 +60,11 @@ __device__ __forceinline__ bool eval_alpha(const GeomA& a, const GeomB& b, float
 // the continuous rectangle (zero if the mean lies inside, else the best of the four edge
 // minima), with a small safety margin: conservative, so compositing results are unchanged.
 // ncu r1g: 60 % of the (warp, Gaussian) steps had no valid pixel and cost ~25 instructions each.
-__device__ __forceinline__ float edge_min(float q_cc, float q_cv, float q_vv, float c, float vlo, float vhi) {
-    // minimise q_cc c^2 + q_cv c v + q_vv v^2 over v in [vlo, vhi]
-    const float v = fminf(fmaxf(-0.5f * q_cv * c / q_vv, vlo), vhi);
-    return fmaf(q_cc * c, c, fmaf(q_cv * c, v, q_vv * v * v));
+// minimise q_cc c^2 + q_cv c v + q_vv v^2 over v in [vlo, vhi]; nh_cv_over_vv = -0.5 q_cv / q_vv
+__device__ __forceinline__ float edge_min(float q_cc, float q_cv, float q_vv, float nh_cv_over_vv, float c, float vlo,
+                                          float vhi) {
+    const float v = fminf(fmaxf(nh_cv_over_vv * c, vlo), vhi);
+    return fmaf(q_cc * c, c, v * fmaf(q_cv, c, q_vv * v));
 }
 
 __device__ __forceinline__ unsigned patch_mask(float mx, float my, float opac, float qa, float qb, float qc,
@@ -71,18 +72,25 @@ __device__ __forceinline__ unsigned patch_mask(float mx, float my, float opac, f
     // tile_x0/tile_y0: centre of the tile's first pixel
     const float thr = __log2f(255.f * opac) * 1.00002f + 2e-4f;
     if (!(thr > 0.f) || !(qa > 0.f) || !(qc > 0.f)) return (thr > 0.f) ? 0xffu : 0u;  // degenerate conic: keep
+    const float kx = -0.5f * qb / qa, ky = -0.5f * qb / qc;  // argmin slopes, shared by all patches
+    // the eight patches share two x-intervals and four y-intervals of delta = mu - p
+    float dxlo[2], dxhi[2], dylo[4], dyhi[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { dxhi[i] = mx - (tile_x0 + 8.f * i); dxlo[i] = dxhi[i] - 7.f; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dyhi[j] = my - (tile_y0 + 4.f * j); dylo[j] = dyhi[j] - 3.f; }
     unsigned mask = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-        const float x0 = tile_x0 + (float)((w & 1) << 3), y0 = tile_y0 + (float)((w >> 1) << 2);
-        // delta = mu - p, p in [x0, x0+7] x [y0, y0+3]
-        const float dxlo = mx - (x0 + 7.f), dxhi = mx - x0, dylo = my - (y0 + 3.f), dyhi = my - y0;
+        const int i = w & 1, j = w >> 1;
         float pmin;
-        if (dxlo <= 0.f && dxhi >= 0.f && dylo <= 0.f && dyhi >= 0.f) {
+        if (dxlo[i] <= 0.f && dxhi[i] >= 0.f && dylo[j] <= 0.f && dyhi[j] >= 0.f) {
             pmin = 0.f;
         } else {
-            pmin = fminf(fminf(edge_min(qa, qb, qc, dxlo, dylo, dyhi), edge_min(qa, qb, qc, dxhi, dylo, dyhi)),
-                         fminf(edge_min(qc, qb, qa, dylo, dxlo, dxhi), edge_min(qc, qb, qa, dyhi, dxlo, dxhi)));
+            pmin = fminf(fminf(edge_min(qa, qb, qc, ky, dxlo[i], dylo[j], dyhi[j]),
+                               edge_min(qa, qb, qc, ky, dxhi[i], dylo[j], dyhi[j])),
+                         fminf(edge_min(qc, qb, qa, kx, dylo[j], dxlo[i], dxhi[i]),
+                               edge_min(qc, qb, qa, kx, dyhi[j], dxlo[i], dxhi[i])));
         }
         if (pmin <= thr) mask |= 1u << w;
     }
