@@ -188,14 +188,28 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     const unsigned lt = (1u << lane) - 1;
+    // software pipeline: the next chunk's (id, mean, radius) gathers are in flight while this chunk
+    // is ranked and written
+    int id_n = 0, r_n = 0;
+    float2 m_n = make_float2(0.f, 0.f);
+    if (start + tid < end) {
+        id_n = coarse_vals[start + tid];
+        m_n = means2d[id_n];
+        r_n = radii[id_n];
+    }
     for (int base = start; base < end; base += 256) {
         const int e = base + tid;
+        const int id = id_n;
+        const float2 m = m_n;
+        const int r = r_n;
+        if (e + 256 < end) {
+            id_n = coarse_vals[e + 256];
+            m_n = means2d[id_n];
+            r_n = radii[id_n];
+        }
         unsigned mask = 0;  // bit (iy*CK + ix) set if the splat overlaps tile (cx*CK+ix, cy*CK+iy)
-        int id = 0;
         if (e < end) {
-            id = coarse_vals[e];
-            const float2 m = means2d[id];
-            const TileRect t = tile_rect(m.x, m.y, radii[id], tile_size, tile_w, tile_h);
+            const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
             const int x0 = max(t.x0 - cx * CK, 0), x1 = min(t.x1 - cx * CK, CK);
             const int y0 = max(t.y0 - cy * CK, 0), y1 = min(t.y1 - cy * CK, CK);
             if (x1 > x0 && y1 > y0) {

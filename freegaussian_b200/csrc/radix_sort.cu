@@ -103,7 +103,10 @@ struct RsSmem {
     int tile_id;
 };
 
-template <typename KeyT>
+// LB_WIN = status words a look-back round keeps in flight.  Small inputs (every tile resident at
+// once, so tile t really has to walk back over t predecessors) use 32; large inputs use 8 to keep
+// the register count at 64 (2 CTAs per SM).
+template <typename KeyT, int LB_WIN>
 __global__ void __launch_bounds__(RS_THREADS)
     rs_onesweep_kernel(long long n, const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                        KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift, int bits,
@@ -191,7 +194,6 @@ __global__ void __launch_bounds__(RS_THREADS)
         // decoupled look-back over predecessor tiles, LB_WIN status words in flight at a time
         uint32_t excl = 0;
         if (tile > 0) {
-            constexpr int LB_WIN = 8;
             int t = tile - 1;
             bool done = false;
             while (!done) {
@@ -283,13 +285,20 @@ static int radix_sort_pairs(long long n, KeyT* keys_in, uint32_t* vals_in, KeyT*
     FG_LAUNCH((rs_histogram_kernel<KeyT>), hist_blocks, RS_THREADS, 0, st, n, keys_in, passes, end_bit, hist);
     FG_LAUNCH(rs_scan_hist_kernel, passes, RS_RADIX, 0, st, hist);
     const size_t smem = sizeof(RsSmem<KeyT>);
-    FG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool small = false;  // a 32-word window was measured: no gain on 1 M-item sorts (per-tile latency dominates), more registers
+    FG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KeyT* kin = keys_in; uint32_t* vin = vals_in; KeyT* kout = keys_out; uint32_t* vout = vals_out;
     for (int p = 0; p < passes; ++p) {
         int shift = 8 * p;
         int bits = end_bit - shift < 8 ? end_bit - shift : 8;
-        FG_LAUNCH((rs_onesweep_kernel<KeyT>), (int)L.tiles, RS_THREADS, smem, st, n, kin, vin, kout, vout, shift, bits,
-                  hist + p * RS_RADIX, status + (size_t)p * L.tiles * RS_RADIX, counters + p);
+        if (small) {
+            FG_LAUNCH((rs_onesweep_kernel<KeyT, 32>), (int)L.tiles, RS_THREADS, smem, st, n, kin, vin, kout, vout, shift,
+                      bits, hist + p * RS_RADIX, status + (size_t)p * L.tiles * RS_RADIX, counters + p);
+        } else {
+            FG_LAUNCH((rs_onesweep_kernel<KeyT, 8>), (int)L.tiles, RS_THREADS, smem, st, n, kin, vin, kout, vout, shift,
+                      bits, hist + p * RS_RADIX, status + (size_t)p * L.tiles * RS_RADIX, counters + p);
+        }
         KeyT* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }

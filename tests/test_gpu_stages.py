@@ -187,3 +187,33 @@ def test_densify_stats_kernel_matches_reference_formula(L):
     assert torch.allclose(a.xys_grad_norm.cpu(), b.xys_grad_norm, rtol=1e-6, atol=1e-6)
     assert torch.equal(a.vis_counts.cpu(), b.vis_counts)
     assert torch.allclose(a.max_2Dsize.cpu(), b.max_2Dsize, rtol=1e-6)
+
+
+@pytest.mark.parametrize("seed,C,W,H,n", [(0, 1, 50, 33, 3000), (1, 3, 333, 190, 20000), (2, 5, 1000, 37, 8000)])
+def test_tile_lists_adversarial(L, seed, C, W, H, n):
+    """All three list builders against the oracle on hand-made splats: radii from 1 px to larger than the
+    image, centres far outside, exact depth ties (tie-break = ascending c*N+n), ragged image sizes."""
+    from freegaussian_b200.rendering import isect_tiles, isect_ids_from_tiles
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    g = torch.Generator().manual_seed(seed)
+    m2d = (torch.rand(C, n, 2, generator=g) * 1.6 - 0.3) * torch.tensor([W, H])
+    radii = torch.randint(1, 40, (C, n), generator=g, dtype=torch.int32)
+    radii[:, ::17] = torch.randint(100, 2000, (C, len(range(0, n, 17))), generator=g, dtype=torch.int32)
+    radii[torch.rand(C, n, generator=g) < 0.3] = 0
+    dep = torch.rand(C, n, generator=g) * 10 + 0.1
+    dep[:, ::5] = 1.25  # many exact ties
+    dep[:, 1::7] = dep[:, 0:1]  # and ties with one particular value per camera
+    m2d[radii == 0] = 0
+    x0, x1, y0, y1 = O.tile_rects(m2d, radii, 16, tw, th)
+    tiles = ((x1 - x0) * (y1 - y0)).to(torch.int32)
+    tpg, r_ids, r_flat = O.isect_tiles(m2d, radii, dep, 16, tw, th)
+    r_offs = O.isect_offset_encode(r_ids, C, tw, th)
+    assert torch.equal(tpg, tiles) and r_ids.numel() > 0
+    for mode in ("key64", "two_level", "binned"):
+        ids, flat, offs, tk = isect_tiles(m2d.cuda(), radii.cuda(), dep.cuda(), tiles.cuda(), 16, tw, th, mode=mode)
+        assert torch.equal(flat.cpu(), r_flat), f"{mode}: list order differs"
+        assert torch.equal(offs.cpu(), r_offs), f"{mode}: tile ranges differ"
+        if ids is None and tk is not None:
+            ids = isect_ids_from_tiles(tk, flat, dep.cuda(), tw, th)
+        if ids is not None:
+            assert torch.equal(ids.cpu(), r_ids)
