@@ -344,7 +344,7 @@ def run_ours(args):
             "kernels": kernels,
             "stage_ms": stage_ms,
         }
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only
             out["cpu_baseline"] = cpu_arm(args, steps=args.cpu_steps, warmup=0)["cpu_baseline"]
     if world > 1:
         dist.barrier()

@@ -50,6 +50,10 @@ SIGNATURES = {
     "fg_rasterize_bwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                 _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_densify_stats": (_i32, [_i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    "fg_assign_masks": (_i32, [_i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "fg_l1_ssim_workspace_floats": (_i64, [_i32, _i32]),
+    "fg_l1_ssim_fwd": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp]),
+    "fg_l1_ssim_bwd": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),
     "fg_knn_workspace_bytes": (_i64, [_i64]),
     "fg_knn_f32": (_i32, [_i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
 }

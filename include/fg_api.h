@@ -213,6 +213,30 @@ int64_t fg_knn_workspace_bytes(int64_t n);
 int fg_knn_f32(int64_t n, const float* points /*[n,3]*/, int k, float* out_dist /*[n,k]*/,
                int32_t* out_idx /*[n,k]*/, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- (5) preprocess: attribute-mask assignment ---------------------------------------------
+ * Loop body of preprocess/knn_gaussian.py:116-132 after the packed "ED" render (:93-113): a visible
+ * Gaussian whose truncated projected centre is inside the image and whose depth is consistent with
+ * the rendered depth D there (-0.1 D < D - z < D) gets gaussian_masks[gaussian_id, a] = 1 for every
+ * attribute a with atrb_masks[y,x,a] && mask_valids[a].  Masks are bytes (torch.bool). */
+int fg_assign_masks(int64_t nnz, const float* means2d, const float* depths, const int64_t* gaussian_ids,
+                    const float* depth_img, int width, int height, const uint8_t* atrb_masks,
+                    const uint8_t* mask_valids, int n_attr, uint8_t* gaussian_masks, void* stream);
+
+/* ---- (6) fused blend + clamp + L1 + SSIM loss ------------------------------------------------
+ * pred = clamp(render[..., :3] + (1 - alpha) bg, 0, 1) (freegaussian_model.py:876-877);
+ * loss = (1-l) mean|gt - pred| + l (1 - SSIM(gt, pred)) (freegaussian_model.py:965-981; SSIM of
+ * pytorch_msssim: 11-tap Gaussian, sigma 1.5, valid separable convolution).
+ * fwd: sums[0] = (1-l) mean|gt-pred|, sums[1] = l * mean SSIM (doubles, device); `partial` =
+ * fg_l1_ssim_workspace_floats(W,H) floats kept for the backward.  bwd: v_render[H,W,render_stride]
+ * (channels >= 3 zeroed), v_alpha[H,W], scaled by the device scalar *v_loss. */
+int64_t fg_l1_ssim_workspace_floats(int width, int height);
+int fg_l1_ssim_fwd(int width, int height, int render_stride, const float* render, const float* alpha,
+                   const float* background, const float* gt, float ssim_lambda, float* partial,
+                   double* sums, void* stream);
+int fg_l1_ssim_bwd(int width, int height, int render_stride, const float* render, const float* alpha,
+                   const float* background, const float* gt, float ssim_lambda, const float* partial,
+                   const float* v_loss, float* v_render, float* v_alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,3 +189,28 @@ def test_covariance_flow_mode_matches_oracle(built_lib):
         e = grad_rel_err(gp[n].grad, op[n].grad)
         assert e < 2 * GRAD_TOL, (n, e)
     assert grad_rel_err(gs.grad, os_.grad) < 2 * GRAD_TOL
+
+
+def test_mask_assignment_matches_reference_logic(built_lib):
+    """preprocess/knn_gaussian.py:93-132: packed ED render, then the attribute-mask scatter -- bit-exact
+    against the statement-by-statement restatement of the reference's own lines."""
+    from freegaussian_b200.preprocess import assign_gaussian_masks
+    from freegaussian_b200.rendering import rasterization
+    from oracle.preprocess import assign_gaussian_masks_reference
+    W, H, N, M = 160, 100, 4000, 5
+    # small, fairly transparent splats so that many centres pass the depth-consistency filter
+    sc = small_scene(N, W, H, views=1, seed=13, scale_mul=0.12).to("cuda")
+    render, alpha, info = rasterization(sc.means, sc.quats, sc.scales, sc.opacities * 0.5, sc.sh, sc.viewmats, sc.Ks,
+                                        W, H, packed=True, render_mode="ED", sh_degree=3, absgrad=True)
+    g = torch.Generator().manual_seed(0)
+    atrb = torch.rand(H, W, M, generator=g) < 0.3
+    valids = torch.tensor([True, True, False, True, True])
+    acc_gpu = torch.zeros(N, M, dtype=torch.bool, device="cuda")
+    acc_gpu[5, 1] = True  # pre-existing entries are kept (the reference ORs over key frames)
+    acc_ref = acc_gpu.cpu().clone()
+    assign_gaussian_masks(render, info, atrb.cuda(), acc_gpu, mask_valids=valids)
+    mask = atrb & valids[None, None]  # knn_gaussian.py:128
+    assign_gaussian_masks_reference(render.cpu(), info["means2d"].cpu(), info["depths"].cpu(),
+                                    info["gaussian_ids"].cpu(), mask, acc_ref)
+    assert acc_ref.sum() > 50
+    assert torch.equal(acc_gpu.cpu(), acc_ref)

@@ -1,0 +1,52 @@
+"""Fused blend + L1 + SSIM loss: oracle self-checks on CPU, kernel parity on GPU."""
+import pytest
+import torch
+
+from oracle import loss as OL
+from util import rel_err, grad_rel_err
+
+
+def _inputs(H, W, seed, rs=4):
+    g = torch.Generator().manual_seed(seed)
+    alpha = torch.rand(1, H, W, 1, generator=g)
+    render = torch.rand(1, H, W, rs, generator=g) * alpha * 1.3 - 0.05  # some pixels clamp at both ends
+    bg = torch.tensor([0.149, 0.1647, 0.2157])  # the reference's default background (model.py:223)
+    gt = torch.rand(H, W, 3, generator=g)
+    return render, alpha, bg, gt
+
+
+def test_oracle_ssim_properties():
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(1, 3, 40, 52, generator=g)
+    assert abs(float(OL.ssim(x, x)) - 1.0) < 1e-6  # identical images
+    y = torch.rand(1, 3, 40, 52, generator=g)
+    assert abs(float(OL.ssim(x, y)) - float(OL.ssim(y, x))) < 1e-6  # symmetric
+    assert float(OL.ssim(x, y)) < 0.2
+    w = OL.gaussian_window()
+    assert abs(float(w.sum()) - 1) < 1e-6 and w.argmax() == 5
+
+
+def test_oracle_loss_gradcheck():
+    render, alpha, bg, gt = _inputs(14, 15, 1)
+    r, a = render.double().requires_grad_(True), alpha.double().requires_grad_(True)
+    f = lambda r_, a_: OL.blend_l1_ssim_loss(r_[0], a_[0], bg.double(), gt.double())
+    assert torch.autograd.gradcheck(f, (r, a), eps=1e-6, atol=1e-5, nondet_tol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,rs", [(11, 11, 3), (37, 53, 4), (128, 200, 4), (540, 960, 4)])
+def test_fused_loss_matches_oracle(built_lib, H, W, rs):
+    from freegaussian_b200.losses import blend_l1_ssim_loss
+    render, alpha, bg, gt = _inputs(H, W, H + W, rs)
+    ro, ao = render.clone().double().requires_grad_(True), alpha.clone().double().requires_grad_(True)
+    ref = OL.blend_l1_ssim_loss(ro[0], ao[0], bg.double(), gt.double())
+    ref.backward()
+    rg, ag = render.cuda().requires_grad_(True), alpha.cuda().requires_grad_(True)
+    out = blend_l1_ssim_loss(rg, ag, bg.cuda(), gt.cuda())
+    (out * 1.7).backward()
+    assert abs(float(out.detach()) - float(ref.detach())) < 1e-5 * max(1.0, abs(float(ref.detach())))
+    want_r = ro.grad.clone() * 1.7
+    if rs > 3:
+        assert (rg.grad[..., 3:] == 0).all()
+    assert grad_rel_err(rg.grad, want_r) < 1e-3
+    assert grad_rel_err(ag.grad, ao.grad * 1.7) < 1e-3
