@@ -42,7 +42,8 @@ SIGNATURES = {
     "fg_isect_ids_from_tiles": (_i32, [_i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "fg_bin_coarse_dims": (_i32, [_i32, _i32, _pi, _pi]),
     "fg_bin_count": (_i32, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "fg_bin_tile_scan": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "fg_bin_tile_scan_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "fg_bin_tile_scan": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "fg_bin_coarse_emit": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fg_bin_fine": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fg_rasterize_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,

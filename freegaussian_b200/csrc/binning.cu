@@ -51,87 +51,44 @@ __global__ void __launch_bounds__(256)
     coarse_cnt[slot] = cnt;
 }
 
-// ---- step 3: one CTA; grids are small (<= ~100k tiles) ---------------------------------------
+// ---- step 3: one CTA per camera turns its difference grid into per-tile counts (2-D prefix sum
+// in place, then compacted to [tile_h][tile_w]); the exclusive scan over all tiles is the generic
+// scan of isect.cu, so many-camera calls (cfg4: 32 views, ~0.7 M tiles) stay parallel.
 __global__ void __launch_bounds__(1024)
-    tile_scan_kernel(int C, int tile_w, int tile_h, int32_t* __restrict__ diff, int32_t* __restrict__ offsets,
-                     long long* __restrict__ total_out) {
+    tile_count_kernel(int tile_w, int tile_h, int32_t* __restrict__ diff, int32_t* __restrict__ counts) {
     const int W1 = tile_w + 1, H1 = tile_h + 1;
-    __shared__ long long warp_sums[33];
-    __shared__ long long carry_s;
-    // row-wise prefix (warp per row, coalesced), then column-wise prefix (thread per column,
-    // next row prefetched): the difference grid becomes the per-tile counts, in place
+    const int c = blockIdx.x;
+    int32_t* g = diff + (long long)c * H1 * W1;
     const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int c = 0; c < C; ++c) {
-        int32_t* g = diff + (long long)c * H1 * W1;
-        for (int y = warp_; y < H1; y += nwarps) {
-            int carry = 0;
-            for (int x0 = 0; x0 < W1; x0 += 32) {
-                const int x = x0 + lane_;
-                int v = x < W1 ? g[y * W1 + x] : 0;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int o = __shfl_up_sync(0xffffffffu, v, d);
-                    if (lane_ >= d) v += o;
-                }
-                v += carry;
-                if (x < W1) g[y * W1 + x] = v;
-                carry = __shfl_sync(0xffffffffu, v, 31);
-            }
-        }
-        __syncthreads();
-        for (int x = threadIdx.x; x < W1; x += blockDim.x) {
-            int run = 0;
-            int next = g[x];
-            for (int y = 0; y < H1; ++y) {
-                const int cur = next;
-                if (y + 1 < H1) next = g[(y + 1) * W1 + x];
-                run += cur;
-                g[y * W1 + x] = run;
-            }
-        }
-        __syncthreads();
-    }
-    // exclusive scan of counts over (c, y, x) in tile order
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const long long n_tiles = (long long)C * tile_w * tile_h;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = 0; base < n_tiles; base += blockDim.x) {
-        const long long t = base + threadIdx.x;
-        long long v = 0;
-        if (t < n_tiles) {
-            const int c = (int)(t / (tile_w * tile_h));
-            const int rem = (int)(t - (long long)c * tile_w * tile_h);
-            const int y = rem / tile_w, x = rem - y * tile_w;
-            v = diff[((long long)c * H1 + y) * W1 + x];
-        }
-        long long incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            long long o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            long long w = warp_sums[lane];
-            long long wi = w;
+    // row-wise prefix (warp per row, coalesced)
+    for (int y = warp_; y < H1; y += nwarps) {
+        int carry = 0;
+        for (int x0 = 0; x0 < W1; x0 += 32) {
+            const int x = x0 + lane_;
+            int v = x < W1 ? g[y * W1 + x] : 0;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                long long o = __shfl_up_sync(0xffffffffu, wi, d);
-                if (lane >= d) wi += o;
+                int o = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane_ >= d) v += o;
             }
-            warp_sums[lane] = wi - w;
-            if (lane == 31) warp_sums[32] = wi;
+            v += carry;
+            if (x < W1) g[y * W1 + x] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
         }
-        __syncthreads();
-        const long long carry = carry_s;
-        if (t < n_tiles) offsets[t] = (int32_t)(carry + warp_sums[warp] + incl - v);
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + warp_sums[32];
-        __syncthreads();
     }
-    if (threadIdx.x == 0) *total_out = carry_s;
+    __syncthreads();
+    // column-wise prefix (thread per column, next row prefetched) + compaction
+    int32_t* out = counts + (long long)c * tile_h * tile_w;
+    for (int x = threadIdx.x; x < tile_w; x += blockDim.x) {
+        int run = 0;
+        int next = g[x];
+        for (int y = 0; y < tile_h; ++y) {
+            const int cur = next;
+            next = g[(y + 1) * W1 + x];
+            run += cur;
+            out[y * tile_w + x] = run;
+        }
+    }
 }
 
 // ---- step 4: emit (splat, coarse cell) pairs in depth order --------------------------------
@@ -276,11 +233,24 @@ extern "C" int fg_bin_count(int C, int N, const int32_t* order, const float* mea
     return FG_OK;
 }
 
+extern "C" int fg_exclusive_scan_i32(int64_t n, const int32_t* counts, int32_t* offsets, int64_t* total,
+                                     void* workspace, int64_t workspace_bytes, void* stream);
+extern "C" int64_t fg_scan_workspace_bytes(int64_t n);
+
+extern "C" int64_t fg_bin_tile_scan_workspace_bytes(int C, int tile_w, int tile_h) {
+    const int64_t n = (int64_t)C * tile_w * tile_h;
+    return ((n * 4 + 255) & ~(int64_t)255) + fg_scan_workspace_bytes(n);
+}
+
 extern "C" int fg_bin_tile_scan(int C, int tile_w, int tile_h, int32_t* diff_grid, int32_t* isect_offsets,
-                                int64_t* total, void* stream) {
-    FG_REQUIRE(C >= 1 && tile_w > 0 && tile_h > 0 && diff_grid && isect_offsets && total, "bad arguments");
-    FG_LAUNCH(tile_scan_kernel, 1, 1024, 0, stream, C, tile_w, tile_h, diff_grid, isect_offsets, (long long*)total);
-    return FG_OK;
+                                int64_t* total, void* workspace, int64_t workspace_bytes, void* stream) {
+    FG_REQUIRE(C >= 1 && tile_w > 0 && tile_h > 0 && diff_grid && isect_offsets && total && workspace, "bad arguments");
+    FG_REQUIRE(workspace_bytes >= fg_bin_tile_scan_workspace_bytes(C, tile_w, tile_h), "tile-scan workspace too small");
+    const int64_t n = (int64_t)C * tile_w * tile_h;
+    int32_t* counts = (int32_t*)workspace;
+    unsigned char* scan_ws = (unsigned char*)workspace + ((n * 4 + 255) & ~(int64_t)255);
+    FG_LAUNCH(tile_count_kernel, C, 1024, 0, stream, tile_w, tile_h, diff_grid, counts);
+    return fg_exclusive_scan_i32(n, counts, isect_offsets, total, scan_ws, fg_scan_workspace_bytes(n), stream);
 }
 
 extern "C" int fg_bin_coarse_emit(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,

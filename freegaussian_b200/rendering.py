@@ -295,7 +295,9 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
             coarse_cnt = torch.empty(total, **i32)
             check(L.fg_bin_count(C, N, ptr(order), ptr(means2d), ptr(radii), tile_size, tile_w, tile_h, ptr(diff),
                                  ptr(coarse_cnt), st))
-            check(L.fg_bin_tile_scan(C, tile_w, tile_h, ptr(diff), ptr(isect_offsets), n2[0:1].data_ptr(), st))
+            ws2 = _ws.get("tile_scan", L.fg_bin_tile_scan_workspace_bytes(C, tile_w, tile_h), dev)
+            check(L.fg_bin_tile_scan(C, tile_w, tile_h, ptr(diff), ptr(isect_offsets), n2[0:1].data_ptr(), ptr(ws2),
+                                     ws2.numel(), st))
             check(L.fg_exclusive_scan_i32(total, ptr(coarse_cnt), ptr(offsets), n2[1:2].data_ptr(), ptr(ws),
                                           ws.numel(), st))
         M, Mc = (int(v) for v in n2.tolist())  # the one host sync: sizes the list buffers

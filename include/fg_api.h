@@ -155,8 +155,9 @@ int fg_isect_ids_from_tiles(int64_t n_isects, const uint32_t* sorted_tile_keys, 
 int fg_bin_coarse_dims(int tile_w, int tile_h, int* cw, int* ch);
 int fg_bin_count(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
                  int tile_size, int tile_w, int tile_h, int32_t* diff_grid, int32_t* coarse_cnt, void* stream);
+int64_t fg_bin_tile_scan_workspace_bytes(int C, int tile_w, int tile_h);
 int fg_bin_tile_scan(int C, int tile_w, int tile_h, int32_t* diff_grid, int32_t* isect_offsets,
-                     int64_t* total, void* stream);
+                     int64_t* total, void* workspace, int64_t workspace_bytes, void* stream);
 int fg_bin_coarse_emit(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
                        const int32_t* coarse_off, int tile_size, int tile_w, int tile_h,
                        uint32_t* coarse_keys, int32_t* coarse_vals, void* stream);
