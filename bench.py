@@ -40,6 +40,7 @@ WORKLOADS = {
     "cfg4": (3_000_000, 2704, 2028),
 }
 N_VIEW_POOL = 8  # distinct cameras cycled through per rank
+REFINE_EVERY = 100  # config/sim/base.yaml:22 (refine_every)
 CPU_CROP = 128   # the CPU arm renders a CPU_CROP x CPU_CROP centre crop of the same frame
 
 
@@ -169,6 +170,7 @@ def run_ours(args):
     dev_K = [k.to(dev) for k in host_K]
     stats = DensificationStats(n, dev)
     info = {}
+    state = {"it": 0}
 
     copy_stream = torch.cuda.Stream(device=dev)
     staged = {}
@@ -206,7 +208,14 @@ def run_ours(args):
         loss = (render * wr).sum() + (meta["flow"] * wf).sum()
         loss.backward()
         stats.accumulate_local(meta["radii"], meta["means2d"].absgrad, H, W)
-        exchange([p.grad for p in params], stats)  # one coalesced SUM all-reduce + one MAX (no-op at N=1)
+        # exchange step: ONE all-reduce over the flat gradient arena (no-op at N=1).  The densification
+        # statistics are folded locally every step and reduced across ranks when they are consumed
+        # (refine_every = 100 steps in the reference configs) -- same numbers, no per-step collective.
+        exchange([p.grad for p in params])
+        stats.reduce(already_reduced=True)
+        state["it"] += 1
+        if state["it"] % REFINE_EVERY == 0:
+            stats.sync()
         info["meta"] = meta
         if e2e:
             return float(loss.item())  # D2H read of the step's result

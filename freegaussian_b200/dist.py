@@ -100,6 +100,20 @@ class DensificationStats:
         return [self._local_size]
 
     @torch.no_grad()
+    def sync(self, group=None) -> None:
+        """Cross-rank reduction of the RUNNING statistics (SUM, SUM, MAX).  All three are plain
+        accumulators, so summing / maxing once right before they are consumed -- the refinement
+        step every ``refine_every`` = 100 iterations (``config/sim/base.yaml:22``) -- gives exactly what a
+        per-step reduction would, and keeps the statistics out of the per-step exchange.  Every rank
+        starts ``vis_counts`` at one (``freegaussian_model.py:380``); the extra ``G - 1`` are removed."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            g = dist.get_world_size(group)
+            packed = torch.stack([self.xys_grad_norm, self.vis_counts])
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+            self.xys_grad_norm, self.vis_counts = packed[0], packed[1] - float(g - 1)
+            dist.all_reduce(self.max_2Dsize, op=dist.ReduceOp.MAX, group=group)
+
+    @torch.no_grad()
     def reduce(self, group=None, already_reduced: bool = False) -> None:
         """The exchange step: SUM, SUM, MAX across ranks, then fold into the running statistics.
         ``already_reduced``: the buffers were reduced by :func:`exchange`; only fold."""
@@ -119,8 +133,9 @@ class DensificationStats:
 
 def exchange(grads: Sequence[Tensor], stats: Optional[DensificationStats] = None, group=None) -> None:
     """THE exchange step of a view-sharded training step: all-reduce(SUM) of every
-    parameter gradient and of the two summed statistics, all-reduce(MAX) of ``max_2Dsize``; then the
-    statistics are folded.
+    parameter gradient.  With ``stats`` given, the two summed statistics and ``max_2Dsize`` are reduced
+    in the same step and folded; the cheaper, equivalent schedule is ``stats.reduce(already_reduced=True)``
+    (local fold) every step and ``stats.sync()`` only when the statistics are consumed.
 
     The projection backward writes all of its parameter gradients into one flat buffer
     (``rendering.last_grad_arena()``); gradients living there are reduced by ONE collective over that

@@ -79,3 +79,34 @@ def test_stats_match_reference_formula():
     c[vis] += 1
     m[vis] = torch.maximum(m[vis], radii[0][vis] / 200.0)
     assert torch.allclose(s.xys_grad_norm, g) and torch.equal(s.vis_counts, c) and torch.allclose(s.max_2Dsize, m)
+
+
+def _worker_sync(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    stats = DensificationStats(n, "cpu")
+    for step in range(3):  # local folds every step, one cross-rank sync at the end
+        radii, absgrad, _ = _views(n, step)
+        for v in shard_views(4, rank, world):
+            stats.accumulate_local(radii[v:v + 1], absgrad[v:v + 1], 100, 200)
+        stats.reduce(already_reduced=True)
+    stats.sync()
+    if rank == 0:
+        torch.save({"g": stats.xys_grad_norm, "c": stats.vis_counts, "m": stats.max_2Dsize}, out)
+    dist.destroy_process_group()
+
+
+def test_deferred_stats_sync_equals_per_step_reduction(tmp_path):
+    n, world = 129, 2
+    out = str(tmp_path / "sync.pt")
+    mp.spawn(_worker_sync, args=(world, 29533, n, out), nprocs=world, join=True)
+    got = torch.load(out)
+    ref = DensificationStats(n, "cpu")
+    for step in range(3):
+        radii, absgrad, _ = _views(n, step)
+        for v in range(4):
+            ref.accumulate_local(radii[v:v + 1], absgrad[v:v + 1], 100, 200)
+        ref.reduce()
+    assert torch.allclose(got["g"], ref.xys_grad_norm, atol=1e-5)
+    assert torch.equal(got["c"], ref.vis_counts) and torch.equal(got["m"], ref.max_2Dsize)
