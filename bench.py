@@ -290,7 +290,6 @@ def run_ours(args):
         else:  # two-level: 32-bit tile keys, ceil(log2(tiles)/8) passes; depth sort of the n splats separately
             passes = (max(1, math.ceil(math.log2(n_tiles))) + 7) // 8
             sort_bytes, emit_bytes = M * (4 + passes * 16), n * 24 + M * 8
-        n_coarse_est = 0
         algo = {  # algorithmic bytes / flops per launch (DESIGN.md "Kernels")
             "project_fwd": ("hbm", n_vis * 276 + (n - n_vis) * 44),
             "project_bwd": ("hbm", n_vis * 548 + (n - n_vis) * (44 + 4 + 236)),

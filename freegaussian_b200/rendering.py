@@ -232,7 +232,7 @@ def _sort_pairs(L, n, keys_a, vals_a, keys_b, vals_b, end_bit, dev, st, u64):
 
 @torch.no_grad()
 def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
-                tile_w: int, tile_h: int, mode: str = "two_level"):
+                tile_w: int, tile_h: int, mode: str = "binned"):
     """Tile intersections sorted by (camera, tile, depth), ties in ascending c*N+n -- the order
     gsplat's 64-bit stable radix sort produces.
 
@@ -240,9 +240,9 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
     once, exact per-tile counts come from a 2-D difference grid, and each 4x4-tile cell appends
     its depth-ordered splats to its tiles' lists (csrc/binning.cu).
     ``mode="key64"``: the reference layout literally -- emit 64-bit (camera|tile|depth) keys in
-    (c,n) order and radix-sort them (6-7 passes).  ``mode="two_level"`` (default): sort the
-    splats once by depth, emit their tiles in that order with 32-bit tile keys and stable-sort
-    by tile (2 passes): the same total order with ~4x less traffic.
+    (c,n) order and radix-sort them (6-7 passes).  ``mode="two_level"``: sort the splats once by
+    depth, emit their tiles in that order with 32-bit tile keys and stable-sort by tile (2 passes).
+    All three produce the identical lists (tests/test_gpu_stages.py).
 
     Returns ``(isect_ids | None, flatten_ids [M] int32, isect_offsets [C,tile_h,tile_w] int32,
     tile_keys | None)``; one host sync (reading M), like gsplat.

@@ -1,9 +1,7 @@
 """Multi-GPU host logic on CPU: view sharding arithmetic and the gradient / densification-statistics exchange
 (SUM, SUM, MAX) with gloo, world_size 2."""
 import os
-import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -41,8 +39,6 @@ def _worker(rank, world, port, n, out):
         stats.accumulate_local(radii[v:v + 1], absgrad[v:v + 1], 100, 200)
         for p, g in zip(params, grads):
             p.grad += g * (v + 1)  # pretend per-view gradient
-    if rank == 0 and world > 1:
-        pass
     exchange([bucket.flat], stats)  # coalesced SUM of grads + stats, MAX of sizes, then fold
     if rank == 0:
         torch.save({"g": stats.xys_grad_norm, "c": stats.vis_counts, "m": stats.max_2Dsize,

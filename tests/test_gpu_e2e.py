@@ -1,5 +1,4 @@
 """End-to-end parity of rasterization(...) against the oracle on the same seeded inputs (-m gpu)."""
-import math
 
 import pytest
 import torch

@@ -3,7 +3,7 @@ import pytest
 import torch
 
 from oracle import loss as OL
-from util import rel_err, grad_rel_err
+from util import grad_rel_err
 
 
 def _inputs(H, W, seed, rs=4):

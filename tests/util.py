@@ -1,7 +1,6 @@
 """Shared helpers for the parity tests (oracle side runs on CPU)."""
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from freegaussian_b200.scenes import make_scene

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """all-reduce of the 1 M-Gaussian gradient arena (59 floats per Gaussian + tail) under torchrun; prints ms and GB/s."""
-import os, sys, torch, torch.distributed as dist
+import os, torch, torch.distributed as dist
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))

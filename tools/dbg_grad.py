@@ -1,7 +1,7 @@
 import sys, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 from oracle import render as O
-from util import small_scene, rel_err, grad_rel_err
+from util import grad_rel_err, small_scene
 from freegaussian_b200.rendering import rasterization
 W, H = 96, 64
 for mode in ("mean", "cov"):
