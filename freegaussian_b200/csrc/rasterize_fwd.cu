@@ -35,7 +35,7 @@ struct RasterFwdParams {
 };
 
 template <int CH, bool AFF>
-__global__ void __launch_bounds__(TILE_PIX) rasterize_fwd_kernel(RasterFwdParams p) {
+__global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdParams p) {
     constexpr int FV = (CH + 3) / 4;  // float4 per Gaussian for the features
     __shared__ float4 sA[BATCH];
     __shared__ float4 sB[BATCH];
