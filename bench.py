@@ -209,10 +209,9 @@ def run_ours(args):
         loss.backward()
         stats.accumulate_local(meta["radii"], meta["means2d"].absgrad, H, W)
         # exchange step: ONE all-reduce over the flat gradient arena (no-op at N=1).  The densification
-        # statistics are folded locally every step and reduced across ranks when they are consumed
-        # (refine_every = 100 steps in the reference configs) -- same numbers, no per-step collective.
+        # statistics are accumulated per rank by one kernel per step and reduced across ranks when they
+        # are consumed (refine_every = 100 steps in the reference configs) -- same numbers.
         exchange([p.grad for p in params])
-        stats.reduce(already_reduced=True)
         state["it"] += 1
         if state["it"] % REFINE_EVERY == 0:
             stats.sync()

@@ -55,6 +55,13 @@ SIGNATURES = {
     "fg_l1_ssim_workspace_floats": (_i64, [_i32, _i32]),
     "fg_l1_ssim_fwd": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp]),
     "fg_l1_ssim_bwd": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "fg_render_front_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "fg_render_front": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _i32,
+                               _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                               _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp, _i64, _vp]),
+    "fg_render_back_workspace_bytes": (_i64, [_i32, _i32, _i32, _i64]),
+    "fg_render_back": (_i32, [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64,
+                              _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "fg_knn_workspace_bytes": (_i64, [_i64]),
     "fg_knn_f32": (_i32, [_i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
 }

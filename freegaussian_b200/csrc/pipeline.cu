@@ -1,0 +1,162 @@
+// Host-side orchestration of the forward pass in two C calls (the native runtime of the path):
+//   fg_render_front: projection -> depth sort -> bin count -> tile scan -> coarse scan -> the ONE host
+//                    sync (M = tile intersections, Mc = coarse pairs size the list buffers)
+//   fg_render_back : coarse emit -> coarse sort -> cell offsets -> fine binning -> compositing forward
+// Same kernels as the granular entry points (which stay for tests, the other list-building modes
+// and per-stage timing); what this removes is ~10 Python/ctypes round trips and a dozen temporary
+// allocations per step: on the 10 k-Gaussian cfg1 scene a step is host-bound (1.0 ms against
+// 0.38 ms of kernels), and after every host sync the GPU waits for the host to catch up.
+#include "common.cuh"
+
+namespace fg {
+
+static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct FrontLayout {
+    size_t dk, dk2, dv2, diff, ccnt, n2, scan, tscan, sort, total;
+};
+static FrontLayout front_layout(int C, int N, int tile_w, int tile_h) {
+    const size_t total = (size_t)C * N;
+    FrontLayout L;
+    size_t o = 0;
+    L.dk = o; o += al(total * 4);
+    L.dk2 = o; o += al(total * 4);
+    L.dv2 = o; o += al(total * 4);
+    L.diff = o; o += al((size_t)C * (tile_h + 1) * (tile_w + 1) * 4);
+    L.ccnt = o; o += al(total * 4);
+    L.n2 = o; o += al(16);
+    L.scan = o; o += al((size_t)fg_scan_workspace_bytes((int64_t)total));
+    L.tscan = o; o += al((size_t)fg_bin_tile_scan_workspace_bytes(C, tile_w, tile_h));
+    L.sort = o; o += al((size_t)fg_radix_sort_workspace_bytes((int64_t)total));
+    L.total = o;
+    return L;
+}
+
+struct BackLayout {
+    size_t ck, cv, ck2, cv2, coff, sort, total;
+};
+static BackLayout back_layout(int C, int tile_w, int tile_h, int64_t Mc) {
+    int cw = 0, chh = 0;
+    fg_bin_coarse_dims(tile_w, tile_h, &cw, &chh);
+    const size_t m = (size_t)(Mc > 0 ? Mc : 1);
+    BackLayout L;
+    size_t o = 0;
+    L.ck = o; o += al(m * 4);
+    L.cv = o; o += al(m * 4);
+    L.ck2 = o; o += al(m * 4);
+    L.cv2 = o; o += al(m * 4);
+    L.coff = o; o += al((size_t)C * cw * chh * 4);
+    L.sort = o; o += al((size_t)fg_radix_sort_workspace_bytes((int64_t)m));
+    L.total = o;
+    return L;
+}
+
+static int64_t* pinned_counts() {
+    static int64_t* p = nullptr;
+    if (!p && cudaHostAlloc((void**)&p, 2 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+    return p;
+}
+
+}  // namespace fg
+
+using namespace fg;
+
+extern "C" int64_t fg_render_front_workspace_bytes(int C, int N, int tile_w, int tile_h) {
+    return (int64_t)front_layout(C, N, tile_w, tile_h).total;
+}
+
+extern "C" int fg_render_front(int C, int N, const float* means, const float* quats, const float* scales,
+                               const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                               float near_plane, float far_plane, float radius_clip, int tile_size, int sh_degree,
+                               int sh_bases, const float* sh_coeffs, const float* means_next, const float* quats_next,
+                               const float* scales_next, int flow_cov, int32_t* radii, float* means2d, float* depths,
+                               float* conics, float* compensations, float* feat, int feat_stride, int rgb_off,
+                               int depth_off, int flow_off, float* flow_affine, int32_t* tiles_per_gauss,
+                               int32_t* order, int32_t* isect_offsets, int32_t* coarse_off, int64_t* counts_host,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
+    FG_REQUIRE(order && isect_offsets && coarse_off && counts_host && workspace, "NULL pointer");
+    const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
+    const FrontLayout L = front_layout(C, N, tile_w, tile_h);
+    FG_REQUIRE((size_t)workspace_bytes >= L.total, "front workspace too small");
+    unsigned char* ws = (unsigned char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = (int64_t)C * N;
+    int e;
+    if ((e = fg_project_fwd(C, N, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                            radius_clip, tile_size, sh_degree, sh_bases, sh_coeffs, means_next, quats_next, scales_next,
+                            flow_cov, radii, means2d, depths, conics, compensations, feat, feat_stride, rgb_off,
+                            depth_off, flow_off, flow_affine, tiles_per_gauss, stream)))
+        return e;
+    uint32_t* dk = (uint32_t*)(ws + L.dk);
+    uint32_t* dk2 = (uint32_t*)(ws + L.dk2);
+    uint32_t* dv2 = (uint32_t*)(ws + L.dv2);
+    if ((e = fg_isect_depth_keys(total, depths, tiles_per_gauss, dk, (uint32_t*)order, stream))) return e;
+    int sel = 0;
+    if ((e = fg_radix_sort_pairs_u32_u32(total, dk, (uint32_t*)order, dk2, dv2, 32, ws + L.sort,
+                                         (int64_t)(L.total - L.sort), &sel, stream)))
+        return e;
+    if (sel == 1 && total > 0) FG_CUDA(cudaMemcpyAsync(order, dv2, (size_t)total * 4, cudaMemcpyDeviceToDevice, st));
+    int64_t* n2 = (int64_t*)(ws + L.n2);
+    if ((e = fg_bin_count(C, N, order, means2d, radii, tile_size, tile_w, tile_h, (int32_t*)(ws + L.diff),
+                          (int32_t*)(ws + L.ccnt), stream)))
+        return e;
+    if ((e = fg_bin_tile_scan(C, tile_w, tile_h, (int32_t*)(ws + L.diff), isect_offsets, n2, ws + L.tscan,
+                              (int64_t)(L.sort - L.tscan), stream)))
+        return e;
+    if ((e = fg_exclusive_scan_i32(total, (const int32_t*)(ws + L.ccnt), coarse_off, n2 + 1, ws + L.scan,
+                                   (int64_t)(L.tscan - L.scan), stream)))
+        return e;
+    int64_t* pin = pinned_counts();
+    FG_REQUIRE(pin != nullptr, "cudaHostAlloc failed");
+    FG_CUDA(cudaMemcpyAsync(pin, n2, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    FG_CUDA(cudaStreamSynchronize(st));  // the one host sync of the forward pass
+    counts_host[0] = pin[0];
+    counts_host[1] = pin[1];
+    return FG_OK;
+}
+
+extern "C" int64_t fg_render_back_workspace_bytes(int C, int tile_w, int tile_h, int64_t n_coarse) {
+    return (int64_t)back_layout(C, tile_w, tile_h, n_coarse).total;
+}
+
+extern "C" int fg_render_back(int C, int N, int64_t n_isects, int64_t n_coarse, const int32_t* order,
+                              const int32_t* coarse_off, const float* means2d, const int32_t* radii, int tile_size,
+                              const int32_t* isect_offsets, int32_t* flatten_ids, void* workspace,
+                              int64_t workspace_bytes, int CH, int width, int height, const float* conics,
+                              const float* feat, const float* opacities, const float* backgrounds,
+                              const float* flow_affine, int flow_ch0, int split, int ed_channel, int opac_shared,
+                              float* render, float* render2, float* alphas, int32_t* last_ids, void* stream) {
+    FG_REQUIRE(workspace, "workspace must not be NULL");
+    const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
+    const BackLayout L = back_layout(C, tile_w, tile_h, n_coarse);
+    FG_REQUIRE((size_t)workspace_bytes >= L.total, "back workspace too small");
+    unsigned char* ws = (unsigned char*)workspace;
+    int e;
+    if (n_isects > 0) {
+        FG_REQUIRE(flatten_ids && order && coarse_off, "NULL pointer");
+        int cw = 0, chh = 0;
+        fg_bin_coarse_dims(tile_w, tile_h, &cw, &chh);
+        uint32_t* ck = (uint32_t*)(ws + L.ck);
+        int32_t* cv = (int32_t*)(ws + L.cv);
+        uint32_t* ck2 = (uint32_t*)(ws + L.ck2);
+        int32_t* cv2 = (int32_t*)(ws + L.cv2);
+        if ((e = fg_bin_coarse_emit(C, N, order, means2d, radii, coarse_off, tile_size, tile_w, tile_h, ck, cv, stream)))
+            return e;
+        int bits = 1;
+        while ((1ll << bits) < (long long)C * cw * chh) ++bits;
+        int sel = 0;
+        if ((e = fg_radix_sort_pairs_u32_u32(n_coarse, ck, (uint32_t*)cv, ck2, (uint32_t*)cv2, bits, ws + L.sort,
+                                             (int64_t)(L.total - L.sort), &sel, stream)))
+            return e;
+        const uint32_t* ks = sel ? ck2 : ck;
+        const int32_t* vs = sel ? cv2 : cv;
+        int32_t* coff = (int32_t*)(ws + L.coff);
+        if ((e = fg_isect_offsets_tiles(n_coarse, ks, C, cw, chh, coff, stream))) return e;
+        if ((e = fg_bin_fine(C, N, n_coarse, coff, vs, means2d, radii, tile_size, tile_w, tile_h, isect_offsets,
+                             flatten_ids, stream)))
+            return e;
+    }
+    return fg_rasterize_fwd(C, N, CH, width, height, tile_size, means2d, conics, feat, opacities, backgrounds,
+                            flow_affine, flow_ch0, split, ed_channel, opac_shared, isect_offsets, flatten_ids, n_isects,
+                            render, render2, alphas, last_ids, stream);
+}

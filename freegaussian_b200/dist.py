@@ -63,7 +63,14 @@ class GradBucket:
 
 
 class DensificationStats:
-    """``xys_grad_norm`` / ``vis_counts`` / ``max_2Dsize`` of ``freegaussian_model.py:369-392``."""
+    """``xys_grad_norm`` / ``vis_counts`` / ``max_2Dsize`` of ``freegaussian_model.py:369-392``.
+
+    Every step costs one fused kernel (``fg_densify_stats``) that folds the rank's views into per-rank
+    accumulators.  All three statistics are plain accumulators (SUM, SUM, MAX), so the cross-rank
+    reduction is only needed when they are consumed -- the refinement step every ``refine_every`` = 100
+    iterations (``config/sim/base.yaml:22``): :meth:`sync` all-reduces what was accumulated since the last
+    sync and folds it into the public running values, which then equal what a single process rendering
+    every view (or a per-step reduction) would hold."""
 
     def __init__(self, n: int, device):
         self.xys_grad_norm = torch.zeros(n, dtype=torch.float32, device=device)
@@ -92,33 +99,11 @@ class DensificationStats:
         size = radii.to(torch.float32) / float(max(height, width))
         self._local_size = torch.maximum(self._local_size, size.max(0).values)
 
-    def sum_tensors(self) -> List[Tensor]:
-        """Per-step buffers reduced with SUM (so they can ride in the gradients' coalesced all-reduce)."""
-        return [self._local_grad, self._local_vis]
-
-    def max_tensors(self) -> List[Tensor]:
-        return [self._local_size]
-
     @torch.no_grad()
     def sync(self, group=None) -> None:
-        """Cross-rank reduction of the RUNNING statistics (SUM, SUM, MAX).  All three are plain
-        accumulators, so summing / maxing once right before they are consumed -- the refinement
-        step every ``refine_every`` = 100 iterations (``config/sim/base.yaml:22``) -- gives exactly what a
-        per-step reduction would, and keeps the statistics out of the per-step exchange.  Every rank
-        starts ``vis_counts`` at one (``freegaussian_model.py:380``); the extra ``G - 1`` are removed."""
+        """SUM, SUM, MAX across ranks of everything accumulated since the last sync, folded into the
+        running statistics.  Call right before the statistics are read (refinement), or every step."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            g = dist.get_world_size(group)
-            packed = torch.stack([self.xys_grad_norm, self.vis_counts])
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-            self.xys_grad_norm, self.vis_counts = packed[0], packed[1] - float(g - 1)
-            dist.all_reduce(self.max_2Dsize, op=dist.ReduceOp.MAX, group=group)
-
-    @torch.no_grad()
-    def reduce(self, group=None, already_reduced: bool = False) -> None:
-        """The exchange step: SUM, SUM, MAX across ranks, then fold into the running statistics.
-        ``already_reduced``: the buffers were reduced by :func:`exchange`; only fold."""
-        if (not already_reduced and dist.is_available() and dist.is_initialized()
-                and dist.get_world_size(group) > 1):
             packed = torch.stack([self._local_grad, self._local_vis])
             dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
             self._local_grad, self._local_vis = packed[0], packed[1]
@@ -130,51 +115,44 @@ class DensificationStats:
         self._local_vis = torch.zeros_like(self._local_vis)
         self._local_size = torch.zeros_like(self._local_size)
 
+    reduce = sync  # per-step use
 
-def exchange(grads: Sequence[Tensor], stats: Optional[DensificationStats] = None, group=None) -> None:
+
+def exchange(grads: Sequence[Tensor], group=None) -> None:
     """THE exchange step of a view-sharded training step: all-reduce(SUM) of every
-    parameter gradient.  With ``stats`` given, the two summed statistics and ``max_2Dsize`` are reduced
-    in the same step and folded; the cheaper, equivalent schedule is ``stats.reduce(already_reduced=True)``
-    (local fold) every step and ``stats.sync()`` only when the statistics are consumed.
+    parameter gradient.  (The densification statistics are reduced by ``DensificationStats.sync``.)
 
     The projection backward writes all of its parameter gradients into one flat buffer
     (``rendering.last_grad_arena()``); gradients living there are reduced by ONE collective over that
-    buffer, and the small leftovers (opacity gradient, the two summed statistics) ride in its spare
-    tail.  Nine separate collectives cost ~0.4 ms of launch latency per step on top of the ~0.35 ms the
-    236 MB need on NVLink at 1 M Gaussians."""
-    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    if multi:
-        from . import rendering
-        grads = [g for g in grads if g is not None]
-        sums = list(stats.sum_tensors()) if stats is not None else []
-        info = rendering.last_grad_arena() if grads and grads[0].is_cuda else None
-        loose = grads
-        if info is not None:
-            arena, used = info
-            base = arena.untyped_storage().data_ptr()
-            inside = [g for g in grads if g.untyped_storage().data_ptr() == base]
-            loose = [g for g in grads if g.untyped_storage().data_ptr() != base]
-            if inside:
-                small = [t for t in loose + sums if t.is_contiguous()]
-                n_small = sum(t.numel() for t in small)
-                if n_small <= arena.numel() - used:
-                    tail = arena[used:used + n_small]
-                    if small:
-                        torch.cat([t.reshape(-1) for t in small], out=tail)
-                    dist.all_reduce(arena[:used + n_small], op=dist.ReduceOp.SUM, group=group)
-                    o = 0
-                    for t in small:
-                        t.copy_(tail[o:o + t.numel()].view_as(t))
-                        o += t.numel()
-                    loose = [t for t in loose + sums if not t.is_contiguous()]
-                    sums = []
-                else:
-                    dist.all_reduce(arena[:used], op=dist.ReduceOp.SUM, group=group)
-        works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in loose + sums]
-        if stats is not None:
-            for t in stats.max_tensors():
-                works.append(dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group, async_op=True))
-        for w in works:
-            w.wait()
-    if stats is not None:
-        stats.reduce(group, already_reduced=multi)
+    buffer, and small leftovers (the opacity gradient) ride in its spare tail.  Separate collectives per
+    tensor cost ~0.25 ms of launch latency per step on top of the ~0.5 ms the 236 MB need on NVLink at
+    1 M Gaussians."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    from . import rendering
+    grads = [g for g in grads if g is not None]
+    info = rendering.last_grad_arena() if grads and grads[0].is_cuda else None
+    loose = grads
+    if info is not None:
+        arena, used = info
+        base = arena.untyped_storage().data_ptr()
+        inside = [g for g in grads if g.untyped_storage().data_ptr() == base]
+        loose = [g for g in grads if g.untyped_storage().data_ptr() != base]
+        if inside:
+            small = [t for t in loose if t.is_contiguous()]
+            n_small = sum(t.numel() for t in small)
+            if n_small <= arena.numel() - used:
+                tail = arena[used:used + n_small]
+                if small:
+                    torch.cat([t.reshape(-1) for t in small], out=tail)
+                dist.all_reduce(arena[:used + n_small], op=dist.ReduceOp.SUM, group=group)
+                o = 0
+                for t in small:
+                    t.copy_(tail[o:o + t.numel()].view_as(t))
+                    o += t.numel()
+                loose = [t for t in loose if not t.is_contiguous()]
+            else:
+                dist.all_reduce(arena[:used], op=dist.ReduceOp.SUM, group=group)
+    works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in loose]
+    for w in works:
+        w.wait()

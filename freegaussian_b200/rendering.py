@@ -28,6 +28,7 @@ from . import _lib
 from ._lib import check, ptr
 
 MAX_CH = 8  # FG_MAX_CHANNELS
+FUSED_CALLS = True  # forward pass through fg_render_front / fg_render_back (two C calls) when possible
 SORT_MODE = "binned"  # "binned" | "two_level" | "key64" (the reference's literal 64-bit key sort); same lists
 
 
@@ -152,13 +153,33 @@ class _Project(torch.autograd.Function):
         feat = torch.empty(C, N, CH, device=dev)
         tiles = torch.empty(C, N, dtype=torch.int32, device=dev)
         flow_affine = torch.empty(C, N, 4, device=dev) if flow_cov else None
-        with _stage("project_fwd"):
-          check(L.fg_project_fwd(
-            C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
-            cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"], cfg["tile_size"],
-            sh_degree if use_sh else -1, sh_bases, ptr(colors) if use_sh else None, ptr(means_next), ptr(quats_next),
-            ptr(scales_next), int(flow_cov), ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(feat),
-            CH, rgb_off, depth_off, flow_off, ptr(flow_affine), ptr(tiles), _stream()))
+        if cfg.get("fused"):
+            # projection + depth sort + binning up to the host sync, in one C call
+            tile_w = math.ceil(cfg["width"] / cfg["tile_size"])
+            tile_h = math.ceil(cfg["height"] / cfg["tile_size"])
+            order = torch.empty(C * N, dtype=torch.int32, device=dev)
+            coarse_off = torch.empty(C * N, dtype=torch.int32, device=dev)
+            isect_offsets = torch.empty(C, tile_h, tile_w, dtype=torch.int32, device=dev)
+            ws = _ws.get("front", L.fg_render_front_workspace_bytes(C, N, tile_w, tile_h), dev)
+            counts = (ctypes.c_int64 * 2)()
+            check(L.fg_render_front(
+                C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
+                cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"], cfg["tile_size"],
+                sh_degree if use_sh else -1, sh_bases, ptr(colors) if use_sh else None, ptr(means_next),
+                ptr(quats_next), ptr(scales_next), int(flow_cov), ptr(radii), ptr(means2d), ptr(depths), ptr(conics),
+                ptr(comps), ptr(feat), CH, rgb_off, depth_off, flow_off, ptr(flow_affine), ptr(tiles), ptr(order),
+                ptr(isect_offsets), ptr(coarse_off), counts, ptr(ws), ws.numel(), _stream()))
+            cfg["_front"] = dict(order=order, coarse_off=coarse_off, isect_offsets=isect_offsets, M=int(counts[0]),
+                                 Mc=int(counts[1]), tile_w=tile_w, tile_h=tile_h)
+        else:
+            with _stage("project_fwd"):
+                check(L.fg_project_fwd(
+                    C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
+                    cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"], cfg["tile_size"],
+                    sh_degree if use_sh else -1, sh_bases, ptr(colors) if use_sh else None, ptr(means_next),
+                    ptr(quats_next), ptr(scales_next), int(flow_cov), ptr(radii), ptr(means2d), ptr(depths),
+                    ptr(conics), ptr(comps), ptr(feat), CH, rgb_off, depth_off, flow_off, ptr(flow_affine),
+                    ptr(tiles), _stream()))
         if not use_sh and colors is not None:
             feat[..., :n_col] = colors if colors.dim() == 3 else colors[None]
         ctx.save_for_backward(means, quats, scales, colors if use_sh else None, means_next, quats_next, scales_next,
@@ -381,7 +402,7 @@ class _Rasterize(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, feat, opacities, backgrounds, isect_offsets, flatten_ids, width, height,
-                tile_size, absgrad, split, ed_channel, chunked, flow_affine=None):
+                tile_size, absgrad, split, ed_channel, chunked, flow_affine=None, front=None):
         L = _lib.lib()
         ctx.chunked = chunked
         C = isect_offsets.shape[0]
@@ -398,11 +419,21 @@ class _Rasterize(torch.autograd.Function):
         alphas = torch.empty(C, height, width, 1, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
         M = flatten_ids.shape[0]
-        with _stage("rasterize_fwd"):
-            check(L.fg_rasterize_fwd(C, n_shared if opac_shared else NN, CH, width, height, tile_size, ptr(means2d_c),
-                                     ptr(conics_c), ptr(feat_c), ptr(opac_c), ptr(bg), ptr(aff), split, split, ed_channel,
-                                     opac_shared, ptr(isect_offsets), ptr(flatten_ids), M, ptr(render), ptr(render2),
-                                     ptr(alphas), ptr(last_ids), _stream()))
+        n_arg = n_shared if opac_shared else NN
+        if front is not None:
+            # coarse emit + sort + cell offsets + fine binning + compositing, in one C call
+            ws = _ws.get("back", L.fg_render_back_workspace_bytes(C, front["tile_w"], front["tile_h"], front["Mc"]), dev)
+            check(L.fg_render_back(C, NN // C, M, front["Mc"], ptr(front["order"]), ptr(front["coarse_off"]),
+                                   ptr(means2d_c), ptr(front["radii"]), tile_size, ptr(isect_offsets), ptr(flatten_ids),
+                                   ptr(ws), ws.numel(), CH, width, height, ptr(conics_c), ptr(feat_c), ptr(opac_c),
+                                   ptr(bg), ptr(aff), split, split, ed_channel, opac_shared, ptr(render), ptr(render2),
+                                   ptr(alphas), ptr(last_ids), _stream()))
+        else:
+            with _stage("rasterize_fwd"):
+                check(L.fg_rasterize_fwd(C, n_arg, CH, width, height, tile_size, ptr(means2d_c), ptr(conics_c),
+                                         ptr(feat_c), ptr(opac_c), ptr(bg), ptr(aff), split, split, ed_channel,
+                                         opac_shared, ptr(isect_offsets), ptr(flatten_ids), M, ptr(render),
+                                         ptr(render2), ptr(alphas), ptr(last_ids), _stream()))
         ctx.save_for_backward(means2d_c, conics_c, feat_c, opac_c, bg, isect_offsets, flatten_ids, alphas, last_ids,
                               render if ed_channel >= 0 else None, aff)
         ctx.dims = (C, NN, CH, width, height, tile_size, absgrad, split, ed_channel, opac_shared, n_shared)
@@ -456,7 +487,7 @@ class _Rasterize(torch.autograd.Function):
                 vr = vr.clone()
                 vr[..., ed_channel] = 0
             v_bg = (vr * (1.0 - alphas)).sum(dim=(1, 2))
-        return (v_means2d, v_conics, v_feat, v_opac, v_bg) + (None,) * 9 + (v_aff,)
+        return (v_means2d, v_conics, v_feat, v_opac, v_bg) + (None,) * 9 + (v_aff, None)
 
 
 def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets,
@@ -555,6 +586,10 @@ def rasterization(
                far_plane=float(far_plane), radius_clip=float(radius_clip), tile_size=int(tile_size),
                sh_degree=None if only_depth else sh_degree, want_depth=want_depth,
                antialiased=rasterize_mode == "antialiased", flow_cov=flow_mode == "cov" and means_next is not None)
+    n_feat = (0 if only_depth else (3 if sh_degree is not None else colors.shape[-1])) + int(want_depth) + (
+        2 if means_next is not None else 0)
+    cfg["fused"] = bool(FUSED_CALLS and SORT_MODE == "binned" and not stage_timer.enabled and not packed
+                        and n_feat <= MAX_CH)
     proj_colors = None if only_depth else colors
     radii, means2d, depths, conics, comps, feat, tiles, flow_affine = _Project.apply(
         means, quats, scales, proj_colors, means_next, quats_next, scales_next, viewmats, Ks, cfg)
@@ -575,8 +610,15 @@ def rasterization(
 
     tile_w = math.ceil(width / tile_size)
     tile_h = math.ceil(height / tile_size)
-    isect_ids, flatten_ids, isect_offsets, tile_keys = isect_tiles(means2d, radii, depths, tiles, tile_size, tile_w,
-                                                                   tile_h, mode=SORT_MODE)
+    front = cfg.pop("_front", None)
+    if front is not None:
+        isect_ids, tile_keys = None, None
+        isect_offsets = front["isect_offsets"]
+        flatten_ids = torch.empty(front["M"], dtype=torch.int32, device=means.device)  # filled by fg_render_back
+        front["radii"] = radii
+    else:
+        isect_ids, flatten_ids, isect_offsets, tile_keys = isect_tiles(means2d, radii, depths, tiles, tile_size, tile_w,
+                                                                       tile_h, mode=SORT_MODE)
 
     meta = _Meta()
     if isect_ids is None:
@@ -616,7 +658,7 @@ def rasterization(
     if CH <= MAX_CH:
         render, flow_img, alphas, last_ids = _Rasterize.apply(
             means2d, conics, feat, opac, backgrounds, isect_offsets, flatten_ids, width, height, tile_size, absgrad,
-            n_user, ed_channel, False, flow_affine)
+            n_user, ed_channel, False, flow_affine, front)
         if means_next is not None:
             flow = flow_img
     else:  # many user colour channels: chunks of 8, normalisation / split done by torch

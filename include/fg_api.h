@@ -204,6 +204,30 @@ int fg_rasterize_bwd(int C, int N, int CH, int width, int height, int tile_size,
 int fg_densify_stats(int C, int N, const int32_t* radii, const float* absgrad, float inv_max_hw,
                      float* grad_norm, float* vis_count, float* max_size, void* stream);
 
+/* ---- (3b) the forward pass in two calls ------------------------------------------------------
+ * fg_render_front = fg_project_fwd + depth sort + fg_bin_count + fg_bin_tile_scan + the coarse scan,
+ * then the ONE host synchronisation of the pass: counts_host[0] = M (tile intersections),
+ * counts_host[1] = Mc (coarse pairs).  The caller allocates flatten_ids[M] and calls
+ * fg_render_back = coarse emit + sort + cell offsets + fg_bin_fine + fg_rasterize_fwd.
+ * Arguments are those of the granular entry points; `order`, `coarse_off` are [C*N] int32. */
+int64_t fg_render_front_workspace_bytes(int C, int N, int tile_w, int tile_h);
+int fg_render_front(int C, int N, const float* means, const float* quats, const float* scales,
+                    const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                    float near_plane, float far_plane, float radius_clip, int tile_size, int sh_degree,
+                    int sh_bases, const float* sh_coeffs, const float* means_next, const float* quats_next,
+                    const float* scales_next, int flow_cov, int32_t* radii, float* means2d, float* depths,
+                    float* conics, float* compensations, float* feat, int feat_stride, int rgb_off,
+                    int depth_off, int flow_off, float* flow_affine, int32_t* tiles_per_gauss, int32_t* order,
+                    int32_t* isect_offsets, int32_t* coarse_off, int64_t* counts_host, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+int64_t fg_render_back_workspace_bytes(int C, int tile_w, int tile_h, int64_t n_coarse);
+int fg_render_back(int C, int N, int64_t n_isects, int64_t n_coarse, const int32_t* order,
+                   const int32_t* coarse_off, const float* means2d, const int32_t* radii, int tile_size,
+                   const int32_t* isect_offsets, int32_t* flatten_ids, void* workspace, int64_t workspace_bytes,
+                   int CH, int width, int height, const float* conics, const float* feat, const float* opacities,
+                   const float* backgrounds, const float* flow_affine, int flow_ch0, int split, int ed_channel,
+                   int opac_shared, float* render, float* render2, float* alphas, int32_t* last_ids, void* stream);
+
 /* ---- (4) exact k-nearest neighbours ----------------------------------------------------
  * Replaces FreeGaussianModel.k_nearest_sklearn (freegaussian_model.py:293-311):
  * sklearn NearestNeighbors(n_neighbors=k+1, metric="euclidean") of the set against itself

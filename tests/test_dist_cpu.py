@@ -39,7 +39,8 @@ def _worker(rank, world, port, n, out):
         stats.accumulate_local(radii[v:v + 1], absgrad[v:v + 1], 100, 200)
         for p, g in zip(params, grads):
             p.grad += g * (v + 1)  # pretend per-view gradient
-    exchange([bucket.flat], stats)  # coalesced SUM of grads + stats, MAX of sizes, then fold
+    exchange([bucket.flat])
+    stats.sync()
     if rank == 0:
         torch.save({"g": stats.xys_grad_norm, "c": stats.vis_counts, "m": stats.max_2Dsize,
                     "p0": params[0].grad.clone(), "p1": params[1].grad.clone()}, out)
@@ -86,7 +87,6 @@ def _worker_sync(rank, world, port, n, out):
         radii, absgrad, _ = _views(n, step)
         for v in shard_views(4, rank, world):
             stats.accumulate_local(radii[v:v + 1], absgrad[v:v + 1], 100, 200)
-        stats.reduce(already_reduced=True)
     stats.sync()
     if rank == 0:
         torch.save({"g": stats.xys_grad_norm, "c": stats.vis_counts, "m": stats.max_2Dsize}, out)

@@ -26,7 +26,7 @@ def step(i, with_stats=True):
     loss = (render * wr).sum() + (meta["flow"] * wf).sum()
     loss.backward()
     if with_stats:
-        stats.accumulate_local(meta["radii"], meta["means2d"].absgrad, H, W); stats.reduce()
+        stats.accumulate_local(meta["radii"], meta["means2d"].absgrad, H, W)
 
 for i in range(5): step(i)
 torch.cuda.synchronize()
