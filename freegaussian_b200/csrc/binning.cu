@@ -118,17 +118,21 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- step 5 -------------------------------------------------------------------------------
-// CTA = coarse cell.  Chunks of 256 list entries (thread = entry); for each of the cell's 16
+// CTA = coarse cell.  Chunks of FB_THREADS list entries (thread = entry); for each of the cell's 16
 // tiles the entries that overlap it are ranked with a ballot + per-warp prefix and appended to
-// the tile's list.  Running per-tile cursors live in shared memory.
-__global__ void __launch_bounds__(256)
+// the tile's list.  Running per-tile cursors live in shared memory.  The chunks of a cell are
+// sequential (three barriers each), so the CTA is made as wide as possible: with 256 threads the
+// kernel time was the longest cell's ~30 chunks (ncu r1_final: 129 us, long-scoreboard bound).
+constexpr int FB_THREADS = 1024;
+constexpr int FB_WARPS = FB_THREADS / 32;
+__global__ void __launch_bounds__(FB_THREADS)
     fine_bin_kernel(int N, const int32_t* __restrict__ coarse_offsets /*[n_cells]*/, long long n_coarse,
                     int n_cells_total, const int32_t* __restrict__ coarse_vals, const float2* __restrict__ means2d,
                     const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
                     const int32_t* __restrict__ isect_offsets, int32_t* __restrict__ flatten_ids) {
     constexpr int NT = CK * CK;
     __shared__ int s_cursor[NT];       // entries already written per tile
-    __shared__ int s_warp_cnt[8][NT];  // per chunk: entries per (warp, tile)
+    __shared__ int s_warp_cnt[FB_WARPS][NT];  // per chunk: entries per (warp, tile)
     __shared__ int s_tile_off[NT];     // isect_offsets of the cell's tiles (-1 = outside the image)
     const int cell = blockIdx.x;
     const int cam = cell / (cw * chh);
@@ -154,13 +158,13 @@ __global__ void __launch_bounds__(256)
         m_n = means2d[id_n];
         r_n = radii[id_n];
     }
-    for (int base = start; base < end; base += 256) {
+    for (int base = start; base < end; base += FB_THREADS) {
         const int e = base + tid;
         const int id = id_n;
         const float2 m = m_n;
         const int r = r_n;
-        if (e + 256 < end) {
-            id_n = coarse_vals[e + 256];
+        if (e + FB_THREADS < end) {
+            id_n = coarse_vals[e + FB_THREADS];
             m_n = means2d[id_n];
             r_n = radii[id_n];
         }
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(256)
         if (tid < NT) {
             int run = s_cursor[tid];
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
+            for (int w = 0; w < FB_WARPS; ++w) {
                 const int c = s_warp_cnt[w][tid];
                 s_warp_cnt[w][tid] = run;
                 run += c;
@@ -275,7 +279,7 @@ extern "C" int fg_bin_fine(int C, int N, int64_t n_coarse, const int32_t* coarse
     FG_REQUIRE(coarse_offsets && coarse_vals_sorted && means2d && radii && isect_offsets && flatten_ids, "NULL pointer");
     const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
     const int n_cells = C * cw * chh;
-    FG_LAUNCH(fine_bin_kernel, n_cells, 256, 0, stream, N, coarse_offsets, (long long)n_coarse, n_cells,
+    FG_LAUNCH(fine_bin_kernel, n_cells, FB_THREADS, 0, stream, N, coarse_offsets, (long long)n_coarse, n_cells,
               coarse_vals_sorted, (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, isect_offsets,
               flatten_ids);
     return FG_OK;

@@ -74,7 +74,8 @@ extern "C" int fg_render_front(int C, int N, const float* means, const float* qu
                                int depth_off, int flow_off, float* flow_affine, int32_t* tiles_per_gauss,
                                int32_t* order, int32_t* isect_offsets, int32_t* coarse_off, int64_t* counts_host,
                                void* workspace, int64_t workspace_bytes, void* stream) {
-    FG_REQUIRE(order && isect_offsets && coarse_off && counts_host && workspace, "NULL pointer");
+    FG_REQUIRE(isect_offsets && counts_host && workspace, "NULL pointer");
+    FG_REQUIRE((long long)C * N == 0 || (order && coarse_off), "order / coarse_off must not be NULL");
     const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
     const FrontLayout L = front_layout(C, N, tile_w, tile_h);
     FG_REQUIRE((size_t)workspace_bytes >= L.total, "front workspace too small");

@@ -54,6 +54,8 @@ struct ProjParams {
     const float* v_comps;
     const float* v_feat;
     const float* v_flow_affine;
+    const float* feat_fwd;      // forward `feat` (its rgb channels give the clamp mask of the SH colours)
+    const float* v_mean_extra;  // [N,3] added to v_means (the SH direction term when SH runs in its own kernel)
     // backward outputs
     float* v_means;
     float* v_quats;
@@ -408,7 +410,8 @@ __global__ void __launch_bounds__(PB, 3) project_bwd_kernel(ProjParams p) {
             } else { v_s[0] += v_sn[0]; v_s[1] += v_sn[1]; v_s[2] += v_sn[2]; }
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) p.v_means[3 * (size_t)n + i] = v_mean[i];
+        for (int i = 0; i < 3; ++i)
+            p.v_means[3 * (size_t)n + i] = v_mean[i] + (p.v_mean_extra ? p.v_mean_extra[3 * (size_t)n + i] : 0.f);
         reinterpret_cast<float4*>(p.v_quats)[n] = make_float4(v_q[0], v_q[1], v_q[2], v_q[3]);
 #pragma unroll
         for (int i = 0; i < 3; ++i) p.v_scales[3 * (size_t)n + i] = v_s[i];
@@ -457,6 +460,123 @@ __global__ void __launch_bounds__(PB, 3) project_bwd_kernel(ProjParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------ SH backward
+// The spherical-harmonics half of the backward pass as its own streaming kernel (16-base rows,
+// 16-byte aligned): v_sh rows are accumulated in shared memory and written with coalesced
+// float4 stores; coefficients are consumed four bases (three float4) at a time straight from a
+// staged copy or from global memory, so no 48-float arrays live in registers (the fused kernel
+// needed 168-250 registers and ran at 12-18 % occupancy).  The clamp mask of max(rgb + 0.5, 0)
+// comes from the forward colours in `feat`.  Also writes the direction term of v_means, which
+// the geometry kernel (project_bwd_kernel<-1>) then adds to its own.
+template <int DEG>
+__global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int K = (DEG + 1) * (DEG + 1);
+    constexpr int NG = (K + 3) / 4;   // groups of four bases
+    constexpr int NV3 = NG * 3;       // float4 per row that carry gradient
+    constexpr int ROW = 13;           // odd float4 row stride: conflict-free own-row access
+    float4* acc = reinterpret_cast<float4*>(smem) + threadIdx.x * ROW;
+    float4* stg_all = reinterpret_cast<float4*>(smem) + PB * ROW;
+    const int n0 = blockIdx.x * PB;
+    const int n = n0 + threadIdx.x;
+    const bool in_range = n < p.N;
+    const int gv = p.sh_row_floats >> 2;
+#pragma unroll
+    for (int j = 0; j < NV3; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool vis_any = false;
+    if (in_range && p.v_feat)
+        for (int c = 0; c < p.C; ++c) vis_any |= p.radii_in[(size_t)c * p.N + n] > 0;
+    const int nvis = __syncthreads_count(vis_any);
+    const bool staged = nvis * 2 >= PB;
+    if (staged) {
+        const float4* src = reinterpret_cast<const float4*>(p.sh);
+        const int rows = min(PB, p.N - n0);
+        for (int q = threadIdx.x; q < rows * NV3; q += PB) {
+            const int g = q / NV3, j = q - g * NV3;
+            stg_all[g * ROW + j] = __ldg(src + (size_t)(n0 + g) * gv + j);
+        }
+        __syncthreads();
+    }
+    float v_md[3] = {0.f, 0.f, 0.f};
+    if (vis_any) {
+        float m[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) m[i] = __ldg(p.means + 3 * (size_t)n + i);
+        const float4* crow = staged ? stg_all + threadIdx.x * ROW
+                                    : reinterpret_cast<const float4*>(p.sh) + (size_t)n * gv;
+        for (int c = 0; c < p.C; ++c) {
+            const size_t i = (size_t)c * p.N + n;
+            if (p.radii_in[i] <= 0) continue;
+            const Camera cam = load_camera(p.viewmats + 16 * c, p.Ks + 9 * c);
+            const float dx = m[0] - cam.pos[0], dy = m[1] - cam.pos[1], dz = m[2] - cam.pos[2];
+            const float inorm = rsqrt_f(dx * dx + dy * dy + dz * dz);
+            const float x = dx * inorm, y = dy * inorm, z = dz * inorm;
+            float B[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) B[k] = 0.f;
+            sh_basis(DEG, x, y, z, B);
+            const float* ff = p.feat_fwd + i * p.feat_stride + p.rgb_off;
+            const float* vf = p.v_feat + i * p.feat_stride + p.rgb_off;
+            float vr[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) vr[ch] = (ff[ch] > 0.f) ? vf[ch] : 0.f;
+            float sk[16];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                float f[12];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float4 v = staged ? crow[3 * g + j] : __ldg(crow + 3 * g + j);
+                    f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+                }
+                float a[12];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float4 v = acc[3 * g + j];
+                    a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int k = 4 * g + b;
+                    sk[k] = f[3 * b] * vr[0] + f[3 * b + 1] * vr[1] + f[3 * b + 2] * vr[2];
+                    a[3 * b] = fmaf(B[k], vr[0], a[3 * b]);
+                    a[3 * b + 1] = fmaf(B[k], vr[1], a[3 * b + 1]);
+                    a[3 * b + 2] = fmaf(B[k], vr[2], a[3 * b + 2]);
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[3 * g + j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+            }
+            float vd[3];
+            sh_basis_vjp(DEG, x, y, z, sk, vd);
+            const float dot = vd[0] * x + vd[1] * y + vd[2] * z;
+            v_md[0] += (vd[0] - dot * x) * inorm;
+            v_md[1] += (vd[1] - dot * y) * inorm;
+            v_md[2] += (vd[2] - dot * z) * inorm;
+        }
+    }
+    if (in_range) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p.v_means[3 * (size_t)n + i] = v_md[i];
+    }
+    __syncthreads();
+    // coalesced write of full rows (zeros beyond the evaluated bases)
+    const int rows = min(PB, p.N - n0);
+    float4* dst = reinterpret_cast<float4*>(p.v_sh);
+    const float4* src = reinterpret_cast<const float4*>(smem);
+    for (int qd = threadIdx.x; qd < rows * gv; qd += PB) {
+        const int g = qd / gv, j = qd - g * gv;
+        dst[(size_t)(n0 + g) * gv + j] = (j < NV3) ? src[g * ROW + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int DEG>
+static int launch_sh_bwd(const ProjParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)2 * PB * 13 * 16;
+    FG_CUDA(cudaFuncSetAttribute(sh_bwd_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FG_LAUNCH((sh_bwd_kernel<DEG>), ceil_div(p.N, PB), PB, smem, st, p);
+    return FG_OK;
+}
+
 template <int DEG, bool VEC4>
 static int launch_fwd(const ProjParams& p, cudaStream_t st) {
     using S = ShShape<(DEG >= 0 ? DEG : 0)>;
@@ -498,6 +618,7 @@ extern "C" int fg_project_fwd(int C, int N, const float* means, const float* qua
                               float* means2d, float* depths, float* conics, float* compensations, float* feat,
                               int feat_stride, int rgb_off, int depth_off, int flow_off, float* flow_affine,
                               int32_t* tiles_per_gauss, void* stream) {
+    if (C >= 1 && N == 0) return FG_OK;  // nothing to project (empty tensors have NULL data pointers)
     if (int e = check_common(C, N, means, quats, scales, viewmats, Ks, sh_degree, sh_bases, sh_coeffs)) return e;
     FG_REQUIRE(width > 0 && height > 0 && tile_size > 0, "width/height/tile_size must be positive");
     FG_REQUIRE(!flow_cov || (means_next && flow_affine), "covariance flow mode needs means_next and flow_affine");
@@ -534,10 +655,11 @@ extern "C" int fg_project_bwd(int C, int N, const float* means, const float* qua
                               const float* quats_next, const float* scales_next, int flow_cov,
                               const int32_t* radii, const float* v_means2d, const float* v_depths,
                               const float* v_conics, const float* v_compensations, const float* v_feat,
-                              int feat_stride, int rgb_off, int depth_off, int flow_off,
+                              const float* feat, int feat_stride, int rgb_off, int depth_off, int flow_off,
                               const float* v_flow_affine, float* v_means, float* v_quats, float* v_scales,
                               float* v_sh, float* v_means_next, float* v_quats_next, float* v_scales_next,
                               void* stream) {
+    if (C >= 1 && N == 0) return FG_OK;
     if (int e = check_common(C, N, means, quats, scales, viewmats, Ks, sh_degree, sh_bases, sh_coeffs)) return e;
     FG_REQUIRE(!flow_cov || means_next, "covariance flow mode needs means_next");
     FG_REQUIRE(radii && v_means && v_quats && v_scales, "radii and v_means/v_quats/v_scales must not be NULL");
@@ -558,6 +680,22 @@ extern "C" int fg_project_bwd(int C, int N, const float* means, const float* qua
     p.v_means = v_means; p.v_quats = v_quats; p.v_scales = v_scales; p.v_sh = v_sh; p.v_means_next = v_means_next;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec4 = (p.sh_row_floats % 4 == 0) && ((uintptr_t)sh_coeffs % 16 == 0) && ((uintptr_t)v_sh % 16 == 0);
+    if (sh_degree >= 0 && vec4 && sh_bases % 4 == 0 && feat != nullptr) {
+        // two kernels: streaming SH backward (writes v_sh and the direction term into v_means), then
+        // the geometry VJP, which adds that term to its own v_means
+        p.feat_fwd = feat;
+        int e;
+        switch (sh_degree) {
+            case 0: e = launch_sh_bwd<0>(p, st); break;
+            case 1: e = launch_sh_bwd<1>(p, st); break;
+            case 2: e = launch_sh_bwd<2>(p, st); break;
+            default: e = launch_sh_bwd<3>(p, st); break;
+        }
+        if (e) return e;
+        p.v_mean_extra = v_means;
+        p.rgb_off = -1;
+        return launch_bwd<-1, true>(p, st);
+    }
     switch (sh_degree) {
         case -1: return launch_bwd<-1, true>(p, st);
         case 0: return vec4 ? launch_bwd<0, true>(p, st) : launch_bwd<0, false>(p, st);

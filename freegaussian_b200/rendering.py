@@ -183,7 +183,7 @@ class _Project(torch.autograd.Function):
         if not use_sh and colors is not None:
             feat[..., :n_col] = colors if colors.dim() == 3 else colors[None]
         ctx.save_for_backward(means, quats, scales, colors if use_sh else None, means_next, quats_next, scales_next,
-                              viewmats, Ks, radii)
+                              viewmats, Ks, radii, feat if use_sh else None)
         ctx.cfg = cfg
         ctx.layout = (CH, n_col, rgb_off, depth_off, flow_off, sh_bases, use_sh,
                       None if colors is None else colors.dim(), flow_cov)
@@ -199,7 +199,7 @@ class _Project(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_feat, _v_tiles, v_flow_affine):
         L = _lib.lib()
-        means, quats, scales, sh, means_next, quats_next, scales_next, viewmats, Ks, radii = ctx.saved_tensors
+        means, quats, scales, sh, means_next, quats_next, scales_next, viewmats, Ks, radii, feat_fwd = ctx.saved_tensors
         cfg = ctx.cfg
         CH, n_col, rgb_off, depth_off, flow_off, sh_bases, use_sh, col_dim, flow_cov = ctx.layout
         C, N = viewmats.shape[0], means.shape[0]
@@ -229,8 +229,8 @@ class _Project(torch.autograd.Function):
             C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
             cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"],
             cfg["sh_degree"] if use_sh else -1, sh_bases, ptr(sh), ptr(means_next), ptr(quats_next), ptr(scales_next),
-            int(flow_cov), ptr(radii), ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_feat), CH,
-            rgb_off, depth_off, flow_off, ptr(v_flow_affine), ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_sh),
+            int(flow_cov), ptr(radii), ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_feat),
+            ptr(feat_fwd), CH, rgb_off, depth_off, flow_off, ptr(v_flow_affine), ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_sh),
             ptr(v_means_next), ptr(v_quats_next), ptr(v_scales_next), _stream()))
         v_colors = None
         if use_sh:

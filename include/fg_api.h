@@ -74,6 +74,8 @@ int fg_project_fwd(int C, int N, const float* means, const float* quats, const f
  *   v_means[N,3] v_quats[N,4] v_scales[N,3] v_sh[N,sh_bases,3] (if sh_degree>=0)
  *   v_means_next[N,3] (if means_next) v_quats_next[N,4] v_scales_next[N,3] (if flow_cov and given)
  * Gradients of the C cameras are summed inside one thread per Gaussian (deterministic).
+ * `feat` is the forward output (or NULL): with it and 16-byte aligned rows of a multiple of four
+ * bases, the SH half runs as its own streaming kernel (clamp mask read from feat's rgb channels).
  */
 int fg_project_bwd(int C, int N, const float* means, const float* quats, const float* scales,
                    const float* viewmats, const float* Ks, int width, int height, float eps2d,
@@ -82,7 +84,7 @@ int fg_project_bwd(int C, int N, const float* means, const float* quats, const f
                    const float* quats_next, const float* scales_next, int flow_cov,
                    const int32_t* radii, const float* v_means2d, const float* v_depths,
                    const float* v_conics, const float* v_compensations, const float* v_feat,
-                   int feat_stride, int rgb_off, int depth_off, int flow_off,
+                   const float* feat, int feat_stride, int rgb_off, int depth_off, int flow_off,
                    const float* v_flow_affine, float* v_means, float* v_quats, float* v_scales,
                    float* v_sh, float* v_means_next, float* v_quats_next, float* v_scales_next,
                    void* stream);

@@ -63,6 +63,24 @@ def test_render_and_grads_match_oracle(built_lib, render_mode, sh_degree, raster
     assert m["means2d"].grad is not None
 
 
+@pytest.mark.parametrize("bases,sh_degree", [(9, 2), (4, 1), (9, 1), (1, 0)])
+def test_sh_rows_of_other_widths(built_lib, bases, sh_degree):
+    """SH tensors narrower than 16 bases: rows that are not float4-sized take the fused backward kernel,
+    rows of 4k bases the streaming SH kernel; both must agree with the oracle."""
+    W, H = 96, 64
+    sc = small_scene(2500, W, H, views=2, seed=11)
+    sc.sh = sc.sh[:, :bases].contiguous()
+    (r, a, m), (rr, ra, rm), gp, op = run_both(sc, W, H, packed=False, render_mode="RGB", sh_degree=sh_degree)
+    assert rel_err(r, rr) < IMG_TOL
+    g = torch.Generator().manual_seed(1)
+    wr = torch.randn(rr.shape, generator=g)
+    (r * wr.cuda()).sum().backward()
+    (rr * wr).sum().backward()
+    for n in ("means", "quats", "scales", "opacities", "sh"):
+        e = grad_rel_err(gp[n].grad, op[n].grad)
+        assert e < GRAD_TOL, (n, e)
+
+
 def test_flow_equals_extra_colour_channels(built_lib):
     """Corollary 1 cross-check: the flow image equals rendering mu2d(t+1)-mu2d(t) as colours."""
     from freegaussian_b200.rendering import rasterization
@@ -129,6 +147,11 @@ def test_edge_cases(built_lib):
     r, a, m = rasterization(sc.means[:1], sc.quats[:1], sc.scales[:1] * 20, sc.opacities[:1], sc.sh[:1], sc.viewmats,
                             sc.Ks, W, H, packed=False, sh_degree=0)
     assert r.shape == (1, H, W, 3)
+    # no Gaussians at all (e.g. everything cropped away, freegaussian_model.py:781-782)
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    r, a, m = rasterization(z(0, 3), z(0, 4), z(0, 3), z(0), z(0, 16, 3), sc.viewmats, sc.Ks, W, H, packed=False,
+                            sh_degree=3, render_mode="RGB+ED")
+    assert r.shape == (1, H, W, 4) and (r == 0).all() and (a == 0).all() and m["radii"].shape == (1, 0)
     # CPU tensors are refused, never silently rendered on the host
     with pytest.raises(RuntimeError):
         rasterization(sc.means.cpu(), sc.quats.cpu(), sc.scales.cpu(), sc.opacities.cpu(), sc.sh.cpu(),
