@@ -15,8 +15,10 @@ call does, and raises if it has not been built.
 from .compat import get_viewmat, num_sh_bases, quat_to_rotmat  # noqa: F401
 from .knn import k_nearest  # noqa: F401
 from .rendering import isect_tiles, rasterization, rasterize_to_pixels  # noqa: F401
+from .optim import GaussianAdam  # noqa: F401
+from .densify import refine  # noqa: F401
 
 __all__ = [
     "rasterization", "rasterize_to_pixels", "isect_tiles", "k_nearest", "num_sh_bases", "quat_to_rotmat",
-    "get_viewmat",
+    "get_viewmat", "GaussianAdam", "refine",
 ]

@@ -11,13 +11,40 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfreegaussian_b200.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pi = C.POINTER(C.c_int)
 
+
+
+class AdamSegment(C.Structure):  # fg_adam_segment
+    _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", _i64), ("first", _i64),
+                ("row_len", C.c_int32), ("split", C.c_int32), ("lr", _f32), ("lr_rest", _f32)]
+
+
+class RefineConfig(C.Structure):  # fg_refine_config
+    _fields_ = [("densify_grad_thresh", _f32), ("densify_size_thresh", _f32), ("split_screen_size", _f32),
+                ("cull_alpha_thresh", _f32), ("cull_scale_thresh", _f32), ("cull_screen_size", _f32),
+                ("max_dim", _f32), ("n_split_samples", C.c_int32), ("use_screen", C.c_int32),
+                ("cull_big", C.c_int32), ("densify", C.c_int32)]
+
+
+class RefineArray(C.Structure):  # fg_refine_array
+    _fields_ = [("in_", _vp), ("out", _vp), ("row_floats", C.c_int32), ("zero_new", C.c_int32)]
+
+
+ADAM_MAX_SEGMENTS = 8
+REFINE_MAX_ARRAYS = 24
+
 # name -> (restype, argtypes); mirrors include/fg_api.h one to one
 SIGNATURES = {
+    "fg_adam_step": (_i32, [_i32, C.POINTER(AdamSegment), _i32, C.c_double, C.c_double, C.c_double, _vp]),
+    "fg_refine_workspace_bytes": (_i64, [_i64]),
+    "fg_refine_plan": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, C.POINTER(RefineConfig), _vp, _vp, _vp, _i64, _vp]),
+    "fg_refine_map": (_i32, [_i64, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "fg_refine_gather": (_i32, [_i64, _i64, _vp, _i32, C.POINTER(RefineArray), _vp]),
+    "fg_refine_children": (_i32, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_last_error": (C.c_char_p, []),
     "fg_abi_version": (_i32, []),
     "fg_launch_count": (C.c_longlong, []),

@@ -264,6 +264,85 @@ int fg_l1_ssim_bwd(int width, int height, int render_stride, const float* render
                    const float* background, const float* gt, float ssim_lambda, const float* partial,
                    const float* v_loss, float* v_render, float* v_alpha, void* stream);
 
+/* ---- (7) "next" row: optimizer step and refinement -----------------------
+ * fg_adam_step: one launch steps every Gaussian parameter group the reference gives its own
+ * torch.optim.Adam (freegaussian_config.py:48-75: eps=1e-15, betas (0.9, 0.999), no weight decay),
+ * following torch's single-tensor update operation by operation.  A segment whose rows hold two
+ * groups (the [N,16,3] SH tensor = features_dc ++ features_rest, freegaussian_model.py:801) takes a
+ * learning rate per column range.  `first` is the index of param[0] inside the whole tensor, so a
+ * rank can step only its shard after a reduce-scatter of the gradient arena.  `step` counts from 1.
+ * betas and eps are doubles because torch derives 1-beta and the bias corrections in double.
+ */
+#define FG_ADAM_MAX_SEGMENTS 8
+typedef struct fg_adam_segment {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t n;       /* elements of this (shard of the) tensor */
+    int64_t first;   /* index of param[0] in the whole tensor (0 unless sharded) */
+    int32_t row_len; /* floats per Gaussian row; 0 = a single learning rate */
+    int32_t split;   /* columns [0,split) use lr, [split,row_len) use lr_rest */
+    float lr;
+    float lr_rest;
+} fg_adam_segment;
+int fg_adam_step(int n_segments, const fg_adam_segment* segments_host, int step, double beta1, double beta2,
+                 double eps, void* stream);
+
+/* Refinement (freegaussian_model.py:404-491 with split_gaussians :513-556, dup_gaussians :558-567,
+ * cull_gaussians :493-511 and the Adam-state surgery :313-367) as a plan / map / gather pipeline.
+ * scales are log-space [N,3], opacities logit-space [N] as the model stores them.
+ *
+ * fg_refine_plan: per Gaussian the reference's masks
+ *     high   = (grad_norm/vis_count) * 0.5 * max(W,H) > densify_grad_thresh            (:421-422)
+ *     split  = (max exp(scale) > densify_size_thresh & high) | (use_screen & max_size > split_screen_size)
+ *     dup    = (max exp(scale') <= densify_size_thresh) & high, scale' = the scale after split_gaussians
+ *              rescaled its parents in place (:536 runs before :430-431)
+ *     cull   = sigmoid(opacity) < cull_alpha_thresh | split | (cull_big & (max exp(scale) > cull_scale_thresh
+ *              | (use_screen & max_size > cull_screen_size)))                          (:499-511)
+ *   (children of a split carry scale - log 1.6 and max_size 0, duplicates the parent's scale and
+ *   max_size 0, and pass through the same cull test), then an exclusive scan.  With densify == 0
+ *   only the cull runs (:467-468) and grad_norm / vis_count / max_size may be NULL.
+ *   plan[4N+1] int32 receives the scanned positions (last = total); counts[4] (device) = kept originals, parents
+ *   whose children survive, surviving duplicates, split parents.
+ * fg_refine_map: src[n_out] = parent row of every output row in the reference's order
+ *   (kept originals, then children sample-major, then duplicates); sample_row[n_out] = row of the
+ *   torch.randn((n_split_samples * n_split, 3)) draw (:519) a child consumes, -1 for copies, -2 for the
+ *   duplicate of a parent that was also split (it copies the rescaled scale).
+ * fg_refine_gather: out[d,:] = in[src[d],:] for every listed array; arrays with zero_new != 0
+ *   (Adam moments, :344-357) get zeros in rows d >= n_keep.
+ * fg_refine_children: for rows with sample_row >= 0: means = parent mean + R(q/|q|) (exp(scale) * z)
+ *   (:520-526), scales = log(exp(scale) / 1.6) (:535); rows with sample_row == -2: scales only.
+ */
+typedef struct fg_refine_config {
+    float densify_grad_thresh, densify_size_thresh, split_screen_size;
+    float cull_alpha_thresh, cull_scale_thresh, cull_screen_size;
+    float max_dim;           /* max(W, H) of the last render (:421) */
+    int32_t n_split_samples; /* :427 */
+    int32_t use_screen;      /* step < stop_screen_size_at */
+    int32_t cull_big;        /* step > refine_every * reset_alpha_every (:505) */
+    int32_t densify;         /* 0 = cull only */
+} fg_refine_config;
+typedef struct fg_refine_array {
+    const float* in;
+    float* out;
+    int32_t row_floats;
+    int32_t zero_new;
+} fg_refine_array;
+#define FG_REFINE_MAX_ARRAYS 24
+int64_t fg_refine_workspace_bytes(int64_t N);
+int fg_refine_plan(int64_t N, const float* scales, const float* opacities, const float* grad_norm,
+                   const float* vis_count, const float* max_size, const fg_refine_config* config_host,
+                   int32_t* plan, int64_t* counts, void* workspace, int64_t workspace_bytes, void* stream);
+int fg_refine_map(int64_t N, const int32_t* plan, const int64_t* counts, int n_split_samples, int64_t n_out,
+                  int32_t* src, int32_t* sample_row, void* stream);
+int fg_refine_gather(int64_t n_out, int64_t n_keep, const int32_t* src, int n_arrays,
+                     const fg_refine_array* arrays_host, void* stream);
+int fg_refine_children(int64_t n_out, int64_t n_keep, int64_t n_children, const int32_t* src,
+                       const int32_t* sample_row, const float* samples, const float* means,
+                       const float* quats, const float* scales, float* means_out, float* scales_out,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
