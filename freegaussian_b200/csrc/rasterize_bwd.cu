@@ -51,23 +51,25 @@ struct RasterBwdParams {
 // Warp reduction of NV (16 or 32) partials per lane through a warp-private shared-memory
 // transpose, 16 partials at a time: every lane stores them as a column (conflict-free STS), then
 // lane l sums partial (l % 16) over lanes [16 (l / 16), +16) with four LDS.128 and the two halves
-// are combined with one shuffle.  ~38 instructions for 16 values;
+// are combined with one shuffle.  ~36 instructions for 16 values;
 // the register butterfly it replaces took 85 (ncu r1g: 40 % of the kernel's instructions).
 // Row stride 36 floats keeps the LDS.128 conflict-free.  On exit val[0] of lane l holds the
-// warp-wide sum of partial slot_of_lane(l) (both 16-lane halves hold every partial).
+// warp-wide sum of partial l % 16 (both 16-lane halves hold every partial); for NV == 32, val[1]
+// holds partial 16 + l % 16.  `wr` = shared address of buf[lane], `rd` = of buf[(l%16)*36 + (l/16)*16].
 constexpr int RED_STRIDE = 36;
-template <int NV>
-__device__ __forceinline__ void transpose_reduce(float (&val)[NV], int lane, float* buf /*[16][RED_STRIDE]*/) {
+template <int NV, int NLIVE>
+__device__ __forceinline__ void transpose_reduce(float (&val)[NV], unsigned wr, unsigned rd) {
     static_assert(NV == 16 || NV == 32, "NV must be 16 or 32");
-    const int j = lane & 15, h = lane >> 4;
     float out[NV / 16];
 #pragma unroll
     for (int grp = 0; grp < NV / 16; ++grp) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) buf[i * RED_STRIDE + lane] = val[grp * 16 + i];
+#define FG_STS_ROW(i) \
+    if (grp * 16 + (i) < NLIVE) sts32<(i) * RED_STRIDE * 4>(wr, val[grp * 16 + (i)]);  // rows >= NLIVE: never consumed
+        FG_STS_ROW(0) FG_STS_ROW(1) FG_STS_ROW(2) FG_STS_ROW(3) FG_STS_ROW(4) FG_STS_ROW(5) FG_STS_ROW(6) FG_STS_ROW(7)
+        FG_STS_ROW(8) FG_STS_ROW(9) FG_STS_ROW(10) FG_STS_ROW(11) FG_STS_ROW(12) FG_STS_ROW(13) FG_STS_ROW(14) FG_STS_ROW(15)
+#undef FG_STS_ROW
         __syncwarp();
-        const float4* row = reinterpret_cast<const float4*>(buf + j * RED_STRIDE + h * 16);
-        const float4 a = row[0], b = row[1], c = row[2], d = row[3];
+        const float4 a = lds128<0>(rd), b = lds128<16>(rd), c = lds128<32>(rd), d = lds128<48>(rd);
         float s = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) + ((c.x + c.y) + (c.z + c.w)) +
                   ((d.x + d.y) + (d.z + d.w));
         out[grp] = s + __shfl_xor_sync(0xffffffffu, s, 16);
@@ -76,21 +78,20 @@ __device__ __forceinline__ void transpose_reduce(float (&val)[NV], int lane, flo
 #pragma unroll
     for (int grp = 0; grp < NV / 16; ++grp) val[grp] = out[grp];
 }
-// which partial lane l ends up holding in val[0] (and, for NV == 32, partial 16 + that in val[1])
-__device__ __forceinline__ int slot_of_lane(int lane) { return lane & 15; }
 
 template <int CH, bool AFF>
 __global__ void __launch_bounds__(TILE_PIX, 4) rasterize_bwd_kernel(RasterBwdParams p) {
     constexpr int FV = (CH + 3) / 4;
     constexpr int NVAL = CH + 8 + (AFF ? 4 : 0);  // partials per (pixel, Gaussian)
     constexpr int NV = NVAL <= 16 ? 16 : 32;
-    __shared__ float4 sA[BATCH];
-    __shared__ float4 sB[BATCH];
-    __shared__ float4 sF[FV][BATCH];
-    __shared__ float4 sM[AFF ? BATCH : 1];
+    constexpr int NREC = 2 + FV + (AFF ? 1 : 0);  // float4 arrays of the staged records: A, B, F.., M
+    constexpr int OFF_F = 2 * REC_STRIDE, OFF_M = (2 + FV) * REC_STRIDE;
+    __shared__ float4 sRec[NREC][BATCH];
     __shared__ unsigned char sMask[BATCH];
     __shared__ unsigned char sList[TILE_PIX / 32][BATCH];
     __shared__ __align__(16) float sRed[TILE_PIX / 32][16 * RED_STRIDE];
+    float4* const sA = sRec[0];
+    float4* const sB = sRec[1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float tile_cx0 = (float)(blockIdx.x * TILE) + 0.5f, tile_cy0 = (float)(blockIdx.y * TILE) + 0.5f;
@@ -107,20 +108,23 @@ __global__ void __launch_bounds__(TILE_PIX, 4) rasterize_bwd_kernel(RasterBwdPar
     const int range_end = (tile_id == p.C * p.tile_h * p.tile_w - 1) ? (int)p.n_isects : p.isect_offsets[tile_id + 1];
     if (range_end <= range_start) return;
 
-    // where this lane's reduced value goes: slot -> (array, elements per Gaussian, offset)
+    // where this lane's reduced value goes: slot -> (array, elements per Gaussian, offset, scale)
     //   [0,CH) v_feat | CH..CH+2 v_conics | CH+3,4 v_means2d | CH+5,6 v_means2d_abs | CH+7 v_opacities | CH+8.. v_flow_affine
-    // lanes 0..15 own partial `lane` (and lanes 16..31 partial 16 + (lane - 16) when NV == 32)
+    // lanes 0..15 own partial `lane` (and lanes 16..31 partial 16 + (lane - 16) when NV == 32).
+    // The constant factors of the conic partials (0.5, 1, 0.5) and of d sigma / d mean (2 ln 2, the
+    // conic being staged pre-scaled) are applied here, once per reduced value instead of per pixel.
     float* out_base = nullptr;
-    int out_stride = 0;
+    unsigned out_stride = 0;  // bytes per row; 0 = this lane owns no partial
+    float out_scale = 1.f;
     bool out_is_opac = false;
     {
         const int slot = (NV == 32) ? lane : (lane < 16 ? lane : NV);  // NV: no partial
-        if (slot < CH) { out_base = p.v_feat + slot; out_stride = CH; }
-        else if (slot < CH + 3) { out_base = p.v_conics + (slot - CH); out_stride = 3; }
-        else if (slot < CH + 5) { out_base = p.v_means2d + (slot - CH - 3); out_stride = 2; }
-        else if (slot < CH + 7) { if (p.v_means2d_abs) { out_base = p.v_means2d_abs + (slot - CH - 5); out_stride = 2; } }
-        else if (slot < CH + 8) { out_base = p.v_opacities; out_stride = 1; out_is_opac = true; }
-        else if (AFF && slot < CH + 12) { out_base = p.v_flow_affine + (slot - CH - 8); out_stride = 4; }
+        if (slot < CH) { out_base = p.v_feat + slot; out_stride = CH * 4; }
+        else if (slot < CH + 3) { out_base = p.v_conics + (slot - CH); out_stride = 12; out_scale = (slot == CH + 1) ? 1.f : 0.5f; }
+        else if (slot < CH + 5) { out_base = p.v_means2d + (slot - CH - 3); out_stride = 8; out_scale = 2.f * LN2; }
+        else if (slot < CH + 7) { if (p.v_means2d_abs) { out_base = p.v_means2d_abs + (slot - CH - 5); out_stride = 8; out_scale = 2.f * LN2; } }
+        else if (slot < CH + 8) { out_base = p.v_opacities; out_stride = 4; out_is_opac = true; }
+        else if (AFF && slot < CH + 12) { out_base = p.v_flow_affine + (slot - CH - 8); out_stride = 16; }
     }
 
     const float a_out = p.alphas[pix];
@@ -155,6 +159,12 @@ __global__ void __launch_bounds__(TILE_PIX, 4) rasterize_bwd_kernel(RasterBwdPar
     const int warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
     const int nb_all = (range_end - range_start + BATCH - 1) / BATCH;
 
+    // explicit shared addresses of everything the inner loop touches
+    const unsigned rec0 = smem_addr(&sRec[0][0]);
+    const unsigned list0 = smem_addr(&sList[warp][0]);
+    const unsigned red_wr = smem_addr(&sRed[warp][lane]);
+    const unsigned red_rd = smem_addr(&sRed[warp][(lane & 15) * RED_STRIDE + (lane >> 4) * 16]);
+
     for (int b = 0; b < nb_all; ++b) {
         // batches run back to front; within a batch, smem slot t holds sorted index batch_end - t
         const int batch_end = range_end - 1 - BATCH * b;
@@ -169,30 +179,32 @@ __global__ void __launch_bounds__(TILE_PIX, 4) rasterize_bwd_kernel(RasterBwdPar
             const float ca = p.conics[3 * (size_t)g], cb = p.conics[3 * (size_t)g + 1], cc = p.conics[3 * (size_t)g + 2];
             const int go = p.opac_shared ? g % p.N : g;
             const float opac = p.opacities[go];
-            sA[tid] = make_float4(m.x, m.y, opac, 0.5f * LOG2E * ca);
-            sMask[tid] = (unsigned char)patch_mask(m.x, m.y, opac, 0.5f * LOG2E * ca, LOG2E * cb, 0.5f * LOG2E * cc,
-                                                   tile_cx0, tile_cy0);
-            // .w: row of the opacity gradient (g, or g % N when one opacity is shared by all cameras)
-            sB[tid] = make_float4(LOG2E * cb, 0.5f * LOG2E * cc, __int_as_float(g),
-                                  __int_as_float(go));
+            const float a1 = 0.5f * LOG2E * ca, b1 = 0.5f * LOG2E * cb, c1 = 0.5f * LOG2E * cc;
+            sA[tid] = make_float4(m.x, m.y, opac, a1);
+            sMask[tid] = (unsigned char)patch_mask(m.x, m.y, opac, a1, 2.f * b1, c1, tile_cx0, tile_cy0);
+            // .z: row of the per-(camera, Gaussian) gradients; .w: row of the opacity gradient (g, or
+            // g % N when one opacity is shared by all cameras)
+            sB[tid] = make_float4(b1, c1, __int_as_float(g), __int_as_float(go));
             float f[FV * 4];
 #pragma unroll
             for (int k = 0; k < FV * 4; ++k) f[k] = (k < CH) ? p.feat[(size_t)g * CH + k] : 0.f;
 #pragma unroll
-            for (int j = 0; j < FV; ++j) sF[j][tid] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            if (AFF) sM[tid] = p.flow_affine[g];
+            for (int j = 0; j < FV; ++j) sRec[2 + j][tid] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (AFF) sRec[2 + FV][tid] = p.flow_affine[g];
         }
         __syncthreads();
         // this warp's 8x4 patch only walks the Gaussians that can reach it (slot t <-> index batch_end - t)
         const int n_list = build_warp_list(sMask, sList[warp], warp, lane, max(0, batch_end - warp_bin_final), bs);
+        const int t_lim = batch_end - bin_final;  // slots below it lie behind this pixel's last contributor
         for (int li = 0; li < n_list; ++li) {
-            const int t = sList[warp][li];
-            const float4 a4 = sA[t], b4 = sB[t];
+            const int t = (int)lds_u8(list0 + li);
+            const unsigned rec = rec0 + t * 16;
+            const float4 a4 = lds128<0>(rec), b4 = lds128<REC_STRIDE>(rec);
             const GeomA ga = {a4.x, a4.y, a4.z, a4.w};
             const GeomB gb = {b4.x, b4.y, 0, 0.f};
-            float dx, dy, vis, alpha;
-            bool valid = eval_alpha(ga, gb, px, py, dx, dy, vis, alpha);
-            valid = valid && (batch_end - t <= bin_final);
+            float dx, dy, u, v, vis, raw, alpha;
+            bool valid = eval_alpha(ga, gb, px, py, dx, dy, u, v, vis, raw, alpha);
+            valid = valid && (t >= t_lim);
             if (!__any_sync(0xffffffffu, valid)) continue;
 
             // Lanes whose pixel skips this Gaussian run the same arithmetic with alpha = vis = 0: every
@@ -204,15 +216,18 @@ __global__ void __launch_bounds__(TILE_PIX, 4) rasterize_bwd_kernel(RasterBwdPar
             for (int k = CH + 8; k < NV; ++k) val[k] = 0.f;
             {
                 float f[FV * 4];
-#pragma unroll
-                for (int j = 0; j < FV; ++j) {
-                    const float4 v = sF[j][t];
-                    f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+                {
+                    const float4 q = lds128<OFF_F>(rec);
+                    f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+                }
+                if (FV > 1) {
+                    const float4 q = lds128<OFF_F + REC_STRIDE>(rec);
+                    f[4 * (FV - 1)] = q.x; f[4 * (FV - 1) + 1] = q.y; f[4 * (FV - 1) + 2] = q.z; f[4 * (FV - 1) + 3] = q.w;
                 }
                 float4 M = make_float4(0.f, 0.f, 0.f, 0.f);
                 float vo0 = 0.f, vo1 = 0.f;  // v_out of the two flow channels
                 if (AFF) {
-                    M = sM[t];
+                    M = lds128<OFF_M>(rec);
                     const float e0 = M.x * dx + M.y * dy, e1 = M.z * dx + M.w * dy;
 #pragma unroll
                     for (int k = 0; k < CH; ++k) {
@@ -232,38 +247,37 @@ __global__ void __launch_bounds__(TILE_PIX, 4) rasterize_bwd_kernel(RasterBwdPar
                 }
                 const float v_alpha = fmaf(T, A, (G - S) * ra);
                 S = fmaf(fac, A, S);
-                float gx = 0.f, gy = 0.f;
+                // gradient only flows through alpha where it is not clamped (opac * vis <= 0.999, where
+                // alpha == opac * vis); on skipped lanes alpha = vis = 0 zero both products
+                const bool gate = raw <= ALPHA_MAX;
+                const float v_sigma = gate ? -alpha * v_alpha : 0.f;
+                const float t1 = v_sigma * dx, t2 = v_sigma * dy;
+                val[CH] = t1 * dx;      // x 0.5 in out_scale
+                val[CH + 1] = t1 * dy;
+                val[CH + 2] = t2 * dy;  // x 0.5
+                const float hx = v_sigma * u, hy = v_sigma * v;  // x 2 ln2
+                val[CH + 5] = fabsf(hx);
+                val[CH + 6] = fabsf(hy);
+                val[CH + 7] = gate ? vis * v_alpha : 0.f;
                 if (AFF) {
                     // f_flow = feat - M delta: d/dM and d/ddelta of the composited flow
                     val[CH + 8] = -fac * vo0 * dx; val[CH + 9] = -fac * vo0 * dy;
                     val[CH + 10] = -fac * vo1 * dx; val[CH + 11] = -fac * vo1 * dy;
-                    gx = -fac * (vo0 * M.x + vo1 * M.z);
-                    gy = -fac * (vo0 * M.y + vo1 * M.w);
+                    constexpr float inv_scale = 1.f / (2.f * LN2);
+                    val[CH + 3] = fmaf(-fac * inv_scale, vo0 * M.x + vo1 * M.z, hx);
+                    val[CH + 4] = fmaf(-fac * inv_scale, vo0 * M.y + vo1 * M.w, hy);
+                } else {
+                    val[CH + 3] = hx;
+                    val[CH + 4] = hy;
                 }
-                {
-                    // gradient only flows through alpha where it is not clamped (opac * vis <= 0.999)
-                    const bool gate = a4.z * vis <= ALPHA_MAX;
-                    const float v_sigma = gate ? -a4.z * vis * v_alpha : 0.f;
-                    val[CH] = 0.5f * v_sigma * dx * dx;
-                    val[CH + 1] = v_sigma * dx * dy;
-                    val[CH + 2] = 0.5f * v_sigma * dy * dy;
-                    // unscaled conic: A = 2 qa / log2e, B = qb / log2e, C = 2 qc / log2e
-                    const float vs = v_sigma * LN2;
-                    const float hx = vs * (2.f * a4.w * dx + b4.x * dy);
-                    const float hy = vs * (b4.x * dx + 2.f * b4.y * dy);
-                    val[CH + 5] = fabsf(hx);
-                    val[CH + 6] = fabsf(hy);
-                    gx += hx;
-                    gy += hy;
-                    val[CH + 7] = gate ? vis * v_alpha : 0.f;
-                }
-                val[CH + 3] = gx;
-                val[CH + 4] = gy;
             }
-            transpose_reduce<NV>(val, lane, sRed[warp]);
-            if (out_base) {
-                const int row = __float_as_int(out_is_opac ? b4.w : b4.z);
-                atomicAdd(out_base + (size_t)row * out_stride, (NV == 32 && lane >= 16) ? val[1] : val[0]);
+            transpose_reduce<NV, NVAL>(val, red_wr, red_rd);
+            if (out_stride) {
+                const unsigned row = __float_as_uint(out_is_opac ? b4.w : b4.z);
+                unsigned long long addr;  // out_base + row * stride
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(out_stride), "l"(out_base));
+                const float sum = (NV == 32 && lane >= 16) ? val[1] : val[0] * out_scale;
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(sum) : "memory");
             }
         }
     }

@@ -23,13 +23,15 @@ __device__ __forceinline__ void tile_pixel(int tid, int& lx, int& ly) {
     ly = ((warp >> 1) << 2) + (lane >> 3);
 }
 
-// Geometry of one staged Gaussian.  Conic is pre-scaled so that
-//   alpha = opac * 2^-(qa dx^2 + qb dx dy + qc dy^2),  qa = 0.5 log2e A, qb = log2e B, qc = 0.5 log2e C.
+// Geometry of one staged Gaussian.  The conic is pre-scaled by 0.5 log2(e),
+//   a1 = 0.5 log2e A,  b1 = 0.5 log2e B,  c1 = 0.5 log2e C,
+// so that with u = a1 dx + b1 dy and v = b1 dx + c1 dy the exponent is p = u dx + v dy = log2e sigma
+// and alpha = opac 2^-p.  u and v are also what the backward pass needs: d sigma / d(dx, dy) = 2 ln2 (u, v).
 struct GeomA {
-    float x, y, opac, qa;
+    float x, y, opac, a1;
 };
 struct GeomB {
-    float qb, qc;
+    float b1, c1;
     int id;  // flatten id c*N+n
     float pad;
 };
@@ -40,17 +42,49 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// power (scaled sigma) and alpha for pixel (px,py).  Returns false when the Gaussian is
-// skipped (sigma < 0 or alpha < 1/255).  vis = exp(-sigma).
+// alpha for pixel (px,py).  Returns false when the Gaussian is skipped (sigma < 0 or alpha < 1/255).
+// vis = exp(-sigma), raw = opac * vis (alpha before the 0.999 clamp).
 __device__ __forceinline__ bool eval_alpha(const GeomA& a, const GeomB& b, float px, float py, float& dx,
-                                           float& dy, float& vis, float& alpha) {
+                                           float& dy, float& u, float& v, float& vis, float& raw, float& alpha) {
     dx = a.x - px;
     dy = a.y - py;
-    float p = fmaf(a.qa * dx, dx, fmaf(b.qc * dy, dy, b.qb * dx * dy));
+    u = fmaf(a.a1, dx, b.b1 * dy);
+    v = fmaf(b.c1, dy, b.b1 * dx);
+    const float p = fmaf(u, dx, v * dy);
     vis = ex2_approx(-p);
-    alpha = fminf(ALPHA_MAX, a.opac * vis);
+    raw = a.opac * vis;
+    alpha = fminf(ALPHA_MAX, raw);
     return (p >= 0.f) && (alpha >= ALPHA_MIN);
 }
+
+// ---- shared memory by explicit 32-bit address --------------------------------------------------
+// The staged Gaussian records live at fixed offsets from one base (slot t at base + 16 t + k * 4096),
+// so the hot loops form ONE address per Gaussian and use immediate offsets; through C++ arrays the
+// compiler re-derived every array's base (via SR_CgaCtaId) inside the loop (ncu r1z: ~11 of 145
+// instructions per step in the backward kernel).
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int OFF>
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float2 lds64(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "f"(v));
+}
+constexpr int REC_STRIDE = BATCH * 16;  // bytes between the float4 arrays of the staged records
 
 // ---- per-warp culling ---------------------------------------------------------------------
 // Which of the tile's eight 8x4 pixel patches (= warps) can a Gaussian touch at all, i.e. has a

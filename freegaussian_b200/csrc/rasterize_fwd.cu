@@ -37,11 +37,12 @@ struct RasterFwdParams {
 template <int CH, bool AFF>
 __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdParams p) {
     constexpr int FV = (CH + 3) / 4;  // float4 per Gaussian for the features
-    __shared__ float4 sA[BATCH];
-    __shared__ float4 sB[BATCH];
-    __shared__ float4 sF[FV][BATCH];
-    __shared__ float4 sM[AFF ? BATCH : 1];
+    constexpr int NREC = 2 + FV + (AFF ? 1 : 0);  // float4 arrays of the staged records: A, B, F.., M
+    constexpr int OFF_F = 2 * REC_STRIDE, OFF_M = (2 + FV) * REC_STRIDE;
+    __shared__ float4 sRec[NREC][BATCH];
     __shared__ unsigned char sMask[BATCH];
+    float4* const sA = sRec[0];
+    float4* const sB = sRec[1];
     __shared__ unsigned char sList[TILE_PIX / 32][BATCH];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -65,6 +66,8 @@ __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdPar
 #pragma unroll
     for (int k = 0; k < CH; ++k) acc[k] = 0.f;
 
+    const unsigned rec0 = smem_addr(&sRec[0][0]);
+    const unsigned list0 = smem_addr(&sList[warp][0]);
     for (int b = 0; b < nb; ++b) {
         // barrier (previous batch fully consumed) + early exit when every pixel is finished
         if (__syncthreads_count(done) >= TILE_PIX) break;
@@ -75,28 +78,30 @@ __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdPar
             const float2 m = p.means2d[g];
             const float ca = p.conics[3 * (size_t)g], cb = p.conics[3 * (size_t)g + 1], cc = p.conics[3 * (size_t)g + 2];
             const float opac = p.opacities[p.opac_shared ? g % p.N : g];
-            sA[tid] = make_float4(m.x, m.y, opac, 0.5f * LOG2E * ca);
-            sB[tid] = make_float4(LOG2E * cb, 0.5f * LOG2E * cc, __int_as_float(g), 0.f);
-            sMask[tid] = (unsigned char)patch_mask(m.x, m.y, opac, 0.5f * LOG2E * ca, LOG2E * cb, 0.5f * LOG2E * cc,
-                                                   tile_cx0, tile_cy0);
+            const float a1 = 0.5f * LOG2E * ca, b1 = 0.5f * LOG2E * cb, c1 = 0.5f * LOG2E * cc;
+            sA[tid] = make_float4(m.x, m.y, opac, a1);
+            sB[tid] = make_float4(b1, c1, __int_as_float(g), 0.f);
+            sMask[tid] = (unsigned char)patch_mask(m.x, m.y, opac, a1, 2.f * b1, c1, tile_cx0, tile_cy0);
             float f[FV * 4];
 #pragma unroll
             for (int k = 0; k < FV * 4; ++k) f[k] = (k < CH) ? p.feat[(size_t)g * CH + k] : 0.f;
 #pragma unroll
-            for (int j = 0; j < FV; ++j) sF[j][tid] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            if (AFF) sM[tid] = p.flow_affine[g];
+            for (int j = 0; j < FV; ++j) sRec[2 + j][tid] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (AFF) sRec[2 + FV][tid] = p.flow_affine[g];
         }
         __syncthreads();
         const int bs = min(BATCH, range_end - batch_start);
         // this warp's 8x4 patch only walks the Gaussians that can reach it
         const int n_list = build_warp_list(sMask, sList[warp], warp, lane, 0, bs);
         for (int li = 0; li < n_list && !done; ++li) {
-            const int t = sList[warp][li];
-            const float4 a4 = sA[t], b4 = sB[t];
+            const int t = (int)lds_u8(list0 + li);
+            const unsigned rec = rec0 + t * 16;
+            const float4 a4 = lds128<0>(rec);
+            const float2 b2 = lds64<REC_STRIDE>(rec);
             const GeomA ga = {a4.x, a4.y, a4.z, a4.w};
-            const GeomB gb = {b4.x, b4.y, 0, 0.f};
-            float dx, dy, vis, alpha;
-            if (!eval_alpha(ga, gb, px, py, dx, dy, vis, alpha)) continue;
+            const GeomB gb = {b2.x, b2.y, 0, 0.f};
+            float dx, dy, u, v, vis, raw, alpha;
+            if (!eval_alpha(ga, gb, px, py, dx, dy, u, v, vis, raw, alpha)) continue;
             const float next_T = T * (1.f - alpha);
             if (next_T <= T_STOP) {  // this Gaussian is not composited
                 done = true;
@@ -104,14 +109,17 @@ __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdPar
             }
             const float w = alpha * T;
             float f[FV * 4];
-#pragma unroll
-            for (int j = 0; j < FV; ++j) {
-                const float4 v = sF[j][t];
-                f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+            {
+                const float4 q = lds128<OFF_F>(rec);
+                f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+            }
+            if (FV > 1) {
+                const float4 q = lds128<OFF_F + REC_STRIDE>(rec);
+                f[4 * (FV - 1)] = q.x; f[4 * (FV - 1) + 1] = q.y; f[4 * (FV - 1) + 2] = q.z; f[4 * (FV - 1) + 3] = q.w;
             }
             float e0 = 0.f, e1 = 0.f;
             if (AFF) {  // flow channels get + A (p - mu) = -A delta
-                const float4 M = sM[t];
+                const float4 M = lds128<OFF_M>(rec);
                 e0 = M.x * dx + M.y * dy;
                 e1 = M.z * dx + M.w * dy;
             }
