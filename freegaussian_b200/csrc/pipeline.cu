@@ -157,6 +157,7 @@ extern "C" int fg_render_back(int C, int N, int64_t n_isects, int64_t n_coarse, 
                              flatten_ids, stream)))
             return e;
     }
+    if (CH == 0) return FG_OK;  // lists only: the caller composites later with fg_rasterize_fwd
     return fg_rasterize_fwd(C, N, CH, width, height, tile_size, means2d, conics, feat, opacities, backgrounds,
                             flow_affine, flow_ch0, split, ed_channel, opac_shared, isect_offsets, flatten_ids, n_isects,
                             render, render2, alphas, last_ids, stream);

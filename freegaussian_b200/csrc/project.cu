@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(PB, 4) project_fwd_kernel(ProjParams p) {
 }
 
 // ------------------------------------------------------------------------------ backward
-template <int DEG, bool VEC4>
-__global__ void __launch_bounds__(PB, 3) project_bwd_kernel(ProjParams p) {
+template <int DEG, bool VEC4, int MINB = (DEG < 0 ? 4 : 3)>
+__global__ void __launch_bounds__(PB, MINB) project_bwd_kernel(ProjParams p) {
     extern __shared__ __align__(16) float smem[];
     using S = ShShape<(DEG >= 0 ? DEG : 0)>;
     const int n0 = blockIdx.x * PB;
@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(PB, 3) project_bwd_kernel(ProjParams p) {
 // needed 168-250 registers and ran at 12-18 % occupancy).  The clamp mask of max(rgb + 0.5, 0)
 // comes from the forward colours in `feat`.  Also writes the direction term of v_means, which
 // the geometry kernel (project_bwd_kernel<-1>) then adds to its own.
+constexpr bool SH_BWD_STAGE = false;  // coefficient rows are read once per camera straight from global memory
 template <int DEG>
 __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
     if (in_range && p.v_feat)
         for (int c = 0; c < p.C; ++c) vis_any |= p.radii_in[(size_t)c * p.N + n] > 0;
     const int nvis = __syncthreads_count(vis_any);
-    const bool staged = nvis * 2 >= PB;
+    const bool staged = SH_BWD_STAGE && nvis * 2 >= PB;
     if (staged) {
         const float4* src = reinterpret_cast<const float4*>(p.sh);
         const int rows = min(PB, p.N - n0);
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
 
 template <int DEG>
 static int launch_sh_bwd(const ProjParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)2 * PB * 13 * 16;
+    const size_t smem = (size_t)(SH_BWD_STAGE ? 2 : 1) * PB * 13 * 16;
     FG_CUDA(cudaFuncSetAttribute(sh_bwd_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FG_LAUNCH((sh_bwd_kernel<DEG>), ceil_div(p.N, PB), PB, smem, st, p);
     return FG_OK;

@@ -169,8 +169,17 @@ class _Project(torch.autograd.Function):
                 ptr(quats_next), ptr(scales_next), int(flow_cov), ptr(radii), ptr(means2d), ptr(depths), ptr(conics),
                 ptr(comps), ptr(feat), CH, rgb_off, depth_off, flow_off, ptr(flow_affine), ptr(tiles), ptr(order),
                 ptr(isect_offsets), ptr(coarse_off), counts, ptr(ws), ws.numel(), _stream()))
-            cfg["_front"] = dict(order=order, coarse_off=coarse_off, isect_offsets=isect_offsets, M=int(counts[0]),
-                                 Mc=int(counts[1]), tile_w=tile_w, tile_h=tile_h)
+            # the host now knows the list sizes: build the tile lists right away (coarse emit + sort + cell
+            # offsets + fine binning), so the GPU works while Python assembles the compositing call
+            M, Mc = int(counts[0]), int(counts[1])
+            flatten_ids = torch.empty(M, dtype=torch.int32, device=dev)
+            ws2 = _ws.get("back", L.fg_render_back_workspace_bytes(C, tile_w, tile_h, Mc), dev)
+            check(L.fg_render_back(C, N, M, Mc, ptr(order), ptr(coarse_off), ptr(means2d), ptr(radii),
+                                   cfg["tile_size"], ptr(isect_offsets), ptr(flatten_ids), ptr(ws2), ws2.numel(), 0,
+                                   cfg["width"], cfg["height"], None, None, None, None, None, -1, 0, -1, 0, None, None,
+                                   None, None, _stream()))
+            cfg["_front"] = dict(isect_offsets=isect_offsets, flatten_ids=flatten_ids, M=M, Mc=Mc, tile_w=tile_w,
+                                 tile_h=tile_h)
         else:
             with _stage("project_fwd"):
                 check(L.fg_project_fwd(
@@ -402,7 +411,7 @@ class _Rasterize(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means2d, conics, feat, opacities, backgrounds, isect_offsets, flatten_ids, width, height,
-                tile_size, absgrad, split, ed_channel, chunked, flow_affine=None, front=None):
+                tile_size, absgrad, split, ed_channel, chunked, flow_affine=None):
         L = _lib.lib()
         ctx.chunked = chunked
         C = isect_offsets.shape[0]
@@ -420,20 +429,11 @@ class _Rasterize(torch.autograd.Function):
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
         M = flatten_ids.shape[0]
         n_arg = n_shared if opac_shared else NN
-        if front is not None:
-            # coarse emit + sort + cell offsets + fine binning + compositing, in one C call
-            ws = _ws.get("back", L.fg_render_back_workspace_bytes(C, front["tile_w"], front["tile_h"], front["Mc"]), dev)
-            check(L.fg_render_back(C, NN // C, M, front["Mc"], ptr(front["order"]), ptr(front["coarse_off"]),
-                                   ptr(means2d_c), ptr(front["radii"]), tile_size, ptr(isect_offsets), ptr(flatten_ids),
-                                   ptr(ws), ws.numel(), CH, width, height, ptr(conics_c), ptr(feat_c), ptr(opac_c),
-                                   ptr(bg), ptr(aff), split, split, ed_channel, opac_shared, ptr(render), ptr(render2),
-                                   ptr(alphas), ptr(last_ids), _stream()))
-        else:
-            with _stage("rasterize_fwd"):
-                check(L.fg_rasterize_fwd(C, n_arg, CH, width, height, tile_size, ptr(means2d_c), ptr(conics_c),
-                                         ptr(feat_c), ptr(opac_c), ptr(bg), ptr(aff), split, split, ed_channel,
-                                         opac_shared, ptr(isect_offsets), ptr(flatten_ids), M, ptr(render),
-                                         ptr(render2), ptr(alphas), ptr(last_ids), _stream()))
+        with _stage("rasterize_fwd"):
+            check(L.fg_rasterize_fwd(C, n_arg, CH, width, height, tile_size, ptr(means2d_c), ptr(conics_c),
+                                     ptr(feat_c), ptr(opac_c), ptr(bg), ptr(aff), split, split, ed_channel,
+                                     opac_shared, ptr(isect_offsets), ptr(flatten_ids), M, ptr(render),
+                                     ptr(render2), ptr(alphas), ptr(last_ids), _stream()))
         ctx.save_for_backward(means2d_c, conics_c, feat_c, opac_c, bg, isect_offsets, flatten_ids, alphas, last_ids,
                               render if ed_channel >= 0 else None, aff)
         ctx.dims = (C, NN, CH, width, height, tile_size, absgrad, split, ed_channel, opac_shared, n_shared)
@@ -487,7 +487,7 @@ class _Rasterize(torch.autograd.Function):
                 vr = vr.clone()
                 vr[..., ed_channel] = 0
             v_bg = (vr * (1.0 - alphas)).sum(dim=(1, 2))
-        return (v_means2d, v_conics, v_feat, v_opac, v_bg) + (None,) * 9 + (v_aff, None)
+        return (v_means2d, v_conics, v_feat, v_opac, v_bg) + (None,) * 9 + (v_aff,)
 
 
 def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets,
@@ -614,8 +614,7 @@ def rasterization(
     if front is not None:
         isect_ids, tile_keys = None, None
         isect_offsets = front["isect_offsets"]
-        flatten_ids = torch.empty(front["M"], dtype=torch.int32, device=means.device)  # filled by fg_render_back
-        front["radii"] = radii
+        flatten_ids = front["flatten_ids"]  # built inside the projection call, right after its host sync
     else:
         isect_ids, flatten_ids, isect_offsets, tile_keys = isect_tiles(means2d, radii, depths, tiles, tile_size, tile_w,
                                                                        tile_h, mode=SORT_MODE)
@@ -658,7 +657,7 @@ def rasterization(
     if CH <= MAX_CH:
         render, flow_img, alphas, last_ids = _Rasterize.apply(
             means2d, conics, feat, opac, backgrounds, isect_offsets, flatten_ids, width, height, tile_size, absgrad,
-            n_user, ed_channel, False, flow_affine, front)
+            n_user, ed_channel, False, flow_affine)
         if means_next is not None:
             flow = flow_img
     else:  # many user colour channels: chunks of 8, normalisation / split done by torch

@@ -211,7 +211,9 @@ int fg_densify_stats(int C, int N, const int32_t* radii, const float* absgrad, f
  * then the ONE host synchronisation of the pass: counts_host[0] = M (tile intersections),
  * counts_host[1] = Mc (coarse pairs).  The caller allocates flatten_ids[M] and calls
  * fg_render_back = coarse emit + sort + cell offsets + fg_bin_fine + fg_rasterize_fwd.
- * Arguments are those of the granular entry points; `order`, `coarse_off` are [C*N] int32. */
+ * Arguments are those of the granular entry points; `order`, `coarse_off` are [C*N] int32.  * fg_render_back with CH == 0 builds the tile lists only (flatten_ids) and skips compositing: the host
+ * mirror calls it right after the sync so the GPU is busy again while Python assembles the compositing call.
+ */
 int64_t fg_render_front_workspace_bytes(int C, int N, int tile_w, int tile_h);
 int fg_render_front(int C, int N, const float* means, const float* quats, const float* scales,
                     const float* viewmats, const float* Ks, int width, int height, float eps2d,

@@ -42,3 +42,21 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for i in range(5): step(i)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=32, max_name_column_width=60))
+
+# chronological device timeline of the last profiled step: kernel, duration, idle gap before it
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+starts = [i for i, e in enumerate(evs) if "project_fwd" in e.name]
+if starts:
+    last = evs[starts[-1]:]
+    t_prev = last[0].time_range.start
+    busy = 0.0
+    print("\n# device timeline of one step (us): gap-before  duration  kernel")
+    for e in last:
+        gap = e.time_range.start - t_prev
+        dur = e.time_range.end - e.time_range.start
+        busy += dur
+        print(f"{gap:9.1f} {dur:9.1f}  {e.name[:90]}")
+        t_prev = max(t_prev, e.time_range.end)
+    span = t_prev - last[0].time_range.start
+    print(f"# span {span:.1f} us, busy {busy:.1f} us, idle {span - busy:.1f} us")
