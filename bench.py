@@ -338,8 +338,9 @@ def run_ours(args):
         # captures (profiles/r1_final_*.txt); only valid for the configuration they were taken on
         ncu_traffic = {}
         if args.workload == "cfg3" and args.recipe == "trained_like":
-            ncu_traffic = {"rasterize_bwd": 128.3e6, "rasterize_fwd": 27.2e6, "project_bwd": 505.8e6,
-                           "project_fwd": 287.5e6, "fine_bin": 107.1e6}
+            # project_bwd = sh_bwd_kernel (271.9 MB) + project_bwd_kernel<-1> (135.9 MB), the two launches of the stage
+            ncu_traffic = {"rasterize_bwd": 127.8e6, "rasterize_fwd": 26.4e6, "project_bwd": 407.8e6,
+                           "project_fwd": 150.3e6, "fine_bin": 102.3e6}
         for name, k in kernels.items():
             k["traffic"] = ncu_traffic.get(name)
         dominant = max(stage_ms, key=stage_ms.get)
