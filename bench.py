@@ -338,9 +338,9 @@ def run_ours(args):
         # captures (profiles/r1_final_*.txt); only valid for the configuration they were taken on
         ncu_traffic = {}
         if args.workload == "cfg3" and args.recipe == "trained_like":
-            # project_bwd = sh_bwd_kernel (271.9 MB) + project_bwd_kernel<-1> (135.9 MB), the two launches of the stage
-            ncu_traffic = {"rasterize_bwd": 127.8e6, "rasterize_fwd": 26.4e6, "project_bwd": 407.8e6,
-                           "project_fwd": 150.3e6, "fine_bin": 102.3e6}
+            # project_bwd = sh_bwd_kernel (269.8 MB) + project_bwd_kernel<-1> (135.4 MB), the two launches of the stage
+            ncu_traffic = {"rasterize_bwd": 127.7e6, "rasterize_fwd": 24.4e6, "project_bwd": 405.2e6,
+                           "project_fwd": 147.7e6, "fine_bin": 100.3e6}
         for name, k in kernels.items():
             k["traffic"] = ncu_traffic.get(name)
         dominant = max(stage_ms, key=stage_ms.get)

@@ -1,4 +1,5 @@
-// (3b) Per-tile alpha compositing, backward (pixel-parallel variant).
+// (3b) Per-tile alpha compositing, backward (pixel-parallel).  Two kernels: rasterize_bwd2_kernel (two pixels per
+// thread, the default) and rasterize_bwd_kernel (one pixel per thread; carries the covariance-flow terms).
 // Replaces gsplat rasterize_to_pixels_bwd behind the
 // loss.backward() of the training step that calls freegaussian_model.py:847-868.
 //
@@ -283,6 +284,225 @@ __global__ void __launch_bounds__(TILE_PIX, 4) rasterize_bwd_kernel(RasterBwdPar
     }
 }
 
+// ---- two pixels per thread ----------------------------------------------------------------------
+// The one-pixel kernel above is bound by shared-memory bandwidth: the transpose moves 30 of the ~36
+// wavefronts a (warp, Gaussian) step costs (ncu r1y: 77 % of the LSU's wavefront rate, top stall
+// short_scoreboard).  Here a warp owns an 8x8 block of the tile and every lane two pixels four rows
+// apart (the two 8x4 patches of the culling mask); their partials are summed in registers -- the
+// products fold into FFMAs -- before ONE transpose per 64 pixels.  A half whose patch bit is clear
+// is skipped with a warp-uniform branch, so the per-patch culling loses nothing.
+constexpr int BWD2_THREADS = 128;
+
+template <int CH>
+__device__ __forceinline__ void bwd_init_pixel(const RasterBwdParams& p, int cam, int ix, int iy, bool inside,
+                                               float (&v_out)[CH], float& T, float& G, int& bin_final) {
+    const size_t pix = ((size_t)cam * p.height + min(iy, p.height - 1)) * p.width + min(ix, p.width - 1);
+    const float a_out = p.alphas[pix];
+    const float T_final = 1.f - a_out;
+    T = T_final;
+    float v_alpha_out = (inside && p.v_alphas) ? p.v_alphas[pix] : 0.f;
+    const int n2 = CH - p.split;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        float v = 0.f;
+        if (inside) {
+            if (k < p.split) v = p.v_render ? p.v_render[pix * p.split + k] : 0.f;
+            else v = p.v_render2 ? p.v_render2[pix * n2 + (k - p.split)] : 0.f;
+        }
+        if (k == p.ed_channel) {
+            const float inv = 1.f / fmaxf(a_out, 1e-10f);
+            if (inside && a_out >= 1e-10f) v_alpha_out -= v * p.render[pix * p.split + k] * inv;
+            v *= inv;
+        }
+        v_out[k] = v;
+    }
+    float bg_dot = 0.f;
+    if (p.backgrounds) {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) bg_dot += p.backgrounds[cam * CH + k] * v_out[k];
+    }
+    G = (v_alpha_out - bg_dot) * T_final;
+    bin_final = inside ? p.last_ids[pix] : -1;
+}
+
+// partials of one pixel for one Gaussian, written (INIT) or added to val[]
+template <int CH, bool INIT, int NF>
+__device__ __forceinline__ void bwd_pixel(bool valid, float alpha, float vis, float raw, float dx, float dy, float u,
+                                          float v, const float (&f)[NF], const float (&v_out)[CH], float& T, float& S,
+                                          float G, float (&val)[16]) {
+    if (!valid) { alpha = 0.f; vis = 0.f; }
+    float ra;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.f - alpha));
+    T *= ra;
+    const float fac = alpha * T;
+    float A = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        A = fmaf(f[k], v_out[k], A);
+        val[k] = INIT ? fac * v_out[k] : fmaf(fac, v_out[k], val[k]);
+    }
+    const float v_alpha = fmaf(T, A, (G - S) * ra);
+    S = fmaf(fac, A, S);
+    const bool gate = raw <= ALPHA_MAX;
+    const float v_sigma = gate ? -alpha * v_alpha : 0.f;
+    const float t1 = v_sigma * dx, t2 = v_sigma * dy;
+    const float hx = v_sigma * u, hy = v_sigma * v;
+    const float vop = gate ? vis * v_alpha : 0.f;
+    if (INIT) {
+        val[CH] = t1 * dx; val[CH + 1] = t1 * dy; val[CH + 2] = t2 * dy;
+        val[CH + 3] = hx; val[CH + 4] = hy; val[CH + 5] = fabsf(hx); val[CH + 6] = fabsf(hy); val[CH + 7] = vop;
+    } else {
+        val[CH] = fmaf(t1, dx, val[CH]); val[CH + 1] = fmaf(t1, dy, val[CH + 1]); val[CH + 2] = fmaf(t2, dy, val[CH + 2]);
+        val[CH + 3] = fmaf(v_sigma, u, val[CH + 3]); val[CH + 4] = fmaf(v_sigma, v, val[CH + 4]);
+        val[CH + 5] += fabsf(hx); val[CH + 6] += fabsf(hy); val[CH + 7] += vop;
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(BWD2_THREADS, 6) rasterize_bwd2_kernel(RasterBwdParams p) {
+    constexpr int FV = (CH + 3) / 4;
+    constexpr int NVAL = CH + 8;
+    constexpr int NREC = 2 + FV;
+    constexpr int OFF_F = 2 * REC_STRIDE;
+    constexpr int NW = BWD2_THREADS / 32;
+    static_assert(NVAL <= 16, "one transpose round");
+    __shared__ float4 sRec[NREC][BATCH];
+    __shared__ unsigned char sMask[BATCH];
+    __shared__ unsigned short sList[NW][BATCH];
+    __shared__ __align__(16) float sRed[NW][16 * RED_STRIDE];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float tile_cx0 = (float)(blockIdx.x * TILE) + 0.5f, tile_cy0 = (float)(blockIdx.y * TILE) + 0.5f;
+    const int cam = blockIdx.z;
+    const int tile_id = (cam * p.tile_h + blockIdx.y) * p.tile_w + blockIdx.x;
+    // warp -> 8x8 block (bx, by); lane -> column lane & 7, rows lane >> 3 and that + 4: the two 8x4
+    // patches (mask bits w0, w0 + 2) of the forward kernel's tile_pixel() mapping
+    const int bx = warp & 1, by = warp >> 1;
+    const int ix = blockIdx.x * TILE + bx * 8 + (lane & 7);
+    const int iy0 = blockIdx.y * TILE + by * 8 + (lane >> 3), iy1 = iy0 + 4;
+    const float px = ix + 0.5f, py0 = iy0 + 0.5f;
+    const int w0 = by * 4 + bx;
+
+    const int range_start = p.isect_offsets[tile_id];
+    const int range_end = (tile_id == p.C * p.tile_h * p.tile_w - 1) ? (int)p.n_isects : p.isect_offsets[tile_id + 1];
+    if (range_end <= range_start) return;
+
+    float* out_base = nullptr;
+    unsigned out_stride = 0;
+    float out_scale = 1.f;
+    bool out_is_opac = false;
+    {
+        const int slot = lane < 16 ? lane : 16;
+        if (slot < CH) { out_base = p.v_feat + slot; out_stride = CH * 4; }
+        else if (slot < CH + 3) { out_base = p.v_conics + (slot - CH); out_stride = 12; out_scale = (slot == CH + 1) ? 1.f : 0.5f; }
+        else if (slot < CH + 5) { out_base = p.v_means2d + (slot - CH - 3); out_stride = 8; out_scale = 2.f * LN2; }
+        else if (slot < CH + 7) { if (p.v_means2d_abs) { out_base = p.v_means2d_abs + (slot - CH - 5); out_stride = 8; out_scale = 2.f * LN2; } }
+        else if (slot < CH + 8) { out_base = p.v_opacities; out_stride = 4; out_is_opac = true; }
+    }
+
+    float v_out0[CH], v_out1[CH];
+    float T0, T1, G0, G1, S0 = 0.f, S1 = 0.f;
+    int bin0, bin1;
+    bwd_init_pixel<CH>(p, cam, ix, iy0, ix < p.width && iy0 < p.height, v_out0, T0, G0, bin0);
+    bwd_init_pixel<CH>(p, cam, ix, iy1, ix < p.width && iy1 < p.height, v_out1, T1, G1, bin1);
+    const int warp_bin_final = __reduce_max_sync(0xffffffffu, max(bin0, bin1));
+    const int nb_all = (range_end - range_start + BATCH - 1) / BATCH;
+
+    const unsigned rec0 = smem_addr(&sRec[0][0]);
+    const unsigned list0 = smem_addr(&sList[warp][0]);
+    const unsigned red_wr = smem_addr(&sRed[warp][lane]);
+    const unsigned red_rd = smem_addr(&sRed[warp][(lane & 15) * RED_STRIDE + (lane >> 4) * 16]);
+
+    for (int b = 0; b < nb_all; ++b) {
+        const int batch_end = range_end - 1 - BATCH * b;
+        const int bs = min(BATCH, batch_end + 1 - range_start);
+        const int need = __syncthreads_or(batch_end - bs + 1 <= warp_bin_final);
+        if (!need) continue;
+#pragma unroll
+        for (int h = 0; h < BATCH / BWD2_THREADS; ++h) {
+            const int slot = tid + h * BWD2_THREADS;
+            const int idx = batch_end - slot;
+            if (idx >= range_start) {
+                const int g = p.flatten_ids[idx];
+                const float2 m = p.means2d[g];
+                const float ca = p.conics[3 * (size_t)g], cb = p.conics[3 * (size_t)g + 1], cc = p.conics[3 * (size_t)g + 2];
+                const int go = p.opac_shared ? g % p.N : g;
+                const float opac = p.opacities[go];
+                const float a1 = 0.5f * LOG2E * ca, b1 = 0.5f * LOG2E * cb, c1 = 0.5f * LOG2E * cc;
+                sRec[0][slot] = make_float4(m.x, m.y, opac, a1);
+                sMask[slot] = (unsigned char)patch_mask(m.x, m.y, opac, a1, 2.f * b1, c1, tile_cx0, tile_cy0);
+                sRec[1][slot] = make_float4(b1, c1, __int_as_float(g), __int_as_float(go));
+                float f[FV * 4];
+#pragma unroll
+                for (int k = 0; k < FV * 4; ++k) f[k] = (k < CH) ? p.feat[(size_t)g * CH + k] : 0.f;
+#pragma unroll
+                for (int j = 0; j < FV; ++j) sRec[2 + j][slot] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            }
+        }
+        __syncthreads();
+        // this warp's list: slot | (which halves can be reached) << 8, in order
+        int n_list = 0;
+        {
+            const int t_min = max(0, batch_end - warp_bin_final);
+            const unsigned lt = (1u << lane) - 1;
+#pragma unroll
+            for (int c = 0; c < BATCH / 32; ++c) {
+                const int t = c * 32 + lane;
+                const unsigned mk = sMask[t];
+                const unsigned hm = ((mk >> w0) & 1u) | (((mk >> (w0 + 2)) & 1u) << 1);
+                const bool keep = t >= t_min && t < bs && hm != 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) sList[warp][n_list + __popc(bal & lt)] = (unsigned short)(t | (hm << 8));
+                n_list += __popc(bal);
+            }
+            __syncwarp();
+        }
+        const int t_lim0 = batch_end - bin0, t_lim1 = batch_end - bin1;
+        for (int li = 0; li < n_list; ++li) {
+            unsigned e;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(list0 + 2 * li));
+            const int t = e & 255;
+            const unsigned rec = rec0 + t * 16;
+            const float4 a4 = lds128<0>(rec), b4 = lds128<REC_STRIDE>(rec);
+            const GeomA ga = {a4.x, a4.y, a4.z, a4.w};
+            const GeomB gb = {b4.x, b4.y, 0, 0.f};
+            const bool h0 = e & 0x100, h1 = e & 0x200;  // warp-uniform
+            float dx, dy0 = 0.f, dy1 = 0.f, u0 = 0.f, v0 = 0.f, u1 = 0.f, v1 = 0.f;
+            float vis0 = 0.f, raw0 = 0.f, alpha0 = 0.f, vis1 = 0.f, raw1 = 0.f, alpha1 = 0.f;
+            bool valid0 = false, valid1 = false;
+            if (h0) valid0 = eval_alpha(ga, gb, px, py0, dx, dy0, u0, v0, vis0, raw0, alpha0) && (t >= t_lim0);
+            if (h1) valid1 = eval_alpha(ga, gb, px, py0 + 4.f, dx, dy1, u1, v1, vis1, raw1, alpha1) && (t >= t_lim1);
+            if (!__any_sync(0xffffffffu, valid0 || valid1)) continue;
+            dx = a4.x - px;
+            float f[FV * 4];
+            {
+                const float4 q = lds128<OFF_F>(rec);
+                f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+            }
+            if (FV > 1) {
+                const float4 q = lds128<OFF_F + REC_STRIDE>(rec);
+                f[4 * (FV - 1)] = q.x; f[4 * (FV - 1) + 1] = q.y; f[4 * (FV - 1) + 2] = q.z; f[4 * (FV - 1) + 3] = q.w;
+            }
+            float val[16];
+            if (h0) {
+                bwd_pixel<CH, true>(valid0, alpha0, vis0, raw0, dx, dy0, u0, v0, f, v_out0, T0, S0, G0, val);
+                if (h1) bwd_pixel<CH, false>(valid1, alpha1, vis1, raw1, dx, dy1, u1, v1, f, v_out1, T1, S1, G1, val);
+            } else {
+                bwd_pixel<CH, true>(valid1, alpha1, vis1, raw1, dx, dy1, u1, v1, f, v_out1, T1, S1, G1, val);
+            }
+#pragma unroll
+            for (int k = NVAL; k < 16; ++k) val[k] = 0.f;
+            transpose_reduce<16, NVAL>(val, red_wr, red_rd);
+            if (out_stride) {
+                const unsigned row = __float_as_uint(out_is_opac ? b4.w : b4.z);
+                unsigned long long addr;
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(out_stride), "l"(out_base));
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(val[0] * out_scale) : "memory");
+            }
+        }
+    }
+}
+
 template <int CH>
 static int launch_raster_bwd(const RasterBwdParams& p, cudaStream_t st) {
     dim3 grid(p.tile_w, p.tile_h, p.C);
@@ -291,7 +511,7 @@ static int launch_raster_bwd(const RasterBwdParams& p, cudaStream_t st) {
             FG_LAUNCH((rasterize_bwd_kernel<(CH >= 2 ? CH : 2), true>), grid, TILE_PIX, 0, st, p);
         }
     } else {
-        FG_LAUNCH((rasterize_bwd_kernel<CH, false>), grid, TILE_PIX, 0, st, p);
+        FG_LAUNCH((rasterize_bwd2_kernel<CH>), grid, BWD2_THREADS, 0, st, p);
     }
     return FG_OK;
 }
