@@ -38,6 +38,7 @@ long long fg_launch_count(void) { return fg::g_launch_count.load(); }
 // chains per thread, 1024 threads per SM-resident CTA, 2 CTAs per SM.
 namespace fg {
 __global__ void __launch_bounds__(1024) fp32_peak_kernel(float* out, int iters, float a, float b) {
+    pdl_wait();
     float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
           x7 = x0 + 7.f;
     for (int i = 0; i < iters; ++i) {

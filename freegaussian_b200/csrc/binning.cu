@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256)
                      const float2* __restrict__ means2d, const int32_t* __restrict__ radii, int tile_size, int tile_w,
                      int tile_h, int32_t* __restrict__ diff /*[C][tile_h+1][tile_w+1]*/,
                      int32_t* __restrict__ coarse_cnt /*[total], in `order`*/) {
+    pdl_wait();
     const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
     if (slot >= total) return;
     const long long idx = order[slot];
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256)
 // scan of isect.cu, so many-camera calls (cfg4: 32 views, ~0.7 M tiles) stay parallel.
 __global__ void __launch_bounds__(1024)
     tile_count_kernel(int tile_w, int tile_h, int32_t* __restrict__ diff, int32_t* __restrict__ counts) {
+    pdl_wait();
     const int W1 = tile_w + 1, H1 = tile_h + 1;
     const int c = blockIdx.x;
     int32_t* g = diff + (long long)c * H1 * W1;
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(256)
                        const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
                        const int32_t* __restrict__ coarse_off, int tile_size, int tile_w, int tile_h, int cw, int chh,
                        uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    pdl_wait();
     const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
     if (slot >= total) return;
     const long long idx = order[slot];
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(FB_THREADS)
                     int n_cells_total, const int32_t* __restrict__ coarse_vals, const float2* __restrict__ means2d,
                     const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
                     const int32_t* __restrict__ isect_offsets, int32_t* __restrict__ flatten_ids) {
+    pdl_wait();
     constexpr int NT = CK * CK;
     __shared__ int s_cursor[NT];       // entries already written per tile
     __shared__ int s_warp_cnt[FB_WARPS][NT];  // per chunk: entries per (warp, tile)

@@ -25,6 +25,7 @@ struct PlanParams {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void __launch_bounds__(RB) refine_flags_kernel(PlanParams p) {
+    pdl_wait();
     const long long n = (long long)blockIdx.x * RB + threadIdx.x;
     if (n >= p.N) return;
     const float s0 = p.scales[3 * n], s1 = p.scales[3 * n + 1], s2 = p.scales[3 * n + 2];
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(RB) refine_flags_kernel(PlanParams p) {
 }
 
 __global__ void refine_counts_kernel(long long N, int* plan, const long long* total, long long* counts) {
+    pdl_wait();
     const int t = (int)*total;
     plan[4 * N] = t;
     counts[0] = plan[N];
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(RB) refine_map_kernel(long long N, const int* 
                                                         const long long* __restrict__ counts, int samps,
                                                         long long n_out, int* __restrict__ src,
                                                         int* __restrict__ sample_row) {
+    pdl_wait();
     const long long n = (long long)blockIdx.x * RB + threadIdx.x;
     if (n >= N) return;
     const long long n_ko = counts[0], n_kc = counts[1], n_split = counts[3];
@@ -103,6 +106,7 @@ struct GatherParams {
 };
 
 __global__ void __launch_bounds__(RB) refine_gather_kernel(const __grid_constant__ GatherParams p) {
+    pdl_wait();
     const fg_refine_array& A = p.a[blockIdx.y];
     const long long total = p.n_out * A.row_floats;
     for (long long e = (long long)blockIdx.x * RB + threadIdx.x; e < total; e += (long long)gridDim.x * RB) {
@@ -123,6 +127,7 @@ __global__ void __launch_bounds__(RB) refine_children_kernel(long long n_keep, l
                                                              const float* __restrict__ scales,
                                                              float* __restrict__ means_out,
                                                              float* __restrict__ scales_out) {
+    pdl_wait();
     const long long i = (long long)blockIdx.x * RB + threadIdx.x;
     if (i >= n_children) return;
     const long long d = n_keep + i;

@@ -46,6 +46,7 @@ __device__ __forceinline__ long long block_excl_scan(long long v, long long* tot
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(long long n, const int32_t* __restrict__ counts,
                                                                    long long* __restrict__ block_sums) {
+    pdl_wait();
     __shared__ long long warp_sums[33];
     const long long base = (long long)blockIdx.x * SCAN_TILE;
     long long s = 0;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(long long n, 
 // single block: exclusive scan of block_sums in place, grand total -> *total
 __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(int nblocks, long long* __restrict__ block_sums,
                                                                   long long* __restrict__ total_out) {
+    pdl_wait();
     __shared__ long long warp_sums[33];
     long long carry = 0;
     for (int base = 0; base < nblocks; base += SCAN_THREADS) {
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(int nblocks, l
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(long long n, const int32_t* __restrict__ counts,
                                                                   const long long* __restrict__ block_sums,
                                                                   int32_t* __restrict__ offsets) {
+    pdl_wait();
     __shared__ long long warp_sums[33];
     // blocked arrangement: thread t owns items [t*ITEMS, (t+1)*ITEMS) of the tile
     const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(EMIT_THREADS)
                       const float* __restrict__ depths, const int32_t* __restrict__ offsets, int tile_size,
                       int tile_w, int tile_h, int tile_bits, int64_t* __restrict__ isect_ids,
                       uint32_t* __restrict__ tile_keys, int32_t* __restrict__ flatten_ids) {
+    pdl_wait();
     const long long slot = (long long)blockIdx.x * EMIT_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0, cnt = 0, off = 0;
@@ -171,6 +175,7 @@ __global__ void __launch_bounds__(256)
     isect_offsets_kernel(long long n_isects, const int64_t* __restrict__ sorted_ids,
                          const uint32_t* __restrict__ sorted_tile_keys, int n_tiles_per_cam, int tile_bits,
                          long long n_tiles_total, int32_t* __restrict__ offsets) {
+    pdl_wait();
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_isects) return;
     auto lin = [&](long long j) -> long long {
@@ -193,6 +198,7 @@ __global__ void __launch_bounds__(256)
 __global__ void depth_keys_kernel(long long total, const float* __restrict__ depths,
                                   const int32_t* __restrict__ tiles_per_gauss, uint32_t* __restrict__ keys,
                                   uint32_t* __restrict__ vals) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     keys[i] = tiles_per_gauss[i] > 0 ? (uint32_t)__float_as_int(depths[i]) : 0xffffffffu;
@@ -200,6 +206,7 @@ __global__ void depth_keys_kernel(long long total, const float* __restrict__ dep
 }
 __global__ void gather_i32_kernel(long long n, const int32_t* __restrict__ src, const int32_t* __restrict__ idx,
                                   int32_t* __restrict__ dst) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
 }
@@ -207,6 +214,7 @@ __global__ void gather_i32_kernel(long long n, const int32_t* __restrict__ src, 
 __global__ void isect_ids_kernel(long long n, const uint32_t* __restrict__ tile_keys,
                                  const int32_t* __restrict__ flatten_ids, const float* __restrict__ depths,
                                  int n_tiles_per_cam, int tile_bits, int64_t* __restrict__ out) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long lin = tile_keys[i];
@@ -218,6 +226,7 @@ __global__ void isect_ids_kernel(long long n, const uint32_t* __restrict__ tile_
 __global__ void densify_stats_kernel(int C, int N, const int32_t* __restrict__ radii, const float2* __restrict__ absgrad,
                                      float inv_max_hw, float* __restrict__ grad_norm, float* __restrict__ vis_count,
                                      float* __restrict__ max_size) {
+    pdl_wait();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float g = 0.f, cnt = 0.f;
@@ -240,6 +249,7 @@ __global__ void densify_stats_kernel(int C, int N, const int32_t* __restrict__ r
 }
 
 __global__ void fill_i32_kernel(long long n, int32_t v, int32_t* out) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = v;
 }

@@ -47,6 +47,7 @@ __host__ __device__ inline float ord2f(unsigned u) {
 }
 
 __global__ void knn_bbox_kernel(long long n, const float* __restrict__ pts, unsigned* __restrict__ bbox /*[6]*/) {
+    pdl_wait();
     unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
 #pragma unroll
@@ -77,6 +78,7 @@ __device__ __forceinline__ int cell_coord(double p, double o, double inv_h, int 
 
 __global__ void knn_count_kernel(long long n, const float* __restrict__ pts, KnnGrid g, int32_t* __restrict__ cell_count,
                                  int32_t* __restrict__ cell_of) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int cx = cell_coord((double)pts[3 * i], g.ox, g.inv_h, g.nx);
@@ -90,6 +92,7 @@ __global__ void knn_count_kernel(long long n, const float* __restrict__ pts, Knn
 __global__ void knn_scatter_kernel(long long n, const float* __restrict__ pts, const int32_t* __restrict__ cell_of,
                                    const int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_fill,
                                    float4* __restrict__ sorted) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int cid = cell_of[i];
@@ -127,6 +130,7 @@ template <int KCAP>
 __global__ void __launch_bounds__(128)
     knn_query_kernel(long long n, const float4* __restrict__ sorted, const int32_t* __restrict__ cell_start,
                      KnnGrid g, int k, float* __restrict__ out_dist, int32_t* __restrict__ out_idx) {
+    pdl_wait();
     long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const float4 me = sorted[q];

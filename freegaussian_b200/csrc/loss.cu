@@ -47,6 +47,7 @@ __device__ __forceinline__ float pred_at(const LossParams& p, int x, int y, int 
 }
 
 __global__ void __launch_bounds__(256) l1_ssim_fwd_kernel(LossParams p) {
+    pdl_wait();
     __shared__ float sx[LHY][LHX + 1], sy[LHY][LHX + 1];
     __shared__ float hm[5][LHY][LTX + 1];  // horizontally filtered moments
     __shared__ double red[2][8];
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(256) l1_ssim_fwd_kernel(LossParams p) {
 }
 
 __global__ void __launch_bounds__(256) l1_ssim_bwd_kernel(LossParams p) {
+    pdl_wait();
     // input pixel block 32x16; needs partial maps at q in [p-10, p] -> halo to the top/left
     __shared__ float sg[3][LHY][LHX + 1];
     __shared__ float hg[3][LHY][LTX + 1];

@@ -46,6 +46,7 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
 }
 
 __global__ void __launch_bounds__(AB) adam_kernel(const __grid_constant__ AdamParams P) {
+    pdl_wait();
     int s = 0;
     while (s < P.n_seg - 1 && (int)blockIdx.x >= P.blk_end[s]) ++s;
     const AdamSegDev& S = P.seg[s];

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256)
                         const int64_t* __restrict__ gaussian_ids, const float* __restrict__ depth_img, int W, int H,
                         const uint8_t* __restrict__ atrb_masks, const uint8_t* __restrict__ mask_valids, int M,
                         uint8_t* __restrict__ gaussian_masks) {
+    pdl_wait();
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= nnz) return;
     const float2 m = means2d[i];

@@ -133,6 +133,7 @@ __device__ __forceinline__ void read_sh_row_global(const float* __restrict__ sh,
 
 template <int DEG, bool VEC4>
 __global__ void __launch_bounds__(PB, 4) project_fwd_kernel(ProjParams p) {
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     const int n0 = blockIdx.x * PB;
     const int n = n0 + threadIdx.x;
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(PB, 4) project_fwd_kernel(ProjParams p) {
 // ------------------------------------------------------------------------------ backward
 template <int DEG, bool VEC4, int MINB = (DEG < 0 ? 4 : 3)>
 __global__ void __launch_bounds__(PB, MINB) project_bwd_kernel(ProjParams p) {
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     using S = ShShape<(DEG >= 0 ? DEG : 0)>;
     const int n0 = blockIdx.x * PB;
@@ -471,6 +473,7 @@ __global__ void __launch_bounds__(PB, MINB) project_bwd_kernel(ProjParams p) {
 constexpr bool SH_BWD_STAGE = false;  // coefficient rows are read once per camera straight from global memory
 template <int DEG>
 __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int NG = (K + 3) / 4;   // groups of four bases

@@ -49,6 +49,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
     rs_histogram_kernel(long long n, const KeyT* __restrict__ keys, int passes, int end_bit,
                         uint32_t* __restrict__ global_hist /*[passes][256]*/) {
+    pdl_wait();
     __shared__ uint32_t hist[8 * RS_RADIX];
     for (int i = threadIdx.x; i < passes * RS_RADIX; i += RS_THREADS) hist[i] = 0;
     __syncthreads();
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 // exclusive scan of each pass's 256 bins, in place; one block of 256 threads per pass
 __global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ global_hist) {
     __shared__ uint32_t warp_tot[8];
+    pdl_wait();
     uint32_t* h = global_hist + blockIdx.x * RS_RADIX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t v = h[threadIdx.x], incl = v;
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(RS_THREADS)
                        KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift, int bits,
                        const uint32_t* __restrict__ global_offs /*[256] exclusive*/,
                        volatile uint32_t* status /*[tiles][256]*/, int* __restrict__ tile_counter) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem<KeyT>& s = *reinterpret_cast<RsSmem<KeyT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -296,8 +299,8 @@ static int radix_sort_pairs(long long n, KeyT* keys_in, uint32_t* vals_in, KeyT*
             FG_LAUNCH((rs_onesweep_kernel<KeyT, 32>), (int)L.tiles, RS_THREADS, smem, st, n, kin, vin, kout, vout, shift,
                       bits, hist + p * RS_RADIX, status + (size_t)p * L.tiles * RS_RADIX, counters + p);
         } else {
-            FG_LAUNCH((rs_onesweep_kernel<KeyT, 8>), (int)L.tiles, RS_THREADS, smem, st, n, kin, vin, kout, vout, shift,
-                      bits, hist + p * RS_RADIX, status + (size_t)p * L.tiles * RS_RADIX, counters + p);
+            FG_LAUNCH((rs_onesweep_kernel<KeyT, 8>), (int)L.tiles, RS_THREADS, smem, st, n, (const KeyT*)kin, (const uint32_t*)vin, kout, vout, shift,
+                          bits, (const uint32_t*)(hist + p * RS_RADIX), status + (size_t)p * L.tiles * RS_RADIX, counters + p);
         }
         KeyT* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;

@@ -82,6 +82,7 @@ __device__ __forceinline__ void transpose_reduce(float (&val)[NV], unsigned wr, 
 
 template <int CH, bool AFF>
 __global__ void __launch_bounds__(TILE_PIX, 4) rasterize_bwd_kernel(RasterBwdParams p) {
+    pdl_wait();
     constexpr int FV = (CH + 3) / 4;
     constexpr int NVAL = CH + 8 + (AFF ? 4 : 0);  // partials per (pixel, Gaussian)
     constexpr int NV = NVAL <= 16 ? 16 : 32;
@@ -360,6 +361,7 @@ __device__ __forceinline__ void bwd_pixel(bool valid, float alpha, float vis, fl
 
 template <int CH>
 __global__ void __launch_bounds__(BWD2_THREADS, 6) rasterize_bwd2_kernel(RasterBwdParams p) {
+    pdl_wait();
     constexpr int FV = (CH + 3) / 4;
     constexpr int NVAL = CH + 8;
     constexpr int NREC = 2 + FV;

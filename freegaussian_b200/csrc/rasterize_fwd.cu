@@ -36,6 +36,7 @@ struct RasterFwdParams {
 
 template <int CH, bool AFF>
 __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdParams p) {
+    pdl_wait();
     constexpr int FV = (CH + 3) / 4;  // float4 per Gaussian for the features
     constexpr int NREC = 2 + FV + (AFF ? 1 : 0);  // float4 arrays of the staged records: A, B, F.., M
     constexpr int OFF_F = 2 * REC_STRIDE, OFF_M = (2 + FV) * REC_STRIDE;

@@ -98,3 +98,26 @@ def test_compat_helpers():
     centre = torch.cat([c2w[:, :, 3], torch.ones(3, 1)], -1)
     assert torch.allclose(torch.einsum("cij,cj->ci", vm, centre)[:, :3], torch.zeros(3, 3), atol=1e-5)
     assert torch.allclose(vm[:, :3, :3], (R * torch.tensor([1.0, -1.0, -1.0])).transpose(1, 2), atol=1e-6)
+
+
+def test_every_kernel_waits_for_its_stream_predecessor():
+    """All launches are programmatic dependent launches (csrc/common.cuh FG_LAUNCH): a kernel that did not start
+    with pdl_wait() could run ahead of the kernel that produces its input."""
+    n = 0
+    for path in sorted((ROOT / "freegaussian_b200" / "csrc").glob("*.cu")):
+        text = path.read_text()
+        assert "<<<" not in text, f"{path.name}: raw launch bypasses FG_LAUNCH"
+        for m in re.finditer(r"__global__[^{;]*\{", text):
+            body = text[m.end():m.end() + 1200]
+            first = [ln.strip() for ln in body.split("\n") if ln.strip() and not ln.strip().startswith("//")]
+            # declarations of shared memory may precede it; nothing that touches memory may
+            head = []
+            for ln in first:
+                head.append(ln)
+                if ln.startswith("pdl_wait();"):
+                    break
+            assert head and head[-1].startswith("pdl_wait();"), f"{path.name}: kernel without pdl_wait: {first[:2]}"
+            for ln in head[:-1]:
+                assert ln.startswith(("extern __shared__", "__shared__", "using ", "constexpr ")), (path.name, ln)
+            n += 1
+    assert n >= 30
