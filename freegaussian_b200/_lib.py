@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfreegaussian_b200.so"
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pi = C.POINTER(C.c_int)
@@ -85,7 +85,8 @@ SIGNATURES = {
     "fg_render_front_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "fg_render_front": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _i32,
                                _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
-                               _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp, _i64, _vp]),
+                               _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp, _i64, _vp,
+                               _i64, _vp, _i64, _vp]),
     "fg_render_back_workspace_bytes": (_i64, [_i32, _i32, _i32, _i64]),
     "fg_render_back": (_i32, [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64,
                               _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

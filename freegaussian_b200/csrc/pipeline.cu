@@ -73,7 +73,9 @@ extern "C" int fg_render_front(int C, int N, const float* means, const float* qu
                                float* conics, float* compensations, float* feat, int feat_stride, int rgb_off,
                                int depth_off, int flow_off, float* flow_affine, int32_t* tiles_per_gauss,
                                int32_t* order, int32_t* isect_offsets, int32_t* coarse_off, int64_t* counts_host,
-                               void* workspace, int64_t workspace_bytes, void* stream) {
+                               void* workspace, int64_t workspace_bytes, int32_t* flatten_ids,
+                               int64_t flatten_capacity, void* back_workspace, int64_t back_workspace_bytes,
+                               void* stream) {
     FG_REQUIRE(isect_offsets && counts_host && workspace, "NULL pointer");
     FG_REQUIRE((long long)C * N == 0 || (order && coarse_off), "order / coarse_off must not be NULL");
     const int tile_w = (width + tile_size - 1) / tile_size, tile_h = (height + tile_size - 1) / tile_size;
@@ -113,6 +115,16 @@ extern "C" int fg_render_front(int C, int N, const float* means, const float* qu
     FG_CUDA(cudaStreamSynchronize(st));  // the one host sync of the forward pass
     counts_host[0] = pin[0];
     counts_host[1] = pin[1];
+    counts_host[2] = 0;
+    // the caller guessed the list size: if it fits, keep the GPU busy without a round trip through the host mirror
+    if (flatten_ids && back_workspace && pin[0] <= flatten_capacity &&
+        fg_render_back_workspace_bytes(C, tile_w, tile_h, pin[1]) <= back_workspace_bytes) {
+        if ((e = fg_render_back(C, N, pin[0], pin[1], order, coarse_off, means2d, radii, tile_size, isect_offsets,
+                                flatten_ids, back_workspace, back_workspace_bytes, 0, width, height, nullptr, nullptr,
+                                nullptr, nullptr, nullptr, -1, 0, -1, 0, nullptr, nullptr, nullptr, nullptr, stream)))
+            return e;
+        counts_host[2] = 1;
+    }
     return FG_OK;
 }
 

@@ -284,13 +284,19 @@ static int radix_sort_pairs(long long n, KeyT* keys_in, uint32_t* vals_in, KeyT*
     int* counters = (int*)(ws + L.off_counters);
     uint32_t* status = (uint32_t*)(ws + L.off_status);
     FG_CUDA(cudaMemsetAsync(ws, 0, L.total, st));
-    int hist_blocks = (int)min((long long)kNumSMs * 4, (n + RS_THREADS - 1) / RS_THREADS);
+    int hist_blocks = (int)min((long long)kNumSMs * 4, (n + RS_THREADS - 1) / RS_THREADS);  // 1 per SM measured slower
     FG_LAUNCH((rs_histogram_kernel<KeyT>), hist_blocks, RS_THREADS, 0, st, n, keys_in, passes, end_bit, hist);
     FG_LAUNCH(rs_scan_hist_kernel, passes, RS_RADIX, 0, st, hist);
     const size_t smem = sizeof(RsSmem<KeyT>);
     const bool small = false;  // a 32-word window was measured: no gain on 1 M-item sorts (per-tile latency dominates), more registers
-    FG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FG_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const cudaError_t attr_once = [] {
+        cudaError_t e = cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(RsSmem<KeyT>));
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(RsSmem<KeyT>));
+    }();
+    FG_CUDA(attr_once);
     KeyT* kin = keys_in; uint32_t* vin = vals_in; KeyT* kout = keys_out; uint32_t* vout = vals_out;
     for (int p = 0; p < passes; ++p) {
         int shift = 8 * p;

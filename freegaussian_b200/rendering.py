@@ -56,6 +56,7 @@ _ws = _Workspace()
 # The flat buffer holding the parameter gradients of the most recent projection backward:
 # (tensor, floats in use).  Read by freegaussian_b200.dist.exchange.
 _grad_arena: Dict[str, tuple] = {}
+_list_guess: Dict[tuple, tuple] = {}  # (C, N, W, H, device) -> (capacity of flatten_ids, of the coarse pairs)
 
 
 def last_grad_arena():
@@ -161,23 +162,33 @@ class _Project(torch.autograd.Function):
             coarse_off = torch.empty(C * N, dtype=torch.int32, device=dev)
             isect_offsets = torch.empty(C, tile_h, tile_w, dtype=torch.int32, device=dev)
             ws = _ws.get("front", L.fg_render_front_workspace_bytes(C, N, tile_w, tile_h), dev)
-            counts = (ctypes.c_int64 * 2)()
+            # the list length M is only known after the call's host sync; a buffer of a guessed capacity
+            # (1.25 x the largest M seen for this shape) lets the C side go on to build the lists without
+            # coming back here first.  A wrong guess costs one extra call, never a wrong result.
+            key = (C, N, cfg["width"], cfg["height"], dev)
+            guess_m, guess_mc = _list_guess.get(key, (0, 0))
+            flat_buf = torch.empty(guess_m, dtype=torch.int32, device=dev) if guess_m else None
+            ws2 = _ws.get("back", L.fg_render_back_workspace_bytes(C, tile_w, tile_h, guess_mc), dev) if guess_m else None
+            counts = (ctypes.c_int64 * 3)()
             check(L.fg_render_front(
                 C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
                 cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"], cfg["tile_size"],
                 sh_degree if use_sh else -1, sh_bases, ptr(colors) if use_sh else None, ptr(means_next),
                 ptr(quats_next), ptr(scales_next), int(flow_cov), ptr(radii), ptr(means2d), ptr(depths), ptr(conics),
                 ptr(comps), ptr(feat), CH, rgb_off, depth_off, flow_off, ptr(flow_affine), ptr(tiles), ptr(order),
-                ptr(isect_offsets), ptr(coarse_off), counts, ptr(ws), ws.numel(), _stream()))
-            # the host now knows the list sizes: build the tile lists right away (coarse emit + sort + cell
-            # offsets + fine binning), so the GPU works while Python assembles the compositing call
+                ptr(isect_offsets), ptr(coarse_off), counts, ptr(ws), ws.numel(), ptr(flat_buf), guess_m,
+                ptr(ws2), ws2.numel() if ws2 is not None else 0, _stream()))
             M, Mc = int(counts[0]), int(counts[1])
-            flatten_ids = torch.empty(M, dtype=torch.int32, device=dev)
-            ws2 = _ws.get("back", L.fg_render_back_workspace_bytes(C, tile_w, tile_h, Mc), dev)
-            check(L.fg_render_back(C, N, M, Mc, ptr(order), ptr(coarse_off), ptr(means2d), ptr(radii),
-                                   cfg["tile_size"], ptr(isect_offsets), ptr(flatten_ids), ptr(ws2), ws2.numel(), 0,
-                                   cfg["width"], cfg["height"], None, None, None, None, None, -1, 0, -1, 0, None, None,
-                                   None, None, _stream()))
+            _list_guess[key] = (max(guess_m, int(1.25 * M) + 1024), max(guess_mc, int(1.25 * Mc) + 1024))
+            if counts[2]:
+                flatten_ids = flat_buf[:M]
+            else:
+                flatten_ids = torch.empty(M, dtype=torch.int32, device=dev)
+                ws2 = _ws.get("back", L.fg_render_back_workspace_bytes(C, tile_w, tile_h, Mc), dev)
+                check(L.fg_render_back(C, N, M, Mc, ptr(order), ptr(coarse_off), ptr(means2d), ptr(radii),
+                                       cfg["tile_size"], ptr(isect_offsets), ptr(flatten_ids), ptr(ws2), ws2.numel(), 0,
+                                       cfg["width"], cfg["height"], None, None, None, None, None, -1, 0, -1, 0, None,
+                                       None, None, None, _stream()))
             cfg["_front"] = dict(isect_offsets=isect_offsets, flatten_ids=flatten_ids, M=M, Mc=Mc, tile_w=tile_w,
                                  tile_h=tile_h)
         else:

@@ -209,7 +209,10 @@ int fg_densify_stats(int C, int N, const int32_t* radii, const float* absgrad, f
 /* ---- (3b) the forward pass in two calls ------------------------------------------------------
  * fg_render_front = fg_project_fwd + depth sort + fg_bin_count + fg_bin_tile_scan + the coarse scan,
  * then the ONE host synchronisation of the pass: counts_host[0] = M (tile intersections),
- * counts_host[1] = Mc (coarse pairs).  The caller allocates flatten_ids[M] and calls
+ * counts_host[1] = Mc (coarse pairs), counts_host[2] = 1 if the lists were built already: when the caller
+ * passes a flatten_ids buffer of a guessed capacity >= M (and a back workspace large enough for Mc), the
+ * list-building half of fg_render_back is enqueued right here, without a round trip through the host mirror
+ * (pass NULL / 0 to opt out).  Otherwise the caller allocates flatten_ids[M] and calls
  * fg_render_back = coarse emit + sort + cell offsets + fg_bin_fine + fg_rasterize_fwd.
  * Arguments are those of the granular entry points; `order`, `coarse_off` are [C*N] int32.  * fg_render_back with CH == 0 builds the tile lists only (flatten_ids) and skips compositing: the host
  * mirror calls it right after the sync so the GPU is busy again while Python assembles the compositing call.
@@ -223,7 +226,8 @@ int fg_render_front(int C, int N, const float* means, const float* quats, const 
                     float* conics, float* compensations, float* feat, int feat_stride, int rgb_off,
                     int depth_off, int flow_off, float* flow_affine, int32_t* tiles_per_gauss, int32_t* order,
                     int32_t* isect_offsets, int32_t* coarse_off, int64_t* counts_host, void* workspace,
-                    int64_t workspace_bytes, void* stream);
+                    int64_t workspace_bytes, int32_t* flatten_ids, int64_t flatten_capacity,
+                    void* back_workspace, int64_t back_workspace_bytes, void* stream);
 int64_t fg_render_back_workspace_bytes(int C, int tile_w, int tile_h, int64_t n_coarse);
 int fg_render_back(int C, int N, int64_t n_isects, int64_t n_coarse, const int32_t* order,
                    const int32_t* coarse_off, const float* means2d, const int32_t* radii, int tile_size,
