@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfreegaussian_b200.so"
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pi = C.POINTER(C.c_int)
@@ -34,7 +34,17 @@ class RefineArray(C.Structure):  # fg_refine_array
     _fields_ = [("in_", _vp), ("out", _vp), ("row_floats", C.c_int32), ("zero_new", C.c_int32)]
 
 
+class MlpPackSegment(C.Structure):  # fg_mlp_pack_segment
+    _fields_ = [("src", _vp), ("dst_hi", _vp), ("dst_lo", _vp), ("src_ld", C.c_int32), ("src_col0", C.c_int32),
+                ("rows", C.c_int32), ("cols", C.c_int32), ("dst_ld", C.c_int32), ("dst_col0", C.c_int32),
+                ("transpose", C.c_int32)]
+
+
 ADAM_MAX_SEGMENTS = 8
+MLP_PACK_MAX_SEGMENTS = 32
+MLP_EMBED_LD = 96
+MLP_HEAD_LD = 32
+MLP_RELU_SPLIT, MLP_LINEAR, MLP_DGRAD = 0, 1, 2
 REFINE_MAX_ARRAYS = 24
 
 # name -> (restype, argtypes); mirrors include/fg_api.h one to one
@@ -90,6 +100,11 @@ SIGNATURES = {
     "fg_render_back_workspace_bytes": (_i64, [_i32, _i32, _i32, _i64]),
     "fg_render_back": (_i32, [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64,
                               _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "fg_mlp_linear": (_i32, [_i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_mlp_pack": (_i32, [_i32, C.POINTER(MlpPackSegment), _vp]),
+    "fg_deform_embed": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "fg_deform_apply_fwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_deform_apply_bwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_knn_workspace_bytes": (_i64, [_i64]),
     "fg_knn_f32": (_i32, [_i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
 }

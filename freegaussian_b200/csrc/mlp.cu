@@ -1,0 +1,622 @@
+// Deformation network: the MLP FreeGaussian evaluates for every Gaussian right before
+// each render call (freegaussian/freegaussian_model.py:832-845, :1054-1114) -- the one dense contraction of
+// the training step, so the one place the 5th-generation tensor cores are used.
+//
+//   fg_mlp_linear     out = epilogue(A . W^T): CTA = 128 rows x BN outputs, persistent over row tiles.
+//                     warp 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, mbarrier pipeline),
+//                     warp 1 = tcgen05.mma issuer (kind::tf32, accumulators in TMEM, double buffered),
+//                     warps 2-5 = epilogue (tcgen05.ld -> bias / ReLU / mask -> global).
+//                     The reference computes in fp32, so the forward runs the error-compensated 3xTF32 scheme:
+//                     every operand is stored as hi (the nearest tf32 value, kept as fp32 with 13 zero low bits)
+//                     and lo = x - hi, and each k-step issues A_hi.W_hi + A_hi.W_lo + A_lo.W_hi into the same
+//                     fp32 accumulator (what is dropped is O(2^-21) relative).  The data-gradient pass runs
+//                     single TF32 (gradient tolerance 1e-3).
+//   fg_mlp_pack       weights -> padded / reordered / transposed hi+lo operand buffers (one launch, segment table)
+//   fg_deform_embed   positional embedding of the means + broadcast time embedding -> hi/lo [N,96]   (utils.py:27-56)
+//   fg_deform_apply_fwd/bwd   screw axis -> SE(3) -> means, scales, quats (utils.py:137-159, model.py:841-845)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fg {
+namespace mlp {
+
+constexpr int BM = 128;      // rows per tile = TMEM lanes
+constexpr int BK = 32;       // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;    // tf32 elements per tcgen05.mma
+constexpr int A_TILE_BYTES = BM * BK * 4;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a pipeline bug traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, both operands K-major, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, stored as TMA's 128-byte swizzle
+// writes them: 8-row groups 1024 bytes apart (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+// [cute/arch/mma_sm100_desc.hpp SmemDescriptor: start >> 4 at bit 0, LBO >> 4 at bit 16 (unused for swizzled K-major,
+// set to 1), SBO >> 4 at bit 32, version at bit 46, layout type at bit 61]
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor for kind::tf32: D fp32 (bit 4), A and B tf32 (2 at bits 7 and 10), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24.  [cute/arch/mma_sm100_desc.hpp InstrDescriptor]
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// nearest tf32 value (10 mantissa bits) as an fp32 bit pattern with the 13 low bits zero: what the tensor core reads is
+// then exact whatever it does with low bits, and x - hi is exact in fp32
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r & 0xFFFFE000u);
+}
+
+// ------------------------------------------------------------------------------------------------ the linear layer
+struct LinearArgs {
+    const float* bias;      // [BN] or NULL
+    const float* mask_src;  // [M, BN]: output kept where mask_src > 0 (EPI_MASK)
+    float* out_hi;          // [M, BN]
+    float* out_lo;          // [M, BN] (EPI_RELU_SPLIT)
+    long long M;
+    int kb0, kb1;  // k-blocks read from A0, then from A1 (the skip connection: [h | embedding])
+};
+
+enum { EPI_RELU_SPLIT = 0, EPI_LINEAR = 1, EPI_MASK = 2 };
+
+template <int BN, int NPROD, int NSTAGE, int EPI>
+__global__ void __launch_bounds__(192, 1)
+    mlp_linear_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_constant__ CUtensorMap mapA0l,
+                      const __grid_constant__ CUtensorMap mapA1h, const __grid_constant__ CUtensorMap mapA1l,
+                      const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, LinearArgs args) {
+    pdl_wait();
+    constexpr int W_TILE_BYTES = BN * BK * 4;
+    constexpr int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators; power of two >= 32
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns");
+    static_assert(BN % 32 == 0 && BN <= 256, "BN");
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_total = args.kb0 + args.kb1;
+    const long long n_tiles = (args.M + BM - 1) / BM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&bar_tfull[a]), 1);
+            mbar_init(smem_u32(&bar_tempty[a]), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int row0 = (int)(tile * BM);
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+                    const uint32_t full = smem_u32(&bar_full[stage]);
+                    const uint32_t sA = smem0 + stage * STAGE_BYTES;
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const bool first = kb < args.kb0;
+                    const int ka = (first ? kb : kb - args.kb0) * BK;
+                    tma_load_2d(sA, first ? &mapA0h : &mapA1h, full, ka, row0);
+                    if (NPROD == 3) {
+                        tma_load_2d(sA + A_TILE_BYTES, first ? &mapA0l : &mapA1l, full, ka, row0);
+                        tma_load_2d(sA + 2 * A_TILE_BYTES, &mapWh, full, kb * BK, 0);
+                        tma_load_2d(sA + 2 * A_TILE_BYTES + W_TILE_BYTES, &mapWl, full, kb * BK, 0);
+                    } else {
+                        tma_load_2d(sA + A_TILE_BYTES, &mapWh, full, kb * BK, 0);
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t t = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+                const uint32_t acc = t & 1;
+                mbar_wait(smem_u32(&bar_tempty[acc]), ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(smem_u32(&bar_full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem0 + stage * STAGE_BYTES;
+                    const uint64_t dAh = make_desc(sA);
+                    const uint64_t dAl = make_desc(sA + A_TILE_BYTES);
+                    const uint64_t dWh = make_desc(sA + (NPROD == 3 ? 2 : 1) * A_TILE_BYTES);
+                    const uint64_t dWl = make_desc(sA + 2 * A_TILE_BYTES + W_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // byte offset inside the swizzle row, >> 4
+                        tc_mma_tf32(d_tmem, dAh + adv, dWh + adv, idesc, (kb | k) != 0);
+                        if (NPROD == 3) {
+                            tc_mma_tf32(d_tmem, dAh + adv, dWl + adv, idesc, 1);
+                            tc_mma_tf32(d_tmem, dAl + adv, dWh + adv, idesc, 1);
+                        }
+                    }
+                    tc_commit(smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(smem_u32(&bar_tfull[acc]));  // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31 =====
+        const int q = warp & 3;
+        uint32_t t = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const uint32_t acc = t & 1;
+            mbar_wait(smem_u32(&bar_tfull[acc]), (t >> 1) & 1);
+            tc_fence_after();
+            const long long row = tile * BM + q * 32 + lane;
+            const bool live = row < args.M;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
+                if (live) {
+                    float* oh = args.out_hi + row * BN + c * 32;
+                    if (EPI == EPI_RELU_SPLIT) {
+                        float* ol = args.out_lo + row * BN + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 h, l;
+                            float x;
+                            x = fmaxf(__uint_as_float(v[j + 0]) + __ldg(args.bias + c * 32 + j + 0), 0.f); h.x = tf32_hi(x); l.x = x - h.x;
+                            x = fmaxf(__uint_as_float(v[j + 1]) + __ldg(args.bias + c * 32 + j + 1), 0.f); h.y = tf32_hi(x); l.y = x - h.y;
+                            x = fmaxf(__uint_as_float(v[j + 2]) + __ldg(args.bias + c * 32 + j + 2), 0.f); h.z = tf32_hi(x); l.z = x - h.z;
+                            x = fmaxf(__uint_as_float(v[j + 3]) + __ldg(args.bias + c * 32 + j + 3), 0.f); h.w = tf32_hi(x); l.w = x - h.w;
+                            *reinterpret_cast<float4*>(oh + j) = h;
+                            *reinterpret_cast<float4*>(ol + j) = l;
+                        }
+                    } else if (EPI == EPI_LINEAR) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 h;
+                            h.x = __uint_as_float(v[j + 0]) + __ldg(args.bias + c * 32 + j + 0);
+                            h.y = __uint_as_float(v[j + 1]) + __ldg(args.bias + c * 32 + j + 1);
+                            h.z = __uint_as_float(v[j + 2]) + __ldg(args.bias + c * 32 + j + 2);
+                            h.w = __uint_as_float(v[j + 3]) + __ldg(args.bias + c * 32 + j + 3);
+                            *reinterpret_cast<float4*>(oh + j) = h;
+                        }
+                    } else {
+                        // rounded to tf32 (nearest) here: the next data-gradient GEMM and the weight-gradient GEMM read it
+                        // as a tf32 operand, and letting the tensor core truncate instead biases every layer the same way
+                        const float* ms = args.mask_src + row * BN + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 m = __ldg(reinterpret_cast<const float4*>(ms + j));
+                            float4 h;
+                            h.x = m.x > 0.f ? tf32_hi(__uint_as_float(v[j + 0])) : 0.f;
+                            h.y = m.y > 0.f ? tf32_hi(__uint_as_float(v[j + 1])) : 0.f;
+                            h.z = m.z > 0.f ? tf32_hi(__uint_as_float(v[j + 2])) : 0.f;
+                            h.w = m.w > 0.f ? tf32_hi(__uint_as_float(v[j + 3])) : 0.f;
+                            *reinterpret_cast<float4*>(oh + j) = h;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [rows, cols] fp32 row-major (pitch = cols), box = box_rows x 32 columns, 128-byte swizzle; rows past the end read 0
+static bool make_map(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int NPROD, int NSTAGE, int EPI>
+static int launch_linear(long long M, const float* a0h, const float* a0l, int k0, const float* a1h, const float* a1l, int k1,
+                         const float* wh, const float* wl, const LinearArgs& args, cudaStream_t st) {
+    CUtensorMap mA0h, mA0l, mA1h, mA1l, mWh, mWl;
+    bool ok = make_map(&mA0h, a0h, M, k0, BM) && make_map(&mWh, wh, BN, k0 + k1, BN);
+    mA0l = mA0h, mA1h = mA0h, mA1l = mA0h, mWl = mWh;
+    if (NPROD == 3) ok = ok && make_map(&mA0l, a0l, M, k0, BM) && make_map(&mWl, wl, BN, k0 + k1, BN);
+    if (k1 > 0) {
+        ok = ok && make_map(&mA1h, a1h, M, k1, BM);
+        mA1l = mA1h;
+        if (NPROD == 3) ok = ok && make_map(&mA1l, a1l, M, k1, BM);
+    }
+    if (!ok) return set_error(FG_ERR_CUDA, "cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)", __FILE__, __LINE__);
+    constexpr int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (A_TILE_BYTES + BN * BK * 4);
+    constexpr int SMEM = NSTAGE * STAGE_BYTES + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    auto kern = mlp_linear_kernel<BN, NPROD, NSTAGE, EPI>;
+    FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const long long n_tiles = (M + BM - 1) / BM;
+    const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+    FG_LAUNCH(kern, grid, 192, SMEM, st, mA0h, mA0l, mA1h, mA1l, mWh, mWl, args);
+    return FG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+struct PackTable {
+    fg_mlp_pack_segment seg[FG_MLP_PACK_MAX_SEGMENTS];
+};
+
+__global__ void __launch_bounds__(256) mlp_pack_kernel(PackTable tab) {
+    pdl_wait();
+    const fg_mlp_pack_segment s = tab.seg[blockIdx.y];
+    const int total = s.rows * s.cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        // i runs over the destination so that the stores coalesce
+        int r, c;
+        float x;
+        if (s.transpose) {  // dst[c_src, r_src]
+            r = i / s.rows;  // source column
+            c = i % s.rows;  // source row
+            x = s.src[(long long)c * s.src_ld + s.src_col0 + r];
+        } else {
+            r = i / s.cols;
+            c = i % s.cols;
+            x = s.src[(long long)r * s.src_ld + s.src_col0 + c];
+        }
+        const long long d = (long long)r * s.dst_ld + s.dst_col0 + c;
+        const float h = tf32_hi(x);
+        s.dst_hi[d] = h;
+        if (s.dst_lo) s.dst_lo[d] = x - h;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding
+// E[n, :] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^9), cos(x 2^9) | t_emb | 0...]   (utils.py:27-56; model.py:1095-1096)
+__global__ void __launch_bounds__(256) deform_embed_kernel(long long N, const float* __restrict__ means, const float* __restrict__ t_emb,
+                                                           int t_ch, int multires, float* __restrict__ e_hi, float* __restrict__ e_lo) {
+    pdl_wait();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * FG_MLP_EMBED_LD) return;
+    const long long n = i / FG_MLP_EMBED_LD;
+    const int j = (int)(i % FG_MLP_EMBED_LD);
+    const int x_ch = 3 + 6 * multires;
+    float v = 0.f;
+    if (j < 3) {
+        v = means[n * 3 + j];
+    } else if (j < x_ch) {
+        const int k = j - 3, f = k / 6, r = k % 6;
+        const float a = means[n * 3 + (r % 3)] * exp2f((float)f);  // x * freq, freq = 2^f exactly
+        v = r < 3 ? sinf(a) : cosf(a);
+    } else if (j < x_ch + t_ch) {
+        v = t_emb[j - x_ch];
+    }
+    const float h = tf32_hi(v);
+    e_hi[i] = h;
+    e_lo[i] = v - h;
+}
+
+// ------------------------------------------------------------------------------------------------ SE(3) application
+struct Screw {
+    float th, w[3], v[3], sn, cs, W[9], W2[9], R[9], G[9];
+};
+
+__device__ __forceinline__ void screw_from_head(const float* o, Screw& s) {
+    // model.py:1103-1109: theta = |w|, w = w / theta + 1e-5, v = v / theta + 1e-5; utils.py:137-159
+    s.th = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s.w[k] = o[k] / s.th + 1e-5f;
+        s.v[k] = o[3 + k] / s.th + 1e-5f;
+    }
+    sincosf(s.th, &s.sn, &s.cs);
+    const float w0 = s.w[0], w1 = s.w[1], w2 = s.w[2];
+    const float W[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            s.W[r * 3 + c] = W[r * 3 + c];
+            s.W2[r * 3 + c] = W[r * 3 + 0] * W[0 * 3 + c] + W[r * 3 + 1] * W[1 * 3 + c] + W[r * 3 + 2] * W[2 * 3 + c];
+        }
+    const float c1 = 1.f - s.cs, c2 = s.th - s.sn;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float eye = (k % 4 == 0) ? 1.f : 0.f;
+        s.R[k] = eye + s.sn * s.W[k] + c1 * s.W2[k];
+        s.G[k] = s.th * eye + c1 * s.W[k] + c2 * s.W2[k];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    deform_apply_fwd_kernel(long long N, const float* __restrict__ head, const float* __restrict__ means, const float* __restrict__ scales_log,
+                            const float* __restrict__ quats, float* __restrict__ means_out, float* __restrict__ scales_out,
+                            float* __restrict__ quats_out) {
+    pdl_wait();
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float o[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(head + n * FG_MLP_HEAD_LD) + k);
+        o[4 * k] = t.x, o[4 * k + 1] = t.y, o[4 * k + 2] = t.z, o[4 * k + 3] = t.w;
+    }
+    Screw s;
+    screw_from_head(o, s);
+    const float m0 = means[n * 3], m1 = means[n * 3 + 1], m2 = means[n * 3 + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float p = s.G[r * 3] * s.v[0] + s.G[r * 3 + 1] * s.v[1] + s.G[r * 3 + 2] * s.v[2];
+        means_out[n * 3 + r] = s.R[r * 3] * m0 + s.R[r * 3 + 1] * m1 + s.R[r * 3 + 2] * m2 + p;  // model.py:841 (w row = 0,0,0,1)
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) scales_out[n * 3 + k] = expf(scales_log[n * 3 + k]) + o[10 + k];  // model.py:844
+    const float4 q = __ldg(reinterpret_cast<const float4*>(quats) + n);
+    const float qn = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    float4 qo;
+    qo.x = q.x / qn + o[6], qo.y = q.y / qn + o[7], qo.z = q.z / qn + o[8], qo.w = q.w / qn + o[9];  // model.py:845
+    reinterpret_cast<float4*>(quats_out)[n] = qo;
+}
+
+__global__ void __launch_bounds__(256)
+    deform_apply_bwd_kernel(long long N, const float* __restrict__ head, const float* __restrict__ means, const float* __restrict__ scales_log,
+                            const float* __restrict__ quats, const float* __restrict__ v_means_out, const float* __restrict__ v_scales_out,
+                            const float* __restrict__ v_quats_out, float* __restrict__ v_head, float* __restrict__ v_means,
+                            float* __restrict__ v_scales_log, float* __restrict__ v_quats) {
+    pdl_wait();
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float o[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(head + n * FG_MLP_HEAD_LD) + k);
+        o[4 * k] = t.x, o[4 * k + 1] = t.y, o[4 * k + 2] = t.z, o[4 * k + 3] = t.w;
+    }
+    Screw s;
+    screw_from_head(o, s);
+    const float m[3] = {means[n * 3], means[n * 3 + 1], means[n * 3 + 2]};
+    const float g[3] = {v_means_out[n * 3], v_means_out[n * 3 + 1], v_means_out[n * 3 + 2]};
+    // means' = R m + G v
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v_means[n * 3 + c] = s.R[c] * g[0] + s.R[3 + c] * g[1] + s.R[6 + c] * g[2];
+    float gR[9], gG[9], gv[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            gR[r * 3 + c] = g[r] * m[c];
+            gG[r * 3 + c] = g[r] * s.v[c];
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gv[c] = s.G[c] * g[0] + s.G[3 + c] * g[1] + s.G[6 + c] * g[2];
+    const float c1 = 1.f - s.cs, c2 = s.th - s.sn;
+    // dL/dW = sn gR + c1 gG + c1 (gR W^T + W^T gR) + c2 (gG W^T + W^T gG);   d(W W) pulls back as X W^T + W^T X
+    float gW[9];
+    float dot_RW = 0.f, dot_RW2 = 0.f, dot_GW = 0.f, dot_GW2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float xr = 0.f, xg = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                xr += gR[r * 3 + k] * s.W[c * 3 + k] + s.W[k * 3 + r] * gR[k * 3 + c];
+                xg += gG[r * 3 + k] * s.W[c * 3 + k] + s.W[k * 3 + r] * gG[k * 3 + c];
+            }
+            gW[r * 3 + c] = s.sn * gR[r * 3 + c] + c1 * gG[r * 3 + c] + c1 * xr + c2 * xg;
+            dot_RW += gR[r * 3 + c] * s.W[r * 3 + c];
+            dot_RW2 += gR[r * 3 + c] * s.W2[r * 3 + c];
+            dot_GW += gG[r * 3 + c] * s.W[r * 3 + c];
+            dot_GW2 += gG[r * 3 + c] * s.W2[r * 3 + c];
+        }
+    const float g_th = s.cs * dot_RW + s.sn * dot_RW2 + (gG[0] + gG[4] + gG[8]) + s.sn * dot_GW + c1 * dot_GW2;
+    const float gw[3] = {gW[7] - gW[5], gW[2] - gW[6], gW[3] - gW[1]};
+    const float inv = 1.f / s.th;
+    const float g_th_total = g_th - (gw[0] * o[0] + gw[1] * o[1] + gw[2] * o[2]) * inv * inv -
+                             (gv[0] * o[3] + gv[1] * o[4] + gv[2] * o[5]) * inv * inv;
+    float vo[FG_MLP_HEAD_LD];
+#pragma unroll
+    for (int k = 0; k < FG_MLP_HEAD_LD; ++k) vo[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        vo[k] = gw[k] * inv + g_th_total * o[k] * inv;
+        vo[3 + k] = gv[k] * inv;
+        const float gs = v_scales_out[n * 3 + k];
+        vo[10 + k] = gs;
+        v_scales_log[n * 3 + k] = gs * expf(scales_log[n * 3 + k]);
+    }
+    const float4 q = __ldg(reinterpret_cast<const float4*>(quats) + n);
+    const float4 gq = __ldg(reinterpret_cast<const float4*>(v_quats_out) + n);
+    vo[6] = gq.x, vo[7] = gq.y, vo[8] = gq.z, vo[9] = gq.w;
+    const float qn = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    const float qh[4] = {q.x / qn, q.y / qn, q.z / qn, q.w / qn};
+    const float d = qh[0] * gq.x + qh[1] * gq.y + qh[2] * gq.z + qh[3] * gq.w;
+    float4 vq;
+    vq.x = (gq.x - qh[0] * d) / qn, vq.y = (gq.y - qh[1] * d) / qn, vq.z = (gq.z - qh[2] * d) / qn, vq.w = (gq.w - qh[3] * d) / qn;
+    reinterpret_cast<float4*>(v_quats)[n] = vq;
+#pragma unroll
+    for (int k = 0; k < FG_MLP_HEAD_LD / 4; ++k)
+        reinterpret_cast<float4*>(v_head + n * FG_MLP_HEAD_LD)[k] = make_float4(vo[4 * k], vo[4 * k + 1], vo[4 * k + 2], vo[4 * k + 3]);
+}
+
+}  // namespace mlp
+}  // namespace fg
+
+// ------------------------------------------------------------------------------------------------ C ABI
+using namespace fg;
+using namespace fg::mlp;
+
+extern "C" int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0_hi, const float* a0_lo, int k0, const float* a1_hi,
+                             const float* a1_lo, int k1, const float* w_hi, const float* w_lo, const float* bias,
+                             const float* mask_src, float* out_hi, float* out_lo, void* stream) {
+    FG_REQUIRE(M >= 0 && M < (1ll << 31) - BM, "fg_mlp_linear: M out of range");
+    FG_REQUIRE(k0 > 0 && k0 % BK == 0 && k1 >= 0 && k1 % BK == 0, "fg_mlp_linear: k0, k1 must be multiples of 32 (k0 > 0)");
+    FG_REQUIRE(a0_hi && w_hi && out_hi && (k1 == 0 || a1_hi), "fg_mlp_linear: NULL operand");
+    if (M == 0) return FG_OK;
+    LinearArgs args = {bias, mask_src, out_hi, out_lo, (long long)M, k0 / BK, k1 / BK};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == FG_MLP_RELU_SPLIT) {
+        FG_REQUIRE(n_out == 256, "fg_mlp_linear: FG_MLP_RELU_SPLIT is built for 256 outputs");
+        FG_REQUIRE(a0_lo && w_lo && out_lo && bias && (k1 == 0 || a1_lo), "fg_mlp_linear: the 3xTF32 modes need the lo operands and a bias");
+        return launch_linear<256, 3, 2, EPI_RELU_SPLIT>(M, a0_hi, a0_lo, k0, a1_hi, a1_lo, k1, w_hi, w_lo, args, st);
+    }
+    if (mode == FG_MLP_LINEAR) {
+        FG_REQUIRE(n_out == FG_MLP_HEAD_LD, "fg_mlp_linear: FG_MLP_LINEAR is built for FG_MLP_HEAD_LD outputs");
+        FG_REQUIRE(a0_lo && w_lo && bias && (k1 == 0 || a1_lo), "fg_mlp_linear: the 3xTF32 modes need the lo operands and a bias");
+        return launch_linear<FG_MLP_HEAD_LD, 3, 4, EPI_LINEAR>(M, a0_hi, a0_lo, k0, a1_hi, a1_lo, k1, w_hi, w_lo, args, st);
+    }
+    if (mode == FG_MLP_DGRAD) {
+        FG_REQUIRE(n_out == 256 && mask_src, "fg_mlp_linear: FG_MLP_DGRAD is built for 256 outputs and needs mask_src");
+        return launch_linear<256, 1, 4, EPI_MASK>(M, a0_hi, nullptr, k0, a1_hi, nullptr, k1, w_hi, nullptr, args, st);
+    }
+    return set_error(FG_ERR_INVALID, "fg_mlp_linear: unknown mode", __FILE__, __LINE__);
+}
+
+extern "C" int fg_mlp_pack(int n_segments, const fg_mlp_pack_segment* segments_host, void* stream) {
+    FG_REQUIRE(n_segments >= 0 && n_segments <= FG_MLP_PACK_MAX_SEGMENTS, "fg_mlp_pack: too many segments");
+    if (n_segments == 0) return FG_OK;
+    PackTable tab;
+    for (int i = 0; i < n_segments; ++i) {
+        const fg_mlp_pack_segment& s = segments_host[i];
+        FG_REQUIRE(s.src && s.dst_hi && s.rows > 0 && s.cols > 0, "fg_mlp_pack: bad segment");
+        tab.seg[i] = s;
+    }
+    FG_LAUNCH(mlp_pack_kernel, dim3(64, n_segments), 256, 0, (cudaStream_t)stream, tab);
+    return FG_OK;
+}
+
+extern "C" int fg_deform_embed(int64_t N, const float* means, const float* t_emb, int t_ch, int multires, float* e_hi, float* e_lo,
+                               void* stream) {
+    FG_REQUIRE(N >= 0 && means && e_hi && e_lo, "fg_deform_embed: NULL argument");
+    FG_REQUIRE(multires >= 0 && t_ch >= 0 && 3 + 6 * multires + t_ch <= FG_MLP_EMBED_LD && (t_ch == 0 || t_emb),
+               "fg_deform_embed: embedding wider than FG_MLP_EMBED_LD");
+    if (N == 0) return FG_OK;
+    FG_LAUNCH(deform_embed_kernel, ceil_div(N * FG_MLP_EMBED_LD, 256), 256, 0, (cudaStream_t)stream, (long long)N, means, t_emb, t_ch,
+              multires, e_hi, e_lo);
+    return FG_OK;
+}
+
+extern "C" int fg_deform_apply_fwd(int64_t N, const float* head, const float* means, const float* scales_log, const float* quats,
+                                   float* means_out, float* scales_out, float* quats_out, void* stream) {
+    FG_REQUIRE(N >= 0 && head && means && scales_log && quats && means_out && scales_out && quats_out, "fg_deform_apply_fwd: NULL argument");
+    if (N == 0) return FG_OK;
+    FG_LAUNCH(deform_apply_fwd_kernel, ceil_div(N, 256), 256, 0, (cudaStream_t)stream, (long long)N, head, means, scales_log, quats,
+              means_out, scales_out, quats_out);
+    return FG_OK;
+}
+
+extern "C" int fg_deform_apply_bwd(int64_t N, const float* head, const float* means, const float* scales_log, const float* quats,
+                                   const float* v_means_out, const float* v_scales_out, const float* v_quats_out, float* v_head,
+                                   float* v_means, float* v_scales_log, float* v_quats, void* stream) {
+    FG_REQUIRE(N >= 0 && head && means && scales_log && quats && v_means_out && v_scales_out && v_quats_out && v_head && v_means &&
+                   v_scales_log && v_quats,
+               "fg_deform_apply_bwd: NULL argument");
+    if (N == 0) return FG_OK;
+    FG_LAUNCH(deform_apply_bwd_kernel, ceil_div(N, 256), 256, 0, (cudaStream_t)stream, (long long)N, head, means, scales_log, quats,
+              v_means_out, v_scales_out, v_quats_out, v_head, v_means, v_scales_log, v_quats);
+    return FG_OK;
+}

@@ -1,0 +1,292 @@
+"""Deformation network of FreeGaussian on the B200 tensor cores.
+
+``DeformNetwork`` mirrors ``FreeGaussianDeformableModel`` (``freegaussian/freegaussian_model.py:1054-1114``): same
+constructor arguments, same parameter names and shapes (a reference ``state_dict`` loads unchanged), same
+``forward(x, t) -> (d_xyz [N,4,4], rotation [N,4], scaling [N,3])``.  ``deform_gaussians`` additionally fuses the
+lines that consume those outputs (``freegaussian_model.py:836-845``) and returns the ``means, scales, quats`` handed
+to ``rasterization``.
+
+Every ``nn.Linear`` of the trunk and the four heads run in ``fg_mlp_linear`` (tcgen05 / TMEM / TMA, csrc/mlp.cu):
+forward in error-compensated 3xTF32 (fp32-accurate, the reference computes in fp32), data gradients in single TF32.
+Weight gradients are plain ``[256, N] x [N, K]`` products and go to cuBLAS (TF32) through ``torch.mm`` for now.
+There is no CPU path.
+
+The reference always evaluates the network with one time value per call (``camera.times.expand(N, -1)``,
+``freegaussian_model.py:836``), so the time branch (embedding + ``timenet``) is evaluated once on a single row with
+ordinary torch ops and broadcast inside the embedding kernel; its gradient comes back through the bias gradients
+of the two layers that read it.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+from ._lib import MLP_EMBED_LD, MLP_HEAD_LD, MlpPackSegment, check, ptr
+
+_W = 256
+_D = 8
+_SKIP = _D // 2  # the embedding is concatenated again after this layer (freegaussian_model.py:1058, 1100-1101)
+_HEADS = (("branch_w", 3), ("branch_v", 3), ("gaussian_rotation", 4), ("gaussian_scaling", 3))
+
+
+def _embed(x: Tensor, multires: int) -> Tensor:
+    """Embedder.embed (utils.py:27-56) with torch ops; used for the single time row only."""
+    out = [x]
+    for k in range(multires):
+        out += [torch.sin(x * (2.0 ** k)), torch.cos(x * (2.0 ** k))]
+    return torch.cat(out, -1)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _linear(mode, M, n_out, a0, k0, a1, k1, w, bias, mask, out_hi, out_lo):
+    """a0 / a1 / w are (hi, lo) pairs (lo may be None)."""
+    check(_lib.lib().fg_mlp_linear(mode, M, n_out, ptr(a0[0]), ptr(a0[1]), k0, ptr(a1[0]) if a1 else None,
+                                   ptr(a1[1]) if a1 else None, k1, ptr(w[0]), ptr(w[1]), ptr(bias), ptr(mask),
+                                   ptr(out_hi), ptr(out_lo), _stream()))
+
+
+class _Packed:
+    """Operand buffers of one parameter set: padded, reordered, hi/lo split, plus the transposes for the data gradient."""
+
+    def __init__(self, params: List[Tensor], emb_ch: int):
+        dev = params[0].device
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731  pads stay zero
+        kp = [MLP_EMBED_LD if i == 0 else (_W + MLP_EMBED_LD if i == _SKIP + 1 else _W) for i in range(_D)]
+        self.kp = kp
+        self.w = [(z(_W, k), z(_W, k)) for k in kp]
+        self.w_head = (z(MLP_HEAD_LD, _W), z(MLP_HEAD_LD, _W))
+        self.wt = [None] + [z(_W, _W) for _ in range(1, _D)]  # wt[l][i, o] = W_l[o, i] over the hidden inputs
+        self.wt_head = z(_W, MLP_HEAD_LD)
+        segs = []
+
+        def seg(src, col0, cols, dst, dst_col0, transpose=False, row0=0):
+            hi, lo = dst if isinstance(dst, tuple) else (dst, None)
+            s = MlpPackSegment()
+            s.src = src.data_ptr()
+            esz = 4
+            s.dst_hi = hi.data_ptr() + row0 * hi.shape[1] * esz
+            s.dst_lo = (lo.data_ptr() + row0 * lo.shape[1] * esz) if lo is not None else None
+            s.src_ld, s.src_col0, s.rows, s.cols = src.shape[1], col0, src.shape[0], cols
+            s.dst_ld, s.dst_col0, s.transpose = hi.shape[1], dst_col0, int(transpose)
+            segs.append(s)
+
+        weights = params[0:2 * _D:2]
+        for i, wt in enumerate(weights):
+            assert wt.is_contiguous()
+            if i == 0:
+                seg(wt, 0, emb_ch, self.w[0], 0)
+            elif i == _SKIP + 1:  # reference input order [embedding | h]; operand order [h | embedding]
+                seg(wt, emb_ch, _W, self.w[i], 0)
+                seg(wt, 0, emb_ch, self.w[i], _W)
+                seg(wt, emb_ch, _W, self.wt[i], 0, transpose=True)
+            else:
+                seg(wt, 0, _W, self.w[i], 0)
+                seg(wt, 0, _W, self.wt[i], 0, transpose=True)
+        row = 0
+        for j, (_, o) in enumerate(_HEADS):
+            hw = params[2 * _D + 2 * j]
+            seg(hw, 0, _W, self.w_head, 0, row0=row)
+            seg(hw, 0, _W, self.wt_head, row, transpose=True)
+            row += o
+        assert len(segs) <= _lib.MLP_PACK_MAX_SEGMENTS
+        arr = (MlpPackSegment * len(segs))(*segs)
+        check(_lib.lib().fg_mlp_pack(len(segs), arr, _stream()))
+        self.bias = [b.contiguous() for b in params[1:2 * _D:2]]
+        hb = torch.cat([params[2 * _D + 2 * j + 1] for j in range(len(_HEADS))])
+        self.bias_head = torch.cat([hb, hb.new_zeros(MLP_HEAD_LD - hb.numel())])
+
+
+class _Trunk(torch.autograd.Function):
+    """x [N,3] (no gradient: the reference passes means.detach()), t_emb [t_ch], 24 parameters -> head [N, 32]."""
+
+    @staticmethod
+    def forward(ctx, x, t_emb, multires, *params):
+        L = _lib.lib()
+        N = x.shape[0]
+        dev = x.device
+        t_ch = t_emb.numel()
+        emb_ch = 3 + 6 * multires + t_ch
+        pk = _Packed(list(params), emb_ch)
+        new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        e = (new(N, MLP_EMBED_LD), new(N, MLP_EMBED_LD))
+        check(L.fg_deform_embed(N, ptr(x), ptr(t_emb), t_ch, multires, ptr(e[0]), ptr(e[1]), _stream()))
+        h_hi: List[Tensor] = []
+        lo_buf = [new(N, _W), new(N, _W)]
+        prev = None
+        for i in range(_D):
+            out_hi, out_lo = new(N, _W), lo_buf[i & 1]
+            if i == 0:
+                _linear(_lib.MLP_RELU_SPLIT, N, _W, e, MLP_EMBED_LD, None, 0, pk.w[0], pk.bias[0], None, out_hi, out_lo)
+            elif i == _SKIP + 1:
+                _linear(_lib.MLP_RELU_SPLIT, N, _W, prev, _W, e, MLP_EMBED_LD, pk.w[i], pk.bias[i], None, out_hi, out_lo)
+            else:
+                _linear(_lib.MLP_RELU_SPLIT, N, _W, prev, _W, None, 0, pk.w[i], pk.bias[i], None, out_hi, out_lo)
+            prev = (out_hi, out_lo)
+            h_hi.append(out_hi)
+        head = new(N, MLP_HEAD_LD)
+        _linear(_lib.MLP_LINEAR, N, MLP_HEAD_LD, prev, _W, None, 0, pk.w_head, pk.bias_head, None, head, None)
+        ctx.save_for_backward(e[0], *h_hi, *params)
+        ctx.pk = pk
+        ctx.dims = (N, t_ch, emb_ch, multires)
+        return head
+
+    @staticmethod
+    def backward(ctx, g_head):
+        N, t_ch, emb_ch, multires = ctx.dims
+        saved = ctx.saved_tensors
+        e_hi, h_hi, params = saved[0], saved[1:1 + _D], saved[1 + _D:]
+        pk = ctx.pk
+        dev = g_head.device
+        g_head = g_head.contiguous()
+        new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        grads: List[Tensor] = [None] * len(params)
+        x_ch = emb_ch - t_ch
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True  # weight gradients: library GEMMs, gradient tolerance 1e-3
+        try:
+            row = 0
+            for j, (_, o) in enumerate(_HEADS):
+                gj = g_head[:, row:row + o]
+                grads[2 * _D + 2 * j] = gj.t() @ h_hi[_D - 1]
+                grads[2 * _D + 2 * j + 1] = gj.sum(0)
+                row += o
+            dz = new(N, _W)
+            _linear(_lib.MLP_DGRAD, N, _W, (g_head, None), MLP_HEAD_LD, None, 0, (pk.wt_head, None), None, h_hi[_D - 1], dz, None)
+            g_t = torch.zeros(t_ch, device=dev) if t_ch else None
+            for i in range(_D - 1, -1, -1):
+                gb = dz.sum(0)
+                grads[2 * i + 1] = gb
+                if i == 0:
+                    grads[0] = dz.t() @ e_hi[:, :emb_ch]
+                elif i == _SKIP + 1:
+                    grads[2 * i] = torch.cat([dz.t() @ e_hi[:, :emb_ch], dz.t() @ h_hi[i - 1]], 1)
+                else:
+                    grads[2 * i] = dz.t() @ h_hi[i - 1]
+                if t_ch and (i == 0 or i == _SKIP + 1):
+                    # every row reads the same t_emb, so its gradient is (column sums of dz) . W[:, t columns]
+                    g_t = g_t + gb @ params[2 * i][:, x_ch:emb_ch]
+                if i > 0:
+                    dz_prev = new(N, _W)
+                    _linear(_lib.MLP_DGRAD, N, _W, (dz, None), _W, None, 0, (pk.wt[i], None), None, h_hi[i - 1], dz_prev, None)
+                    dz = dz_prev
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        return (None, g_t, None, *grads)
+
+
+class _Apply(torch.autograd.Function):
+    """head [N,32], means, scales_log, quats -> (means', scales', quats')   (freegaussian_model.py:841-845)."""
+
+    @staticmethod
+    def forward(ctx, head, means, scales_log, quats):
+        N = means.shape[0]
+        head, means, scales_log, quats = head.contiguous(), means.contiguous(), scales_log.contiguous(), quats.contiguous()
+        mo, so, qo = torch.empty_like(means), torch.empty_like(scales_log), torch.empty_like(quats)
+        check(_lib.lib().fg_deform_apply_fwd(N, ptr(head), ptr(means), ptr(scales_log), ptr(quats), ptr(mo), ptr(so), ptr(qo),
+                                             _stream()))
+        ctx.save_for_backward(head, means, scales_log, quats)
+        return mo, so, qo
+
+    @staticmethod
+    def backward(ctx, g_m, g_s, g_q):
+        head, means, scales_log, quats = ctx.saved_tensors
+        N = means.shape[0]
+        zero = lambda g, ref: torch.zeros_like(ref) if g is None else g.contiguous()  # noqa: E731
+        g_m, g_s, g_q = zero(g_m, means), zero(g_s, scales_log), zero(g_q, quats)
+        v_head = torch.empty_like(head)
+        v_m, v_s, v_q = torch.empty_like(means), torch.empty_like(scales_log), torch.empty_like(quats)
+        check(_lib.lib().fg_deform_apply_bwd(N, ptr(head), ptr(means), ptr(scales_log), ptr(quats), ptr(g_m), ptr(g_s), ptr(g_q),
+                                             ptr(v_head), ptr(v_m), ptr(v_s), ptr(v_q), _stream()))
+        return v_head, v_m, v_s, v_q
+
+
+def _skew(w: Tensor) -> Tensor:
+    z = torch.zeros_like(w[:, 0])
+    return torch.stack([z, -w[:, 2], w[:, 1], w[:, 2], z, -w[:, 0], -w[:, 1], w[:, 0], z], -1).reshape(-1, 3, 3)
+
+
+def exp_se3(S: Tensor, theta: Tensor) -> Tensor:
+    """Same contract as ``freegaussian/utils.py:137-159``: screw axis [N,6], magnitude [N,1] -> [N,4,4]."""
+    w, v = S[:, :3], S[:, 3:]
+    Wm = _skew(w)
+    W2 = torch.bmm(Wm, Wm)
+    eye = torch.eye(3, device=S.device, dtype=S.dtype).expand_as(Wm)
+    th = theta.view(-1, 1, 1)
+    R = eye + torch.sin(th) * Wm + (1.0 - torch.cos(th)) * W2
+    p = torch.bmm(th * eye + (1.0 - torch.cos(th)) * Wm + (th - torch.sin(th)) * W2, v.unsqueeze(-1))
+    bottom = torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=S.device, dtype=S.dtype).expand(Wm.shape[0], 1, 4)
+    return torch.cat([torch.cat([R, p], -1), bottom], 1)
+
+
+class DeformNetwork(nn.Module):
+    """Drop-in for ``FreeGaussianDeformableModel`` (freegaussian_model.py:1054-1114) with the trunk on tcgen05."""
+
+    def __init__(self, D: int = 8, W: int = 256, multires: int = 10, is_blender: bool = False):
+        super().__init__()
+        assert D == _D and W == _W, "the tensor-core kernels are built for the reference's D=8, W=256"
+        self.D, self.W, self.multires = D, W, multires
+        self.t_multires = 6 if is_blender else 10
+        self.skips = [D // 2]
+        self.is_blender = is_blender
+        time_input_ch = 1 + 2 * self.t_multires
+        xyz_input_ch = 3 + 6 * multires
+        if is_blender:
+            self.time_out = 30
+            self.timenet = nn.Sequential(nn.Linear(time_input_ch, 256), nn.ReLU(inplace=True), nn.Linear(256, self.time_out))
+            t_ch = self.time_out
+        else:
+            t_ch = time_input_ch
+        self.input_ch = xyz_input_ch + t_ch
+        assert self.input_ch <= MLP_EMBED_LD
+        self.linear = nn.ModuleList(
+            [nn.Linear(self.input_ch, W)]
+            + [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + self.input_ch, W) for i in range(D - 1)])
+        self.branch_w = nn.Linear(W, 3)
+        self.branch_v = nn.Linear(W, 3)
+        self.gaussian_rotation = nn.Linear(W, 4)
+        self.gaussian_scaling = nn.Linear(W, 3)
+
+    def _params(self) -> List[Tensor]:
+        ps: List[Tensor] = []
+        for lin in self.linear:
+            ps += [lin.weight, lin.bias]
+        for name, _ in _HEADS:
+            lin = getattr(self, name)
+            ps += [lin.weight, lin.bias]
+        return ps
+
+    def _time_row(self, t: Tensor) -> Tensor:
+        """One time value per call (freegaussian_model.py:836 expands ``camera.times``); returns t_emb [t_ch]."""
+        t0 = t.reshape(-1)[:1].reshape(1, 1).to(torch.float32)
+        t_emb = _embed(t0, self.t_multires)
+        if self.is_blender:
+            t_emb = self.timenet(t_emb)
+        return t_emb.reshape(-1)
+
+    def head(self, x: Tensor, t: Tensor) -> Tensor:
+        """[N, 32]: branch_w (3) | branch_v (3) | gaussian_rotation (4) | gaussian_scaling (3) | zero padding."""
+        if not x.is_cuda:
+            raise RuntimeError("DeformNetwork: `x` is not a CUDA tensor (there is no CPU path)")
+        assert x.ndim == 2 and x.shape[1] == 3 and x.dtype == torch.float32
+        return _Trunk.apply(x.detach().contiguous(), self._time_row(t).contiguous(), self.multires, *self._params())
+
+    def forward(self, x: Tensor, t: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        h = self.head(x, t)
+        w, v = h[:, 0:3], h[:, 3:6]
+        theta = torch.norm(w, dim=-1, keepdim=True)
+        w = w / theta + 1e-5
+        v = v / theta + 1e-5
+        d_xyz = exp_se3(torch.cat([w, v], -1), theta)
+        return d_xyz, h[:, 6:10], h[:, 10:13]
+
+    def deform_gaussians(self, means: Tensor, scales_log: Tensor, quats: Tensor, t: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """freegaussian_model.py:836-845 in one call: returns the (means, scales, quats) passed to ``rasterization``."""
+        return _Apply.apply(self.head(means, t), means, scales_log, quats)

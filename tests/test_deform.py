@@ -1,0 +1,257 @@
+"""Deformation network: oracle vs the reference's own outputs (CPU), kernels vs oracle (GPU).
+
+Tolerances: the forward runs in 3xTF32 = fp32 accuracy, so outputs are held to 1e-5 of the tensor's scale (the
+north-star budget for everything that feeds the renderer is 1e-4); gradients to 1e-3 of the reference gradient's
+max magnitude (north_star), the data/weight-gradient GEMMs run in single TF32.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import deform as OD
+from util import grad_rel_err, rel_err
+
+GOLDEN = Path(__file__).parent / "golden"
+FIXTURES = ["blender_n300", "blender_n129_hot", "real_n200"]
+GRAD_STRIDE = 97  # tests/golden/make_golden_deform.py
+
+
+def _sample(g):
+    """Small gradients are stored whole, large ones as a strided sample (make_golden_deform.py)."""
+    return g if g.numel() <= 4096 else g[::GRAD_STRIDE]
+
+
+def _load(name):
+    z = np.load(GOLDEN / f"deform_{name}.npz")
+    isb = bool(z["is_blender"])
+    params = OD.init_params(is_blender=isb, seed=int(z["seed"]), scale=float(z["scale"]))
+    return z, isb, params
+
+
+def _oracle_run(z, isb, params, dtype=torch.float32):
+    P = {k: v.to(dtype).requires_grad_(True) for k, v in params.items()}
+    m = torch.tensor(z["means"], dtype=dtype, requires_grad=True)
+    s = torch.tensor(z["scales_log"], dtype=dtype, requires_grad=True)
+    q = torch.tensor(z["quats"], dtype=dtype, requires_grad=True)
+    t = torch.tensor([[float(z["t"])]], dtype=dtype).expand(m.shape[0], -1)
+    nm, ns, nq = OD.deform_gaussians(P, m, s, q, t, isb)
+    loss = ((nm * torch.tensor(z["w_means"], dtype=dtype)).sum() + (ns * torch.tensor(z["w_scales"], dtype=dtype)).sum()
+            + (nq * torch.tensor(z["w_quats"], dtype=dtype)).sum())
+    loss.backward()
+    return P, (m, s, q), (nm, ns, nq)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_matches_reference_outputs(name):
+    """The restatement against what the reference's own class bodies produced (fixtures made in the build container)."""
+    z, isb, params = _load(name)
+    P, (m, s, q), (nm, ns, nq) = _oracle_run(z, isb, params)
+    t = torch.tensor([[float(z["t"])]]).expand(m.shape[0], -1)
+    d_xyz, rot, scl = OD.deform_forward({k: v.detach() for k, v in P.items()}, m.detach(), t, isb)
+    for got, key in ((d_xyz, "d_xyz"), (rot, "d_rotation"), (scl, "d_scaling"), (nm, "new_means"), (ns, "new_scales"), (nq, "new_quats")):
+        assert rel_err(got, torch.tensor(z[key])) < 1e-6, key
+    for got, key in ((m, "grad_means"), (s, "grad_scales_log"), (q, "grad_quats")):
+        assert grad_rel_err(got.grad, torch.tensor(z[key])) < 1e-5, key
+    for k, v in P.items():
+        g = v.grad.double().flatten()
+        assert grad_rel_err(_sample(g), torch.tensor(z["grad." + k]).double()) < 1e-4, k
+        assert abs(float(g.norm()) - float(z["gnorm." + k])) <= 1e-4 * float(z["gnorm." + k]), k
+
+
+def test_oracle_float64_agrees_with_float32():
+    z, isb, params = _load("blender_n300")
+    _, _, out32 = _oracle_run(z, isb, params, torch.float32)
+    _, _, out64 = _oracle_run(z, isb, params, torch.float64)
+    for a, b in zip(out32, out64):
+        assert rel_err(a, b) < 2e-6
+
+
+def test_module_mirrors_reference_state_dict():
+    """Parameter names and shapes are the reference's (a reference checkpoint loads unchanged)."""
+    from freegaussian_b200.deform import DeformNetwork
+
+    for isb in (True, False):
+        net = DeformNetwork(is_blender=isb)
+        ref = OD.init_params(is_blender=isb)
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.items()}
+        net.load_state_dict(ref, strict=True)
+    with pytest.raises(RuntimeError):
+        DeformNetwork(is_blender=True).head(torch.zeros(4, 3), torch.zeros(4, 1))  # no CPU path
+
+
+# ------------------------------------------------------------------------------------------------------- GPU
+def _hilo(x):
+    """Host model of the operand split (round to nearest tf32, ties away): hi, lo."""
+    b = x.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    b = (b + 0x1000) & 0xFFFFE000
+    b = torch.where(b >= 2 ** 31, b - 2 ** 32, b).to(torch.int32)
+    hi = b.view(torch.float32)
+    return hi, x - hi
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 1000, 148 * 128 * 2 + 77])
+def test_linear_relu_split_is_fp32_accurate(built_lib, M):
+    from freegaussian_b200 import _lib
+    from freegaussian_b200.deform import _linear
+
+    g = torch.Generator().manual_seed(M)
+    for k0, k1 in ((96, 0), (256, 0), (256, 96)):
+        a = torch.randn(M, k0 + k1, generator=g)
+        w = torch.randn(256, k0 + k1, generator=g) / (k0 + k1) ** 0.5
+        bias = torch.randn(256, generator=g)
+        want = torch.relu(a.double() @ w.double().T + bias.double())
+        ad, wd, bd = a.cuda(), w.cuda(), bias.cuda()
+        a0, a1 = ad[:, :k0].contiguous(), ad[:, k0:].contiguous()
+        out_hi, out_lo = torch.empty(M, 256, device="cuda"), torch.empty(M, 256, device="cuda")
+        _linear(_lib.MLP_RELU_SPLIT, M, 256, _hilo(a0), k0, _hilo(a1) if k1 else None, k1, _hilo(wd), bd, None, out_hi, out_lo)
+        got = out_hi.double() + out_lo.double()
+        assert rel_err(got, want) < 3e-6, (M, k0, k1)
+        # hi is an exact tf32 value and hi + lo reproduces the fp32 result
+        assert int((out_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+        assert float((out_hi + out_lo - got.float()).abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [5, 4096 + 3])
+def test_linear_head_and_dgrad_modes(built_lib, M):
+    from freegaussian_b200 import _lib
+    from freegaussian_b200.deform import _linear
+
+    g = torch.Generator().manual_seed(M)
+    a = torch.randn(M, 256, generator=g)
+    w = torch.randn(32, 256, generator=g) / 16
+    bias = torch.randn(32, generator=g)
+    out = torch.empty(M, 32, device="cuda")
+    _linear(_lib.MLP_LINEAR, M, 32, _hilo(a.cuda()), 256, None, 0, _hilo(w.cuda()), bias.cuda(), None, out, None)
+    assert rel_err(out, a.double() @ w.double().T + bias.double()) < 3e-6
+    # data gradient: dz_prev = (dz . Wt^T) * (h_prev > 0), single TF32
+    for k in (32, 256):
+        dz = torch.randn(M, k, generator=g)
+        wt = torch.randn(256, k, generator=g) / k ** 0.5
+        hp = torch.randn(M, 256, generator=g)
+        got = torch.empty(M, 256, device="cuda")
+        _linear(_lib.MLP_DGRAD, M, 256, (dz.cuda(), None), k, None, 0, (wt.cuda(), None), None, hp.cuda(), got, None)
+        want = (dz.double() @ wt.double().T) * (hp > 0)
+        assert grad_rel_err(got, want) < 1e-3
+        assert bool(((got.cpu() == 0) | (hp > 0)).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("t_ch,multires", [(30, 10), (21, 10), (0, 4)])
+def test_embedding_matches_reference_layout(built_lib, t_ch, multires):
+    from freegaussian_b200 import _lib
+    from freegaussian_b200._lib import check, ptr
+
+    g = torch.Generator().manual_seed(1)
+    n = 1001
+    x = (torch.rand(n, 3, generator=g) - 0.5) * 6.0
+    t_emb = torch.randn(t_ch, generator=g)
+    e_hi, e_lo = torch.empty(n, 96, device="cuda"), torch.empty(n, 96, device="cuda")
+    xd, td = x.cuda(), t_emb.cuda()
+    check(_lib.lib().fg_deform_embed(n, ptr(xd), ptr(td) if t_ch else None, t_ch, multires, ptr(e_hi), ptr(e_lo),
+                                     torch.cuda.current_stream().cuda_stream))
+    want = torch.cat([OD.embed(x, multires), t_emb.expand(n, -1)], -1)
+    got = (e_hi + e_lo).cpu()
+    worst = float((got[:, :want.shape[1]] - want).abs().max())
+    assert worst < 1e-6, worst  # sin / cos of arguments up to 3 * 2^9, same fp32 argument on both sides
+    assert float(got[:, want.shape[1]:].abs().max()) == 0.0
+    assert int((e_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+@pytest.mark.gpu
+def test_apply_kernels_match_autograd(built_lib):
+    from freegaussian_b200.deform import _Apply
+
+    g = torch.Generator().manual_seed(2)
+    n = 777
+    head = torch.zeros(n, 32)
+    head[:, :13] = torch.randn(n, 13, generator=g) * 0.3
+    m, s, q = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g) - 3, torch.randn(n, 4, generator=g)
+    ws = [torch.randn(n, k, generator=g) for k in (3, 3, 4)]
+
+    def ref(head, m, s, q):
+        w, v = head[:, 0:3], head[:, 3:6]
+        th = w.norm(dim=-1, keepdim=True)
+        T = OD.exp_se3(torch.cat([w / th + 1e-5, v / th + 1e-5], -1), th)
+        mh = torch.bmm(T, torch.cat([m, torch.ones_like(m[:, :1])], -1).unsqueeze(-1)).squeeze(-1)
+        return mh[:, :3] / mh[:, 3:], torch.exp(s) + head[:, 10:13], q / q.norm(dim=-1, keepdim=True) + head[:, 6:10]
+
+    cpu = [t.clone().double().requires_grad_(True) for t in (head, m, s, q)]
+    outs = ref(*cpu)
+    sum((o * w.double()).sum() for o, w in zip(outs, ws)).backward()
+    dev = [t.clone().cuda().requires_grad_(True) for t in (head, m, s, q)]
+    got = _Apply.apply(*dev)
+    sum((o * w.cuda()).sum() for o, w in zip(got, ws)).backward()
+    for a, b in zip(got, outs):
+        assert rel_err(a, b) < 2e-6
+    for a, b in zip(dev, cpu):
+        assert grad_rel_err(a.grad[:, :13] if a.shape[1] == 32 else a.grad, b.grad[:, :13] if b.shape[1] == 32 else b.grad) < 1e-5
+    assert float(dev[0].grad[:, 13:].abs().max()) == 0.0
+
+
+def _net_from(params, isb):
+    from freegaussian_b200.deform import DeformNetwork
+
+    net = DeformNetwork(is_blender=isb)
+    net.load_state_dict(params, strict=True)
+    return net.cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FIXTURES)
+def test_network_matches_reference_fixture(built_lib, name):
+    """End to end against the outputs and gradients of the reference's own code (tests/golden/deform_*.npz)."""
+    z, isb, params = _load(name)
+    net = _net_from(params, isb)
+    m, s, q = (torch.tensor(z[k]).cuda().requires_grad_(True) for k in ("means", "scales_log", "quats"))
+    t = torch.tensor([[float(z["t"])]]).cuda().expand(m.shape[0], -1)
+    nm, ns, nq = net.deform_gaussians(m, s, q, t)
+    for got, key in ((nm, "new_means"), (ns, "new_scales"), (nq, "new_quats")):
+        assert rel_err(got, torch.tensor(z[key])) < 1e-5, key
+    loss = (nm * torch.tensor(z["w_means"]).cuda()).sum() + (ns * torch.tensor(z["w_scales"]).cuda()).sum() + \
+        (nq * torch.tensor(z["w_quats"]).cuda()).sum()
+    loss.backward()
+    for got, key in ((m, "grad_means"), (s, "grad_scales_log"), (q, "grad_quats")):
+        assert grad_rel_err(got.grad, torch.tensor(z[key])) < 1e-5, key
+    for k, v in net.named_parameters():
+        assert grad_rel_err(_sample(v.grad.double().flatten().cpu()), torch.tensor(z["grad." + k]).double()) < 1e-3, k
+        assert abs(float(v.grad.double().norm()) - float(z["gnorm." + k])) <= 1e-3 * float(z["gnorm." + k]), k
+    # the reference-signature forward: same d_xyz / rotation / scaling
+    d_xyz, rot, scl = net(m.detach(), t)
+    for got, key in ((d_xyz, "d_xyz"), (rot, "d_rotation"), (scl, "d_scaling")):
+        assert rel_err(got, torch.tensor(z[key])) < 1e-5, key
+
+
+@pytest.mark.gpu
+def test_full_size_rows_are_independent(built_lib):
+    """cfg3 size (1 M Gaussians): every row depends on its own Gaussian only, so a random sample of rows must equal
+    the oracle evaluated on just those rows; and the weight gradient is linear in the row set (two halves sum to the whole)."""
+    isb = True
+    params = OD.init_params(is_blender=isb, seed=11)
+    net = _net_from(params, isb)
+    n = 1_000_000
+    g = torch.Generator().manual_seed(5)
+    m = (torch.rand(n, 3, generator=g) - 0.5) * 6.0
+    s = torch.log(torch.rand(n, 3, generator=g) * 0.05 + 0.005)
+    q = torch.randn(n, 4, generator=g)
+    t = torch.tensor([[0.25]])
+    md, sd, qd = m.cuda(), s.cuda(), q.cuda()
+    with torch.no_grad():
+        nm, ns, nq = net.deform_gaussians(md, sd, qd, t.cuda().expand(n, -1))
+    idx = torch.randperm(n, generator=g)[:3000]
+    om, os_, oq = OD.deform_gaussians(params, m[idx], s[idx], q[idx], t.expand(len(idx), -1), isb)
+    assert rel_err(nm[idx.cuda()], om) < 1e-5 and rel_err(ns[idx.cuda()], os_) < 1e-5 and rel_err(nq[idx.cuda()], oq) < 1e-5
+    assert bool(torch.isfinite(nm).all())
+
+    def wgrad(lo, hi):
+        net.zero_grad()
+        a, b, c = net.deform_gaussians(md[lo:hi], sd[lo:hi], qd[lo:hi], t.cuda().expand(hi - lo, -1))
+        (a.sum() + b.sum() + c.sum()).backward()
+        return torch.cat([p.grad.flatten() for p in net.parameters()]).double()
+
+    k = 200_000
+    whole, first, second = wgrad(0, k), wgrad(0, k // 2 + 13), wgrad(k // 2 + 13, k)
+    assert grad_rel_err(first + second, whole) < 1e-3
