@@ -44,7 +44,7 @@ ADAM_MAX_SEGMENTS = 8
 MLP_PACK_MAX_SEGMENTS = 32
 MLP_EMBED_LD = 96
 MLP_HEAD_LD = 32
-MLP_RELU_SPLIT, MLP_LINEAR, MLP_DGRAD = 0, 1, 2
+MLP_RELU, MLP_LINEAR, MLP_DGRAD = 0, 1, 2
 REFINE_MAX_ARRAYS = 24
 
 # name -> (restype, argtypes); mirrors include/fg_api.h one to one
@@ -100,9 +100,9 @@ SIGNATURES = {
     "fg_render_back_workspace_bytes": (_i64, [_i32, _i32, _i32, _i64]),
     "fg_render_back": (_i32, [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64,
                               _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "fg_mlp_linear": (_i32, [_i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_mlp_linear": (_i32, [_i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_mlp_pack": (_i32, [_i32, C.POINTER(MlpPackSegment), _vp]),
-    "fg_deform_embed": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "fg_deform_embed": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "fg_deform_apply_fwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_deform_apply_bwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_knn_workspace_bytes": (_i64, [_i64]),

@@ -5,14 +5,16 @@
 //   fg_mlp_linear     out = epilogue(A . W^T): CTA = 128 rows x BN outputs, persistent over row tiles.
 //                     warp 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, mbarrier pipeline),
 //                     warp 1 = tcgen05.mma issuer (kind::tf32, accumulators in TMEM, double buffered),
-//                     warps 2-5 = epilogue (tcgen05.ld -> bias / ReLU / mask -> global).
-//                     The reference computes in fp32, so the forward runs the error-compensated 3xTF32 scheme:
-//                     every operand is stored as hi (the nearest tf32 value, kept as fp32 with 13 zero low bits)
-//                     and lo = x - hi, and each k-step issues A_hi.W_hi + A_hi.W_lo + A_lo.W_hi into the same
-//                     fp32 accumulator (what is dropped is O(2^-21) relative).  The data-gradient pass runs
-//                     single TF32 (gradient tolerance 1e-3).
+//                     warps 2-5 = epilogue (tcgen05.ld -> bias / ReLU / mask -> smem transpose -> coalesced stores),
+//                     warps 6-9 = operand split (below).
+//                     The reference computes in fp32, so every product runs the error-compensated 3xTF32 scheme:
+//                     x = hi + lo with hi the nearest tf32 value (an fp32 with 13 zero low bits) and lo = x - hi, and
+//                     each k-step issues A_lo.W_hi + A_hi.W_lo + A_hi.W_hi into the same fp32 accumulator (what is
+//                     dropped is O(2^-21) relative).  Activations and gradients stay plain fp32 in HBM (4 bytes per
+//                     element each way): the split of the A tile happens in shared memory between TMA and MMA;
+//                     the weights are split once per step by fg_mlp_pack.
 //   fg_mlp_pack       weights -> padded / reordered / transposed hi+lo operand buffers (one launch, segment table)
-//   fg_deform_embed   positional embedding of the means + broadcast time embedding -> hi/lo [N,96]   (utils.py:27-56)
+//   fg_deform_embed   positional embedding of the means + broadcast time embedding -> [N,96]   (utils.py:27-56)
 //   fg_deform_apply_fwd/bwd   screw axis -> SE(3) -> means, scales, quats (utils.py:137-159, model.py:841-845)
 #include <cuda.h>
 
@@ -110,33 +112,38 @@ __device__ __forceinline__ float tf32_hi(float x) {
 
 // ------------------------------------------------------------------------------------------------ the linear layer
 struct LinearArgs {
-    const float* bias;      // [BN] or NULL
-    const float* mask_src;  // [M, BN]: output kept where mask_src > 0 (EPI_MASK)
-    float* out_hi;          // [M, BN]
-    float* out_lo;          // [M, BN] (EPI_RELU_SPLIT)
+    const float* bias;         // [BN] or NULL
+    const uint32_t* mask_in;   // [M, BN/32] bit j of word c = (input of the ReLU at column 32 c + j was > 0)   (EPI_MASK)
+    float* out;                // [M, BN]
+    uint32_t* mask_out;        // [M, BN/32] (EPI_RELU)
     long long M;
     int kb0, kb1;  // k-blocks read from A0, then from A1 (the skip connection: [h | embedding])
 };
 
-enum { EPI_RELU_SPLIT = 0, EPI_LINEAR = 1, EPI_MASK = 2 };
+enum { EPI_RELU = 0, EPI_LINEAR = 1, EPI_MASK = 2 };
 
-template <int BN, int NPROD, int NSTAGE, int EPI>
-__global__ void __launch_bounds__(192, 1)
-    mlp_linear_kernel(const __grid_constant__ CUtensorMap mapA0h, const __grid_constant__ CUtensorMap mapA0l,
-                      const __grid_constant__ CUtensorMap mapA1h, const __grid_constant__ CUtensorMap mapA1l,
+constexpr int kThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-9 operand split
+constexpr int STG_PITCH = 36;        // floats per staged row (32 + 4: conflict-free 128-bit writes by row and reads by 4 rows)
+constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;
+
+template <int BN, int NSTAGE, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+    mlp_linear_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, LinearArgs args) {
     pdl_wait();
     constexpr int W_TILE_BYTES = BN * BK * 4;
-    constexpr int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
-    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators; power of two >= 32
+    constexpr int STAGE_BYTES = 2 * (A_TILE_BYTES + W_TILE_BYTES);  // [A -> A_hi | A_lo | W_hi | W_lo]
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;            // two accumulators; power of two >= 32
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns");
     static_assert(BN % 32 == 0 && BN <= 256, "BN");
+    constexpr int NCHUNK = BN / 32;
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_tfull[2], bar_tempty[2];
+    __shared__ uint64_t bar_full[NSTAGE], bar_conv[NSTAGE], bar_empty[NSTAGE], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_slot;
 
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
+    const uint32_t stg0 = smem0 + NSTAGE * STAGE_BYTES;            // epilogue staging, one 32 x 36 tile per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_total = args.kb0 + args.kb1;
     const long long n_tiles = (args.M + BM - 1) / BM;
@@ -144,6 +151,7 @@ __global__ void __launch_bounds__(192, 1)
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_conv[s]), 4);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(192, 1)
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer: the fp32 activation tile and the pre-split weight tiles =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -174,23 +182,17 @@ __global__ void __launch_bounds__(192, 1)
                     mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
                     const uint32_t full = smem_u32(&bar_full[stage]);
                     const uint32_t sA = smem0 + stage * STAGE_BYTES;
-                    mbar_expect_tx(full, STAGE_BYTES);
+                    mbar_expect_tx(full, A_TILE_BYTES + 2 * W_TILE_BYTES);
                     const bool first = kb < args.kb0;
-                    const int ka = (first ? kb : kb - args.kb0) * BK;
-                    tma_load_2d(sA, first ? &mapA0h : &mapA1h, full, ka, row0);
-                    if (NPROD == 3) {
-                        tma_load_2d(sA + A_TILE_BYTES, first ? &mapA0l : &mapA1l, full, ka, row0);
-                        tma_load_2d(sA + 2 * A_TILE_BYTES, &mapWh, full, kb * BK, 0);
-                        tma_load_2d(sA + 2 * A_TILE_BYTES + W_TILE_BYTES, &mapWl, full, kb * BK, 0);
-                    } else {
-                        tma_load_2d(sA + A_TILE_BYTES, &mapWh, full, kb * BK, 0);
-                    }
+                    tma_load_2d(sA, first ? &mapA0 : &mapA1, full, (first ? kb : kb - args.kb0) * BK, row0);
+                    tma_load_2d(sA + 2 * A_TILE_BYTES, &mapWh, full, kb * BK, 0);
+                    tma_load_2d(sA + 2 * A_TILE_BYTES + W_TILE_BYTES, &mapWl, full, kb * BK, 0);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
+        // ===== MMA issuer (one thread): A_hi.W_hi + A_hi.W_lo + A_lo.W_hi per k-step =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN);
             int stage = 0;
@@ -202,21 +204,19 @@ __global__ void __launch_bounds__(192, 1)
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < kb_total; ++kb) {
-                    mbar_wait(smem_u32(&bar_full[stage]), phase);
+                    mbar_wait(smem_u32(&bar_conv[stage]), phase);
                     tc_fence_after();
                     const uint32_t sA = smem0 + stage * STAGE_BYTES;
                     const uint64_t dAh = make_desc(sA);
                     const uint64_t dAl = make_desc(sA + A_TILE_BYTES);
-                    const uint64_t dWh = make_desc(sA + (NPROD == 3 ? 2 : 1) * A_TILE_BYTES);
+                    const uint64_t dWh = make_desc(sA + 2 * A_TILE_BYTES);
                     const uint64_t dWl = make_desc(sA + 2 * A_TILE_BYTES + W_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // byte offset inside the swizzle row, >> 4
-                        tc_mma_tf32(d_tmem, dAh + adv, dWh + adv, idesc, (kb | k) != 0);
-                        if (NPROD == 3) {
-                            tc_mma_tf32(d_tmem, dAh + adv, dWl + adv, idesc, 1);
-                            tc_mma_tf32(d_tmem, dAl + adv, dWh + adv, idesc, 1);
-                        }
+                        tc_mma_tf32(d_tmem, dAl + adv, dWh + adv, idesc, (kb | k) != 0);  // small terms first
+                        tc_mma_tf32(d_tmem, dAh + adv, dWl + adv, idesc, 1);
+                        tc_mma_tf32(d_tmem, dAh + adv, dWh + adv, idesc, 1);
                     }
                     tc_commit(smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -224,65 +224,97 @@ __global__ void __launch_bounds__(192, 1)
                 tc_commit(smem_u32(&bar_tfull[acc]));  // accumulator complete
             }
         }
-    } else {
-        // ===== epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31 =====
+    } else if (warp < 6) {
+        // ===== epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31; lane = row =====
         const int q = warp & 3;
+        const uint32_t stg = stg0 + q * (32 * STG_PITCH * 4);
         uint32_t t = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
             const uint32_t acc = t & 1;
+            const long long wrow0 = tile * BM + q * 32;  // first row of this warp
+            uint32_t bits[NCHUNK];
+            if (EPI == EPI_MASK) {
+#pragma unroll
+                for (int c = 0; c < NCHUNK; ++c) bits[c] = (wrow0 + lane < args.M) ? __ldg(args.mask_in + (wrow0 + lane) * NCHUNK + c) : 0u;
+            }
             mbar_wait(smem_u32(&bar_tfull[acc]), (t >> 1) & 1);
             tc_fence_after();
-            const long long row = tile * BM + q * 32 + lane;
-            const bool live = row < args.M;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
-                if (live) {
-                    float* oh = args.out_hi + row * BN + c * 32;
-                    if (EPI == EPI_RELU_SPLIT) {
-                        float* ol = args.out_lo + row * BN + c * 32;
+                if (EPI == EPI_RELU) {
+                    uint32_t m = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 h, l;
-                            float x;
-                            x = fmaxf(__uint_as_float(v[j + 0]) + __ldg(args.bias + c * 32 + j + 0), 0.f); h.x = tf32_hi(x); l.x = x - h.x;
-                            x = fmaxf(__uint_as_float(v[j + 1]) + __ldg(args.bias + c * 32 + j + 1), 0.f); h.y = tf32_hi(x); l.y = x - h.y;
-                            x = fmaxf(__uint_as_float(v[j + 2]) + __ldg(args.bias + c * 32 + j + 2), 0.f); h.z = tf32_hi(x); l.z = x - h.z;
-                            x = fmaxf(__uint_as_float(v[j + 3]) + __ldg(args.bias + c * 32 + j + 3), 0.f); h.w = tf32_hi(x); l.w = x - h.w;
-                            *reinterpret_cast<float4*>(oh + j) = h;
-                            *reinterpret_cast<float4*>(ol + j) = l;
-                        }
-                    } else if (EPI == EPI_LINEAR) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 h;
-                            h.x = __uint_as_float(v[j + 0]) + __ldg(args.bias + c * 32 + j + 0);
-                            h.y = __uint_as_float(v[j + 1]) + __ldg(args.bias + c * 32 + j + 1);
-                            h.z = __uint_as_float(v[j + 2]) + __ldg(args.bias + c * 32 + j + 2);
-                            h.w = __uint_as_float(v[j + 3]) + __ldg(args.bias + c * 32 + j + 3);
-                            *reinterpret_cast<float4*>(oh + j) = h;
-                        }
-                    } else {
-                        // rounded to tf32 (nearest) here: the next data-gradient GEMM and the weight-gradient GEMM read it
-                        // as a tf32 operand, and letting the tensor core truncate instead biases every layer the same way
-                        const float* ms = args.mask_src + row * BN + c * 32;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 m = __ldg(reinterpret_cast<const float4*>(ms + j));
-                            float4 h;
-                            h.x = m.x > 0.f ? tf32_hi(__uint_as_float(v[j + 0])) : 0.f;
-                            h.y = m.y > 0.f ? tf32_hi(__uint_as_float(v[j + 1])) : 0.f;
-                            h.z = m.z > 0.f ? tf32_hi(__uint_as_float(v[j + 2])) : 0.f;
-                            h.w = m.w > 0.f ? tf32_hi(__uint_as_float(v[j + 3])) : 0.f;
-                            *reinterpret_cast<float4*>(oh + j) = h;
-                        }
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = __uint_as_float(v[j]) + __ldg(args.bias + c * 32 + j);
+                        m |= (x > 0.f ? 1u : 0u) << j;
+                        v[j] = __float_as_uint(fmaxf(x, 0.f));
                     }
+                    bits[c] = m;
+                } else if (EPI == EPI_LINEAR) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(args.bias + c * 32 + j));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (bits[c] >> j) & 1u ? v[j] : 0u;
+                }
+                // transpose through shared memory: written by row (lane = row), read back four rows per instruction so that
+                // every global store instruction covers four complete 128-byte lines
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (lane * STG_PITCH + 4 * j) * 4), "r"(v[4 * j]),
+                                 "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                                 : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + (lane >> 3), cc = (lane & 7) * 4;
+                    uint4 o;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                                 : "r"(stg + (rr * STG_PITCH + cc) * 4)
+                                 : "memory");
+                    if (wrow0 + rr < args.M) *reinterpret_cast<uint4*>(args.out + (wrow0 + rr) * BN + c * 32 + cc) = o;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
+            if constexpr (EPI == EPI_RELU) {
+                if (wrow0 + lane < args.M)
+#pragma unroll
+                for (int c = 0; c < NCHUNK; c += 4)
+                    *reinterpret_cast<uint4*>(args.mask_out + (wrow0 + lane) * NCHUNK + c) = make_uint4(bits[c], bits[c + 1], bits[c + 2], bits[c + 3]);
+            }
+        }
+    } else {
+        // ===== operand split: the landed fp32 tile becomes hi (in place) and lo (next tile); element-wise, so the swizzle
+        // TMA applied is irrelevant -- lo lands at the same swizzled offset of its own tile =====
+        const int tid = threadIdx.x - 192;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < kb_total; ++kb) {
+                mbar_wait(smem_u32(&bar_full[stage]), phase);
+                const uint32_t sA = smem0 + stage * STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
+                    const uint32_t addr = sA + (i * 128 + tid) * 16;
+                    float4 x;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr) : "memory");
+                    const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + A_TILE_BYTES), "f"(x.x - h.x), "f"(x.y - h.y),
+                                 "f"(x.z - h.z), "f"(x.w - h.w)
+                                 : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_conv[stage]));
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
         }
     }
 
@@ -322,27 +354,22 @@ static bool make_map(CUtensorMap* m, const float* base, long long rows, int cols
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int NPROD, int NSTAGE, int EPI>
-static int launch_linear(long long M, const float* a0h, const float* a0l, int k0, const float* a1h, const float* a1l, int k1,
-                         const float* wh, const float* wl, const LinearArgs& args, cudaStream_t st) {
-    CUtensorMap mA0h, mA0l, mA1h, mA1l, mWh, mWl;
-    bool ok = make_map(&mA0h, a0h, M, k0, BM) && make_map(&mWh, wh, BN, k0 + k1, BN);
-    mA0l = mA0h, mA1h = mA0h, mA1l = mA0h, mWl = mWh;
-    if (NPROD == 3) ok = ok && make_map(&mA0l, a0l, M, k0, BM) && make_map(&mWl, wl, BN, k0 + k1, BN);
-    if (k1 > 0) {
-        ok = ok && make_map(&mA1h, a1h, M, k1, BM);
-        mA1l = mA1h;
-        if (NPROD == 3) ok = ok && make_map(&mA1l, a1l, M, k1, BM);
-    }
+template <int BN, int NSTAGE, int EPI>
+static int launch_linear(long long M, const float* a0, int k0, const float* a1, int k1, const float* wh, const float* wl,
+                         const LinearArgs& args, cudaStream_t st) {
+    CUtensorMap mA0, mA1, mWh, mWl;
+    bool ok = make_map(&mA0, a0, M, k0, BM) && make_map(&mWh, wh, BN, k0 + k1, BN) && make_map(&mWl, wl, BN, k0 + k1, BN);
+    mA1 = mA0;
+    if (k1 > 0) ok = ok && make_map(&mA1, a1, M, k1, BM);
     if (!ok) return set_error(FG_ERR_CUDA, "cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)", __FILE__, __LINE__);
-    constexpr int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (A_TILE_BYTES + BN * BK * 4);
-    constexpr int SMEM = NSTAGE * STAGE_BYTES + 1024;
+    constexpr int STAGE_BYTES = 2 * (A_TILE_BYTES + BN * BK * 4);
+    constexpr int SMEM = NSTAGE * STAGE_BYTES + STG_BYTES + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory");
-    auto kern = mlp_linear_kernel<BN, NPROD, NSTAGE, EPI>;
+    auto kern = mlp_linear_kernel<BN, NSTAGE, EPI>;
     FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const long long n_tiles = (M + BM - 1) / BM;
     const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-    FG_LAUNCH(kern, grid, 192, SMEM, st, mA0h, mA0l, mA1h, mA1l, mWh, mWl, args);
+    FG_LAUNCH(kern, grid, kThreads, SMEM, st, mA0, mA1, mWh, mWl, args);
     return FG_OK;
 }
 
@@ -378,7 +405,7 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(PackTable tab) {
 // ------------------------------------------------------------------------------------------------ embedding
 // E[n, :] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^9), cos(x 2^9) | t_emb | 0...]   (utils.py:27-56; model.py:1095-1096)
 __global__ void __launch_bounds__(256) deform_embed_kernel(long long N, const float* __restrict__ means, const float* __restrict__ t_emb,
-                                                           int t_ch, int multires, float* __restrict__ e_hi, float* __restrict__ e_lo) {
+                                                           int t_ch, int multires, float* __restrict__ e) {
     pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * FG_MLP_EMBED_LD) return;
@@ -395,9 +422,7 @@ __global__ void __launch_bounds__(256) deform_embed_kernel(long long N, const fl
     } else if (j < x_ch + t_ch) {
         v = t_emb[j - x_ch];
     }
-    const float h = tf32_hi(v);
-    e_hi[i] = h;
-    e_lo[i] = v - h;
+    e[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------------ SE(3) application
@@ -550,28 +575,26 @@ __global__ void __launch_bounds__(256)
 using namespace fg;
 using namespace fg::mlp;
 
-extern "C" int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0_hi, const float* a0_lo, int k0, const float* a1_hi,
-                             const float* a1_lo, int k1, const float* w_hi, const float* w_lo, const float* bias,
-                             const float* mask_src, float* out_hi, float* out_lo, void* stream) {
+extern "C" int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, int k0, const float* a1, int k1, const float* w_hi,
+                             const float* w_lo, const float* bias, const uint32_t* mask_in, float* out, uint32_t* mask_out,
+                             void* stream) {
     FG_REQUIRE(M >= 0 && M < (1ll << 31) - BM, "fg_mlp_linear: M out of range");
     FG_REQUIRE(k0 > 0 && k0 % BK == 0 && k1 >= 0 && k1 % BK == 0, "fg_mlp_linear: k0, k1 must be multiples of 32 (k0 > 0)");
-    FG_REQUIRE(a0_hi && w_hi && out_hi && (k1 == 0 || a1_hi), "fg_mlp_linear: NULL operand");
+    FG_REQUIRE(a0 && w_hi && w_lo && out && (k1 == 0 || a1), "fg_mlp_linear: NULL operand");
     if (M == 0) return FG_OK;
-    LinearArgs args = {bias, mask_src, out_hi, out_lo, (long long)M, k0 / BK, k1 / BK};
+    LinearArgs args = {bias, mask_in, out, mask_out, (long long)M, k0 / BK, k1 / BK};
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == FG_MLP_RELU_SPLIT) {
-        FG_REQUIRE(n_out == 256, "fg_mlp_linear: FG_MLP_RELU_SPLIT is built for 256 outputs");
-        FG_REQUIRE(a0_lo && w_lo && out_lo && bias && (k1 == 0 || a1_lo), "fg_mlp_linear: the 3xTF32 modes need the lo operands and a bias");
-        return launch_linear<256, 3, 2, EPI_RELU_SPLIT>(M, a0_hi, a0_lo, k0, a1_hi, a1_lo, k1, w_hi, w_lo, args, st);
+    if (mode == FG_MLP_RELU) {
+        FG_REQUIRE(n_out == 256 && bias && mask_out, "fg_mlp_linear: FG_MLP_RELU is built for 256 outputs and needs bias and mask_out");
+        return launch_linear<256, 2, EPI_RELU>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
     }
     if (mode == FG_MLP_LINEAR) {
-        FG_REQUIRE(n_out == FG_MLP_HEAD_LD, "fg_mlp_linear: FG_MLP_LINEAR is built for FG_MLP_HEAD_LD outputs");
-        FG_REQUIRE(a0_lo && w_lo && bias && (k1 == 0 || a1_lo), "fg_mlp_linear: the 3xTF32 modes need the lo operands and a bias");
-        return launch_linear<FG_MLP_HEAD_LD, 3, 4, EPI_LINEAR>(M, a0_hi, a0_lo, k0, a1_hi, a1_lo, k1, w_hi, w_lo, args, st);
+        FG_REQUIRE(n_out == FG_MLP_HEAD_LD && bias, "fg_mlp_linear: FG_MLP_LINEAR is built for FG_MLP_HEAD_LD outputs and needs a bias");
+        return launch_linear<FG_MLP_HEAD_LD, 4, EPI_LINEAR>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
     }
     if (mode == FG_MLP_DGRAD) {
-        FG_REQUIRE(n_out == 256 && mask_src, "fg_mlp_linear: FG_MLP_DGRAD is built for 256 outputs and needs mask_src");
-        return launch_linear<256, 1, 4, EPI_MASK>(M, a0_hi, nullptr, k0, a1_hi, nullptr, k1, w_hi, nullptr, args, st);
+        FG_REQUIRE(n_out == 256 && mask_in, "fg_mlp_linear: FG_MLP_DGRAD is built for 256 outputs and needs mask_in");
+        return launch_linear<256, 2, EPI_MASK>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
     }
     return set_error(FG_ERR_INVALID, "fg_mlp_linear: unknown mode", __FILE__, __LINE__);
 }
@@ -589,14 +612,13 @@ extern "C" int fg_mlp_pack(int n_segments, const fg_mlp_pack_segment* segments_h
     return FG_OK;
 }
 
-extern "C" int fg_deform_embed(int64_t N, const float* means, const float* t_emb, int t_ch, int multires, float* e_hi, float* e_lo,
-                               void* stream) {
-    FG_REQUIRE(N >= 0 && means && e_hi && e_lo, "fg_deform_embed: NULL argument");
+extern "C" int fg_deform_embed(int64_t N, const float* means, const float* t_emb, int t_ch, int multires, float* e, void* stream) {
+    FG_REQUIRE(N >= 0 && means && e, "fg_deform_embed: NULL argument");
     FG_REQUIRE(multires >= 0 && t_ch >= 0 && 3 + 6 * multires + t_ch <= FG_MLP_EMBED_LD && (t_ch == 0 || t_emb),
                "fg_deform_embed: embedding wider than FG_MLP_EMBED_LD");
     if (N == 0) return FG_OK;
     FG_LAUNCH(deform_embed_kernel, ceil_div(N * FG_MLP_EMBED_LD, 256), 256, 0, (cudaStream_t)stream, (long long)N, means, t_emb, t_ch,
-              multires, e_hi, e_lo);
+              multires, e);
     return FG_OK;
 }
 

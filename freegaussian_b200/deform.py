@@ -6,8 +6,8 @@ constructor arguments, same parameter names and shapes (a reference ``state_dict
 lines that consume those outputs (``freegaussian_model.py:836-845``) and returns the ``means, scales, quats`` handed
 to ``rasterization``.
 
-Every ``nn.Linear`` of the trunk and the four heads run in ``fg_mlp_linear`` (tcgen05 / TMEM / TMA, csrc/mlp.cu):
-forward in error-compensated 3xTF32 (fp32-accurate, the reference computes in fp32), data gradients in single TF32.
+Every ``nn.Linear`` of the trunk and the four heads, forward and data gradient, run in ``fg_mlp_linear`` (tcgen05 /
+TMEM / TMA, csrc/mlp.cu) in error-compensated 3xTF32 (fp32-accurate: the reference computes these layers in fp32).
 Weight gradients are plain ``[256, N] x [N, K]`` products and go to cuBLAS (TF32) through ``torch.mm`` for now.
 There is no CPU path.
 
@@ -46,11 +46,10 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def _linear(mode, M, n_out, a0, k0, a1, k1, w, bias, mask, out_hi, out_lo):
-    """a0 / a1 / w are (hi, lo) pairs (lo may be None)."""
-    check(_lib.lib().fg_mlp_linear(mode, M, n_out, ptr(a0[0]), ptr(a0[1]), k0, ptr(a1[0]) if a1 else None,
-                                   ptr(a1[1]) if a1 else None, k1, ptr(w[0]), ptr(w[1]), ptr(bias), ptr(mask),
-                                   ptr(out_hi), ptr(out_lo), _stream()))
+def _linear(mode, M, n_out, a0, k0, a1, k1, w, bias, mask_in, out, mask_out):
+    """``w`` is the (hi, lo) pair of a packed weight; activations are plain fp32."""
+    check(_lib.lib().fg_mlp_linear(mode, M, n_out, ptr(a0), k0, ptr(a1), k1, ptr(w[0]), ptr(w[1]), ptr(bias), ptr(mask_in),
+                                   ptr(out), ptr(mask_out), _stream()))
 
 
 class _Packed:
@@ -63,8 +62,8 @@ class _Packed:
         self.kp = kp
         self.w = [(z(_W, k), z(_W, k)) for k in kp]
         self.w_head = (z(MLP_HEAD_LD, _W), z(MLP_HEAD_LD, _W))
-        self.wt = [None] + [z(_W, _W) for _ in range(1, _D)]  # wt[l][i, o] = W_l[o, i] over the hidden inputs
-        self.wt_head = z(_W, MLP_HEAD_LD)
+        self.wt = [None] + [(z(_W, _W), z(_W, _W)) for _ in range(1, _D)]  # wt[l][i, o] = W_l[o, i] over the hidden inputs
+        self.wt_head = (z(_W, MLP_HEAD_LD), z(_W, MLP_HEAD_LD))
         segs = []
 
         def seg(src, col0, cols, dst, dst_col0, transpose=False, row0=0):
@@ -116,24 +115,25 @@ class _Trunk(torch.autograd.Function):
         emb_ch = 3 + 6 * multires + t_ch
         pk = _Packed(list(params), emb_ch)
         new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
-        e = (new(N, MLP_EMBED_LD), new(N, MLP_EMBED_LD))
-        check(L.fg_deform_embed(N, ptr(x), ptr(t_emb), t_ch, multires, ptr(e[0]), ptr(e[1]), _stream()))
-        h_hi: List[Tensor] = []
-        lo_buf = [new(N, _W), new(N, _W)]
+        e = new(N, MLP_EMBED_LD)
+        check(L.fg_deform_embed(N, ptr(x), ptr(t_emb), t_ch, multires, ptr(e), _stream()))
+        hs: List[Tensor] = []
+        masks: List[Tensor] = []
         prev = None
         for i in range(_D):
-            out_hi, out_lo = new(N, _W), lo_buf[i & 1]
+            out, bits = new(N, _W), torch.empty(N, _W // 32, device=dev, dtype=torch.int32)
             if i == 0:
-                _linear(_lib.MLP_RELU_SPLIT, N, _W, e, MLP_EMBED_LD, None, 0, pk.w[0], pk.bias[0], None, out_hi, out_lo)
+                _linear(_lib.MLP_RELU, N, _W, e, MLP_EMBED_LD, None, 0, pk.w[0], pk.bias[0], None, out, bits)
             elif i == _SKIP + 1:
-                _linear(_lib.MLP_RELU_SPLIT, N, _W, prev, _W, e, MLP_EMBED_LD, pk.w[i], pk.bias[i], None, out_hi, out_lo)
+                _linear(_lib.MLP_RELU, N, _W, prev, _W, e, MLP_EMBED_LD, pk.w[i], pk.bias[i], None, out, bits)
             else:
-                _linear(_lib.MLP_RELU_SPLIT, N, _W, prev, _W, None, 0, pk.w[i], pk.bias[i], None, out_hi, out_lo)
-            prev = (out_hi, out_lo)
-            h_hi.append(out_hi)
+                _linear(_lib.MLP_RELU, N, _W, prev, _W, None, 0, pk.w[i], pk.bias[i], None, out, bits)
+            prev = out
+            hs.append(out)
+            masks.append(bits)
         head = new(N, MLP_HEAD_LD)
         _linear(_lib.MLP_LINEAR, N, MLP_HEAD_LD, prev, _W, None, 0, pk.w_head, pk.bias_head, None, head, None)
-        ctx.save_for_backward(e[0], *h_hi, *params)
+        ctx.save_for_backward(e, *hs, *masks, *params)
         ctx.pk = pk
         ctx.dims = (N, t_ch, emb_ch, multires)
         return head
@@ -142,7 +142,7 @@ class _Trunk(torch.autograd.Function):
     def backward(ctx, g_head):
         N, t_ch, emb_ch, multires = ctx.dims
         saved = ctx.saved_tensors
-        e_hi, h_hi, params = saved[0], saved[1:1 + _D], saved[1 + _D:]
+        e, hs, masks, params = saved[0], saved[1:1 + _D], saved[1 + _D:1 + 2 * _D], saved[1 + 2 * _D:]
         pk = ctx.pk
         dev = g_head.device
         g_head = g_head.contiguous()
@@ -155,27 +155,27 @@ class _Trunk(torch.autograd.Function):
             row = 0
             for j, (_, o) in enumerate(_HEADS):
                 gj = g_head[:, row:row + o]
-                grads[2 * _D + 2 * j] = gj.t() @ h_hi[_D - 1]
+                grads[2 * _D + 2 * j] = gj.t() @ hs[_D - 1]
                 grads[2 * _D + 2 * j + 1] = gj.sum(0)
                 row += o
             dz = new(N, _W)
-            _linear(_lib.MLP_DGRAD, N, _W, (g_head, None), MLP_HEAD_LD, None, 0, (pk.wt_head, None), None, h_hi[_D - 1], dz, None)
+            _linear(_lib.MLP_DGRAD, N, _W, g_head, MLP_HEAD_LD, None, 0, pk.wt_head, None, masks[_D - 1], dz, None)
             g_t = torch.zeros(t_ch, device=dev) if t_ch else None
             for i in range(_D - 1, -1, -1):
                 gb = dz.sum(0)
                 grads[2 * i + 1] = gb
                 if i == 0:
-                    grads[0] = dz.t() @ e_hi[:, :emb_ch]
+                    grads[0] = dz.t() @ e[:, :emb_ch]
                 elif i == _SKIP + 1:
-                    grads[2 * i] = torch.cat([dz.t() @ e_hi[:, :emb_ch], dz.t() @ h_hi[i - 1]], 1)
+                    grads[2 * i] = torch.cat([dz.t() @ e[:, :emb_ch], dz.t() @ hs[i - 1]], 1)
                 else:
-                    grads[2 * i] = dz.t() @ h_hi[i - 1]
+                    grads[2 * i] = dz.t() @ hs[i - 1]
                 if t_ch and (i == 0 or i == _SKIP + 1):
                     # every row reads the same t_emb, so its gradient is (column sums of dz) . W[:, t columns]
                     g_t = g_t + gb @ params[2 * i][:, x_ch:emb_ch]
                 if i > 0:
                     dz_prev = new(N, _W)
-                    _linear(_lib.MLP_DGRAD, N, _W, (dz, None), _W, None, 0, (pk.wt[i], None), None, h_hi[i - 1], dz_prev, None)
+                    _linear(_lib.MLP_DGRAD, N, _W, dz, _W, None, 0, pk.wt[i], None, masks[i - 1], dz_prev, None)
                     dz = dz_prev
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32

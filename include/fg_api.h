@@ -355,20 +355,22 @@ int fg_refine_children(int64_t n_out, int64_t n_keep, int64_t n_children, const 
  * layer 4, four linear heads) and the application of its outputs (freegaussian_model.py:836-845).
  * These entry points replace the torch.nn.Linear / F.relu / torch.cat / exp_se3 / torch.bmm calls of those lines.
  *
- * Operand convention of the tensor-core kernel: every fp32 matrix that feeds a tcgen05.mma is held as two fp32
- * arrays, hi (x rounded to the nearest tf32 value, 13 low mantissa bits zero) and lo = x - hi, row-major with a row length
- * that is a multiple of 32 floats (zero padded).
+ * Numerics of the tensor-core kernel: error-compensated 3xTF32.  Each fp32 operand x is used as hi + lo, hi = x rounded
+ * to the nearest tf32 value and lo = x - hi; every k-step accumulates A_lo.W_hi + A_hi.W_lo + A_hi.W_hi in fp32, which is
+ * fp32-accurate (the reference computes these layers in fp32).  Activations are plain fp32 row-major arrays whose row
+ * length is a multiple of 32 floats (zero padded); they are split on chip.  Weights are passed pre-split (fg_mlp_pack).
  *
- * fg_mlp_linear: out[M, n_out] = epilogue( [A0 | A1] . W^T ),  A0 [M,k0], A1 [M,k1] (k1 may be 0), W [n_out, k0+k1].
- *   FG_MLP_RELU_SPLIT  n_out = 256, 3xTF32 (A_hi.W_hi + A_hi.W_lo + A_lo.W_hi, fp32 accumulate),
- *                      out = max(. + bias, 0) written as out_hi / out_lo            (nn.Linear + F.relu, :1097-1099)
- *   FG_MLP_LINEAR      n_out = FG_MLP_HEAD_LD, 3xTF32, out_hi = . + bias (full fp32) (the four heads, :1103-1112)
- *   FG_MLP_DGRAD       n_out = 256, single TF32 on the hi arrays, out_hi = mask_src > 0 ? . : 0
- *                      (data gradient of Linear + ReLU: A0 = dL/d(out of layer l), W = W_l^T, mask_src = input of layer l)
+ * fg_mlp_linear: out[M, n_out] = epilogue( [A0 | A1] . W^T ),  A0 [M,k0], A1 [M,k1] (k1 may be 0), W [n_out, k0+k1] as
+ *   w_hi / w_lo.
+ *   FG_MLP_RELU    n_out = 256: out = max(. + bias, 0); mask_out[M, 8] uint32, bit j of word c = (column 32c+j > 0)
+ *                  (nn.Linear + F.relu, :1097-1099)
+ *   FG_MLP_LINEAR  n_out = FG_MLP_HEAD_LD: out = . + bias                              (the four heads, :1103-1112)
+ *   FG_MLP_DGRAD   n_out = 256: out = mask_in bit ? . : 0   (data gradient of Linear + ReLU: A0 = dL/d(output of
+ *                  layer l), W = W_l^T, mask_in = the mask_out of layer l-1)
  * fg_mlp_pack: copies column ranges of reference-layout weights ([rows, src_ld] row-major) into the padded operand
  *   buffers (optionally transposed), splitting hi / lo (dst_lo may be NULL).  One launch for the whole table.
- * fg_deform_embed: E[n,:] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^(multires-1)), cos(..) | t_emb[t_ch] | 0]
- *   as hi / lo [N, FG_MLP_EMBED_LD]  (Embedder.embed, utils.py:27-56; torch.cat at freegaussian_model.py:1096).
+ * fg_deform_embed: E[n,:] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^(multires-1)), cos(..) | t_emb[t_ch] | 0],
+ *   [N, FG_MLP_EMBED_LD]  (Embedder.embed, utils.py:27-56; torch.cat at freegaussian_model.py:1096).
  * fg_deform_apply_fwd: head[N, FG_MLP_HEAD_LD] = (branch_w 3 | branch_v 3 | gaussian_rotation 4 | gaussian_scaling 3 | 0)
  *   -> theta = |w|, screw axis (w, v) / theta + 1e-5, exp_se3 (utils.py:137-159), means' = R means + p,
  *   scales' = exp(scales_log) + d_scaling, quats' = quats / |quats| + d_rotation   (freegaussian_model.py:841-845).
@@ -378,7 +380,7 @@ int fg_refine_children(int64_t n_out, int64_t n_keep, int64_t n_children, const 
 #define FG_MLP_EMBED_LD 96
 #define FG_MLP_HEAD_LD 32
 #define FG_MLP_PACK_MAX_SEGMENTS 32
-#define FG_MLP_RELU_SPLIT 0
+#define FG_MLP_RELU 0
 #define FG_MLP_LINEAR 1
 #define FG_MLP_DGRAD 2
 typedef struct fg_mlp_pack_segment {
@@ -389,12 +391,10 @@ typedef struct fg_mlp_pack_segment {
     int32_t dst_ld, dst_col0;             /* destination row length and first column */
     int32_t transpose;                    /* != 0: dst[c, r] = src[r, c] */
 } fg_mlp_pack_segment;
-int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0_hi, const float* a0_lo, int k0, const float* a1_hi,
-                  const float* a1_lo, int k1, const float* w_hi, const float* w_lo, const float* bias,
-                  const float* mask_src, float* out_hi, float* out_lo, void* stream);
+int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, int k0, const float* a1, int k1, const float* w_hi,
+                  const float* w_lo, const float* bias, const uint32_t* mask_in, float* out, uint32_t* mask_out, void* stream);
 int fg_mlp_pack(int n_segments, const fg_mlp_pack_segment* segments_host, void* stream);
-int fg_deform_embed(int64_t N, const float* means, const float* t_emb, int t_ch, int multires, float* e_hi, float* e_lo,
-                    void* stream);
+int fg_deform_embed(int64_t N, const float* means, const float* t_emb, int t_ch, int multires, float* e, void* stream);
 int fg_deform_apply_fwd(int64_t N, const float* head, const float* means, const float* scales_log, const float* quats,
                         float* means_out, float* scales_out, float* quats_out, void* stream);
 int fg_deform_apply_bwd(int64_t N, const float* head, const float* means, const float* scales_log, const float* quats,

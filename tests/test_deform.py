@@ -1,8 +1,8 @@
 """Deformation network: oracle vs the reference's own outputs (CPU), kernels vs oracle (GPU).
 
-Tolerances: the forward runs in 3xTF32 = fp32 accuracy, so outputs are held to 1e-5 of the tensor's scale (the
-north-star budget for everything that feeds the renderer is 1e-4); gradients to 1e-3 of the reference gradient's
-max magnitude (north_star), the data/weight-gradient GEMMs run in single TF32.
+Tolerances: forward and data gradient run in 3xTF32 = fp32 accuracy, so outputs are held to 1e-5 of the tensor's scale
+(the north-star budget for everything that feeds the renderer is 1e-4); weight gradients to 1e-3 of the reference
+gradient's max magnitude (north_star): their GEMMs are cuBLAS TF32.
 """
 from pathlib import Path
 
@@ -91,9 +91,15 @@ def _hilo(x):
     return hi, x - hi
 
 
+def _unpack_bits(bits, n_cols):
+    """[M, n_cols/32] int32 words -> bool [M, n_cols]."""
+    b = bits.cpu().to(torch.int64) & 0xFFFFFFFF
+    return ((b.unsqueeze(-1) >> torch.arange(32)) & 1).reshape(bits.shape[0], n_cols).bool()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("M", [1, 127, 128, 129, 1000, 148 * 128 * 2 + 77])
-def test_linear_relu_split_is_fp32_accurate(built_lib, M):
+def test_linear_relu_is_fp32_accurate(built_lib, M):
     from freegaussian_b200 import _lib
     from freegaussian_b200.deform import _linear
 
@@ -102,16 +108,15 @@ def test_linear_relu_split_is_fp32_accurate(built_lib, M):
         a = torch.randn(M, k0 + k1, generator=g)
         w = torch.randn(256, k0 + k1, generator=g) / (k0 + k1) ** 0.5
         bias = torch.randn(256, generator=g)
-        want = torch.relu(a.double() @ w.double().T + bias.double())
+        pre = a.double() @ w.double().T + bias.double()
         ad, wd, bd = a.cuda(), w.cuda(), bias.cuda()
         a0, a1 = ad[:, :k0].contiguous(), ad[:, k0:].contiguous()
-        out_hi, out_lo = torch.empty(M, 256, device="cuda"), torch.empty(M, 256, device="cuda")
-        _linear(_lib.MLP_RELU_SPLIT, M, 256, _hilo(a0), k0, _hilo(a1) if k1 else None, k1, _hilo(wd), bd, None, out_hi, out_lo)
-        got = out_hi.double() + out_lo.double()
-        assert rel_err(got, want) < 3e-6, (M, k0, k1)
-        # hi is an exact tf32 value and hi + lo reproduces the fp32 result
-        assert int((out_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
-        assert float((out_hi + out_lo - got.float()).abs().max()) == 0.0
+        out = torch.empty(M, 256, device="cuda")
+        bits = torch.empty(M, 8, dtype=torch.int32, device="cuda")
+        _linear(_lib.MLP_RELU, M, 256, a0, k0, a1 if k1 else None, k1, _hilo(wd), bd, None, out, bits)
+        assert rel_err(out, torch.relu(pre)) < 3e-6, (M, k0, k1)
+        # the mask the data-gradient pass reads is exactly (output > 0)
+        assert bool((_unpack_bits(bits, 256) == (out.cpu() > 0)).all())
 
 
 @pytest.mark.gpu
@@ -125,18 +130,22 @@ def test_linear_head_and_dgrad_modes(built_lib, M):
     w = torch.randn(32, 256, generator=g) / 16
     bias = torch.randn(32, generator=g)
     out = torch.empty(M, 32, device="cuda")
-    _linear(_lib.MLP_LINEAR, M, 32, _hilo(a.cuda()), 256, None, 0, _hilo(w.cuda()), bias.cuda(), None, out, None)
+    ad, wd, bd = a.cuda(), w.cuda(), bias.cuda()
+    _linear(_lib.MLP_LINEAR, M, 32, ad, 256, None, 0, _hilo(wd), bd, None, out, None)
     assert rel_err(out, a.double() @ w.double().T + bias.double()) < 3e-6
-    # data gradient: dz_prev = (dz . Wt^T) * (h_prev > 0), single TF32
+    # data gradient: dz_prev = (dz . Wt^T) where the ReLU input was positive
     for k in (32, 256):
         dz = torch.randn(M, k, generator=g)
         wt = torch.randn(256, k, generator=g) / k ** 0.5
-        hp = torch.randn(M, 256, generator=g)
+        keep = torch.rand(M, 256, generator=g) > 0.5
+        words = (keep.reshape(M, 8, 32).to(torch.int64) << torch.arange(32)).sum(-1)
+        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).cuda()
         got = torch.empty(M, 256, device="cuda")
-        _linear(_lib.MLP_DGRAD, M, 256, (dz.cuda(), None), k, None, 0, (wt.cuda(), None), None, hp.cuda(), got, None)
-        want = (dz.double() @ wt.double().T) * (hp > 0)
-        assert grad_rel_err(got, want) < 1e-3
-        assert bool(((got.cpu() == 0) | (hp > 0)).all())
+        dzd, wtd = dz.cuda(), wt.cuda()
+        _linear(_lib.MLP_DGRAD, M, 256, dzd, k, None, 0, _hilo(wtd), None, words, got, None)
+        want = (dz.double() @ wt.double().T) * keep
+        assert grad_rel_err(got, want) < 3e-6
+        assert bool(((got.cpu() == 0) | keep).all())
 
 
 @pytest.mark.gpu
@@ -149,16 +158,15 @@ def test_embedding_matches_reference_layout(built_lib, t_ch, multires):
     n = 1001
     x = (torch.rand(n, 3, generator=g) - 0.5) * 6.0
     t_emb = torch.randn(t_ch, generator=g)
-    e_hi, e_lo = torch.empty(n, 96, device="cuda"), torch.empty(n, 96, device="cuda")
+    e = torch.empty(n, 96, device="cuda")
     xd, td = x.cuda(), t_emb.cuda()
-    check(_lib.lib().fg_deform_embed(n, ptr(xd), ptr(td) if t_ch else None, t_ch, multires, ptr(e_hi), ptr(e_lo),
+    check(_lib.lib().fg_deform_embed(n, ptr(xd), ptr(td) if t_ch else None, t_ch, multires, ptr(e),
                                      torch.cuda.current_stream().cuda_stream))
     want = torch.cat([OD.embed(x, multires), t_emb.expand(n, -1)], -1)
-    got = (e_hi + e_lo).cpu()
+    got = e.cpu()
     worst = float((got[:, :want.shape[1]] - want).abs().max())
     assert worst < 1e-6, worst  # sin / cos of arguments up to 3 * 2^9, same fp32 argument on both sides
     assert float(got[:, want.shape[1]:].abs().max()) == 0.0
-    assert int((e_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
 
 
 @pytest.mark.gpu
