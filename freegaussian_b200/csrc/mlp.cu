@@ -118,9 +118,12 @@ struct LinearArgs {
     uint32_t* mask_out;        // [M, BN/32] (EPI_RELU)
     long long M;
     int kb0, kb1;  // k-blocks read from A0, then from A1 (the skip connection: [h | embedding])
+    int dbg;       // timing experiments only (fg_mlp_debug_flags): 1 = W tiles loaded once per CTA, 2 = no operand split,
+                   // 4 = no global stores, 8 = one product instead of three.  Results are wrong with any bit set.
 };
 
 enum { EPI_RELU = 0, EPI_LINEAR = 1, EPI_MASK = 2 };
+static int g_dbg_flags = 0;
 
 constexpr int kThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-9 operand split
 constexpr int STG_PITCH = 36;        // floats per staged row (32 + 4: conflict-free 128-bit writes by row and reads by 4 rows)
@@ -182,11 +185,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                     mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
                     const uint32_t full = smem_u32(&bar_full[stage]);
                     const uint32_t sA = smem0 + stage * STAGE_BYTES;
-                    mbar_expect_tx(full, A_TILE_BYTES + 2 * W_TILE_BYTES);
+                    const bool load_w = !(args.dbg & 1) || (tile == blockIdx.x && kb < NSTAGE);
+                    mbar_expect_tx(full, A_TILE_BYTES + (load_w ? 2 * W_TILE_BYTES : 0));
                     const bool first = kb < args.kb0;
                     tma_load_2d(sA, first ? &mapA0 : &mapA1, full, (first ? kb : kb - args.kb0) * BK, row0);
-                    tma_load_2d(sA + 2 * A_TILE_BYTES, &mapWh, full, kb * BK, 0);
-                    tma_load_2d(sA + 2 * A_TILE_BYTES + W_TILE_BYTES, &mapWl, full, kb * BK, 0);
+                    if (load_w) {
+                        tma_load_2d(sA + 2 * A_TILE_BYTES, &mapWh, full, kb * BK, 0);
+                        tma_load_2d(sA + 2 * A_TILE_BYTES + W_TILE_BYTES, &mapWl, full, kb * BK, 0);
+                    }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
@@ -214,9 +220,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // byte offset inside the swizzle row, >> 4
-                        tc_mma_tf32(d_tmem, dAl + adv, dWh + adv, idesc, (kb | k) != 0);  // small terms first
-                        tc_mma_tf32(d_tmem, dAh + adv, dWl + adv, idesc, 1);
-                        tc_mma_tf32(d_tmem, dAh + adv, dWh + adv, idesc, 1);
+                        if (!(args.dbg & 8)) {
+                            tc_mma_tf32(d_tmem, dAl + adv, dWh + adv, idesc, (kb | k) != 0);  // small terms first
+                            tc_mma_tf32(d_tmem, dAh + adv, dWl + adv, idesc, 1);
+                            tc_mma_tf32(d_tmem, dAh + adv, dWh + adv, idesc, 1);
+                        } else {
+                            tc_mma_tf32(d_tmem, dAh + adv, dWh + adv, idesc, (kb | k) != 0);
+                        }
                     }
                     tc_commit(smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                  : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
                                  : "r"(stg + (rr * STG_PITCH + cc) * 4)
                                  : "memory");
-                    if (wrow0 + rr < args.M) *reinterpret_cast<uint4*>(args.out + (wrow0 + rr) * BN + c * 32 + cc) = o;
+                    if (wrow0 + rr < args.M && !(args.dbg & 4)) *reinterpret_cast<uint4*>(args.out + (wrow0 + rr) * BN + c * 32 + cc) = o;
                 }
             }
             tc_fence_before();
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int kb = 0; kb < kb_total; ++kb) {
                 mbar_wait(smem_u32(&bar_full[stage]), phase);
                 const uint32_t sA = smem0 + stage * STAGE_BYTES;
+                if (!(args.dbg & 2))
 #pragma unroll
                 for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
                     const uint32_t addr = sA + (i * 128 + tid) * 16;
@@ -343,7 +354,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 // [rows, cols] fp32 row-major (pitch = cols), box = box_rows x 32 columns, 128-byte swizzle; rows past the end read 0
-static bool make_map(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows) {
+static bool make_map(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows,
+                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -351,7 +363,7 @@ static bool make_map(CUtensorMap* m, const float* base, long long rows, int cols
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int BN, int NSTAGE, int EPI>
@@ -370,6 +382,247 @@ static int launch_linear(long long M, const float* a0, int k0, const float* a1, 
     const long long n_tiles = (M + BM - 1) / BM;
     const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
     FG_LAUNCH(kern, grid, kThreads, SMEM, st, mA0, mA1, mWh, mWl, args);
+    return FG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[256, KIN] += dz^T . a   and   db[256] += column sums of dz,   dz [N, 256], a [N, KIN], both row-major fp32.
+// The contraction runs over the rows, so both operands are "MN-major" for the tensor core: a TMA box of 16 rows x 32
+// columns lands as 16 swizzled 128-byte rows = four 4-row atoms of the canonical MN-major layout (make_desc_mn).  Split-K: CTA c owns a contiguous range of row blocks, accumulates the whole
+// [256, KIN] product in TMEM (two 128-lane halves x KIN columns) and adds it to dW with vector reductions at the end.
+// Same 3xTF32 scheme and on-chip operand split as the linear layer; the split warps also accumulate db.
+constexpr int WG_ROWS = 16;                       // rows (K extent) per stage = two tcgen05.mma k-steps
+constexpr int WG_CHUNK_BYTES = WG_ROWS * 128;     // one 32-column chunk of a stage
+constexpr int WG_DZ_BYTES = 8 * WG_CHUNK_BYTES;   // [16, 256] fp32
+
+struct WgradArgs {
+    float* dw;       // [256, ld_dw], written at column col0
+    float* db;       // [256] or NULL
+    long long N;
+    int ld_dw, col0;
+};
+
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) { return make_idesc(m, n) | (1u << 15) | (1u << 16); }
+
+// 32-bit MN-major operands have exactly one legal shared-memory layout, SWIZZLE_128B_BASE32B (layout type 1;
+// cutlass/gemm/collective/builders/sm100_common.inl "for mn-major tf32 operands, SW128_32B is the only available smem
+// layout"): rows of 128 bytes (32 columns), the 32-byte chunk index XORed with (row % 4) -- what TMA's
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes -- atoms of 4 rows (SBO = 512 bytes between them), LBO = distance between
+// 32-column atoms.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(WG_CHUNK_BYTES >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+           (1ull << 61);
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, uint4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                 "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+
+template <int KIN, int NSTAGE>
+__global__ void __launch_bounds__(kThreads, 1)
+    mlp_wgrad_kernel(const __grid_constant__ CUtensorMap mapDz, const __grid_constant__ CUtensorMap mapA, WgradArgs args) {
+    pdl_wait();
+    constexpr int A_BYTES = (KIN / 32) * WG_CHUNK_BYTES;
+    constexpr int STAGE_BYTES = 2 * (WG_DZ_BYTES + A_BYTES);  // [dz -> dz_hi | dz_lo | a -> a_hi | a_lo]
+    constexpr int TMEM_COLS = 2 * KIN <= 256 ? 256 : 512;
+    static_assert(KIN % 32 == 0 && KIN <= 256, "KIN");
+    constexpr int NCHUNK = KIN / 32;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[NSTAGE], bar_conv[NSTAGE], bar_empty[NSTAGE], bar_done;
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stg0 = smem0 + NSTAGE * STAGE_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // contiguous range of 16-row blocks of this CTA
+    const long long n_blocks = (args.N + WG_ROWS - 1) / WG_ROWS;
+    const long long per = (n_blocks + gridDim.x - 1) / gridDim.x;
+    const long long blk0 = (long long)blockIdx.x * per;
+    const long long blk1 = blk0 + per < n_blocks ? blk0 + per : n_blocks;
+    const int n_kb = blk1 > blk0 ? (int)(blk1 - blk0) : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_conv[s]), 4);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&bar_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (n_kb > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+                    const uint32_t full = smem_u32(&bar_full[stage]);
+                    const uint32_t sD = smem0 + stage * STAGE_BYTES;
+                    const uint32_t sA = sD + 2 * WG_DZ_BYTES;
+                    const int row0 = (int)((blk0 + kb) * WG_ROWS);
+                    mbar_expect_tx(full, WG_DZ_BYTES + A_BYTES);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) tma_load_2d(sD + c * WG_CHUNK_BYTES, &mapDz, full, c * 32, row0);
+#pragma unroll
+                    for (int c = 0; c < NCHUNK; ++c) tma_load_2d(sA + c * WG_CHUNK_BYTES, &mapA, full, c * 32, row0);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc_mn(128, KIN);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(smem_u32(&bar_conv[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sD = smem0 + stage * STAGE_BYTES;
+                    const uint32_t sA = sD + 2 * WG_DZ_BYTES;
+#pragma unroll
+                    for (int k = 0; k < WG_ROWS / UMMA_K; ++k) {
+                        const uint64_t bh = make_desc_mn(sA + k * 1024), bl = make_desc_mn(sA + A_BYTES + k * 1024);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {  // output rows 128 h .. 128 h + 127 = dz columns = chunks 4 h .. 4 h + 3
+                            const uint64_t ah = make_desc_mn(sD + h * 4 * WG_CHUNK_BYTES + k * 1024);
+                            const uint64_t al = make_desc_mn(sD + WG_DZ_BYTES + h * 4 * WG_CHUNK_BYTES + k * 1024);
+                            const uint32_t d = tmem_base + h * KIN;
+                            tc_mma_tf32(d, al, bh, idesc, (kb | k) != 0);
+                            tc_mma_tf32(d, ah, bl, idesc, 1);
+                            tc_mma_tf32(d, ah, bh, idesc, 1);
+                        }
+                    }
+                    tc_commit(smem_u32(&bar_empty[stage]));
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(smem_u32(&bar_done));
+            }
+        } else if (warp < 6) {
+            // ===== epilogue: TMEM lane = output row (dz column), TMEM column = input feature =====
+            const int q = warp & 3;
+            const uint32_t stg = stg0 + q * (32 * STG_PITCH * 4);
+            mbar_wait(smem_u32(&bar_done), 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int orow0 = h * 128 + q * 32;
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK; ++c) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * KIN + c * 32, v);
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (lane * STG_PITCH + 4 * j) * 4), "r"(v[4 * j]),
+                                     "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                                     : "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = i * 4 + (lane >> 3), cc = (lane & 7) * 4;
+                        uint4 o;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                                     : "r"(stg + (rr * STG_PITCH + cc) * 4)
+                                     : "memory");
+                        red_add_v4(args.dw + (long long)(orow0 + rr) * args.ld_dw + args.col0 + c * 32 + cc, o);
+                    }
+                }
+            }
+            tc_fence_before();
+        } else {
+            // ===== operand split of both tiles (+ column sums of dz for the bias gradient) =====
+            const int tid = threadIdx.x - 192;
+            // this thread always sees row r = tid / 8 of a stage and the 16-byte slot s = tid % 8 of every chunk; the 32-byte
+            // chunk s / 2 holds logical chunk (s / 2) ^ (r % 4), so the thread owns columns 32 c + col4 .. + 3 of chunk c
+            const int col4 = 4 * (((((tid & 7) >> 1) ^ ((tid >> 3) & 3)) << 1) | (tid & 1));
+            float4 sum[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(smem_u32(&bar_full[stage]), phase);
+                const uint32_t sD = smem0 + stage * STAGE_BYTES;
+                const uint32_t sA = sD + 2 * WG_DZ_BYTES;
+#pragma unroll
+                for (int c = 0; c < 8 + NCHUNK; ++c) {
+                    const bool is_dz = c < 8;
+                    const uint32_t addr = (is_dz ? sD + c * WG_CHUNK_BYTES : sA + (c - 8) * WG_CHUNK_BYTES) + tid * 16;
+                    float4 x;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr) : "memory");
+                    if (is_dz) { sum[c & 7].x += x.x; sum[c & 7].y += x.y; sum[c & 7].z += x.z; sum[c & 7].w += x.w; }
+                    const float4 hh = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + (is_dz ? WG_DZ_BYTES : A_BYTES)), "f"(x.x - hh.x),
+                                 "f"(x.y - hh.y), "f"(x.z - hh.z), "f"(x.w - hh.w)
+                                 : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_conv[stage]));
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            if (args.db) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    // reduce over the 4 rows of this warp (lane = 8 (r % 4) + s) that hold the same columns, then one atomic
+                    // per column
+                    float4 t = sum[c];
+#pragma unroll
+                    for (int ofs = 8; ofs < 32; ofs <<= 1) {
+                        // partner row r' = r ^ (ofs / 8) keeps the same columns in slot s' = s ^ 2 (ofs / 8)
+                        const int src = lane ^ ofs ^ (ofs >> 2);
+                        t.x += __shfl_sync(0xffffffffu, t.x, src);
+                        t.y += __shfl_sync(0xffffffffu, t.y, src);
+                        t.z += __shfl_sync(0xffffffffu, t.z, src);
+                        t.w += __shfl_sync(0xffffffffu, t.w, src);
+                    }
+                    if ((lane >> 3) == 0) {
+                        float* p = args.db + c * 32 + col4;
+                        atomicAdd(p, t.x); atomicAdd(p + 1, t.y); atomicAdd(p + 2, t.z); atomicAdd(p + 3, t.w);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+template <int KIN, int NSTAGE>
+static int launch_wgrad(long long N, const float* dz, const float* a, const WgradArgs& args, cudaStream_t st) {
+    CUtensorMap mDz, mA;
+    if (!(make_map(&mDz, dz, N, 256, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+          make_map(&mA, a, N, KIN, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)))
+        return set_error(FG_ERR_CUDA, "cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)", __FILE__, __LINE__);
+    constexpr int STAGE_BYTES = 2 * (WG_DZ_BYTES + (KIN / 32) * WG_CHUNK_BYTES);
+    constexpr int SMEM = NSTAGE * STAGE_BYTES + STG_BYTES + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    auto kern = mlp_wgrad_kernel<KIN, NSTAGE>;
+    FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const long long n_blocks = (N + WG_ROWS - 1) / WG_ROWS;
+    const long long want = (n_blocks + 63) / 64;  // at least 64 row blocks (1024 rows) per CTA
+    const int grid = (int)(want < 1 ? 1 : (want < kNumSMs ? want : kNumSMs));
+    FG_LAUNCH(kern, grid, kThreads, SMEM, st, mDz, mA, args);
     return FG_OK;
 }
 
@@ -582,7 +835,7 @@ extern "C" int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, in
     FG_REQUIRE(k0 > 0 && k0 % BK == 0 && k1 >= 0 && k1 % BK == 0, "fg_mlp_linear: k0, k1 must be multiples of 32 (k0 > 0)");
     FG_REQUIRE(a0 && w_hi && w_lo && out && (k1 == 0 || a1), "fg_mlp_linear: NULL operand");
     if (M == 0) return FG_OK;
-    LinearArgs args = {bias, mask_in, out, mask_out, (long long)M, k0 / BK, k1 / BK};
+    LinearArgs args = {bias, mask_in, out, mask_out, (long long)M, k0 / BK, k1 / BK, g_dbg_flags};
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == FG_MLP_RELU) {
         FG_REQUIRE(n_out == 256 && bias && mask_out, "fg_mlp_linear: FG_MLP_RELU is built for 256 outputs and needs bias and mask_out");
@@ -597,6 +850,24 @@ extern "C" int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, in
         return launch_linear<256, 2, EPI_MASK>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
     }
     return set_error(FG_ERR_INVALID, "fg_mlp_linear: unknown mode", __FILE__, __LINE__);
+}
+
+extern "C" int fg_mlp_wgrad(int64_t N, const float* dz, const float* a, int k_in, float* dw, int ld_dw, int col0, float* db, void* stream) {
+    FG_REQUIRE(N >= 0 && N < (1ll << 31) - 256, "fg_mlp_wgrad: N out of range");
+    FG_REQUIRE(dz && a && dw, "fg_mlp_wgrad: NULL operand");
+    FG_REQUIRE(col0 >= 0 && col0 % 4 == 0 && ld_dw % 4 == 0 && col0 + k_in <= ld_dw, "fg_mlp_wgrad: dw columns must be 16-byte aligned and in range");
+    if (N == 0) return FG_OK;
+    WgradArgs args = {dw, db, (long long)N, ld_dw, col0};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k_in == 256) return launch_wgrad<256, 3>(N, dz, a, args, st);
+    if (k_in == FG_MLP_EMBED_LD) return launch_wgrad<FG_MLP_EMBED_LD, 4>(N, dz, a, args, st);
+    return set_error(FG_ERR_INVALID, "fg_mlp_wgrad: k_in must be 256 or FG_MLP_EMBED_LD", __FILE__, __LINE__);
+}
+
+extern "C" int fg_mlp_debug_flags(int flags) {
+    const int old = fg::mlp::g_dbg_flags;
+    fg::mlp::g_dbg_flags = flags;
+    return old;
 }
 
 extern "C" int fg_mlp_pack(int n_segments, const fg_mlp_pack_segment* segments_host, void* stream) {

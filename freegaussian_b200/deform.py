@@ -6,9 +6,9 @@ constructor arguments, same parameter names and shapes (a reference ``state_dict
 lines that consume those outputs (``freegaussian_model.py:836-845``) and returns the ``means, scales, quats`` handed
 to ``rasterization``.
 
-Every ``nn.Linear`` of the trunk and the four heads, forward and data gradient, run in ``fg_mlp_linear`` (tcgen05 /
-TMEM / TMA, csrc/mlp.cu) in error-compensated 3xTF32 (fp32-accurate: the reference computes these layers in fp32).
-Weight gradients are plain ``[256, N] x [N, K]`` products and go to cuBLAS (TF32) through ``torch.mm`` for now.
+Every ``nn.Linear`` of the trunk runs on tcgen05 / TMEM / TMA (csrc/mlp.cu) in error-compensated 3xTF32 (fp32-accurate:
+the reference computes these layers in fp32): forward and data gradient in ``fg_mlp_linear``, weight and bias gradients
+in ``fg_mlp_wgrad`` (split-K, MN-major operands).  Only the 13-row head weight gradients are library fp32 GEMMs.
 There is no CPU path.
 
 The reference always evaluates the network with one time value per call (``camera.times.expand(N, -1)``,
@@ -19,7 +19,6 @@ of the two layers that read it.
 
 from __future__ import annotations
 
-import ctypes as C
 from typing import List, Tuple
 
 import torch
@@ -149,36 +148,47 @@ class _Trunk(torch.autograd.Function):
         new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         grads: List[Tensor] = [None] * len(params)
         x_ch = emb_ch - t_ch
-        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True  # weight gradients: library GEMMs, gradient tolerance 1e-3
-        try:
-            row = 0
-            for j, (_, o) in enumerate(_HEADS):
-                gj = g_head[:, row:row + o]
-                grads[2 * _D + 2 * j] = gj.t() @ hs[_D - 1]
-                grads[2 * _D + 2 * j + 1] = gj.sum(0)
-                row += o
-            dz = new(N, _W)
-            _linear(_lib.MLP_DGRAD, N, _W, g_head, MLP_HEAD_LD, None, 0, pk.wt_head, None, masks[_D - 1], dz, None)
-            g_t = torch.zeros(t_ch, device=dev) if t_ch else None
-            for i in range(_D - 1, -1, -1):
-                gb = dz.sum(0)
-                grads[2 * i + 1] = gb
-                if i == 0:
-                    grads[0] = dz.t() @ e[:, :emb_ch]
-                elif i == _SKIP + 1:
-                    grads[2 * i] = torch.cat([dz.t() @ e[:, :emb_ch], dz.t() @ hs[i - 1]], 1)
-                else:
-                    grads[2 * i] = dz.t() @ hs[i - 1]
-                if t_ch and (i == 0 or i == _SKIP + 1):
-                    # every row reads the same t_emb, so its gradient is (column sums of dz) . W[:, t columns]
-                    g_t = g_t + gb @ params[2 * i][:, x_ch:emb_ch]
-                if i > 0:
-                    dz_prev = new(N, _W)
-                    _linear(_lib.MLP_DGRAD, N, _W, dz, _W, None, 0, pk.wt[i], None, masks[i - 1], dz_prev, None)
-                    dz = dz_prev
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        L = _lib.lib()
+        # head gradients: [13, N] x [N, 256], small, plain fp32 library GEMMs
+        row = 0
+        for j, (_, o) in enumerate(_HEADS):
+            gj = g_head[:, row:row + o]
+            grads[2 * _D + 2 * j] = gj.t() @ hs[_D - 1]
+            grads[2 * _D + 2 * j + 1] = gj.sum(0)
+            row += o
+        # trunk: one zero-filled arena for everything fg_mlp_wgrad adds into
+        arena = torch.zeros(_D * (_W * _W + _W) + 2 * _W * MLP_EMBED_LD, device=dev, dtype=torch.float32)
+        dw_h = [arena[i * _W * _W:(i + 1) * _W * _W].view(_W, _W) for i in range(_D)]  # dw_h[0] unused
+        db = [arena[_D * _W * _W + i * _W:_D * _W * _W + (i + 1) * _W] for i in range(_D)]
+        off = _D * (_W * _W + _W)
+        dw_e = [arena[off + k * _W * MLP_EMBED_LD:off + (k + 1) * _W * MLP_EMBED_LD].view(_W, MLP_EMBED_LD) for k in range(2)]
+        st = _stream()
+
+        def wgrad(dz, a, k_in, dw, db_):
+            check(L.fg_mlp_wgrad(N, ptr(dz), ptr(a), k_in, ptr(dw), k_in, 0, ptr(db_) if db_ is not None else None, st))
+
+        dz = new(N, _W)
+        _linear(_lib.MLP_DGRAD, N, _W, g_head, MLP_HEAD_LD, None, 0, pk.wt_head, None, masks[_D - 1], dz, None)
+        g_t = torch.zeros(t_ch, device=dev) if t_ch else None
+        for i in range(_D - 1, -1, -1):
+            if i == 0:
+                wgrad(dz, e, MLP_EMBED_LD, dw_e[0], db[0])
+                grads[0] = dw_e[0][:, :emb_ch]
+            elif i == _SKIP + 1:  # reference column order: [embedding | h]
+                wgrad(dz, hs[i - 1], _W, dw_h[i], db[i])
+                wgrad(dz, e, MLP_EMBED_LD, dw_e[1], None)
+                grads[2 * i] = torch.cat([dw_e[1][:, :emb_ch], dw_h[i]], 1)
+            else:
+                wgrad(dz, hs[i - 1], _W, dw_h[i], db[i])
+                grads[2 * i] = dw_h[i]
+            grads[2 * i + 1] = db[i]
+            if t_ch and (i == 0 or i == _SKIP + 1):
+                # every row reads the same t_emb, so its gradient is (column sums of dz) . W[:, t columns]
+                g_t = g_t + db[i] @ params[2 * i][:, x_ch:emb_ch]
+            if i > 0:
+                dz_prev = new(N, _W)
+                _linear(_lib.MLP_DGRAD, N, _W, dz, _W, None, 0, pk.wt[i], None, masks[i - 1], dz_prev, None)
+                dz = dz_prev
         return (None, g_t, None, *grads)
 
 

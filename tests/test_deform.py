@@ -1,8 +1,8 @@
 """Deformation network: oracle vs the reference's own outputs (CPU), kernels vs oracle (GPU).
 
 Tolerances: forward and data gradient run in 3xTF32 = fp32 accuracy, so outputs are held to 1e-5 of the tensor's scale
-(the north-star budget for everything that feeds the renderer is 1e-4); weight gradients to 1e-3 of the reference
-gradient's max magnitude (north_star): their GEMMs are cuBLAS TF32.
+(the north-star budget for everything that feeds the renderer is 1e-4); weight gradients (also 3xTF32, split-K with
+atomic adds) are held to 5e-5 of the reference gradient's max magnitude, far inside north_star's 1e-3.
 """
 from pathlib import Path
 
@@ -149,6 +149,31 @@ def test_linear_head_and_dgrad_modes(built_lib, M):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 15, 16, 1000, 100_003])
+def test_weight_gradient_kernel(built_lib, N):
+    """dW += dz^T a and db += column sums, 3xTF32: fp32-accurate, additive, every row counted once."""
+    from freegaussian_b200 import _lib
+    from freegaussian_b200._lib import check, ptr
+
+    g = torch.Generator().manual_seed(N)
+    st = torch.cuda.current_stream().cuda_stream
+    for k_in in (256, 96):
+        dz = torch.randn(N, 256, generator=g)
+        a = torch.randn(N, k_in, generator=g)
+        dzd, ad = dz.cuda(), a.cuda()
+        dw = torch.zeros(256, k_in, device="cuda")
+        db = torch.zeros(256, device="cuda")
+        check(_lib.lib().fg_mlp_wgrad(N, ptr(dzd), ptr(ad), k_in, ptr(dw), k_in, 0, ptr(db), st))
+        want_w, want_b = dz.double().T @ a.double(), dz.double().sum(0)
+        # fp32 accumulation over up to 1e5 rows (the reference's fp32 GEMM rounds the same way): 2e-5 of the largest entry
+        assert grad_rel_err(dw, want_w) < 2e-5, (N, k_in)
+        assert grad_rel_err(db, want_b) < 2e-5, (N, k_in)
+        check(_lib.lib().fg_mlp_wgrad(N, ptr(dzd), ptr(ad), k_in, ptr(dw), k_in, 0, None, st))  # adds; db untouched
+        assert grad_rel_err(dw, 2 * want_w) < 2e-5
+        assert grad_rel_err(db, want_b) < 2e-5
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("t_ch,multires", [(30, 10), (21, 10), (0, 4)])
 def test_embedding_matches_reference_layout(built_lib, t_ch, multires):
     from freegaussian_b200 import _lib
@@ -224,9 +249,13 @@ def test_network_matches_reference_fixture(built_lib, name):
     loss.backward()
     for got, key in ((m, "grad_means"), (s, "grad_scales_log"), (q, "grad_quats")):
         assert grad_rel_err(got.grad, torch.tensor(z[key])) < 1e-5, key
+    # The "hot" fixture (weights x2: activations grow ~2^8 through the trunk) has ReLU inputs that sit within fp32
+    # rounding of zero; any fp32 implementation with another summation order flips a few of them, and with 129 rows one
+    # flipped unit moves a gradient entry by ~1e-4.  It is held to north_star's 1e-3, the others to 5e-5.
+    tol = 1e-3 if "hot" in name else 5e-5
     for k, v in net.named_parameters():
-        assert grad_rel_err(_sample(v.grad.double().flatten().cpu()), torch.tensor(z["grad." + k]).double()) < 1e-3, k
-        assert abs(float(v.grad.double().norm()) - float(z["gnorm." + k])) <= 1e-3 * float(z["gnorm." + k]), k
+        assert grad_rel_err(_sample(v.grad.double().flatten().cpu()), torch.tensor(z["grad." + k]).double()) < tol, k
+        assert abs(float(v.grad.double().norm()) - float(z["gnorm." + k])) <= tol * float(z["gnorm." + k]), k
     # the reference-signature forward: same d_xyz / rotation / scaling
     d_xyz, rot, scl = net(m.detach(), t)
     for got, key in ((d_xyz, "d_xyz"), (rot, "d_rotation"), (scl, "d_scaling")):

@@ -47,6 +47,30 @@ def stage_linear():
             print("   cols err", [(c, err(got[:, c], want[:, c])) for c in (0, 1, 7, 8, 31, 32, 128, 255)])
 
 
+def stage_wgrad():
+    from freegaussian_b200._lib import check, ptr
+
+    g = torch.Generator().manual_seed(3)
+    st = torch.cuda.current_stream().cuda_stream
+    for N, k_in in ((16, 256), (1000, 256), (1000, 96), (100_003, 256)):
+        dz = torch.randn(N, 256, generator=g)
+        a = torch.randn(N, k_in, generator=g)
+        dzd, ad = dz.cuda(), a.cuda()
+        dw, db = torch.zeros(256, k_in, device="cuda"), torch.zeros(256, device="cuda")
+        check(_lib.lib().fg_mlp_wgrad(N, ptr(dzd), ptr(ad), k_in, ptr(dw), k_in, 0, ptr(db), st))
+        torch.cuda.synchronize()
+        want = dz.double().T @ a.double()
+        print(f"wgrad N={N} k_in={k_in}: dW rel err {err(dw, want):.3e}  db rel err {err(db, dz.double().sum(0)):.3e}", flush=True)
+        if err(dw, want) > 1e-3:
+            got = dw.double().cpu()
+            print("   got[0,:6]", got[0, :6].tolist(), "\n   want[0,:6]", want[0, :6].tolist())
+            print("   got^T match?", err(got, want.T) if k_in == 256 else None)
+            print("   row blocks err", [(r, f"{err(got[r:r + 32], want[r:r + 32]):.1e}") for r in range(0, 256, 32)])
+            print("   col blocks err", [(c, f"{err(got[:, c:c + 32], want[:, c:c + 32]):.1e}") for c in range(0, k_in, 32)])
+            for nn in (8, 16):
+                print(f"   vs first {nn} rows only:", err(got, dz[:nn].double().T @ a[:nn].double()))
+
+
 def stage_modes():
     import pytest
 
@@ -81,6 +105,32 @@ def stage_e2e():
             worst[k] = err(gg if gg.numel() <= 4096 else gg[::97], torch.tensor(z["grad." + k]).double())
         print("  weight grads worst", max(worst.values()), max(worst, key=worst.get), flush=True)
         print("  per param", {k: f"{v:.1e}" for k, v in worst.items() if "linear" in k}, flush=True)
+
+
+def stage_variants():
+    """Where does the time of one 256x256 layer go?  Timing with parts of the kernel disabled (results are wrong)."""
+    n = 1_000_000
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(n, 256, generator=g).cuda()
+    w = _hilo((torch.randn(256, 256, generator=g) / 16).cuda())
+    bias = torch.zeros(256, device="cuda")
+    out = torch.empty(n, 256, device="cuda")
+    bits = torch.empty(n, 8, dtype=torch.int32, device="cuda")
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    for flags, name in ((0, "full"), (1, "W once"), (2, "no split"), (4, "no stores"), (8, "1 product"), (1 | 8, "W once, 1 product"),
+                        (1 | 2 | 4 | 8, "A stream + 1 product only"), (1 | 2 | 4, "W once, no split, no stores")):
+        L.fg_mlp_debug_flags(flags)
+        ts = []
+        for it in range(6):
+            e0, e1 = ev(), ev()
+            e0.record()
+            _linear(_lib.MLP_RELU, n, 256, a, 256, None, 0, w, bias, None, out, bits)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        print(f"flags {flags:2d} {name:32s}: {min(ts[2:]) * 1e3:7.1f} us", flush=True)
+    L.fg_mlp_debug_flags(0)
 
 
 def stage_perf():
@@ -131,5 +181,5 @@ def stage_perf():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"linear": stage_linear, "modes": stage_modes, "aux": stage_aux, "e2e": stage_e2e, "perf": stage_perf}[sys.argv[1]]()
+    {"linear": stage_linear, "modes": stage_modes, "aux": stage_aux, "e2e": stage_e2e, "perf": stage_perf, "variants": stage_variants, "wgrad": stage_wgrad}[sys.argv[1]]()
     print(f"[{sys.argv[1]} done in {time.time() - t0:.1f}s]")
