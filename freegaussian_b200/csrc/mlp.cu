@@ -861,7 +861,8 @@ extern "C" int fg_mlp_wgrad(int64_t N, const float* dz, const float* a, int k_in
     cudaStream_t st = (cudaStream_t)stream;
     if (k_in == 256) return launch_wgrad<256, 3>(N, dz, a, args, st);
     if (k_in == FG_MLP_EMBED_LD) return launch_wgrad<FG_MLP_EMBED_LD, 4>(N, dz, a, args, st);
-    return set_error(FG_ERR_INVALID, "fg_mlp_wgrad: k_in must be 256 or FG_MLP_EMBED_LD", __FILE__, __LINE__);
+    if (k_in == FG_MLP_HEAD_LD) return launch_wgrad<FG_MLP_HEAD_LD, 4>(N, dz, a, args, st);
+    return set_error(FG_ERR_INVALID, "fg_mlp_wgrad: k_in must be 256, FG_MLP_EMBED_LD or FG_MLP_HEAD_LD", __FILE__, __LINE__);
 }
 
 extern "C" int fg_mlp_debug_flags(int flags) {

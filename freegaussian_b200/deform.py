@@ -8,7 +8,7 @@ to ``rasterization``.
 
 Every ``nn.Linear`` of the trunk runs on tcgen05 / TMEM / TMA (csrc/mlp.cu) in error-compensated 3xTF32 (fp32-accurate:
 the reference computes these layers in fp32): forward and data gradient in ``fg_mlp_linear``, weight and bias gradients
-in ``fg_mlp_wgrad`` (split-K, MN-major operands).  Only the 13-row head weight gradients are library fp32 GEMMs.
+in ``fg_mlp_wgrad`` (split-K, MN-major operands), the heads' included.
 There is no CPU path.
 
 The reference always evaluates the network with one time value per call (``camera.times.expand(N, -1)``,
@@ -149,12 +149,14 @@ class _Trunk(torch.autograd.Function):
         grads: List[Tensor] = [None] * len(params)
         x_ch = emb_ch - t_ch
         L = _lib.lib()
-        # head gradients: [13, N] x [N, 256], small, plain fp32 library GEMMs
+        # head gradients: dW_head^T [256, 32] = h_last^T . g_head, one pass of the same kernel; biases = column sums of g_head
+        dw_head_t = torch.zeros(_W, MLP_HEAD_LD, device=dev, dtype=torch.float32)
+        check(L.fg_mlp_wgrad(N, ptr(hs[_D - 1]), ptr(g_head), MLP_HEAD_LD, ptr(dw_head_t), MLP_HEAD_LD, 0, None, _stream()))
+        db_head = g_head.sum(0)
         row = 0
         for j, (_, o) in enumerate(_HEADS):
-            gj = g_head[:, row:row + o]
-            grads[2 * _D + 2 * j] = gj.t() @ hs[_D - 1]
-            grads[2 * _D + 2 * j + 1] = gj.sum(0)
+            grads[2 * _D + 2 * j] = dw_head_t[:, row:row + o].t()
+            grads[2 * _D + 2 * j + 1] = db_head[row:row + o]
             row += o
         # trunk: one zero-filled arena for everything fg_mlp_wgrad adds into
         arena = torch.zeros(_D * (_W * _W + _W) + 2 * _W * MLP_EMBED_LD, device=dev, dtype=torch.float32)

@@ -394,8 +394,9 @@ typedef struct fg_mlp_pack_segment {
 int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, int k0, const float* a1, int k1, const float* w_hi,
                   const float* w_lo, const float* bias, const uint32_t* mask_in, float* out, uint32_t* mask_out, void* stream);
 /* fg_mlp_wgrad: dw[256, ld_dw] columns col0 .. col0 + k_in - 1 += dz^T . a, and (db != NULL) db[256] += column sums of dz;
- * dz [N, 256], a [N, k_in] with k_in = 256 or FG_MLP_EMBED_LD, fp32 row-major.  The weight / bias gradient of
- * nn.Linear (dL/dW = dz^T a, dL/db = sum_n dz).  3xTF32 on chip, split-K over row ranges, results ADDED with
+ * dz [N, 256], a [N, k_in] with k_in = 256, FG_MLP_EMBED_LD or FG_MLP_HEAD_LD, fp32 row-major.  The weight / bias gradient
+ * of nn.Linear (dL/dW = dz^T a, dL/db = sum_n dz); with dz = the last hidden layer and a = the head gradient it yields
+ * the TRANSPOSED head weight gradient.  3xTF32 on chip, split-K over row ranges, results ADDED with
  * red.global (zero dw / db first; the order of the additions is not deterministic). */
 int fg_mlp_wgrad(int64_t N, const float* dz, const float* a, int k_in, float* dw, int ld_dw, int col0, float* db, void* stream);
 /* Timing experiments only (tools/dbg_mlp.py variants): 1 = weight tiles loaded once per CTA, 2 = no operand split, 4 = no

@@ -157,7 +157,7 @@ def test_weight_gradient_kernel(built_lib, N):
 
     g = torch.Generator().manual_seed(N)
     st = torch.cuda.current_stream().cuda_stream
-    for k_in in (256, 96):
+    for k_in in (256, 96, 32):
         dz = torch.randn(N, 256, generator=g)
         a = torch.randn(N, k_in, generator=g)
         dzd, ad = dz.cuda(), a.cuda()
