@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--views-per-gpu", type=int, default=1, help="views each rank renders per step (cfg4: 4)")
+    ap.add_argument("--no-train-iter", action="store_true", help="skip the stage-1 training-iteration section (train_iter)")
     return ap.parse_args()
 
 
@@ -375,6 +376,8 @@ def run_ours(args):
             "kernels": kernels,
             "stage_ms": stage_ms,
         }
+        if world == 1 and not args.no_train_iter:
+            out["train_iter"] = train_iter_section(d, dev, W, H, dev_vm[0], dev_K[0])
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only
             out["cpu_baseline"] = cpu_arm(args, steps=args.cpu_steps, warmup=0)["cpu_baseline"]
     if world > 1:
@@ -382,6 +385,125 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------ stage-1 training iteration
+def train_iter_section(d, dev, W, H, vm, K, steps=10, warmup=4):
+    """ms per stage-1 training iteration (BASELINE.json metric, second half): deformation network
+    (freegaussian_model.py:832-845) -> rasterization (:847-868) -> blend + L1 + SSIM loss (:875-877, 965-981) ->
+    backward -> Adam step of the Gaussian groups and of the network (freegaussian_config.py:48-85).  Everything on
+    the device is this repo's kernels except the network's Adam (torch, fused) and a few scalar glue ops.
+    The same network in plain torch fp32 (what the reference executes) is timed beside it."""
+    from freegaussian_b200.deform import DeformNetwork
+    from freegaussian_b200.losses import blend_l1_ssim_loss
+    from freegaussian_b200.optim import GaussianAdam
+    from freegaussian_b200.rendering import rasterization
+
+    n = d.means.shape[0]
+    gen = torch.Generator().manual_seed(7)
+    torch.manual_seed(7)
+    net = DeformNetwork(is_blender=True).to(dev)  # freegaussian_model.py:198
+    means = d.means.detach().clone().requires_grad_(True)
+    scales_log = d.scales.detach().log().requires_grad_(True)        # the model stores log scales (:844)
+    quats = d.quats.detach().clone().requires_grad_(True)
+    op_logit = torch.logit(d.opacities.detach().clamp(1e-4, 1 - 1e-4)).requires_grad_(True)  # and logit opacities (:851)
+    sh = d.sh.detach().clone().requires_grad_(True)
+    gt = torch.rand(H, W, 3, generator=gen).to(dev)
+    bg = torch.zeros(3, device=dev)
+    t = torch.tensor([[0.3]], device=dev).expand(n, -1)
+    adam = GaussianAdam.for_reference_groups(means, sh, op_logit, scales_log, quats)
+    adam_net = torch.optim.Adam(net.parameters(), lr=1.6e-4 * 5, eps=1e-15, fused=True)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    last = {}
+
+    def iteration(with_deform: bool):
+        for p in (means, scales_log, quats, op_logit, sh):
+            p.grad = None
+        adam_net.zero_grad(set_to_none=True)
+        e0, e1 = ev(), ev()
+        e0.record()
+        if with_deform:
+            m2, s2, q2 = net.deform_gaussians(means, scales_log, quats, t)
+        else:  # warm-up phase of the reference (step < warm_up, :832-833): no deformation
+            m2, s2, q2 = means, torch.exp(scales_log), quats
+        e1.record()
+        render, alpha, meta = rasterization(m2, q2, s2, torch.sigmoid(op_logit), sh, vm, K, W, H, packed=False,
+                                            near_plane=0.01, far_plane=1e10, render_mode="RGB+ED", sh_degree=3,
+                                            sparse_grad=False, absgrad=True, rasterize_mode="classic")
+        loss = blend_l1_ssim_loss(render, alpha, bg, gt, 0.2)
+        loss.backward()
+        adam.step()
+        if with_deform:
+            adam_net.step()
+        last["radii"] = meta["radii"]
+        return e0, e1
+
+    def timed(with_deform: bool):
+        for _ in range(warmup):
+            iteration(with_deform)
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        marks = [iteration(with_deform) for _ in range(steps)]
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps, statistics.median(m[0].elapsed_time(m[1]) for m in marks)
+
+    l0 = None
+    from freegaussian_b200 import _lib
+    ms_plain, _ = timed(False)
+    l0 = _lib.launch_count()
+    ms_full, ms_deform_fwd = timed(True)
+    launches = (_lib.launch_count() - l0) / (steps + warmup)
+    n_vis = int((last["radii"] > 0).sum())
+
+    # the reference's own execution of the network: torch fp32 nn.Linear / relu / cat on this GPU, forward + backward
+    x = means.detach()
+    lins = [net.linear[i] for i in range(8)]
+
+    def torch_trunk():
+        t_emb = net._time_row(t).expand(n, -1)
+        x_emb = torch.cat([x] + [f(x * (2.0 ** k)) for k in range(10) for f in (torch.sin, torch.cos)], -1)
+        h = torch.cat([x_emb, t_emb], -1)
+        for i in range(8):
+            h = torch.relu(torch.nn.functional.linear(h, lins[i].weight, lins[i].bias))
+            if i == 4:
+                h = torch.cat([x_emb, t_emb, h], -1)
+        return torch.cat([torch.nn.functional.linear(h, getattr(net, nm).weight, getattr(net, nm).bias)
+                          for nm in ("branch_w", "branch_v", "gaussian_rotation", "gaussian_scaling")], -1)
+
+    tt = []
+    for i in range(4):
+        net.zero_grad(set_to_none=True)
+        a, b, c = ev(), ev(), ev()
+        a.record()
+        out = torch_trunk()
+        b.record()
+        out.sum().backward()
+        c.record()
+        torch.cuda.synchronize()
+        tt.append((a.elapsed_time(b), b.elapsed_time(c)))
+    net.zero_grad(set_to_none=True)
+    torch_fwd, torch_bwd = min(v[0] for v in tt[1:]), min(v[1] for v in tt[1:])
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2  # tf32 runs at half the bf16 rate on this tensor core
+    flop_fwd = 3 * 2.0 * n * (96 * 256 + 6 * 256 * 256 + 352 * 256 + 256 * 32)  # 3 tf32 products per fp32 product
+    ach = flop_fwd / (ms_deform_fwd * 1e-3) / 1e12
+    return {
+        "ms": ms_full, "ms_without_deform": ms_plain, "deform_fwd_ms": ms_deform_fwd,
+        "deform_bwd_ms": ms_full - ms_plain - ms_deform_fwd,
+        "gaussians": n, "visible": n_vis, "launches_per_iter": launches,
+        "config": "stage-1 step: DeformNetwork(is_blender=True) -> RGB+ED render -> blend+L1+SSIM -> backward -> Adam",
+        "deform_roofline": {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                            "note": "forward; tf32 MMA flops issued (3xTF32) / CUDA-event time; peak = measured bf16 GEMM peak / 2"},
+        "torch_fp32_network": {"fwd_ms": torch_fwd, "bwd_ms": torch_bwd,
+                               "note": "the same network with torch.nn.functional.linear in fp32 on this GPU (what the reference runs)"},
+    }
 
 
 # ------------------------------------------------------------------------------ CPU arm

@@ -833,8 +833,8 @@ extern "C" int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, in
                              void* stream) {
     FG_REQUIRE(M >= 0 && M < (1ll << 31) - BM, "fg_mlp_linear: M out of range");
     FG_REQUIRE(k0 > 0 && k0 % BK == 0 && k1 >= 0 && k1 % BK == 0, "fg_mlp_linear: k0, k1 must be multiples of 32 (k0 > 0)");
+    if (M == 0) return FG_OK;  // empty inputs have NULL data pointers
     FG_REQUIRE(a0 && w_hi && w_lo && out && (k1 == 0 || a1), "fg_mlp_linear: NULL operand");
-    if (M == 0) return FG_OK;
     LinearArgs args = {bias, mask_in, out, mask_out, (long long)M, k0 / BK, k1 / BK, g_dbg_flags};
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == FG_MLP_RELU) {
@@ -854,9 +854,9 @@ extern "C" int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, in
 
 extern "C" int fg_mlp_wgrad(int64_t N, const float* dz, const float* a, int k_in, float* dw, int ld_dw, int col0, float* db, void* stream) {
     FG_REQUIRE(N >= 0 && N < (1ll << 31) - 256, "fg_mlp_wgrad: N out of range");
-    FG_REQUIRE(dz && a && dw, "fg_mlp_wgrad: NULL operand");
     FG_REQUIRE(col0 >= 0 && col0 % 4 == 0 && ld_dw % 4 == 0 && col0 + k_in <= ld_dw, "fg_mlp_wgrad: dw columns must be 16-byte aligned and in range");
-    if (N == 0) return FG_OK;
+    if (N == 0) return FG_OK;  // empty inputs have NULL data pointers
+    FG_REQUIRE(dz && a && dw, "fg_mlp_wgrad: NULL operand");
     WgradArgs args = {dw, db, (long long)N, ld_dw, col0};
     cudaStream_t st = (cudaStream_t)stream;
     if (k_in == 256) return launch_wgrad<256, 3>(N, dz, a, args, st);

@@ -31,6 +31,9 @@ _W = 256
 _D = 8
 _SKIP = _D // 2  # the embedding is concatenated again after this layer (freegaussian_model.py:1058, 1100-1101)
 _HEADS = (("branch_w", 3), ("branch_v", 3), ("gaussian_rotation", 4), ("gaussian_scaling", 3))
+# backward over the rows with a non-zero incoming gradient only, when they are fewer than this fraction of all rows
+SPARSE_BACKWARD = True
+SPARSE_BACKWARD_MAX_FRACTION = 0.75
 
 
 def _embed(x: Tensor, multires: int) -> Tensor:
@@ -149,9 +152,26 @@ class _Trunk(torch.autograd.Function):
         grads: List[Tensor] = [None] * len(params)
         x_ch = emb_ch - t_ch
         L = _lib.lib()
+        # Rows whose incoming gradient is exactly zero (Gaussians that were culled or never reached a pixel in this
+        # step's views) contribute exactly nothing to any weight gradient: run the backward on the other rows only.
+        # One host read of the count; the saved activations are gathered layer by layer as they are needed.
+        sel = lambda t: t  # noqa: E731
+        if SPARSE_BACKWARD and N > 0:
+            active = (g_head != 0).any(1)
+            n_act = int(active.sum())
+            if n_act < SPARSE_BACKWARD_MAX_FRACTION * N:
+                idx = active.nonzero().squeeze(1)
+                sel = lambda t: t.index_select(0, idx)  # noqa: E731
+                g_head = sel(g_head)
+                N = n_act
+        e = sel(e)
+        h_in = lambda i: sel(hs[i])  # noqa: E731  activations of layer i (input of layer i + 1)
+        m_in = lambda i: sel(masks[i])  # noqa: E731
         # head gradients: dW_head^T [256, 32] = h_last^T . g_head, one pass of the same kernel; biases = column sums of g_head
         dw_head_t = torch.zeros(_W, MLP_HEAD_LD, device=dev, dtype=torch.float32)
-        check(L.fg_mlp_wgrad(N, ptr(hs[_D - 1]), ptr(g_head), MLP_HEAD_LD, ptr(dw_head_t), MLP_HEAD_LD, 0, None, _stream()))
+        h_last = h_in(_D - 1)
+        check(L.fg_mlp_wgrad(N, ptr(h_last), ptr(g_head), MLP_HEAD_LD, ptr(dw_head_t), MLP_HEAD_LD, 0, None, _stream()))
+        del h_last
         db_head = g_head.sum(0)
         row = 0
         for j, (_, o) in enumerate(_HEADS):
@@ -170,18 +190,18 @@ class _Trunk(torch.autograd.Function):
             check(L.fg_mlp_wgrad(N, ptr(dz), ptr(a), k_in, ptr(dw), k_in, 0, ptr(db_) if db_ is not None else None, st))
 
         dz = new(N, _W)
-        _linear(_lib.MLP_DGRAD, N, _W, g_head, MLP_HEAD_LD, None, 0, pk.wt_head, None, masks[_D - 1], dz, None)
+        _linear(_lib.MLP_DGRAD, N, _W, g_head, MLP_HEAD_LD, None, 0, pk.wt_head, None, m_in(_D - 1), dz, None)
         g_t = torch.zeros(t_ch, device=dev) if t_ch else None
         for i in range(_D - 1, -1, -1):
             if i == 0:
                 wgrad(dz, e, MLP_EMBED_LD, dw_e[0], db[0])
                 grads[0] = dw_e[0][:, :emb_ch]
             elif i == _SKIP + 1:  # reference column order: [embedding | h]
-                wgrad(dz, hs[i - 1], _W, dw_h[i], db[i])
+                wgrad(dz, h_in(i - 1), _W, dw_h[i], db[i])
                 wgrad(dz, e, MLP_EMBED_LD, dw_e[1], None)
                 grads[2 * i] = torch.cat([dw_e[1][:, :emb_ch], dw_h[i]], 1)
             else:
-                wgrad(dz, hs[i - 1], _W, dw_h[i], db[i])
+                wgrad(dz, h_in(i - 1), _W, dw_h[i], db[i])
                 grads[2 * i] = dw_h[i]
             grads[2 * i + 1] = db[i]
             if t_ch and (i == 0 or i == _SKIP + 1):
@@ -189,7 +209,7 @@ class _Trunk(torch.autograd.Function):
                 g_t = g_t + db[i] @ params[2 * i][:, x_ch:emb_ch]
             if i > 0:
                 dz_prev = new(N, _W)
-                _linear(_lib.MLP_DGRAD, N, _W, dz, _W, None, 0, pk.wt[i], None, masks[i - 1], dz_prev, None)
+                _linear(_lib.MLP_DGRAD, N, _W, dz, _W, None, 0, pk.wt[i], None, m_in(i - 1), dz_prev, None)
                 dz = dz_prev
         return (None, g_t, None, *grads)
 

@@ -263,6 +263,40 @@ def test_network_matches_reference_fixture(built_lib, name):
 
 
 @pytest.mark.gpu
+def test_sparse_backward_equals_dense(built_lib):
+    """Rows with a zero incoming gradient (culled Gaussians) are skipped by the backward: same gradients as the dense pass."""
+    from freegaussian_b200 import deform as D
+
+    params = OD.init_params(is_blender=True, seed=21)
+    net = _net_from(params, True)
+    g = torch.Generator().manual_seed(9)
+    n = 5000
+    m = ((torch.rand(n, 3, generator=g) - 0.5) * 6.0).cuda()
+    s = torch.log(torch.rand(n, 3, generator=g) * 0.05 + 0.005).cuda()
+    q = torch.randn(n, 4, generator=g).cuda()
+    t = torch.tensor([[0.6]]).cuda().expand(n, -1)
+    seen = (torch.rand(n, 1, generator=g) < 0.3).float().cuda()  # 30 % of the Gaussians receive a gradient
+    ws = [torch.randn(n, k, generator=g).cuda() * seen for k in (3, 3, 4)]
+
+    def run(sparse):
+        D.SPARSE_BACKWARD = sparse
+        try:
+            net.zero_grad()
+            leaves = [x.clone().requires_grad_(True) for x in (m, s, q)]
+            outs = net.deform_gaussians(*leaves, t)
+            sum((o * w).sum() for o, w in zip(outs, ws)).backward()
+            return [p.grad.clone() for p in net.parameters()] + [x.grad for x in leaves]
+        finally:
+            D.SPARSE_BACKWARD = True
+
+    for a, b in zip(run(True), run(False)):
+        assert grad_rel_err(a, b) < 1e-5
+    # nothing visible at all: every gradient is exactly zero
+    ws = [w * 0 for w in ws]
+    assert all(float(x.abs().max()) == 0.0 for x in run(True)[:-3])
+
+
+@pytest.mark.gpu
 def test_full_size_rows_are_independent(built_lib):
     """cfg3 size (1 M Gaussians): every row depends on its own Gaussian only, so a random sample of rows must equal
     the oracle evaluated on just those rows; and the weight gradient is linear in the row set (two halves sum to the whole)."""
