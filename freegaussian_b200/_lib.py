@@ -102,7 +102,6 @@ SIGNATURES = {
                               _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "fg_mlp_linear": (_i32, [_i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_mlp_wgrad": (_i32, [_i64, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
-    "fg_mlp_debug_flags": (_i32, [_i32]),
     "fg_mlp_pack": (_i32, [_i32, C.POINTER(MlpPackSegment), _vp]),
     "fg_deform_embed": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "fg_deform_apply_fwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

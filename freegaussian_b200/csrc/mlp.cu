@@ -3,7 +3,7 @@
 // the training step, so the one place the 5th-generation tensor cores are used.
 //
 //   fg_mlp_linear     out = epilogue(A . W^T): CTA = 128 rows x BN outputs, persistent over row tiles.
-//                     warp 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, mbarrier pipeline),
+//                     warp 0 / warp 10 = TMA producers of the activation / weight rings (cp.async.bulk.tensor, mbarriers),
 //                     warp 1 = tcgen05.mma issuer (kind::tf32, accumulators in TMEM, double buffered),
 //                     warps 2-5 = epilogue (tcgen05.ld -> bias / ReLU / mask -> smem transpose -> coalesced stores),
 //                     warps 6-9 = operand split (below).
@@ -118,44 +118,60 @@ struct LinearArgs {
     uint32_t* mask_out;        // [M, BN/32] (EPI_RELU)
     long long M;
     int kb0, kb1;  // k-blocks read from A0, then from A1 (the skip connection: [h | embedding])
-    int dbg;       // timing experiments only (fg_mlp_debug_flags): 1 = W tiles loaded once per CTA, 2 = no operand split,
-                   // 4 = no global stores, 8 = one product instead of three.  Results are wrong with any bit set.
 };
 
 enum { EPI_RELU = 0, EPI_LINEAR = 1, EPI_MASK = 2 };
-static int g_dbg_flags = 0;
 
 constexpr int kThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-9 operand split
 constexpr int STG_PITCH = 36;        // floats per staged row (32 + 4: conflict-free 128-bit writes by row and reads by 4 rows)
 constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;
 
-template <int BN, int NSTAGE, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kLinThreads = 352;     // + warp 10: weight-tile TMA producer
+constexpr int WK = 16;               // columns per weight tile (64-byte rows, SWIZZLE_64B): two tcgen05.mma k-steps
+
+// K-major tile with 64-byte rows as TMA's 64-byte swizzle writes it: 8-row groups 512 bytes apart, layout type 4
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+
+// Two independent rings, because what bounds this kernel is the latency of the ACTIVATION stream from HBM:
+//   activation ring: NA slots of [A -> A_hi | A_lo], 128 rows x 32 columns each (filled by warp 0, split by warps 6-9)
+//   weight ring:     NW slots of [W_hi | W_lo], BN rows x 16 columns each (filled by warp 10 from L2)
+// so that NA activation tiles are in flight whatever the weight tiles do.
+template <int BN, int NA, int NW, int EPI>
+__global__ void __launch_bounds__(kLinThreads, 1)
     mlp_linear_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, LinearArgs args) {
     pdl_wait();
-    constexpr int W_TILE_BYTES = BN * BK * 4;
-    constexpr int STAGE_BYTES = 2 * (A_TILE_BYTES + W_TILE_BYTES);  // [A -> A_hi | A_lo | W_hi | W_lo]
-    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;            // two accumulators; power of two >= 32
+    constexpr int A_SLOT_BYTES = 2 * A_TILE_BYTES;
+    constexpr int W_TILE_BYTES = BN * WK * 4;
+    constexpr int W_SLOT_BYTES = 2 * W_TILE_BYTES;
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators; power of two >= 32
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns");
     static_assert(BN % 32 == 0 && BN <= 256, "BN");
+    static_assert(W_SLOT_BYTES % 1024 == 0, "weight slots keep the 1024-byte alignment");
     constexpr int NCHUNK = BN / 32;
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[NSTAGE], bar_conv[NSTAGE], bar_empty[NSTAGE], bar_tfull[2], bar_tempty[2];
+    __shared__ uint64_t bar_afull[NA], bar_aconv[NA], bar_aempty[NA], bar_wfull[NW], bar_wempty[NW], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_slot;
 
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
-    const uint32_t stg0 = smem0 + NSTAGE * STAGE_BYTES;            // epilogue staging, one 32 x 36 tile per warp
+    const uint32_t smemW = smem0 + NA * A_SLOT_BYTES;
+    const uint32_t stg0 = smemW + NW * W_SLOT_BYTES;  // epilogue staging, one 32 x 36 tile per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_total = args.kb0 + args.kb1;
     const long long n_tiles = (args.M + BM - 1) / BM;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(smem_u32(&bar_full[s]), 1);
-            mbar_init(smem_u32(&bar_conv[s]), 4);
-            mbar_init(smem_u32(&bar_empty[s]), 1);
+        for (int s = 0; s < NA; ++s) {
+            mbar_init(smem_u32(&bar_afull[s]), 1);
+            mbar_init(smem_u32(&bar_aconv[s]), 4);
+            mbar_init(smem_u32(&bar_aempty[s]), 1);
+        }
+        for (int s = 0; s < NW; ++s) {
+            mbar_init(smem_u32(&bar_wfull[s]), 1);
+            mbar_init(smem_u32(&bar_wempty[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&bar_tfull[a]), 1);
@@ -175,34 +191,45 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
-        // ===== TMA producer: the fp32 activation tile and the pre-split weight tiles =====
+        // ===== activation TMA producer =====
         if (lane == 0) {
-            int stage = 0;
+            int slot = 0;
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int row0 = (int)(tile * BM);
                 for (int kb = 0; kb < kb_total; ++kb) {
-                    mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
-                    const uint32_t full = smem_u32(&bar_full[stage]);
-                    const uint32_t sA = smem0 + stage * STAGE_BYTES;
-                    const bool load_w = !(args.dbg & 1) || (tile == blockIdx.x && kb < NSTAGE);
-                    mbar_expect_tx(full, A_TILE_BYTES + (load_w ? 2 * W_TILE_BYTES : 0));
+                    mbar_wait(smem_u32(&bar_aempty[slot]), phase ^ 1);
+                    const uint32_t full = smem_u32(&bar_afull[slot]);
+                    mbar_expect_tx(full, A_TILE_BYTES);
                     const bool first = kb < args.kb0;
-                    tma_load_2d(sA, first ? &mapA0 : &mapA1, full, (first ? kb : kb - args.kb0) * BK, row0);
-                    if (load_w) {
-                        tma_load_2d(sA + 2 * A_TILE_BYTES, &mapWh, full, kb * BK, 0);
-                        tma_load_2d(sA + 2 * A_TILE_BYTES + W_TILE_BYTES, &mapWl, full, kb * BK, 0);
-                    }
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    tma_load_2d(smem0 + slot * A_SLOT_BYTES, first ? &mapA0 : &mapA1, full, (first ? kb : kb - args.kb0) * BK, row0);
+                    if (++slot == NA) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===== weight TMA producer (pre-split hi / lo tiles, L2 resident) =====
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int kw = 0; kw < kb_total * (BK / WK); ++kw) {
+                    mbar_wait(smem_u32(&bar_wempty[slot]), phase ^ 1);
+                    const uint32_t full = smem_u32(&bar_wfull[slot]);
+                    const uint32_t sW = smemW + slot * W_SLOT_BYTES;
+                    mbar_expect_tx(full, W_SLOT_BYTES);
+                    tma_load_2d(sW, &mapWh, full, kw * WK, 0);
+                    tma_load_2d(sW + W_TILE_BYTES, &mapWl, full, kw * WK, 0);
+                    if (++slot == NW) { slot = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread): A_hi.W_hi + A_hi.W_lo + A_lo.W_hi per k-step =====
+        // ===== MMA issuer (one thread): A_lo.W_hi + A_hi.W_lo + A_hi.W_hi per k-step =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
+            int aslot = 0, wslot = 0;
+            uint32_t aphase = 0, wphase = 0;
             uint32_t t = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
                 const uint32_t acc = t & 1;
@@ -210,26 +237,29 @@ __global__ void __launch_bounds__(kThreads, 1)
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < kb_total; ++kb) {
-                    mbar_wait(smem_u32(&bar_conv[stage]), phase);
-                    tc_fence_after();
-                    const uint32_t sA = smem0 + stage * STAGE_BYTES;
-                    const uint64_t dAh = make_desc(sA);
-                    const uint64_t dAl = make_desc(sA + A_TILE_BYTES);
-                    const uint64_t dWh = make_desc(sA + 2 * A_TILE_BYTES);
-                    const uint64_t dWl = make_desc(sA + 2 * A_TILE_BYTES + W_TILE_BYTES);
+                    mbar_wait(smem_u32(&bar_aconv[aslot]), aphase);
+                    const uint32_t sA = smem0 + aslot * A_SLOT_BYTES;
+                    const uint64_t dAh = make_desc(sA), dAl = make_desc(sA + A_TILE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // byte offset inside the swizzle row, >> 4
-                        if (!(args.dbg & 8)) {
-                            tc_mma_tf32(d_tmem, dAl + adv, dWh + adv, idesc, (kb | k) != 0);  // small terms first
-                            tc_mma_tf32(d_tmem, dAh + adv, dWl + adv, idesc, 1);
-                            tc_mma_tf32(d_tmem, dAh + adv, dWh + adv, idesc, 1);
-                        } else {
-                            tc_mma_tf32(d_tmem, dAh + adv, dWh + adv, idesc, (kb | k) != 0);
+                    for (int half = 0; half < BK / WK; ++half) {
+                        mbar_wait(smem_u32(&bar_wfull[wslot]), wphase);
+                        tc_fence_after();
+                        const uint32_t sW = smemW + wslot * W_SLOT_BYTES;
+                        const uint64_t dWh = make_desc_sw64(sW), dWl = make_desc_sw64(sW + W_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < WK / UMMA_K; ++k) {
+                            // byte offsets inside the swizzled rows, >> 4
+                            const uint64_t adv_a = (uint64_t)(((half * (WK / UMMA_K) + k) * UMMA_K * 4) >> 4);
+                            const uint64_t adv_w = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            tc_mma_tf32(d_tmem, dAl + adv_a, dWh + adv_w, idesc, (kb | half | k) != 0);  // small terms first
+                            tc_mma_tf32(d_tmem, dAh + adv_a, dWl + adv_w, idesc, 1);
+                            tc_mma_tf32(d_tmem, dAh + adv_a, dWh + adv_w, idesc, 1);
                         }
+                        tc_commit(smem_u32(&bar_wempty[wslot]));  // frees the weight slot when these MMAs retire
+                        if (++wslot == NW) { wslot = 0; wphase ^= 1; }
                     }
-                    tc_commit(smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    tc_commit(smem_u32(&bar_aempty[aslot]));
+                    if (++aslot == NA) { aslot = 0; aphase ^= 1; }
                 }
                 tc_commit(smem_u32(&bar_tfull[acc]));  // accumulator complete
             }
@@ -286,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                  : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
                                  : "r"(stg + (rr * STG_PITCH + cc) * 4)
                                  : "memory");
-                    if (wrow0 + rr < args.M && !(args.dbg & 4)) *reinterpret_cast<uint4*>(args.out + (wrow0 + rr) * BN + c * 32 + cc) = o;
+                    if (wrow0 + rr < args.M) *reinterpret_cast<uint4*>(args.out + (wrow0 + rr) * BN + c * 32 + cc) = o;
                 }
             }
             tc_fence_before();
@@ -299,17 +329,16 @@ __global__ void __launch_bounds__(kThreads, 1)
                     *reinterpret_cast<uint4*>(args.mask_out + (wrow0 + lane) * NCHUNK + c) = make_uint4(bits[c], bits[c + 1], bits[c + 2], bits[c + 3]);
             }
         }
-    } else {
+    } else if (warp < 10) {
         // ===== operand split: the landed fp32 tile becomes hi (in place) and lo (next tile); element-wise, so the swizzle
         // TMA applied is irrelevant -- lo lands at the same swizzled offset of its own tile =====
         const int tid = threadIdx.x - 192;
-        int stage = 0;
+        int slot = 0;
         uint32_t phase = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < kb_total; ++kb) {
-                mbar_wait(smem_u32(&bar_full[stage]), phase);
-                const uint32_t sA = smem0 + stage * STAGE_BYTES;
-                if (!(args.dbg & 2))
+                mbar_wait(smem_u32(&bar_afull[slot]), phase);
+                const uint32_t sA = smem0 + slot * A_SLOT_BYTES;
 #pragma unroll
                 for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
                     const uint32_t addr = sA + (i * 128 + tid) * 16;
@@ -323,8 +352,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_conv[stage]));
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                if (lane == 0) mbar_arrive(smem_u32(&bar_aconv[slot]));
+                if (++slot == NA) { slot = 0; phase ^= 1; }
             }
         }
     }
@@ -353,35 +382,35 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// [rows, cols] fp32 row-major (pitch = cols), box = box_rows x 32 columns, 128-byte swizzle; rows past the end read 0
+// [rows, cols] fp32 row-major (pitch = cols), box = box_rows x box_cols columns; rows past the end read 0
 static bool make_map(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows,
-                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int box_cols = BK) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int NSTAGE, int EPI>
+template <int BN, int NA, int NW, int EPI>
 static int launch_linear(long long M, const float* a0, int k0, const float* a1, int k1, const float* wh, const float* wl,
                          const LinearArgs& args, cudaStream_t st) {
     CUtensorMap mA0, mA1, mWh, mWl;
-    bool ok = make_map(&mA0, a0, M, k0, BM) && make_map(&mWh, wh, BN, k0 + k1, BN) && make_map(&mWl, wl, BN, k0 + k1, BN);
+    bool ok = make_map(&mA0, a0, M, k0, BM) && make_map(&mWh, wh, BN, k0 + k1, BN, CU_TENSOR_MAP_SWIZZLE_64B, WK) &&
+              make_map(&mWl, wl, BN, k0 + k1, BN, CU_TENSOR_MAP_SWIZZLE_64B, WK);
     mA1 = mA0;
     if (k1 > 0) ok = ok && make_map(&mA1, a1, M, k1, BM);
     if (!ok) return set_error(FG_ERR_CUDA, "cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)", __FILE__, __LINE__);
-    constexpr int STAGE_BYTES = 2 * (A_TILE_BYTES + BN * BK * 4);
-    constexpr int SMEM = NSTAGE * STAGE_BYTES + STG_BYTES + 1024;
+    constexpr int SMEM = NA * 2 * A_TILE_BYTES + NW * 2 * BN * WK * 4 + STG_BYTES + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory");
-    auto kern = mlp_linear_kernel<BN, NSTAGE, EPI>;
+    auto kern = mlp_linear_kernel<BN, NA, NW, EPI>;
     FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const long long n_tiles = (M + BM - 1) / BM;
     const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-    FG_LAUNCH(kern, grid, kThreads, SMEM, st, mA0, mA1, mWh, mWl, args);
+    FG_LAUNCH(kern, grid, kLinThreads, SMEM, st, mA0, mA1, mWh, mWl, args);
     return FG_OK;
 }
 
@@ -657,25 +686,34 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(PackTable tab) {
 
 // ------------------------------------------------------------------------------------------------ embedding
 // E[n, :] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^9), cos(x 2^9) | t_emb | 0...]   (utils.py:27-56; model.py:1095-1096)
+// thread = (row, group of 4 columns): one 16-byte store per thread
 __global__ void __launch_bounds__(256) deform_embed_kernel(long long N, const float* __restrict__ means, const float* __restrict__ t_emb,
                                                            int t_ch, int multires, float* __restrict__ e) {
     pdl_wait();
+    constexpr int G = FG_MLP_EMBED_LD / 4;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N * FG_MLP_EMBED_LD) return;
-    const long long n = i / FG_MLP_EMBED_LD;
-    const int j = (int)(i % FG_MLP_EMBED_LD);
+    if (i >= N * G) return;
+    const long long n = i / G;
+    const int j0 = (int)(i % G) * 4;
     const int x_ch = 3 + 6 * multires;
-    float v = 0.f;
-    if (j < 3) {
-        v = means[n * 3 + j];
-    } else if (j < x_ch) {
-        const int k = j - 3, f = k / 6, r = k % 6;
-        const float a = means[n * 3 + (r % 3)] * exp2f((float)f);  // x * freq, freq = 2^f exactly
-        v = r < 3 ? sinf(a) : cosf(a);
-    } else if (j < x_ch + t_ch) {
-        v = t_emb[j - x_ch];
+    const float x[3] = {means[n * 3], means[n * 3 + 1], means[n * 3 + 2]};
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        float r = 0.f;
+        if (j < 3) {
+            r = x[j];
+        } else if (j < x_ch) {
+            const int k = j - 3, f = k / 6, c = k % 6;
+            const float a = x[c % 3] * exp2f((float)f);  // x * freq, freq = 2^f exactly
+            r = c < 3 ? sinf(a) : cosf(a);
+        } else if (j < x_ch + t_ch) {
+            r = t_emb[j - x_ch];
+        }
+        v[u] = r;
     }
-    e[i] = v;
+    reinterpret_cast<float4*>(e)[i] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // ------------------------------------------------------------------------------------------------ SE(3) application
@@ -835,19 +873,19 @@ extern "C" int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, in
     FG_REQUIRE(k0 > 0 && k0 % BK == 0 && k1 >= 0 && k1 % BK == 0, "fg_mlp_linear: k0, k1 must be multiples of 32 (k0 > 0)");
     if (M == 0) return FG_OK;  // empty inputs have NULL data pointers
     FG_REQUIRE(a0 && w_hi && w_lo && out && (k1 == 0 || a1), "fg_mlp_linear: NULL operand");
-    LinearArgs args = {bias, mask_in, out, mask_out, (long long)M, k0 / BK, k1 / BK, g_dbg_flags};
+    LinearArgs args = {bias, mask_in, out, mask_out, (long long)M, k0 / BK, k1 / BK};
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == FG_MLP_RELU) {
         FG_REQUIRE(n_out == 256 && bias && mask_out, "fg_mlp_linear: FG_MLP_RELU is built for 256 outputs and needs bias and mask_out");
-        return launch_linear<256, 2, EPI_RELU>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
+        return launch_linear<256, 3, 3, EPI_RELU>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
     }
     if (mode == FG_MLP_LINEAR) {
         FG_REQUIRE(n_out == FG_MLP_HEAD_LD && bias, "fg_mlp_linear: FG_MLP_LINEAR is built for FG_MLP_HEAD_LD outputs and needs a bias");
-        return launch_linear<FG_MLP_HEAD_LD, 4, EPI_LINEAR>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
+        return launch_linear<FG_MLP_HEAD_LD, 4, 4, EPI_LINEAR>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
     }
     if (mode == FG_MLP_DGRAD) {
         FG_REQUIRE(n_out == 256 && mask_in, "fg_mlp_linear: FG_MLP_DGRAD is built for 256 outputs and needs mask_in");
-        return launch_linear<256, 2, EPI_MASK>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
+        return launch_linear<256, 3, 3, EPI_MASK>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
     }
     return set_error(FG_ERR_INVALID, "fg_mlp_linear: unknown mode", __FILE__, __LINE__);
 }
@@ -863,12 +901,6 @@ extern "C" int fg_mlp_wgrad(int64_t N, const float* dz, const float* a, int k_in
     if (k_in == FG_MLP_EMBED_LD) return launch_wgrad<FG_MLP_EMBED_LD, 4>(N, dz, a, args, st);
     if (k_in == FG_MLP_HEAD_LD) return launch_wgrad<FG_MLP_HEAD_LD, 4>(N, dz, a, args, st);
     return set_error(FG_ERR_INVALID, "fg_mlp_wgrad: k_in must be 256, FG_MLP_EMBED_LD or FG_MLP_HEAD_LD", __FILE__, __LINE__);
-}
-
-extern "C" int fg_mlp_debug_flags(int flags) {
-    const int old = fg::mlp::g_dbg_flags;
-    fg::mlp::g_dbg_flags = flags;
-    return old;
 }
 
 extern "C" int fg_mlp_pack(int n_segments, const fg_mlp_pack_segment* segments_host, void* stream) {
@@ -889,7 +921,7 @@ extern "C" int fg_deform_embed(int64_t N, const float* means, const float* t_emb
     FG_REQUIRE(multires >= 0 && t_ch >= 0 && 3 + 6 * multires + t_ch <= FG_MLP_EMBED_LD && (t_ch == 0 || t_emb),
                "fg_deform_embed: embedding wider than FG_MLP_EMBED_LD");
     if (N == 0) return FG_OK;
-    FG_LAUNCH(deform_embed_kernel, ceil_div(N * FG_MLP_EMBED_LD, 256), 256, 0, (cudaStream_t)stream, (long long)N, means, t_emb, t_ch,
+    FG_LAUNCH(deform_embed_kernel, ceil_div(N * (FG_MLP_EMBED_LD / 4), 256), 256, 0, (cudaStream_t)stream, (long long)N, means, t_emb, t_ch,
               multires, e);
     return FG_OK;
 }

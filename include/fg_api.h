@@ -399,9 +399,6 @@ int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, int k0, const
  * the TRANSPOSED head weight gradient.  3xTF32 on chip, split-K over row ranges, results ADDED with
  * red.global (zero dw / db first; the order of the additions is not deterministic). */
 int fg_mlp_wgrad(int64_t N, const float* dz, const float* a, int k_in, float* dw, int ld_dw, int col0, float* db, void* stream);
-/* Timing experiments only (tools/dbg_mlp.py variants): 1 = weight tiles loaded once per CTA, 2 = no operand split, 4 = no
- * global stores, 8 = one product instead of three.  Any non-zero value makes fg_mlp_linear's results wrong.  Returns the old value. */
-int fg_mlp_debug_flags(int flags);
 int fg_mlp_pack(int n_segments, const fg_mlp_pack_segment* segments_host, void* stream);
 int fg_deform_embed(int64_t N, const float* means, const float* t_emb, int t_ch, int multires, float* e, void* stream);
 int fg_deform_apply_fwd(int64_t N, const float* head, const float* means, const float* scales_log, const float* quats,

@@ -107,30 +107,36 @@ def stage_e2e():
         print("  per param", {k: f"{v:.1e}" for k, v in worst.items() if "linear" in k}, flush=True)
 
 
-def stage_variants():
-    """Where does the time of one 256x256 layer go?  Timing with parts of the kernel disabled (results are wrong)."""
+def stage_layer():
+    """Time of one 256 -> 256 layer at 1 M rows (forward / data gradient / weight gradient)."""
+    from freegaussian_b200._lib import check, ptr
+
     n = 1_000_000
-    L = _lib.lib()
     g = torch.Generator().manual_seed(0)
     a = torch.randn(n, 256, generator=g).cuda()
     w = _hilo((torch.randn(256, 256, generator=g) / 16).cuda())
     bias = torch.zeros(256, device="cuda")
     out = torch.empty(n, 256, device="cuda")
     bits = torch.empty(n, 8, dtype=torch.int32, device="cuda")
+    dw, db = torch.zeros(256, 256, device="cuda"), torch.zeros(256, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    for flags, name in ((0, "full"), (1, "W once"), (2, "no split"), (4, "no stores"), (8, "1 product"), (1 | 8, "W once, 1 product"),
-                        (1 | 2 | 4 | 8, "A stream + 1 product only"), (1 | 2 | 4, "W once, no split, no stores")):
-        L.fg_mlp_debug_flags(flags)
+    runs = {
+        "relu": lambda: _linear(_lib.MLP_RELU, n, 256, a, 256, None, 0, w, bias, None, out, bits),
+        "dgrad": lambda: _linear(_lib.MLP_DGRAD, n, 256, a, 256, None, 0, w, None, bits, out, None),
+        "wgrad": lambda: check(_lib.lib().fg_mlp_wgrad(n, ptr(a), ptr(out), 256, ptr(dw), 256, 0, ptr(db), st)),
+    }
+    for name, fn in runs.items():
         ts = []
         for it in range(6):
             e0, e1 = ev(), ev()
             e0.record()
-            _linear(_lib.MLP_RELU, n, 256, a, 256, None, 0, w, bias, None, out, bits)
+            fn()
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        print(f"flags {flags:2d} {name:32s}: {min(ts[2:]) * 1e3:7.1f} us", flush=True)
-    L.fg_mlp_debug_flags(0)
+        us = min(ts[2:]) * 1e3
+        print(f"{name:6s}: {us:7.1f} us  ({3 * 2 * n * 256 * 256 / us / 1e6:.0f} TFLOP/s of tf32 MMA issued, {2 * n * 1024 / us / 1e3:.0f} GB/s)", flush=True)
 
 
 def stage_perf():
@@ -181,5 +187,5 @@ def stage_perf():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"linear": stage_linear, "modes": stage_modes, "aux": stage_aux, "e2e": stage_e2e, "perf": stage_perf, "variants": stage_variants, "wgrad": stage_wgrad}[sys.argv[1]]()
+    {"linear": stage_linear, "modes": stage_modes, "aux": stage_aux, "e2e": stage_e2e, "perf": stage_perf, "layer": stage_layer, "wgrad": stage_wgrad}[sys.argv[1]]()
     print(f"[{sys.argv[1]} done in {time.time() - t0:.1f}s]")
