@@ -21,6 +21,9 @@ WANT = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
     "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum",
     "smsp__thread_inst_executed_per_inst_executed.ratio",
+    # tensor-core kernels (csrc/mlp.cu)
+    "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.sum", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__cycles_elapsed.avg", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
 ]
 
 
