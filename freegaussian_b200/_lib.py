@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfreegaussian_b200.so"
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pi = C.POINTER(C.c_int)
@@ -103,7 +103,8 @@ SIGNATURES = {
     "fg_mlp_linear": (_i32, [_i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_mlp_wgrad": (_i32, [_i64, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "fg_mlp_pack": (_i32, [_i32, C.POINTER(MlpPackSegment), _vp]),
-    "fg_deform_embed": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "fg_deform_embed": (_i32, [_i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "fg_deform_embed_bwd": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "fg_deform_apply_fwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_deform_apply_bwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_knn_workspace_bytes": (_i64, [_i64]),

@@ -14,7 +14,8 @@
 //                     element each way): the split of the A tile happens in shared memory between TMA and MMA;
 //                     the weights are split once per step by fg_mlp_pack.
 //   fg_mlp_pack       weights -> padded / reordered / transposed hi+lo operand buffers (one launch, segment table)
-//   fg_deform_embed   positional embedding of the means + broadcast time embedding -> [N,96]   (utils.py:27-56)
+//   fg_deform_embed   positional embedding of the means (+ a second point set) + broadcast time embedding -> [N,ld]  (utils.py:27-56)
+//   fg_deform_embed_bwd  its VJP with respect to the means (the stage-2 control network does not detach them)
 //   fg_deform_apply_fwd/bwd   screw axis -> SE(3) -> means, scales, quats (utils.py:137-159, model.py:841-845)
 #include <cuda.h>
 
@@ -686,34 +687,59 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(PackTable tab) {
 
 // ------------------------------------------------------------------------------------------------ embedding
 // E[n, :] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^9), cos(x 2^9) | t_emb | 0...]   (utils.py:27-56; model.py:1095-1096)
-// thread = (row, group of 4 columns): one 16-byte store per thread
-__global__ void __launch_bounds__(256) deform_embed_kernel(long long N, const float* __restrict__ means, const float* __restrict__ t_emb,
-                                                           int t_ch, int multires, float* __restrict__ e) {
+// thread = (row, group of 4 columns): one 16-byte store per thread.  Row layout: embed(x) | embed(x2) (if given) | t_emb | 0.
+__global__ void __launch_bounds__(256) deform_embed_kernel(long long N, const float* __restrict__ x, const float* __restrict__ x2,
+                                                           const float* __restrict__ t_emb, int t_ch, int multires, int ld,
+                                                           float* __restrict__ e) {
     pdl_wait();
-    constexpr int G = FG_MLP_EMBED_LD / 4;
+    const int G = ld / 4;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * G) return;
     const long long n = i / G;
     const int j0 = (int)(i % G) * 4;
     const int x_ch = 3 + 6 * multires;
-    const float x[3] = {means[n * 3], means[n * 3 + 1], means[n * 3 + 2]};
+    const int p_ch = x2 ? 2 * x_ch : x_ch;
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const int j = j0 + u;
+        int j = j0 + u;
         float r = 0.f;
-        if (j < 3) {
-            r = x[j];
-        } else if (j < x_ch) {
-            const int k = j - 3, f = k / 6, c = k % 6;
-            const float a = x[c % 3] * exp2f((float)f);  // x * freq, freq = 2^f exactly
-            r = c < 3 ? sinf(a) : cosf(a);
-        } else if (j < x_ch + t_ch) {
-            r = t_emb[j - x_ch];
+        if (j < p_ch) {
+            const float* src = x;
+            if (j >= x_ch) { src = x2; j -= x_ch; }
+            if (j < 3) {
+                r = src[n * 3 + j];
+            } else {
+                const int k = j - 3, f = k / 6, c = k % 6;
+                const float a = src[n * 3 + (c % 3)] * exp2f((float)f);  // x * freq, freq = 2^f exactly
+                r = c < 3 ? sinf(a) : cosf(a);
+            }
+        } else if (j < p_ch + t_ch) {
+            r = t_emb[j - p_ch];
         }
         v[u] = r;
     }
     reinterpret_cast<float4*>(e)[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// VJP of embed(x) (the first 3 + 6 multires columns of a row): dx = de_x + sum_f 2^f (cos(x 2^f) de_sin,f - sin(x 2^f) de_cos,f)
+__global__ void __launch_bounds__(256) deform_embed_bwd_kernel(long long N, const float* __restrict__ x, const float* __restrict__ de,
+                                                               int multires, int ld, float* __restrict__ dx) {
+    pdl_wait();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * 3) return;
+    const long long n = i / 3;
+    const int c = (int)(i % 3);
+    const float* row = de + n * ld;
+    const float xv = x[i];
+    float g = row[c];
+    for (int f = 0; f < multires; ++f) {
+        const float w = exp2f((float)f);
+        float sn, cs;
+        sincosf(xv * w, &sn, &cs);
+        g += w * (cs * row[3 + 6 * f + c] - sn * row[3 + 6 * f + 3 + c]);
+    }
+    dx[i] = g;
 }
 
 // ------------------------------------------------------------------------------------------------ SE(3) application
@@ -880,7 +906,8 @@ extern "C" int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, in
         return launch_linear<256, 3, 3, EPI_RELU>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
     }
     if (mode == FG_MLP_LINEAR) {
-        FG_REQUIRE(n_out == FG_MLP_HEAD_LD && bias, "fg_mlp_linear: FG_MLP_LINEAR is built for FG_MLP_HEAD_LD outputs and needs a bias");
+        FG_REQUIRE((n_out == FG_MLP_HEAD_LD || n_out == 128) && bias, "fg_mlp_linear: FG_MLP_LINEAR is built for 32 or 128 outputs and needs a bias");
+        if (n_out == 128) return launch_linear<128, 3, 3, EPI_LINEAR>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
         return launch_linear<FG_MLP_HEAD_LD, 4, 4, EPI_LINEAR>(M, a0, k0, a1, k1, w_hi, w_lo, args, st);
     }
     if (mode == FG_MLP_DGRAD) {
@@ -900,7 +927,8 @@ extern "C" int fg_mlp_wgrad(int64_t N, const float* dz, const float* a, int k_in
     if (k_in == 256) return launch_wgrad<256, 3>(N, dz, a, args, st);
     if (k_in == FG_MLP_EMBED_LD) return launch_wgrad<FG_MLP_EMBED_LD, 4>(N, dz, a, args, st);
     if (k_in == FG_MLP_HEAD_LD) return launch_wgrad<FG_MLP_HEAD_LD, 4>(N, dz, a, args, st);
-    return set_error(FG_ERR_INVALID, "fg_mlp_wgrad: k_in must be 256, FG_MLP_EMBED_LD or FG_MLP_HEAD_LD", __FILE__, __LINE__);
+    if (k_in == 128) return launch_wgrad<128, 3>(N, dz, a, args, st);
+    return set_error(FG_ERR_INVALID, "fg_mlp_wgrad: k_in must be 256, 128, 96 or 32", __FILE__, __LINE__);
 }
 
 extern "C" int fg_mlp_pack(int n_segments, const fg_mlp_pack_segment* segments_host, void* stream) {
@@ -916,13 +944,21 @@ extern "C" int fg_mlp_pack(int n_segments, const fg_mlp_pack_segment* segments_h
     return FG_OK;
 }
 
-extern "C" int fg_deform_embed(int64_t N, const float* means, const float* t_emb, int t_ch, int multires, float* e, void* stream) {
-    FG_REQUIRE(N >= 0 && means && e, "fg_deform_embed: NULL argument");
-    FG_REQUIRE(multires >= 0 && t_ch >= 0 && 3 + 6 * multires + t_ch <= FG_MLP_EMBED_LD && (t_ch == 0 || t_emb),
-               "fg_deform_embed: embedding wider than FG_MLP_EMBED_LD");
+extern "C" int fg_deform_embed(int64_t N, const float* x, const float* x2, const float* t_emb, int t_ch, int multires, int ld, float* e,
+                               void* stream) {
+    FG_REQUIRE(N >= 0 && multires >= 0 && t_ch >= 0 && ld > 0 && ld % 32 == 0, "fg_deform_embed: bad sizes (ld must be a multiple of 32)");
+    FG_REQUIRE((x2 ? 2 : 1) * (3 + 6 * multires) + t_ch <= ld && (t_ch == 0 || t_emb), "fg_deform_embed: embedding wider than ld");
     if (N == 0) return FG_OK;
-    FG_LAUNCH(deform_embed_kernel, ceil_div(N * (FG_MLP_EMBED_LD / 4), 256), 256, 0, (cudaStream_t)stream, (long long)N, means, t_emb, t_ch,
-              multires, e);
+    FG_REQUIRE(x && e, "fg_deform_embed: NULL argument");
+    FG_LAUNCH(deform_embed_kernel, ceil_div(N * (ld / 4), 256), 256, 0, (cudaStream_t)stream, (long long)N, x, x2, t_emb, t_ch, multires, ld, e);
+    return FG_OK;
+}
+
+extern "C" int fg_deform_embed_bwd(int64_t N, const float* x, const float* de, int multires, int ld, float* dx, void* stream) {
+    FG_REQUIRE(N >= 0 && multires >= 0 && 3 + 6 * multires <= ld, "fg_deform_embed_bwd: bad sizes");
+    if (N == 0) return FG_OK;
+    FG_REQUIRE(x && de && dx, "fg_deform_embed_bwd: NULL argument");
+    FG_LAUNCH(deform_embed_bwd_kernel, ceil_div(N * 3, 256), 256, 0, (cudaStream_t)stream, (long long)N, x, de, multires, ld, dx);
     return FG_OK;
 }
 

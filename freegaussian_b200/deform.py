@@ -1,10 +1,10 @@
-"""Deformation network of FreeGaussian on the B200 tensor cores.
+"""Deformation and control networks of FreeGaussian on the B200 tensor cores.
 
 ``DeformNetwork`` mirrors ``FreeGaussianDeformableModel`` (``freegaussian/freegaussian_model.py:1054-1114``): same
 constructor arguments, same parameter names and shapes (a reference ``state_dict`` loads unchanged), same
 ``forward(x, t) -> (d_xyz [N,4,4], rotation [N,4], scaling [N,3])``.  ``deform_gaussians`` additionally fuses the
 lines that consume those outputs (``freegaussian_model.py:836-845``) and returns the ``means, scales, quats`` handed
-to ``rasterization``.
+to ``rasterization``.  ``ControlNetwork`` mirrors the stage-2 ``FreeGaussianControllableModel`` (``:1117-1145``) the same way.
 
 Every ``nn.Linear`` of the trunk runs on tcgen05 / TMEM / TMA (csrc/mlp.cu) in error-compensated 3xTF32 (fp32-accurate:
 the reference computes these layers in fp32): forward and data gradient in ``fg_mlp_linear``, weight and bias gradients
@@ -54,27 +54,39 @@ def _linear(mode, M, n_out, a0, k0, a1, k1, w, bias, mask_in, out, mask_out):
                                    ptr(out), ptr(mask_out), _stream()))
 
 
+class _Spec:
+    """Shape of one network: embedding row length (96 / 128), used embedding channels, heads, whether the data gradient
+    has to reach the embedded points (stage 2 does not detach them)."""
+
+    def __init__(self, emb_ld: int, emb_ch: int, multires: int, heads, input_grad: bool):
+        self.emb_ld, self.emb_ch, self.multires, self.heads, self.input_grad = emb_ld, emb_ch, multires, tuple(heads), input_grad
+        assert emb_ch <= emb_ld and emb_ld % 32 == 0 and sum(o for _, o in heads) <= MLP_HEAD_LD
+        assert not input_grad or emb_ld == 128, "the embedding-gradient GEMM is built for 128 columns"
+
+
 class _Packed:
     """Operand buffers of one parameter set: padded, reordered, hi/lo split, plus the transposes for the data gradient."""
 
-    def __init__(self, params: List[Tensor], emb_ch: int):
+    def __init__(self, params: List[Tensor], spec: _Spec):
         dev = params[0].device
+        ld, emb_ch = spec.emb_ld, spec.emb_ch
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731  pads stay zero
-        kp = [MLP_EMBED_LD if i == 0 else (_W + MLP_EMBED_LD if i == _SKIP + 1 else _W) for i in range(_D)]
-        self.kp = kp
-        self.w = [(z(_W, k), z(_W, k)) for k in kp]
-        self.w_head = (z(MLP_HEAD_LD, _W), z(MLP_HEAD_LD, _W))
-        self.wt = [None] + [(z(_W, _W), z(_W, _W)) for _ in range(1, _D)]  # wt[l][i, o] = W_l[o, i] over the hidden inputs
-        self.wt_head = (z(_W, MLP_HEAD_LD), z(_W, MLP_HEAD_LD))
+        pair = lambda *s: (z(*s), z(*s))  # noqa: E731
+        kp = [ld if i == 0 else (_W + ld if i == _SKIP + 1 else _W) for i in range(_D)]
+        self.w = [pair(_W, k) for k in kp]
+        self.w_head = pair(MLP_HEAD_LD, _W)
+        self.wt = [None] + [pair(_W, _W) for _ in range(1, _D)]  # wt[l][i, o] = W_l[o, i] over the hidden inputs
+        self.wt_head = pair(_W, MLP_HEAD_LD)
+        # wt_emb[e, :] = [W_0[:, e] | W_skip[:, e]]: d(loss)/d(embedding) = [dz_0 | dz_skip] . wt_emb^T
+        self.wt_emb = pair(ld, 2 * _W) if spec.input_grad else None
         segs = []
 
         def seg(src, col0, cols, dst, dst_col0, transpose=False, row0=0):
-            hi, lo = dst if isinstance(dst, tuple) else (dst, None)
+            hi, lo = dst
             s = MlpPackSegment()
             s.src = src.data_ptr()
-            esz = 4
-            s.dst_hi = hi.data_ptr() + row0 * hi.shape[1] * esz
-            s.dst_lo = (lo.data_ptr() + row0 * lo.shape[1] * esz) if lo is not None else None
+            s.dst_hi = hi.data_ptr() + row0 * hi.shape[1] * 4
+            s.dst_lo = lo.data_ptr() + row0 * lo.shape[1] * 4
             s.src_ld, s.src_col0, s.rows, s.cols = src.shape[1], col0, src.shape[0], cols
             s.dst_ld, s.dst_col0, s.transpose = hi.shape[1], dst_col0, int(transpose)
             segs.append(s)
@@ -84,15 +96,19 @@ class _Packed:
             assert wt.is_contiguous()
             if i == 0:
                 seg(wt, 0, emb_ch, self.w[0], 0)
+                if spec.input_grad:
+                    seg(wt, 0, emb_ch, self.wt_emb, 0, transpose=True)
             elif i == _SKIP + 1:  # reference input order [embedding | h]; operand order [h | embedding]
                 seg(wt, emb_ch, _W, self.w[i], 0)
                 seg(wt, 0, emb_ch, self.w[i], _W)
                 seg(wt, emb_ch, _W, self.wt[i], 0, transpose=True)
+                if spec.input_grad:
+                    seg(wt, 0, emb_ch, self.wt_emb, _W, transpose=True)
             else:
                 seg(wt, 0, _W, self.w[i], 0)
                 seg(wt, 0, _W, self.wt[i], 0, transpose=True)
         row = 0
-        for j, (_, o) in enumerate(_HEADS):
+        for j, (_, o) in enumerate(spec.heads):
             hw = params[2 * _D + 2 * j]
             seg(hw, 0, _W, self.w_head, 0, row0=row)
             seg(hw, 0, _W, self.wt_head, row, transpose=True)
@@ -101,33 +117,33 @@ class _Packed:
         arr = (MlpPackSegment * len(segs))(*segs)
         check(_lib.lib().fg_mlp_pack(len(segs), arr, _stream()))
         self.bias = [b.contiguous() for b in params[1:2 * _D:2]]
-        hb = torch.cat([params[2 * _D + 2 * j + 1] for j in range(len(_HEADS))])
+        hb = torch.cat([params[2 * _D + 2 * j + 1] for j in range(len(spec.heads))])
         self.bias_head = torch.cat([hb, hb.new_zeros(MLP_HEAD_LD - hb.numel())])
 
 
 class _Trunk(torch.autograd.Function):
-    """x [N,3] (no gradient: the reference passes means.detach()), t_emb [t_ch], 24 parameters -> head [N, 32]."""
+    """x [N,3], x2 [N,3] or None (embedded like x, no gradient), t_emb [t_ch] or None, spec, parameters -> head [N, 32]."""
 
     @staticmethod
-    def forward(ctx, x, t_emb, multires, *params):
+    def forward(ctx, x, x2, t_emb, spec, *params):
         L = _lib.lib()
         N = x.shape[0]
         dev = x.device
-        t_ch = t_emb.numel()
-        emb_ch = 3 + 6 * multires + t_ch
-        pk = _Packed(list(params), emb_ch)
+        ld = spec.emb_ld
+        t_ch = t_emb.numel() if t_emb is not None else 0
+        pk = _Packed(list(params), spec)
         new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
-        e = new(N, MLP_EMBED_LD)
-        check(L.fg_deform_embed(N, ptr(x), ptr(t_emb), t_ch, multires, ptr(e), _stream()))
+        e = new(N, ld)
+        check(L.fg_deform_embed(N, ptr(x), ptr(x2), ptr(t_emb), t_ch, spec.multires, ld, ptr(e), _stream()))
         hs: List[Tensor] = []
         masks: List[Tensor] = []
         prev = None
         for i in range(_D):
             out, bits = new(N, _W), torch.empty(N, _W // 32, device=dev, dtype=torch.int32)
             if i == 0:
-                _linear(_lib.MLP_RELU, N, _W, e, MLP_EMBED_LD, None, 0, pk.w[0], pk.bias[0], None, out, bits)
+                _linear(_lib.MLP_RELU, N, _W, e, ld, None, 0, pk.w[0], pk.bias[0], None, out, bits)
             elif i == _SKIP + 1:
-                _linear(_lib.MLP_RELU, N, _W, prev, _W, e, MLP_EMBED_LD, pk.w[i], pk.bias[i], None, out, bits)
+                _linear(_lib.MLP_RELU, N, _W, prev, _W, e, ld, pk.w[i], pk.bias[i], None, out, bits)
             else:
                 _linear(_lib.MLP_RELU, N, _W, prev, _W, None, 0, pk.w[i], pk.bias[i], None, out, bits)
             prev = out
@@ -135,26 +151,26 @@ class _Trunk(torch.autograd.Function):
             masks.append(bits)
         head = new(N, MLP_HEAD_LD)
         _linear(_lib.MLP_LINEAR, N, MLP_HEAD_LD, prev, _W, None, 0, pk.w_head, pk.bias_head, None, head, None)
-        ctx.save_for_backward(e, *hs, *masks, *params)
-        ctx.pk = pk
-        ctx.dims = (N, t_ch, emb_ch, multires)
+        ctx.save_for_backward(x, e, *hs, *masks, *params)
+        ctx.pk, ctx.spec, ctx.t_ch = pk, spec, t_ch
         return head
 
     @staticmethod
     def backward(ctx, g_head):
-        N, t_ch, emb_ch, multires = ctx.dims
+        spec, pk, t_ch = ctx.spec, ctx.pk, ctx.t_ch
+        ld, emb_ch = spec.emb_ld, spec.emb_ch
         saved = ctx.saved_tensors
-        e, hs, masks, params = saved[0], saved[1:1 + _D], saved[1 + _D:1 + 2 * _D], saved[1 + 2 * _D:]
-        pk = ctx.pk
+        x, e, hs, masks, params = saved[0], saved[1], saved[2:2 + _D], saved[2 + _D:2 + 2 * _D], saved[2 + 2 * _D:]
+        N_all = N = x.shape[0]
         dev = g_head.device
         g_head = g_head.contiguous()
         new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         grads: List[Tensor] = [None] * len(params)
-        x_ch = emb_ch - t_ch
         L = _lib.lib()
         # Rows whose incoming gradient is exactly zero (Gaussians that were culled or never reached a pixel in this
-        # step's views) contribute exactly nothing to any weight gradient: run the backward on the other rows only.
+        # step's views) contribute exactly nothing to any gradient: run the backward on the other rows only.
         # One host read of the count; the saved activations are gathered layer by layer as they are needed.
+        idx = None
         sel = lambda t: t  # noqa: E731
         if SPARSE_BACKWARD and N > 0:
             active = (g_head != 0).any(1)
@@ -174,16 +190,16 @@ class _Trunk(torch.autograd.Function):
         del h_last
         db_head = g_head.sum(0)
         row = 0
-        for j, (_, o) in enumerate(_HEADS):
+        for j, (_, o) in enumerate(spec.heads):
             grads[2 * _D + 2 * j] = dw_head_t[:, row:row + o].t()
             grads[2 * _D + 2 * j + 1] = db_head[row:row + o]
             row += o
         # trunk: one zero-filled arena for everything fg_mlp_wgrad adds into
-        arena = torch.zeros(_D * (_W * _W + _W) + 2 * _W * MLP_EMBED_LD, device=dev, dtype=torch.float32)
+        arena = torch.zeros(_D * (_W * _W + _W) + 2 * _W * ld, device=dev, dtype=torch.float32)
         dw_h = [arena[i * _W * _W:(i + 1) * _W * _W].view(_W, _W) for i in range(_D)]  # dw_h[0] unused
         db = [arena[_D * _W * _W + i * _W:_D * _W * _W + (i + 1) * _W] for i in range(_D)]
         off = _D * (_W * _W + _W)
-        dw_e = [arena[off + k * _W * MLP_EMBED_LD:off + (k + 1) * _W * MLP_EMBED_LD].view(_W, MLP_EMBED_LD) for k in range(2)]
+        dw_e = [arena[off + k * _W * ld:off + (k + 1) * _W * ld].view(_W, ld) for k in range(2)]
         st = _stream()
 
         def wgrad(dz, a, k_in, dw, db_):
@@ -192,26 +208,37 @@ class _Trunk(torch.autograd.Function):
         dz = new(N, _W)
         _linear(_lib.MLP_DGRAD, N, _W, g_head, MLP_HEAD_LD, None, 0, pk.wt_head, None, m_in(_D - 1), dz, None)
         g_t = torch.zeros(t_ch, device=dev) if t_ch else None
+        dz_skip = None
         for i in range(_D - 1, -1, -1):
             if i == 0:
-                wgrad(dz, e, MLP_EMBED_LD, dw_e[0], db[0])
+                wgrad(dz, e, ld, dw_e[0], db[0])
                 grads[0] = dw_e[0][:, :emb_ch]
             elif i == _SKIP + 1:  # reference column order: [embedding | h]
                 wgrad(dz, h_in(i - 1), _W, dw_h[i], db[i])
-                wgrad(dz, e, MLP_EMBED_LD, dw_e[1], None)
+                wgrad(dz, e, ld, dw_e[1], None)
                 grads[2 * i] = torch.cat([dw_e[1][:, :emb_ch], dw_h[i]], 1)
+                dz_skip = dz
             else:
                 wgrad(dz, h_in(i - 1), _W, dw_h[i], db[i])
                 grads[2 * i] = dw_h[i]
             grads[2 * i + 1] = db[i]
             if t_ch and (i == 0 or i == _SKIP + 1):
                 # every row reads the same t_emb, so its gradient is (column sums of dz) . W[:, t columns]
-                g_t = g_t + db[i] @ params[2 * i][:, x_ch:emb_ch]
+                g_t = g_t + db[i] @ params[2 * i][:, emb_ch - t_ch:emb_ch]
             if i > 0:
                 dz_prev = new(N, _W)
                 _linear(_lib.MLP_DGRAD, N, _W, dz, _W, None, 0, pk.wt[i], None, m_in(i - 1), dz_prev, None)
                 dz = dz_prev
-        return (None, g_t, None, *grads)
+        g_x = None
+        if spec.input_grad and ctx.needs_input_grad[0]:
+            # d(loss)/d(embedding) = dz_0 . W_0[:, emb] + dz_skip . W_skip[:, emb] as ONE product over K = 512, then the VJP
+            # of the positional embedding of x (sin / cos derivatives)
+            de = new(N, ld)
+            _linear(_lib.MLP_LINEAR, N, ld, dz, _W, dz_skip, _W, pk.wt_emb, torch.zeros(ld, device=dev), None, de, None)
+            dx = new(N, 3)
+            check(L.fg_deform_embed_bwd(N, ptr(sel(x)), ptr(de), spec.multires, ld, ptr(dx), st))
+            g_x = dx if idx is None else torch.zeros(N_all, 3, device=dev).index_copy_(0, idx, dx)
+        return (g_x, None, g_t, None, *grads)
 
 
 class _Apply(torch.autograd.Function):
@@ -308,7 +335,8 @@ class DeformNetwork(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("DeformNetwork: `x` is not a CUDA tensor (there is no CPU path)")
         assert x.ndim == 2 and x.shape[1] == 3 and x.dtype == torch.float32
-        return _Trunk.apply(x.detach().contiguous(), self._time_row(t).contiguous(), self.multires, *self._params())
+        spec = _Spec(MLP_EMBED_LD, self.input_ch, self.multires, _HEADS, input_grad=False)
+        return _Trunk.apply(x.detach().contiguous(), None, self._time_row(t).contiguous(), spec, *self._params())
 
     def forward(self, x: Tensor, t: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         h = self.head(x, t)
@@ -322,3 +350,46 @@ class DeformNetwork(nn.Module):
     def deform_gaussians(self, means: Tensor, scales_log: Tensor, quats: Tensor, t: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         """freegaussian_model.py:836-845 in one call: returns the (means, scales, quats) passed to ``rasterization``."""
         return _Apply.apply(self.head(means, t), means, scales_log, quats)
+
+
+_CONTROL_HEADS = (("d_xyz", 3), ("d_rot", 4), ("d_scale", 3))
+_CONTROL_LD = 128
+
+
+class ControlNetwork(nn.Module):
+    """Drop-in for ``FreeGaussianControllableModel`` (freegaussian_model.py:1117-1145), the stage-2 network: the same trunk
+    on the embedded control points and the embedded per-point control value.  ``x`` keeps its gradient (stage 2 passes
+    ``means_crop[mask]`` without detaching, freegaussian_control_model.py:122, 143); ``value`` is built under ``no_grad``
+    there (:127-142) and gets none."""
+
+    def __init__(self, D: int = 8, W: int = 256, multires: int = 10):
+        super().__init__()
+        assert D == _D and W == _W, "the tensor-core kernels are built for the reference's D=8, W=256"
+        self.D, self.W, self.multires = D, W, multires
+        self.skips = [D // 2]
+        self.input_ch = 2 * (3 + 6 * multires)
+        assert self.input_ch <= _CONTROL_LD
+        self.linear = nn.ModuleList(
+            [nn.Linear(self.input_ch, W)]
+            + [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + self.input_ch, W) for i in range(D - 1)])
+        self.d_xyz = nn.Linear(W, 3)
+        self.d_scale = nn.Linear(W, 3)
+        self.d_rot = nn.Linear(W, 4)
+
+    def _params(self) -> List[Tensor]:
+        ps: List[Tensor] = []
+        for lin in self.linear:
+            ps += [lin.weight, lin.bias]
+        for name, _ in _CONTROL_HEADS:
+            lin = getattr(self, name)
+            ps += [lin.weight, lin.bias]
+        return ps
+
+    def forward(self, x: Tensor, value: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """(d_xyz [N,3], d_rot [N,4], d_scale [N,3]) -- the reference's return order (:1144-1145)."""
+        if not x.is_cuda:
+            raise RuntimeError("ControlNetwork: `x` is not a CUDA tensor (there is no CPU path)")
+        assert x.ndim == 2 and x.shape[1] == 3 and value.shape == x.shape and x.dtype == torch.float32
+        spec = _Spec(_CONTROL_LD, self.input_ch, self.multires, _CONTROL_HEADS, input_grad=True)
+        h = _Trunk.apply(x.contiguous(), value.detach().contiguous().to(torch.float32), None, spec, *self._params())
+        return h[:, 0:3], h[:, 3:7], h[:, 7:10]

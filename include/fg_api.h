@@ -364,13 +364,16 @@ int fg_refine_children(int64_t n_out, int64_t n_keep, int64_t n_children, const 
  *   w_hi / w_lo.
  *   FG_MLP_RELU    n_out = 256: out = max(. + bias, 0); mask_out[M, 8] uint32, bit j of word c = (column 32c+j > 0)
  *                  (nn.Linear + F.relu, :1097-1099)
- *   FG_MLP_LINEAR  n_out = FG_MLP_HEAD_LD: out = . + bias                              (the four heads, :1103-1112)
+ *   FG_MLP_LINEAR  n_out = FG_MLP_HEAD_LD or 128: out = . + bias   (the heads, :1103-1112 / :1144; 128: the gradient
+ *                  of the embedding, A0 / A1 = dL/d(output) of the two layers that read it, zero bias)
  *   FG_MLP_DGRAD   n_out = 256: out = mask_in bit ? . : 0   (data gradient of Linear + ReLU: A0 = dL/d(output of
  *                  layer l), W = W_l^T, mask_in = the mask_out of layer l-1)
  * fg_mlp_pack: copies column ranges of reference-layout weights ([rows, src_ld] row-major) into the padded operand
  *   buffers (optionally transposed), splitting hi / lo (dst_lo may be NULL).  One launch for the whole table.
- * fg_deform_embed: E[n,:] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^(multires-1)), cos(..) | t_emb[t_ch] | 0],
- *   [N, FG_MLP_EMBED_LD]  (Embedder.embed, utils.py:27-56; torch.cat at freegaussian_model.py:1096).
+ * fg_deform_embed: E[n,:] = [embed(x[n]) | embed(x2[n]) if x2 | t_emb[t_ch] | 0], [N, ld], ld a multiple of 32, with
+ *   embed(p) = [p, sin(p 2^0), cos(p 2^0), ..., sin(p 2^(multires-1)), cos(..)]  (Embedder.embed, utils.py:27-56; the
+ *   torch.cat at freegaussian_model.py:1096 (x, time) and :1137 (x, value; stage 2)).
+ * fg_deform_embed_bwd: dx[N,3] = VJP of embed(x) for de[N, ld] (columns of x2 / t_emb ignored).
  * fg_deform_apply_fwd: head[N, FG_MLP_HEAD_LD] = (branch_w 3 | branch_v 3 | gaussian_rotation 4 | gaussian_scaling 3 | 0)
  *   -> theta = |w|, screw axis (w, v) / theta + 1e-5, exp_se3 (utils.py:137-159), means' = R means + p,
  *   scales' = exp(scales_log) + d_scaling, quats' = quats / |quats| + d_rotation   (freegaussian_model.py:841-845).
@@ -394,13 +397,15 @@ typedef struct fg_mlp_pack_segment {
 int fg_mlp_linear(int mode, int64_t M, int n_out, const float* a0, int k0, const float* a1, int k1, const float* w_hi,
                   const float* w_lo, const float* bias, const uint32_t* mask_in, float* out, uint32_t* mask_out, void* stream);
 /* fg_mlp_wgrad: dw[256, ld_dw] columns col0 .. col0 + k_in - 1 += dz^T . a, and (db != NULL) db[256] += column sums of dz;
- * dz [N, 256], a [N, k_in] with k_in = 256, FG_MLP_EMBED_LD or FG_MLP_HEAD_LD, fp32 row-major.  The weight / bias gradient
+ * dz [N, 256], a [N, k_in] with k_in = 256, 128, FG_MLP_EMBED_LD or FG_MLP_HEAD_LD, fp32 row-major.  The weight / bias gradient
  * of nn.Linear (dL/dW = dz^T a, dL/db = sum_n dz); with dz = the last hidden layer and a = the head gradient it yields
  * the TRANSPOSED head weight gradient.  3xTF32 on chip, split-K over row ranges, results ADDED with
  * red.global (zero dw / db first; the order of the additions is not deterministic). */
 int fg_mlp_wgrad(int64_t N, const float* dz, const float* a, int k_in, float* dw, int ld_dw, int col0, float* db, void* stream);
 int fg_mlp_pack(int n_segments, const fg_mlp_pack_segment* segments_host, void* stream);
-int fg_deform_embed(int64_t N, const float* means, const float* t_emb, int t_ch, int multires, float* e, void* stream);
+int fg_deform_embed(int64_t N, const float* x, const float* x2, const float* t_emb, int t_ch, int multires, int ld, float* e,
+                    void* stream);
+int fg_deform_embed_bwd(int64_t N, const float* x, const float* de, int multires, int ld, float* dx, void* stream);
 int fg_deform_apply_fwd(int64_t N, const float* head, const float* means, const float* scales_log, const float* quats,
                         float* means_out, float* scales_out, float* quats_out, void* stream);
 int fg_deform_apply_bwd(int64_t N, const float* head, const float* means, const float* scales_log, const float* quats,

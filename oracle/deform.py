@@ -5,10 +5,11 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  A plain-torch CPU restatemen
 * ``Embedder`` / ``get_embedder``                       ``freegaussian/utils.py:8-56``
 * ``skew`` / ``exp_so3`` / ``exp_se3``                  ``freegaussian/utils.py:82-159``
 * ``FreeGaussianDeformableModel.forward``               ``freegaussian/freegaussian_model.py:1054-1114``
+* ``FreeGaussianControllableModel.forward`` (stage 2)   ``freegaussian/freegaussian_model.py:1117-1145``
 * the application of its outputs in ``get_outputs``     ``freegaussian/freegaussian_model.py:832-845``
 
 PARITY PINNED: the logic lives in the reference repository itself (no un-vendored dependency), and
-``tests/golden/deform_*.npz`` hold outputs and gradients produced by executing the reference's own
+``tests/golden/deform_*.npz`` / ``control_*.npz`` hold outputs and gradients produced by executing the reference's own
 class and function bodies (``tests/golden/make_golden_deform.py`` extracts them from
 ``/root/reference`` with ``ast``; only ``nerfstudio``'s ``torch_compile`` decorator import is stubbed).
 ``tests/test_deform.py`` checks this restatement against those fixtures.
@@ -102,6 +103,39 @@ def deform_gaussians(params: Dict[str, Tensor], means: Tensor, scales_log: Tenso
     new_scales = torch.exp(scales_log) + d_scaling
     new_quats = quats / quats.norm(dim=-1, keepdim=True) + d_rotation
     return new_means, new_scales, new_quats
+
+
+def control_forward(params: Dict[str, Tensor], x: Tensor, value: Tensor, D: int = 8, multires: int = 10
+                    ) -> Tuple[Tensor, Tensor, Tensor]:
+    """FreeGaussianControllableModel.forward, model.py:1135-1145: (d_xyz [N,3], d_rot [N,4], d_scale [N,3])."""
+    v_emb = embed(value, multires)
+    x_emb = embed(x, multires)
+    h = torch.cat([x_emb, v_emb], -1)
+    for i in range(D):
+        h = torch.relu(h @ params[f"linear.{i}.weight"].T + params[f"linear.{i}.bias"])
+        if i == D // 2:
+            h = torch.cat([x_emb, v_emb, h], -1)
+    lin = lambda n: h @ params[n + ".weight"].T + params[n + ".bias"]  # noqa: E731
+    return lin("d_xyz"), lin("d_rot"), lin("d_scale")
+
+
+def init_control_params(seed: int = 0, D: int = 8, W: int = 256, multires: int = 10, scale: float = 1.0) -> Dict[str, Tensor]:
+    """Seeded parameters of the stage-2 control network (same recipe as ``init_params``)."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    in_ch = 2 * (3 + 3 * 2 * multires)
+    shapes = {}
+    for i in range(D):
+        shapes[f"linear.{i}"] = (W, in_ch if i == 0 else (W + in_ch if i == D // 2 + 1 else W))
+    for name, o in (("d_xyz", 3), ("d_scale", 3), ("d_rot", 4)):
+        shapes[name] = (o, W)
+    out = {}
+    for name, (o, i) in shapes.items():
+        b = scale / np.sqrt(i)
+        out[name + ".weight"] = torch.from_numpy(rng.uniform(-b, b, size=(o, i)).astype(np.float32))
+        out[name + ".bias"] = torch.from_numpy(rng.uniform(-b, b, size=(o,)).astype(np.float32))
+    return out
 
 
 def init_params(is_blender: bool = True, seed: int = 0, D: int = 8, W: int = 256, multires: int = 10,

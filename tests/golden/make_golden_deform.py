@@ -79,12 +79,7 @@ def deform_fixture(utils, Deform, name, n, seed, is_blender, t_val, scale):
     loss = (new_means * wts[0]).sum() + (new_scales * wts[1]).sum() + (new_quats * wts[2]).sum()
     loss.backward()
     # weight gradients: a strided sample, the sum and the norm of each (the full set is 0.6 M floats per fixture)
-    grads = {}
-    for k, v in net.named_parameters():
-        g = v.grad.double().flatten()
-        grads["grad." + k] = (g if g.numel() <= 4096 else g[::GRAD_STRIDE]).float().numpy()
-        grads["gsum." + k] = np.float64(g.sum())
-        grads["gnorm." + k] = np.float64(g.norm())
+    grads = sampled_grads(net)
     np.savez_compressed(
         os.path.join(OUT, f"deform_{name}.npz"), n=n, seed=seed, is_blender=is_blender, t=t_val, scale=scale,
         means=means.detach().numpy(), scales_log=scales_log.detach().numpy(), quats=quats.detach().numpy(),
@@ -94,9 +89,36 @@ def deform_fixture(utils, Deform, name, n, seed, is_blender, t_val, scale):
         grad_means=means.grad.numpy(), grad_scales_log=scales_log.grad.numpy(), grad_quats=quats.grad.numpy(), **grads)
 
 
+def sampled_grads(net):
+    grads = {}
+    for k, v in net.named_parameters():
+        g = v.grad.double().flatten()
+        grads["grad." + k] = (g if g.numel() <= 4096 else g[::GRAD_STRIDE]).float().numpy()
+        grads["gsum." + k] = np.float64(g.sum())
+        grads["gnorm." + k] = np.float64(g.norm())
+    return grads
+
+
+def control_fixture(Control, name, n, seed):
+    """FreeGaussianControllableModel (stage 2): x keeps its gradient (freegaussian_control_model.py:122, 143)."""
+    net = Control()
+    net.load_state_dict(OD.init_control_params(seed=seed), strict=True)
+    g = torch.Generator().manual_seed(seed)
+    x = ((torch.rand(n, 3, generator=g) - 0.5) * 6.0).requires_grad_(True)
+    value = torch.randn(n, 3, generator=g) * 0.1
+    wts = [torch.randn(n, k, generator=g) for k in (3, 4, 3)]
+    d_xyz, d_rot, d_scale = net(x, value)
+    ((d_xyz * wts[0]).sum() + (d_rot * wts[1]).sum() + (d_scale * wts[2]).sum()).backward()
+    np.savez_compressed(os.path.join(OUT, f"control_{name}.npz"), n=n, seed=seed, x=x.detach().numpy(), value=value.numpy(),
+                        w_xyz=wts[0].numpy(), w_rot=wts[1].numpy(), w_scale=wts[2].numpy(),
+                        d_xyz=d_xyz.detach().numpy(), d_rot=d_rot.detach().numpy(), d_scale=d_scale.detach().numpy(),
+                        grad_x=x.grad.numpy(), **sampled_grads(net))
+
+
 if __name__ == "__main__":
     utils, Deform, Control = load_reference()
     deform_fixture(utils, Deform, "blender_n300", 300, 3, True, 0.37, 1.0)
     deform_fixture(utils, Deform, "blender_n129_hot", 129, 4, True, 0.81, 2.0)   # larger weights: bigger motions
     deform_fixture(utils, Deform, "real_n200", 200, 5, False, 0.55, 1.0)
-    print("wrote", sorted(f for f in os.listdir(OUT) if f.startswith("deform_")))
+    control_fixture(Control, "n250", 250, 6)
+    print("wrote", sorted(f for f in os.listdir(OUT) if f.startswith(("deform_", "control_"))))

@@ -68,6 +68,19 @@ def test_oracle_float64_agrees_with_float32():
         assert rel_err(a, b) < 2e-6
 
 
+def test_control_oracle_matches_reference_outputs():
+    z = np.load(GOLDEN / "control_n250.npz")
+    P = {k: v.requires_grad_(True) for k, v in OD.init_control_params(seed=int(z["seed"])).items()}
+    x = torch.tensor(z["x"], requires_grad=True)
+    d_xyz, d_rot, d_scale = OD.control_forward(P, x, torch.tensor(z["value"]))
+    for got, key in ((d_xyz, "d_xyz"), (d_rot, "d_rot"), (d_scale, "d_scale")):
+        assert rel_err(got, torch.tensor(z[key])) < 1e-6, key
+    ((d_xyz * torch.tensor(z["w_xyz"])).sum() + (d_rot * torch.tensor(z["w_rot"])).sum() + (d_scale * torch.tensor(z["w_scale"])).sum()).backward()
+    assert grad_rel_err(x.grad, torch.tensor(z["grad_x"])) < 1e-5
+    for k, v in P.items():
+        assert grad_rel_err(_sample(v.grad.double().flatten()), torch.tensor(z["grad." + k]).double()) < 1e-4, k
+
+
 def test_module_mirrors_reference_state_dict():
     """Parameter names and shapes are the reference's (a reference checkpoint loads unchanged)."""
     from freegaussian_b200.deform import DeformNetwork
@@ -79,6 +92,14 @@ def test_module_mirrors_reference_state_dict():
         net.load_state_dict(ref, strict=True)
     with pytest.raises(RuntimeError):
         DeformNetwork(is_blender=True).head(torch.zeros(4, 3), torch.zeros(4, 1))  # no CPU path
+    from freegaussian_b200.deform import ControlNetwork
+
+    net = ControlNetwork()
+    ref = OD.init_control_params()
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.items()}
+    net.load_state_dict(ref, strict=True)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(4, 3), torch.zeros(4, 3))
 
 
 # ------------------------------------------------------------------------------------------------------- GPU
@@ -157,7 +178,7 @@ def test_weight_gradient_kernel(built_lib, N):
 
     g = torch.Generator().manual_seed(N)
     st = torch.cuda.current_stream().cuda_stream
-    for k_in in (256, 96, 32):
+    for k_in in (256, 128, 96, 32):
         dz = torch.randn(N, 256, generator=g)
         a = torch.randn(N, k_in, generator=g)
         dzd, ad = dz.cuda(), a.cuda()
@@ -174,24 +195,50 @@ def test_weight_gradient_kernel(built_lib, N):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("t_ch,multires", [(30, 10), (21, 10), (0, 4)])
-def test_embedding_matches_reference_layout(built_lib, t_ch, multires):
+@pytest.mark.parametrize("t_ch,multires,two,ld", [(30, 10, False, 96), (21, 10, False, 96), (0, 4, False, 96), (0, 10, True, 128)])
+def test_embedding_matches_reference_layout(built_lib, t_ch, multires, two, ld):
     from freegaussian_b200 import _lib
     from freegaussian_b200._lib import check, ptr
 
     g = torch.Generator().manual_seed(1)
     n = 1001
     x = (torch.rand(n, 3, generator=g) - 0.5) * 6.0
+    x2 = torch.randn(n, 3, generator=g) * 0.1
     t_emb = torch.randn(t_ch, generator=g)
-    e = torch.empty(n, 96, device="cuda")
-    xd, td = x.cuda(), t_emb.cuda()
-    check(_lib.lib().fg_deform_embed(n, ptr(xd), ptr(td) if t_ch else None, t_ch, multires, ptr(e),
-                                     torch.cuda.current_stream().cuda_stream))
-    want = torch.cat([OD.embed(x, multires), t_emb.expand(n, -1)], -1)
+    e = torch.empty(n, ld, device="cuda")
+    xd, x2d, td = x.cuda(), x2.cuda(), t_emb.cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    check(_lib.lib().fg_deform_embed(n, ptr(xd), ptr(x2d) if two else None, ptr(td) if t_ch else None, t_ch, multires, ld, ptr(e), st))
+    parts = [OD.embed(x, multires)] + ([OD.embed(x2, multires)] if two else []) + [t_emb.expand(n, -1)]
+    want = torch.cat(parts, -1)
     got = e.cpu()
     worst = float((got[:, :want.shape[1]] - want).abs().max())
     assert worst < 1e-6, worst  # sin / cos of arguments up to 3 * 2^9, same fp32 argument on both sides
     assert float(got[:, want.shape[1]:].abs().max()) == 0.0
+    # VJP with respect to x against autograd
+    de = torch.randn(n, ld, generator=g)
+    xr = x.clone().double().requires_grad_(True)
+    (OD.embed(xr, multires) * de[:, :3 + 6 * multires].double()).sum().backward()
+    dx = torch.empty(n, 3, device="cuda")
+    ded = de.cuda()
+    check(_lib.lib().fg_deform_embed_bwd(n, ptr(xd), ptr(ded), multires, ld, ptr(dx), st))
+    assert grad_rel_err(dx, xr.grad) < 1e-5
+
+
+@pytest.mark.gpu
+def test_embedding_gradient_gemm(built_lib):
+    """FG_MLP_LINEAR with 128 outputs over two activation sources (K = 512): the gradient of the embedding."""
+    from freegaussian_b200 import _lib
+    from freegaussian_b200.deform import _linear
+
+    g = torch.Generator().manual_seed(4)
+    M = 3001
+    a0, a1 = torch.randn(M, 256, generator=g), torch.randn(M, 256, generator=g)
+    w = torch.randn(128, 512, generator=g) / 22
+    out = torch.empty(M, 128, device="cuda")
+    a0d, a1d, wd = a0.cuda(), a1.cuda(), w.cuda()
+    _linear(_lib.MLP_LINEAR, M, 128, a0d, 256, a1d, 256, _hilo(wd), torch.zeros(128, device="cuda"), None, out, None)
+    assert rel_err(out, torch.cat([a0, a1], 1).double() @ w.double().T) < 6e-6  # fp32 accumulation over K = 512
 
 
 @pytest.mark.gpu
@@ -260,6 +307,31 @@ def test_network_matches_reference_fixture(built_lib, name):
     d_xyz, rot, scl = net(m.detach(), t)
     for got, key in ((d_xyz, "d_xyz"), (rot, "d_rotation"), (scl, "d_scaling")):
         assert rel_err(got, torch.tensor(z[key])) < 1e-5, key
+
+
+@pytest.mark.gpu
+def test_control_network_matches_reference_fixture(built_lib):
+    """Stage-2 network against the outputs and gradients of the reference's own class, including d(loss)/dx."""
+    from freegaussian_b200.deform import ControlNetwork
+
+    z = np.load(GOLDEN / "control_n250.npz")
+    net = ControlNetwork()
+    net.load_state_dict(OD.init_control_params(seed=int(z["seed"])), strict=True)
+    net = net.cuda()
+    x = torch.tensor(z["x"]).cuda().requires_grad_(True)
+    outs = net(x, torch.tensor(z["value"]).cuda())
+    for got, key in zip(outs, ("d_xyz", "d_rot", "d_scale")):
+        assert rel_err(got, torch.tensor(z[key])) < 1e-5, key
+    sum((o * torch.tensor(z[k]).cuda()).sum() for o, k in zip(outs, ("w_xyz", "w_rot", "w_scale"))).backward()
+    assert grad_rel_err(x.grad, torch.tensor(z["grad_x"])) < 5e-5
+    for k, v in net.named_parameters():
+        assert grad_rel_err(_sample(v.grad.double().flatten().cpu()), torch.tensor(z["grad." + k]).double()) < 5e-5, k
+    # rows without a gradient are skipped and get an exactly-zero d(loss)/dx
+    x2 = torch.tensor(z["x"]).cuda().requires_grad_(True)
+    keep = (torch.arange(x2.shape[0], device="cuda") % 3 == 0).float()[:, None]
+    sum((o * torch.tensor(z[k]).cuda() * keep).sum() for o, k in zip(net(x2, torch.tensor(z["value"]).cuda()), ("w_xyz", "w_rot", "w_scale"))).backward()
+    assert float(x2.grad[keep[:, 0] == 0].abs().max()) == 0.0
+    assert grad_rel_err(x2.grad[keep[:, 0] == 1], torch.tensor(z["grad_x"]).cuda()[keep[:, 0] == 1]) < 5e-5
 
 
 @pytest.mark.gpu
