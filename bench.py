@@ -449,6 +449,40 @@ def train_iter_section(d, dev, W, H, vm, K, steps=10, warmup=4):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / steps, statistics.median(m[0].elapsed_time(m[1]) for m in marks)
 
+    # stage-2 step (freegaussian_control_model.py:122-179): the control network on the controllable subset (here the
+    # "articulated part" of the scene: the Gaussians that move between the two frames), scattered back, same render + loss
+    from freegaussian_b200.deform import ControlNetwork
+    control = ControlNetwork().to(dev)
+    adam_ctl = torch.optim.Adam(control.parameters(), lr=1.6e-4 * 5, eps=1e-15, fused=True)
+    part = ((d.means_next - d.means).abs().sum(-1) > 0).nonzero().squeeze(1)
+    value = torch.randn(part.numel(), 3, generator=gen).to(dev) * 0.05
+
+    def iteration2():
+        for p in (means, scales_log, quats, op_logit, sh):
+            p.grad = None
+        adam_ctl.zero_grad(set_to_none=True)
+        d_xyz, d_rot, d_scale = control(means[part], value)                 # :122, :143
+        m2 = means + torch.zeros_like(means).index_copy(0, part, d_xyz)      # :147-149
+        s2 = torch.exp(scales_log) + torch.zeros_like(scales_log).index_copy(0, part, d_scale)   # :151-153
+        q2 = quats / quats.norm(dim=-1, keepdim=True) + torch.zeros_like(quats).index_copy(0, part, d_rot)  # :155-157
+        render, alpha, meta = rasterization(m2, q2, s2, torch.sigmoid(op_logit), sh, vm, K, W, H, packed=False,
+                                            near_plane=0.01, far_plane=1e10, render_mode="RGB+ED", sh_degree=3,
+                                            sparse_grad=False, absgrad=True, rasterize_mode="classic")
+        blend_l1_ssim_loss(render, alpha, bg, gt, 0.2).backward()
+        adam.step()
+        adam_ctl.step()
+
+    for _ in range(warmup):
+        iteration2()
+    torch.cuda.synchronize()
+    a2, b2 = ev(), ev()
+    a2.record()
+    for _ in range(steps):
+        iteration2()
+    b2.record()
+    torch.cuda.synchronize()
+    ms_stage2 = a2.elapsed_time(b2) / steps
+
     l0 = None
     from freegaussian_b200 import _lib
     ms_plain, _ = timed(False)
@@ -497,8 +531,10 @@ def train_iter_section(d, dev, W, H, vm, K, steps=10, warmup=4):
     return {
         "ms": ms_full, "ms_without_deform": ms_plain, "deform_fwd_ms": ms_deform_fwd,
         "deform_bwd_ms": ms_full - ms_plain - ms_deform_fwd,
+        "stage2_ms": ms_stage2, "stage2_controlled_gaussians": int(part.numel()),
         "gaussians": n, "visible": n_vis, "launches_per_iter": launches,
-        "config": "stage-1 step: DeformNetwork(is_blender=True) -> RGB+ED render -> blend+L1+SSIM -> backward -> Adam",
+        "config": "stage-1 step: DeformNetwork(is_blender=True) -> RGB+ED render -> blend+L1+SSIM -> backward -> Adam; "
+                  "stage2_ms: ControlNetwork on the controlled subset -> the same render / loss / backward / Adam",
         "deform_roofline": {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
                             "note": "forward; tf32 MMA flops issued (3xTF32) / CUDA-event time; peak = measured bf16 GEMM peak / 2"},
         "torch_fp32_network": {"fwd_ms": torch_fwd, "bwd_ms": torch_bwd,

@@ -369,6 +369,38 @@ def test_sparse_backward_equals_dense(built_lib):
 
 
 @pytest.mark.gpu
+def test_network_then_render_matches_chained_oracles(built_lib):
+    """The stage-1 forward/backward as the model runs it (freegaussian_model.py:836-868): network -> rasterization -> loss,
+    kernels against the two oracles chained with torch.autograd.  Image tolerance 1e-4, gradient tolerance 1e-3 (north_star)."""
+    from freegaussian_b200.rendering import rasterization
+    from oracle import render as OR
+    from util import small_scene
+
+    sc = small_scene(700, 80, 48, views=1, seed=3)
+    W, H = 80, 48
+    params = OD.init_params(is_blender=True, seed=31, scale=0.5)  # small motions: the scene stays in view
+    net = _net_from(params, True)
+    g = torch.Generator().manual_seed(8)
+    w_img = torch.rand(1, H, W, 4, generator=g)
+    t = torch.tensor([[0.45]])
+    leaves_cpu = [sc.means.clone().requires_grad_(True), torch.log(sc.scales).requires_grad_(True), sc.quats.clone().requires_grad_(True)]
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    m2, s2, q2 = OD.deform_gaussians(P, *leaves_cpu, t.expand(700, -1), True)
+    ro, ao, _ = OR.rasterization(m2, q2, s2, sc.opacities, sc.sh, sc.viewmats, sc.Ks, W, H, render_mode="RGB+ED", sh_degree=3)
+    (ro * w_img).sum().backward()
+    d = sc.to("cuda")
+    leaves = [d.means.clone().requires_grad_(True), torch.log(d.scales).requires_grad_(True), d.quats.clone().requires_grad_(True)]
+    gm2, gs2, gq2 = net.deform_gaussians(*leaves, t.cuda().expand(700, -1))
+    r, a, _ = rasterization(gm2, gq2, gs2, d.opacities, d.sh, d.viewmats, d.Ks, W, H, render_mode="RGB+ED", sh_degree=3)
+    (r * w_img.cuda()).sum().backward()
+    assert rel_err(r, ro) < 1e-4 and rel_err(a, ao) < 1e-4
+    for got, want in zip(leaves, leaves_cpu):
+        assert grad_rel_err(got.grad, want.grad) < 1e-3
+    for k, v in net.named_parameters():
+        assert grad_rel_err(v.grad, P[k].grad) < 1e-3, k
+
+
+@pytest.mark.gpu
 def test_full_size_rows_are_independent(built_lib):
     """cfg3 size (1 M Gaussians): every row depends on its own Gaussian only, so a random sample of rows must equal
     the oracle evaluated on just those rows; and the weight gradient is linear in the row set (two halves sum to the whole)."""
