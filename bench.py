@@ -421,11 +421,18 @@ def train_iter_section(d, dev, W, H, vm, K, steps=10, warmup=4):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     last = {}
 
+    cpu_phase = {}  # host time spent enqueueing each phase (FG_BENCH_CPU_PHASES=1 prints it): is the step launch-bound?
+
+    def tick(name, t0):
+        cpu_phase[name] = cpu_phase.get(name, 0.0) + (time.perf_counter() - t0)
+        return time.perf_counter()
+
     def iteration(with_deform: bool):
         for p in (means, scales_log, quats, op_logit, sh):
             p.grad = None
         adam_net.zero_grad(set_to_none=True)
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        tc = time.perf_counter()
         e0.record()
         if with_deform:
             m2, s2, q2 = net.deform_gaussians(means, scales_log, quats, t)
@@ -434,15 +441,19 @@ def train_iter_section(d, dev, W, H, vm, K, steps=10, warmup=4):
         else:  # warm-up phase of the reference (step < warm_up, :832-833): no deformation
             m2, s2, q2 = means, torch.exp(scales_log), quats
         e1.record()
+        tc = tick("deform_fwd", tc)
         render, alpha, meta = rasterization(m2, q2, s2, torch.sigmoid(op_logit), sh, vm, K, W, H, packed=False,
                                             near_plane=0.01, far_plane=1e10, render_mode="RGB+ED", sh_degree=3,
                                             sparse_grad=False, absgrad=True, rasterize_mode="classic")
         loss = blend_l1_ssim_loss(render, alpha, bg, gt, 0.2)
+        tc = tick("render_fwd+loss", tc)
         loss.backward()
         e3.record()
+        tc = tick("backward", tc)
         adam.step()
         if with_deform:
             adam_net.step()
+        tick("adam", tc)
         last["radii"] = meta["radii"]
         return e0, e1, e2, e3
 
@@ -450,6 +461,7 @@ def train_iter_section(d, dev, W, H, vm, K, steps=10, warmup=4):
         for _ in range(warmup):
             iteration(with_deform)
         torch.cuda.synchronize()
+        cpu_phase.clear()
         a, b = ev(), ev()
         a.record()
         marks = [iteration(with_deform) for _ in range(steps)]
@@ -464,6 +476,8 @@ def train_iter_section(d, dev, W, H, vm, K, steps=10, warmup=4):
     ms_plain, _, _ = timed(False)
     l0 = _lib.launch_count()
     ms_full, ms_deform_fwd, ms_deform_bwd = timed(True)
+    if os.environ.get("FG_BENCH_CPU_PHASES"):
+        print("host ms per iteration spent enqueueing:", {k: round(v * 1e3 / steps, 3) for k, v in cpu_phase.items()}, file=sys.stderr)
     launches = (_lib.launch_count() - l0) / (steps + warmup)
     n_vis = int((last["radii"] > 0).sum())
 
