@@ -143,6 +143,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION prints a banner on stdout; stdout is the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from freegaussian_b200 import _build
     if rank == 0:
