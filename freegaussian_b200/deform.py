@@ -169,17 +169,16 @@ class _Trunk(torch.autograd.Function):
         L = _lib.lib()
         # Rows whose incoming gradient is exactly zero (Gaussians that were culled or never reached a pixel in this
         # step's views) contribute exactly nothing to any gradient: run the backward on the other rows only.
-        # One host read of the count; the saved activations are gathered layer by layer as they are needed.
+        # One host read (the number of such rows); the saved activations are gathered layer by layer as they are needed.
         idx = None
         sel = lambda t: t  # noqa: E731
         if SPARSE_BACKWARD and N > 0:
-            active = (g_head != 0).any(1)
-            n_act = int(active.sum())
-            if n_act < SPARSE_BACKWARD_MAX_FRACTION * N:
-                idx = active.nonzero().squeeze(1)
+            act = (g_head != 0).any(1).nonzero().squeeze(1)  # the one host read (nonzero sizes its result)
+            if act.numel() < SPARSE_BACKWARD_MAX_FRACTION * N:
+                idx = act
                 sel = lambda t: t.index_select(0, idx)  # noqa: E731
                 g_head = sel(g_head)
-                N = n_act
+                N = idx.numel()
         e = sel(e)
         h_in = lambda i: sel(hs[i])  # noqa: E731  activations of layer i (input of layer i + 1)
         m_in = lambda i: sel(masks[i])  # noqa: E731
