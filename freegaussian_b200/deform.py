@@ -64,58 +64,73 @@ class _Spec:
         assert not input_grad or emb_ld == 128, "the embedding-gradient GEMM is built for 128 columns"
 
 
+def _pack_plan(spec: _Spec):
+    """The weight-packing table as plain data: one tuple per segment,
+    ``(param index, source column 0, columns, destination, destination column 0, transpose, destination row 0)`` with
+    destination one of ``("w", layer) | ("wt", layer) | ("w_head",) | ("wt_head",) | ("wt_emb",)``.
+    Pure host logic (tests/test_deform.py::test_pack_plan_rebuilds_the_layers applies it with numpy)."""
+    emb_ch = spec.emb_ch
+    plan = []
+    for i in range(_D):
+        p = 2 * i
+        if i == 0:
+            plan.append((p, 0, emb_ch, ("w", 0), 0, False, 0))
+            if spec.input_grad:
+                plan.append((p, 0, emb_ch, ("wt_emb",), 0, True, 0))
+        elif i == _SKIP + 1:  # reference input order [embedding | h]; operand order [h | embedding]
+            plan.append((p, emb_ch, _W, ("w", i), 0, False, 0))
+            plan.append((p, 0, emb_ch, ("w", i), _W, False, 0))
+            plan.append((p, emb_ch, _W, ("wt", i), 0, True, 0))
+            if spec.input_grad:
+                plan.append((p, 0, emb_ch, ("wt_emb",), _W, True, 0))
+        else:
+            plan.append((p, 0, _W, ("w", i), 0, False, 0))
+            plan.append((p, 0, _W, ("wt", i), 0, True, 0))
+    row = 0
+    for j, (_, o) in enumerate(spec.heads):
+        p = 2 * _D + 2 * j
+        plan.append((p, 0, _W, ("w_head",), 0, False, row))
+        plan.append((p, 0, _W, ("wt_head",), row, True, 0))
+        row += o
+    return plan
+
+
+def _packed_shapes(spec: _Spec):
+    """Shapes of the operand buffers the plan writes into."""
+    ld = spec.emb_ld
+    shapes = {("w", i): (_W, ld if i == 0 else (_W + ld if i == _SKIP + 1 else _W)) for i in range(_D)}
+    shapes.update({("wt", i): (_W, _W) for i in range(1, _D)})
+    shapes[("w_head",)] = (MLP_HEAD_LD, _W)
+    shapes[("wt_head",)] = (_W, MLP_HEAD_LD)
+    if spec.input_grad:
+        shapes[("wt_emb",)] = (ld, 2 * _W)  # wt_emb[e, :] = [W_0[:, e] | W_skip[:, e]]
+    return shapes
+
+
 class _Packed:
     """Operand buffers of one parameter set: padded, reordered, hi/lo split, plus the transposes for the data gradient."""
 
     def __init__(self, params: List[Tensor], spec: _Spec):
         dev = params[0].device
-        ld, emb_ch = spec.emb_ld, spec.emb_ch
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731  pads stay zero
-        pair = lambda *s: (z(*s), z(*s))  # noqa: E731
-        kp = [ld if i == 0 else (_W + ld if i == _SKIP + 1 else _W) for i in range(_D)]
-        self.w = [pair(_W, k) for k in kp]
-        self.w_head = pair(MLP_HEAD_LD, _W)
-        self.wt = [None] + [pair(_W, _W) for _ in range(1, _D)]  # wt[l][i, o] = W_l[o, i] over the hidden inputs
-        self.wt_head = pair(_W, MLP_HEAD_LD)
-        # wt_emb[e, :] = [W_0[:, e] | W_skip[:, e]]: d(loss)/d(embedding) = [dz_0 | dz_skip] . wt_emb^T
-        self.wt_emb = pair(ld, 2 * _W) if spec.input_grad else None
-        segs = []
-
-        def seg(src, col0, cols, dst, dst_col0, transpose=False, row0=0):
-            hi, lo = dst
-            s = MlpPackSegment()
+        bufs = {k: (z(*shape), z(*shape)) for k, shape in _packed_shapes(spec).items()}
+        plan = _pack_plan(spec)
+        assert len(plan) <= _lib.MLP_PACK_MAX_SEGMENTS
+        arr = (MlpPackSegment * len(plan))()
+        for s, (p, col0, cols, dst, dst_col0, transpose, row0) in zip(arr, plan):
+            src = params[p]
+            assert src.is_contiguous()
+            hi, lo = bufs[dst]
             s.src = src.data_ptr()
             s.dst_hi = hi.data_ptr() + row0 * hi.shape[1] * 4
             s.dst_lo = lo.data_ptr() + row0 * lo.shape[1] * 4
             s.src_ld, s.src_col0, s.rows, s.cols = src.shape[1], col0, src.shape[0], cols
             s.dst_ld, s.dst_col0, s.transpose = hi.shape[1], dst_col0, int(transpose)
-            segs.append(s)
-
-        weights = params[0:2 * _D:2]
-        for i, wt in enumerate(weights):
-            assert wt.is_contiguous()
-            if i == 0:
-                seg(wt, 0, emb_ch, self.w[0], 0)
-                if spec.input_grad:
-                    seg(wt, 0, emb_ch, self.wt_emb, 0, transpose=True)
-            elif i == _SKIP + 1:  # reference input order [embedding | h]; operand order [h | embedding]
-                seg(wt, emb_ch, _W, self.w[i], 0)
-                seg(wt, 0, emb_ch, self.w[i], _W)
-                seg(wt, emb_ch, _W, self.wt[i], 0, transpose=True)
-                if spec.input_grad:
-                    seg(wt, 0, emb_ch, self.wt_emb, _W, transpose=True)
-            else:
-                seg(wt, 0, _W, self.w[i], 0)
-                seg(wt, 0, _W, self.wt[i], 0, transpose=True)
-        row = 0
-        for j, (_, o) in enumerate(spec.heads):
-            hw = params[2 * _D + 2 * j]
-            seg(hw, 0, _W, self.w_head, 0, row0=row)
-            seg(hw, 0, _W, self.wt_head, row, transpose=True)
-            row += o
-        assert len(segs) <= _lib.MLP_PACK_MAX_SEGMENTS
-        arr = (MlpPackSegment * len(segs))(*segs)
-        check(_lib.lib().fg_mlp_pack(len(segs), arr, _stream()))
+        check(_lib.lib().fg_mlp_pack(len(plan), arr, _stream()))
+        self.w = [bufs[("w", i)] for i in range(_D)]
+        self.wt = [None] + [bufs[("wt", i)] for i in range(1, _D)]  # wt[l][i, o] = W_l[o, i] over the hidden inputs
+        self.w_head, self.wt_head = bufs[("w_head",)], bufs[("wt_head",)]
+        self.wt_emb = bufs.get(("wt_emb",))
         self.bias = [b.contiguous() for b in params[1:2 * _D:2]]
         hb = torch.cat([params[2 * _D + 2 * j + 1] for j in range(len(spec.heads))])
         self.bias_head = torch.cat([hb, hb.new_zeros(MLP_HEAD_LD - hb.numel())])

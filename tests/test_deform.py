@@ -102,6 +102,64 @@ def test_module_mirrors_reference_state_dict():
         net(torch.zeros(4, 3), torch.zeros(4, 3))
 
 
+@pytest.mark.parametrize("kind", ["deform", "control"])
+def test_pack_plan_rebuilds_the_layers(kind):
+    """Host logic of the weight packing (column ranges, [h | embedding] reorder, transposes), applied with numpy: the packed
+    operands must reproduce every layer of the reference network and the transposes its data gradients."""
+    from freegaussian_b200 import deform as D
+
+    if kind == "deform":
+        params = OD.init_params(is_blender=True, seed=2)
+        spec = D._Spec(96, 93, 10, D._HEADS, input_grad=False)
+        heads = D._HEADS
+    else:
+        params = OD.init_control_params(seed=2)
+        spec = D._Spec(128, 126, 10, D._CONTROL_HEADS, input_grad=True)
+        heads = D._CONTROL_HEADS
+    flat = []
+    for i in range(8):
+        flat += [params[f"linear.{i}.weight"].numpy(), params[f"linear.{i}.bias"].numpy()]
+    for name, _ in heads:
+        flat += [params[name + ".weight"].numpy(), params[name + ".bias"].numpy()]
+    bufs = {k: np.zeros(shape, np.float32) for k, shape in D._packed_shapes(spec).items()}
+    plan = D._pack_plan(spec)
+    assert len(plan) <= 32
+    for p, col0, cols, dst, dst_col0, transpose, row0 in plan:
+        block = flat[p][:, col0:col0 + cols]
+        if transpose:
+            block = block.T
+        bufs[dst][row0:row0 + block.shape[0], dst_col0:dst_col0 + block.shape[1]] = block
+    rng = np.random.default_rng(0)
+    emb = np.zeros((5, spec.emb_ld), np.float32)
+    emb[:, :spec.emb_ch] = rng.standard_normal((5, spec.emb_ch))
+    h = rng.standard_normal((5, 256)).astype(np.float32)
+    for i in range(8):
+        W = flat[2 * i]
+        if i == 0:
+            want, got = emb[:, :spec.emb_ch] @ W.T, emb @ bufs[("w", 0)].T
+        elif i == 5:
+            want = np.concatenate([emb[:, :spec.emb_ch], h], 1) @ W.T          # reference order [embedding | h]
+            got = np.concatenate([h, emb], 1) @ bufs[("w", 5)].T               # operand order [h | embedding]
+        else:
+            want, got = h @ W.T, h @ bufs[("w", i)].T
+        assert np.allclose(got, want, atol=1e-5), i
+        if i > 0:  # data gradient with respect to the hidden input: dz . W[:, hidden columns]
+            dz = rng.standard_normal((5, 256)).astype(np.float32)
+            Wh = W[:, spec.emb_ch:] if i == 5 else W
+            assert np.allclose(dz @ bufs[("wt", i)].T, dz @ Wh, atol=1e-5), i
+    Whead = np.concatenate([flat[16 + 2 * j] for j in range(len(heads))], 0)
+    n_out = Whead.shape[0]
+    assert np.allclose((h @ bufs[("w_head",)].T)[:, :n_out], h @ Whead.T, atol=1e-5)
+    assert np.all(bufs[("w_head",)][n_out:] == 0)
+    g = rng.standard_normal((5, 32)).astype(np.float32)
+    assert np.allclose(g @ bufs[("wt_head",)].T, g[:, :n_out] @ Whead, atol=1e-5)
+    if spec.input_grad:  # d/d(embedding) = [dz_0 | dz_5] . wt_emb^T
+        dz0, dz5 = rng.standard_normal((5, 256)).astype(np.float32), rng.standard_normal((5, 256)).astype(np.float32)
+        want = dz0 @ flat[0] + dz5 @ flat[10][:, :spec.emb_ch]
+        got = np.concatenate([dz0, dz5], 1) @ bufs[("wt_emb",)].T
+        assert np.allclose(got[:, :spec.emb_ch], want, atol=1e-4) and np.all(got[:, spec.emb_ch:] == 0)
+
+
 # ------------------------------------------------------------------------------------------------------- GPU
 def _hilo(x):
     """Host model of the operand split (round to nearest tf32, ties away): hi, lo."""
