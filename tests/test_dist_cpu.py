@@ -106,3 +106,31 @@ def test_deferred_stats_sync_equals_per_step_reduction(tmp_path):
         ref.reduce()
     assert torch.allclose(got["g"], ref.xys_grad_norm, atol=1e-5)
     assert torch.equal(got["c"], ref.vis_counts) and torch.equal(got["m"], ref.max_2Dsize)
+
+
+def _network_worker(rank, world, port, out):
+    """Each rank holds the same deformation network and a rank-dependent gradient for every parameter."""
+    from freegaussian_b200.deform import DeformNetwork
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = DeformNetwork(is_blender=True)
+    for k, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float(k + 1)) * (rank + 1)
+    exchange([p.grad for p in net.parameters()])
+    if rank == 0:
+        torch.save([p.grad.clone() for p in net.parameters()], out)
+    dist.destroy_process_group()
+
+
+def test_network_gradients_ride_the_same_exchange(tmp_path):
+    """The deformation network's weight gradients (28 tensors, 2.4 MB) are summed by the exchange step like any other."""
+    world = 2
+    out = str(tmp_path / "net.pt")
+    mp.spawn(_network_worker, args=(world, 29533, out), nprocs=world, join=True)
+    got = torch.load(out)
+    assert len(got) == 28
+    for k, g in enumerate(got):
+        assert torch.equal(g, torch.full_like(g, float(k + 1) * 3))  # rank 0 (x1) + rank 1 (x2)
