@@ -688,39 +688,42 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(PackTable tab) {
 
 // ------------------------------------------------------------------------------------------------ embedding
 // E[n, :] = [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^9), cos(x 2^9) | t_emb | 0...]   (utils.py:27-56; model.py:1095-1096)
-// thread = (row, group of 4 columns): one 16-byte store per thread.  Row layout: embed(x) | embed(x2) (if given) | t_emb | 0.
+// thread = (row, unit): units 0 .. multires-1 of a point set are its frequencies (one sincosf per coordinate -> the six
+// columns [sin | cos] of that frequency), the following unit copies the raw coordinates; after the point sets come the
+// t_emb / zero-padding columns, one unit per column.  Row layout: embed(x) | embed(x2) (if given) | t_emb | 0.
 __global__ void __launch_bounds__(256) deform_embed_kernel(long long N, const float* __restrict__ x, const float* __restrict__ x2,
                                                            const float* __restrict__ t_emb, int t_ch, int multires, int ld,
                                                            float* __restrict__ e) {
     pdl_wait();
-    const int G = ld / 4;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N * G) return;
-    const long long n = i / G;
-    const int j0 = (int)(i % G) * 4;
     const int x_ch = 3 + 6 * multires;
-    const int p_ch = x2 ? 2 * x_ch : x_ch;
-    float v[4];
+    const int sets = x2 ? 2 : 1;
+    const int p_ch = sets * x_ch;
+    const int units = sets * (multires + 1) + (ld - p_ch);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * units) return;
+    const long long n = i / units;
+    int u = (int)(i % units);
+    float* row = e + n * ld;
+    if (u < sets * (multires + 1)) {
+        const int set = u / (multires + 1), f = u % (multires + 1);
+        const float* src = (set ? x2 : x) + n * 3;
+        float* dst = row + set * x_ch;
+        if (f == multires) {
+            dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
+        } else {
+            const float w = exp2f((float)f);  // freq = 2^f exactly, so x * freq is the reference's product
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        int j = j0 + u;
-        float r = 0.f;
-        if (j < p_ch) {
-            const float* src = x;
-            if (j >= x_ch) { src = x2; j -= x_ch; }
-            if (j < 3) {
-                r = src[n * 3 + j];
-            } else {
-                const int k = j - 3, f = k / 6, c = k % 6;
-                const float a = src[n * 3 + (c % 3)] * exp2f((float)f);  // x * freq, freq = 2^f exactly
-                r = c < 3 ? sinf(a) : cosf(a);
+            for (int c = 0; c < 3; ++c) {
+                float sn, cs;
+                sincosf(src[c] * w, &sn, &cs);
+                dst[3 + 6 * f + c] = sn;
+                dst[3 + 6 * f + 3 + c] = cs;
             }
-        } else if (j < p_ch + t_ch) {
-            r = t_emb[j - p_ch];
         }
-        v[u] = r;
+    } else {
+        const int j = p_ch + (u - sets * (multires + 1));
+        row[j] = j < p_ch + t_ch ? t_emb[j - p_ch] : 0.f;
     }
-    reinterpret_cast<float4*>(e)[i] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // VJP of embed(x) (the first 3 + 6 multires columns of a row): dx = de_x + sum_f 2^f (cos(x 2^f) de_sin,f - sin(x 2^f) de_cos,f)
@@ -951,7 +954,8 @@ extern "C" int fg_deform_embed(int64_t N, const float* x, const float* x2, const
     FG_REQUIRE((x2 ? 2 : 1) * (3 + 6 * multires) + t_ch <= ld && (t_ch == 0 || t_emb), "fg_deform_embed: embedding wider than ld");
     if (N == 0) return FG_OK;
     FG_REQUIRE(x && e, "fg_deform_embed: NULL argument");
-    FG_LAUNCH(deform_embed_kernel, ceil_div(N * (ld / 4), 256), 256, 0, (cudaStream_t)stream, (long long)N, x, x2, t_emb, t_ch, multires, ld, e);
+    const int units = (x2 ? 2 : 1) * (multires + 1) + (ld - (x2 ? 2 : 1) * (3 + 6 * multires));
+    FG_LAUNCH(deform_embed_kernel, ceil_div(N * units, 256), 256, 0, (cudaStream_t)stream, (long long)N, x, x2, t_emb, t_ch, multires, ld, e);
     return FG_OK;
 }
 

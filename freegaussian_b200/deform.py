@@ -112,8 +112,13 @@ class _Packed:
 
     def __init__(self, params: List[Tensor], spec: _Spec):
         dev = params[0].device
-        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731  pads stay zero
-        bufs = {k: (z(*shape), z(*shape)) for k, shape in _packed_shapes(spec).items()}
+        shapes = _packed_shapes(spec)
+        total = sum(r * c for r, c in shapes.values())
+        arena = torch.zeros(2, total, device=dev, dtype=torch.float32)  # one memset: the pads stay zero
+        bufs, o = {}, 0
+        for k, (r, c) in shapes.items():  # every size is a multiple of 32 floats, so the slices stay 128-byte aligned
+            bufs[k] = (arena[0, o:o + r * c].view(r, c), arena[1, o:o + r * c].view(r, c))
+            o += r * c
         plan = _pack_plan(spec)
         assert len(plan) <= _lib.MLP_PACK_MAX_SEGMENTS
         arr = (MlpPackSegment * len(plan))()
@@ -151,10 +156,10 @@ class _Trunk(torch.autograd.Function):
         e = new(N, ld)
         check(L.fg_deform_embed(N, ptr(x), ptr(x2), ptr(t_emb), t_ch, spec.multires, ld, ptr(e), _stream()))
         hs: List[Tensor] = []
-        masks: List[Tensor] = []
+        masks = torch.empty(_D, N, _W // 32, device=dev, dtype=torch.int32)  # ReLU bit masks of all layers, one tensor
         prev = None
         for i in range(_D):
-            out, bits = new(N, _W), torch.empty(N, _W // 32, device=dev, dtype=torch.int32)
+            out, bits = new(N, _W), masks[i]
             if i == 0:
                 _linear(_lib.MLP_RELU, N, _W, e, ld, None, 0, pk.w[0], pk.bias[0], None, out, bits)
             elif i == _SKIP + 1:
@@ -163,10 +168,9 @@ class _Trunk(torch.autograd.Function):
                 _linear(_lib.MLP_RELU, N, _W, prev, _W, None, 0, pk.w[i], pk.bias[i], None, out, bits)
             prev = out
             hs.append(out)
-            masks.append(bits)
         head = new(N, MLP_HEAD_LD)
         _linear(_lib.MLP_LINEAR, N, MLP_HEAD_LD, prev, _W, None, 0, pk.w_head, pk.bias_head, None, head, None)
-        ctx.save_for_backward(x, e, *hs, *masks, *params)
+        ctx.save_for_backward(x, e, masks, *hs, *params)
         ctx.pk, ctx.spec, ctx.t_ch = pk, spec, t_ch
         return head
 
@@ -175,7 +179,7 @@ class _Trunk(torch.autograd.Function):
         spec, pk, t_ch = ctx.spec, ctx.pk, ctx.t_ch
         ld, emb_ch = spec.emb_ld, spec.emb_ch
         saved = ctx.saved_tensors
-        x, e, hs, masks, params = saved[0], saved[1], saved[2:2 + _D], saved[2 + _D:2 + 2 * _D], saved[2 + 2 * _D:]
+        x, e, masks, hs, params = saved[0], saved[1], saved[2], saved[3:3 + _D], saved[3 + _D:]
         N_all = N = x.shape[0]
         dev = g_head.device
         g_head = g_head.contiguous()
@@ -195,8 +199,10 @@ class _Trunk(torch.autograd.Function):
                 g_head = sel(g_head)
                 N = idx.numel()
         e = sel(e)
+        if idx is not None:
+            masks = masks.index_select(1, idx)  # all eight layers in one gather
         h_in = lambda i: sel(hs[i])  # noqa: E731  activations of layer i (input of layer i + 1)
-        m_in = lambda i: sel(masks[i])  # noqa: E731
+        m_in = lambda i: masks[i]  # noqa: E731
         # head gradients: dW_head^T [256, 32] = h_last^T . g_head, one pass of the same kernel; biases = column sums of g_head
         dw_head_t = torch.zeros(_W, MLP_HEAD_LD, device=dev, dtype=torch.float32)
         h_last = h_in(_D - 1)
