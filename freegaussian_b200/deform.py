@@ -34,6 +34,7 @@ _HEADS = (("branch_w", 3), ("branch_v", 3), ("gaussian_rotation", 4), ("gaussian
 # backward over the rows with a non-zero incoming gradient only, when they are fewer than this fraction of all rows
 SPARSE_BACKWARD = True
 SPARSE_BACKWARD_MAX_FRACTION = 0.75
+_ROW_QUANT = 65536  # granule of the backward's row buffers (rows)
 
 
 def _embed(x: Tensor, multires: int) -> Tensor:
@@ -183,26 +184,34 @@ class _Trunk(torch.autograd.Function):
         N_all = N = x.shape[0]
         dev = g_head.device
         g_head = g_head.contiguous()
-        new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         grads: List[Tensor] = [None] * len(params)
         L = _lib.lib()
         # Rows whose incoming gradient is exactly zero (Gaussians that were culled or never reached a pixel in this
         # step's views) contribute exactly nothing to any gradient: run the backward on the other rows only.
         # One host read (the number of such rows); the saved activations are gathered layer by layer as they are needed.
         idx = None
-        sel = lambda t: t  # noqa: E731
         if SPARSE_BACKWARD and N > 0:
             act = (g_head != 0).any(1).nonzero().squeeze(1)  # the one host read (nonzero sizes its result)
             if act.numel() < SPARSE_BACKWARD_MAX_FRACTION * N:
-                idx = act
-                sel = lambda t: t.index_select(0, idx)  # noqa: E731
-                g_head = sel(g_head)
-                N = idx.numel()
+                idx, N = act, act.numel()
+        # Row buffers are carved from allocations whose size is rounded up to _ROW_QUANT rows: the number of active rows
+        # changes every step, and a fresh size every step would send the caching allocator to cudaMalloc every step.
+        cap = N if idx is None else -(-N // _ROW_QUANT) * _ROW_QUANT
+
+        def rows(width, dtype=torch.float32):
+            return torch.empty(cap, width, device=dev, dtype=dtype)[:N]
+
+        new = lambda n_, w_: rows(w_)  # noqa: E731  (every [N, w] temporary of the backward)
+        if idx is None:
+            sel = lambda t: t  # noqa: E731
+            m_in = lambda i: masks[i]  # noqa: E731
+        else:
+            sel = lambda t: torch.index_select(t, 0, idx, out=rows(t.shape[1], t.dtype))  # noqa: E731
+            mask_rows = torch.empty(_D, cap, _W // 32, device=dev, dtype=torch.int32)
+            m_in = lambda i: torch.index_select(masks[i], 0, idx, out=mask_rows[i, :N])  # noqa: E731
+            g_head = sel(g_head)
         e = sel(e)
-        if idx is not None:
-            masks = masks.index_select(1, idx)  # all eight layers in one gather
         h_in = lambda i: sel(hs[i])  # noqa: E731  activations of layer i (input of layer i + 1)
-        m_in = lambda i: masks[i]  # noqa: E731
         # head gradients: dW_head^T [256, 32] = h_last^T . g_head, one pass of the same kernel; biases = column sums of g_head
         dw_head_t = torch.zeros(_W, MLP_HEAD_LD, device=dev, dtype=torch.float32)
         h_last = h_in(_D - 1)
