@@ -121,3 +121,45 @@ def test_every_kernel_waits_for_its_stream_predecessor():
                 assert ln.startswith(("extern __shared__", "__shared__", "using ", "constexpr ")), (path.name, ln)
             n += 1
     assert n >= 30
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct of fg_api.h as gcc lays them out == the ctypes mirrors in _lib.py."""
+    from freegaussian_b200 import _lib
+
+    structs = {"fg_adam_segment": _lib.AdamSegment, "fg_refine_config": _lib.RefineConfig, "fg_refine_array": _lib.RefineArray,
+               "fg_mlp_pack_segment": _lib.MlpPackSegment}
+    header_fields = {"fg_refine_array": {"in_": "in"}}  # ctypes cannot name a field `in`
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "fg_api.h"}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            hname = header_fields.get(cname, {}).get(fname, fname)
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {hname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.strip().splitlines():
+        cname, field, value = line.split()
+        cls = structs[cname]
+        want = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(value) == want, line
+
+
+def test_network_entry_points_validate_arguments(built_lib):
+    """The tensor-core entry points reject bad shapes / NULL operands with an error code before touching the device."""
+    from freegaussian_b200 import _lib
+    L = _lib.lib()
+    assert L.fg_mlp_linear(_lib.MLP_RELU, 128, 256, None, 33, None, 0, None, None, None, None, None, None, None) == 1
+    assert b"multiples of 32" in L.fg_last_error()
+    assert L.fg_mlp_linear(_lib.MLP_RELU, 128, 256, None, 256, None, 0, None, None, None, None, None, None, None) == 1
+    assert b"NULL" in L.fg_last_error()
+    assert L.fg_mlp_linear(_lib.MLP_RELU, 0, 256, None, 256, None, 0, None, None, None, None, None, None, None) == 0  # empty input
+    assert L.fg_mlp_wgrad(16, None, None, 256, None, 256, 0, None, None) == 1
+    assert L.fg_mlp_wgrad(16, None, None, 256, None, 255, 0, None, None) == 1 and b"aligned" in L.fg_last_error()
+    assert L.fg_mlp_wgrad(0, None, None, 256, None, 256, 0, None, None) == 0
+    assert L.fg_deform_embed(10, None, None, None, 40, 10, 96, None, None) == 1 and b"wider" in L.fg_last_error()
+    assert L.fg_mlp_pack(99, None, None) == 1
