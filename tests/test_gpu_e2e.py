@@ -206,7 +206,7 @@ def test_covariance_flow_mode_matches_oracle(built_lib):
     ((rr * wr.double()).sum() + (rm["flow"] * wf.double()).sum()).backward()
     # The affine term makes per-pixel flow features ~100x larger than the mean flow (A ~ 0.1 times a
     # pixel offset of tens of pixels), so float32 accumulation noise is larger relative to the max
-    # gradient: 2e-3 here (1e-3 holds for the mean mode above; tools/dbg_grad.py prints both).
+    # gradient: 2e-3 here (1e-3 holds for the mean mode above; tests/tools/dbg_grad.py prints both).
     for n in names:
         e = grad_rel_err(gp[n].grad, op[n].grad)
         assert e < 2 * GRAD_TOL, (n, e)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """k-NN kernel timing (cfg5 shape: k=16 over 3 M points) next to the reference's sklearn call on a sample."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from freegaussian_b200.knn import k_nearest
 from oracle import knn as OK

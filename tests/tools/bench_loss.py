@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Fused blend+L1+SSIM loss vs the torch formulation the reference uses (pytorch_msssim-style conv2d ops), 1080p, GPU."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from freegaussian_b200.losses import blend_l1_ssim_loss
 from oracle import loss as OL  # used here only as "the torch formulation" to time beside the kernel

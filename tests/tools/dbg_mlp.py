@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Stage-by-stage check of the deformation-network kernels on a GPU (prints errors, asserts nothing).
 
-    python tools/dbg_mlp.py linear|modes|aux|e2e|perf
+    python tests/tools/dbg_mlp.py linear|modes|wgrad|aux|e2e|layer|perf
+
+Lives under tests/ because it checks against the oracle and the golden fixtures (test infrastructure).
 
 Each stage is a separate process on purpose: a trapped kernel poisons the CUDA context.
 """
@@ -12,7 +14,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from freegaussian_b200 import _lib  # noqa: E402

@@ -8,12 +8,10 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from freegaussian_b200.deform import DeformNetwork  # noqa: E402
-from oracle import deform as OD  # noqa: E402  (seeded weights only)
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-net = DeformNetwork(is_blender=True)
-net.load_state_dict(OD.init_params(True, seed=1))
-net = net.cuda()
+torch.manual_seed(1)
+net = DeformNetwork(is_blender=True).cuda()  # nn.Linear's default initialisation
 g = torch.Generator().manual_seed(0)
 m = ((torch.rand(n, 3, generator=g) - 0.5) * 6).cuda().requires_grad_(True)
 s = torch.log(torch.rand(n, 3, generator=g) * 0.05 + 0.005).cuda().requires_grad_(True)
