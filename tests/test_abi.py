@@ -163,3 +163,18 @@ def test_network_entry_points_validate_arguments(built_lib):
     assert L.fg_mlp_wgrad(0, None, None, 256, None, 256, 0, None, None) == 0
     assert L.fg_deform_embed(10, None, None, None, 40, 10, 96, None, None) == 1 and b"wider" in L.fg_last_error()
     assert L.fg_mlp_pack(99, None, None) == 1
+
+
+def test_oracle_is_test_infrastructure_only():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU arm may import the oracle; the product and tools/ never do."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
+    offenders = []
+    for path in list((ROOT / "freegaussian_b200").rglob("*.py")) + list((ROOT / "tools").rglob("*.py")):
+        if pat.search(path.read_text()):
+            offenders.append(str(path.relative_to(ROOT)))
+    assert not offenders, offenders
+    bench = (ROOT / "bench.py").read_text()
+    body = bench[bench.index("def cpu_arm("):bench.index("def run_reference(")]
+    assert len(pat.findall(bench)) == len(pat.findall(body)) > 0  # every oracle import of bench.py sits inside cpu_arm()
+    entry = (ROOT / "__graft_entry__.py").read_text()
+    assert len(pat.findall(entry)) == len(pat.findall(entry[entry.index("def smoke("):]))  # and inside smoke()
