@@ -261,19 +261,21 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for i in range(max(args.warmup, 3)):
-        step(i, False)
+    # nvidia-smi takes a few hundred ms to deliver its first sample, longer than a timed region: it is started before
+    # the warm-up and stopped after the second timed region, so its samples cover warm-up + both timed regions (all under load)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(max(args.warmup, 3)):
+        step(i, False)
     l0 = _lib.launch_count()
     ms_dev = timed(args.steps, False)
     launches = _lib.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     step(0, True)
     staged.clear()
     ms_e2e = timed(args.steps, True)
     staged.clear()
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel timing + roofline (every rank runs the steps -- they contain collectives --
     #      rank 0 records the CUDA-event time of each C-ABI stage)
