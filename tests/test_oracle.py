@@ -141,3 +141,56 @@ def test_packed_meta_layout():
     nnz = int((m0["radii"] > 0).sum())
     assert m1["means2d"].shape == (nnz, 2) and m1["gaussian_ids"].shape == (nnz,)
     assert (np.diff((m1["camera_ids"] * 300 + m1["gaussian_ids"]).numpy()) > 0).all()
+
+
+def test_compositing_matches_a_scalar_pixel_loop():
+    """Second, independent statement of Appendix A.4-A.6: per tile the Gaussians whose tile rectangle covers it, sorted by
+    (float32 depth bits, index) with Python's sort; per pixel a plain loop (skip sigma < 0 or alpha < 1/255, alpha capped at
+    0.999, stop BEFORE the Gaussian that would take T to <= 1e-4).  Cross-checks the oracle's vectorised emission, key sort,
+    offsets, cumulative-product compositing and `last_ids` against 30 lines of scalar code, in float64."""
+    W, H, ts = 56, 40, 16
+    sc = small_scene(260, W, H, views=1, seed=11)
+    dbl = lambda t: t.double()  # noqa: E731
+    r, a, m = O.rasterization(dbl(sc.means), dbl(sc.quats), dbl(sc.scales), dbl(sc.opacities), dbl(sc.sh), dbl(sc.viewmats), dbl(sc.Ks),
+                              W, H, render_mode="RGB+ED", sh_degree=3, means_next=dbl(sc.means_next))
+    radii, m2, conics, depths, opac, cols = (m[k][0].numpy() for k in ("radii", "means2d", "conics", "depths", "opacities", "colors"))
+    tile_w, tile_h = math.ceil(W / ts), math.ceil(H / ts)
+    m2f, rf = m2.astype(np.float32), radii.astype(np.float32)
+    depth_key = depths.astype(np.float32).view(np.int32).astype(np.int64) & 0xFFFFFFFF
+    out = np.zeros((H, W, cols.shape[1]))
+    alpha_img = np.zeros((H, W))
+    last = np.zeros((H, W), np.int64)
+    pos = 0  # running position in the global sorted list = what last_ids indexes
+    for ty in range(tile_h):
+        for tx in range(tile_w):
+            lst = []
+            for g in np.nonzero(radii > 0)[0]:
+                x0 = min(max(math.floor(m2f[g, 0] / np.float32(ts) - rf[g] / np.float32(ts)), 0), tile_w)
+                x1 = min(max(math.ceil(m2f[g, 0] / np.float32(ts) + rf[g] / np.float32(ts)), 0), tile_w)
+                y0 = min(max(math.floor(m2f[g, 1] / np.float32(ts) - rf[g] / np.float32(ts)), 0), tile_h)
+                y1 = min(max(math.ceil(m2f[g, 1] / np.float32(ts) + rf[g] / np.float32(ts)), 0), tile_h)
+                if x0 <= tx < x1 and y0 <= ty < y1:
+                    lst.append((int(depth_key[g]), int(g)))
+            lst.sort()
+            for py in range(ty * ts, min((ty + 1) * ts, H)):
+                for px in range(tx * ts, min((tx + 1) * ts, W)):
+                    T, acc = 1.0, np.zeros(cols.shape[1])
+                    for k, (_, g) in enumerate(lst):
+                        dx, dy = m2[g, 0] - (px + 0.5), m2[g, 1] - (py + 0.5)
+                        sigma = 0.5 * (conics[g, 0] * dx * dx + conics[g, 2] * dy * dy) + conics[g, 1] * dx * dy
+                        alpha = min(0.999, opac[g] * math.exp(-sigma))
+                        if sigma < 0 or alpha < 1.0 / 255.0:
+                            continue
+                        if T * (1 - alpha) <= 1e-4:
+                            break
+                        acc += alpha * T * cols[g]
+                        T *= 1 - alpha
+                        last[py, px] = pos + k
+                    out[py, px], alpha_img[py, px] = acc, 1 - T
+            pos += len(lst)
+    assert pos == m["flatten_ids"].numel()
+    want = np.concatenate([out[..., :3], out[..., 3:4] / np.maximum(alpha_img[..., None], 1e-10)], -1)  # "ED"
+    assert np.abs(r[0].numpy() - want).max() < 1e-9
+    assert np.abs(a[0, ..., 0].numpy() - alpha_img).max() < 1e-12
+    assert np.abs(m["flow"][0].numpy() - out[..., 4:6]).max() < 1e-9
+    assert np.array_equal(m["last_ids"][0].numpy(), last)
