@@ -194,3 +194,50 @@ def test_compositing_matches_a_scalar_pixel_loop():
     assert np.abs(a[0, ..., 0].numpy() - alpha_img).max() < 1e-12
     assert np.abs(m["flow"][0].numpy() - out[..., 4:6]).max() < 1e-9
     assert np.array_equal(m["last_ids"][0].numpy(), last)
+
+
+def test_projection_matches_a_scalar_restatement():
+    """Appendix A.2 per Gaussian with plain Python floats (float64), from the spec, against the oracle's vectorised
+    `fully_fused_projection` run in float64: radii exact, means2d / depths / conics / compensation to 1e-10."""
+    W, H = 72, 40
+    sc = small_scene(400, W, H, views=2, seed=23)
+    mu, q, s = sc.means.double().numpy(), sc.quats.double().numpy(), sc.scales.double().numpy()
+    vms, Ks = sc.viewmats.double().numpy(), sc.Ks.double().numpy()
+    radii, means2d, depths, conics, comp, _ = O.fully_fused_projection(
+        sc.means.double(), sc.quats.double(), sc.scales.double(), sc.viewmats.double(), sc.Ks.double(), W, H, 0.3, 0.01, 1e10, 0.0)
+    n_vis = 0
+    for c in range(vms.shape[0]):
+        Rcw, tcw = vms[c, :3, :3], vms[c, :3, 3]
+        fx, fy, cx, cy = Ks[c, 0, 0], Ks[c, 1, 1], Ks[c, 0, 2], Ks[c, 1, 2]
+        for n in range(mu.shape[0]):
+            w_, x_, y_, z_ = q[n] / np.linalg.norm(q[n])
+            R = np.array([[1 - 2 * (y_ * y_ + z_ * z_), 2 * (x_ * y_ - w_ * z_), 2 * (x_ * z_ + w_ * y_)],
+                          [2 * (x_ * y_ + w_ * z_), 1 - 2 * (x_ * x_ + z_ * z_), 2 * (y_ * z_ - w_ * x_)],
+                          [2 * (x_ * z_ - w_ * y_), 2 * (y_ * z_ + w_ * x_), 1 - 2 * (x_ * x_ + y_ * y_)]])
+            M = R * s[n][None, :]
+            cov_c = Rcw @ (M @ M.T) @ Rcw.T
+            x, y, z = Rcw @ mu[n] + tcw
+            r_want = 0
+            if 0.01 <= z <= 1e10:
+                tan_x, tan_y = 0.5 * W / fx, 0.5 * H / fy
+                tx = z * min(max(x / z, -(cx / fx + 0.3 * tan_x)), (W - cx) / fx + 0.3 * tan_x)
+                ty = z * min(max(y / z, -(cy / fy + 0.3 * tan_y)), (H - cy) / fy + 0.3 * tan_y)
+                J = np.array([[fx / z, 0.0, -fx * tx / (z * z)], [0.0, fy / z, -fy * ty / (z * z)]])
+                c2 = J @ cov_c @ J.T
+                det_orig = c2[0, 0] * c2[1, 1] - c2[0, 1] ** 2
+                a_, b_, c_ = c2[0, 0] + 0.3, c2[0, 1], c2[1, 1] + 0.3
+                det = a_ * c_ - b_ * b_
+                u, v = fx * x / z + cx, fy * y / z + cy
+                if det > 0:
+                    mid = 0.5 * (a_ + c_)
+                    rad = math.ceil(3.0 * math.sqrt(mid + math.sqrt(max(0.01, mid * mid - det))))
+                    if not (u + rad <= 0 or u - rad >= W or v + rad <= 0 or v - rad >= H):
+                        r_want = rad
+            assert int(radii[c, n]) == r_want, (c, n)
+            if r_want:
+                n_vis += 1
+                assert abs(means2d[c, n, 0] - u) < 1e-9 and abs(means2d[c, n, 1] - v) < 1e-9 and abs(depths[c, n] - z) < 1e-12
+                want_conic = np.array([c_ / det, -b_ / det, a_ / det])
+                assert np.abs(conics[c, n].numpy() - want_conic).max() < 1e-10 * max(1.0, np.abs(want_conic).max())
+                assert abs(comp[c, n] - math.sqrt(max(0.0, det_orig / det))) < 1e-10
+    assert n_vis > 200
