@@ -241,3 +241,23 @@ def test_projection_matches_a_scalar_restatement():
                 assert np.abs(conics[c, n].numpy() - want_conic).max() < 1e-10 * max(1.0, np.abs(want_conic).max())
                 assert abs(comp[c, n] - math.sqrt(max(0.0, det_orig / det))) < 1e-10
     assert n_vis > 200
+
+
+def test_sh_basis_is_the_real_spherical_harmonics():
+    """The 16 basis functions of Appendix A.3 against their mathematical definition: the real spherical harmonics with the
+    Condon-Shortley phase, Y_l0, sqrt(2) Re Y_l^m (m > 0), sqrt(2) Im Y_l^|m| (m < 0), from scipy's complex Y_l^m."""
+    import scipy.special as sp
+
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal((64, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    theta, phi = np.arccos(d[:, 2]), np.arctan2(d[:, 1], d[:, 0])
+    basis = O.eval_sh_bases(3, torch.from_numpy(d)).numpy()
+    k = 0
+    for l in range(4):  # noqa: E741
+        for m in range(-l, l + 1):
+            Y = sp.sph_harm_y(l, abs(m), theta, phi) if hasattr(sp, "sph_harm_y") else sp.sph_harm(abs(m), l, phi, theta)
+            want = Y.real if m == 0 else np.sqrt(2) * (Y.real if m > 0 else Y.imag)
+            assert np.abs(basis[:, k] - want).max() < 1e-14, (l, m)
+            k += 1
+    assert k == 16 == O.num_sh_bases(3)
