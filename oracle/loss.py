@@ -8,7 +8,8 @@ TEST INFRASTRUCTURE ONLY.  Restates, in plain torch:
 * ``pytorch_msssim.SSIM(data_range=1.0, size_average=True, channel=3)`` (``freegaussian_model.py:22, 217``), an
   un-vendored dependency that is not installed here: 11-tap Gaussian window, sigma 1.5, separable "valid"
   convolution (H first, then W), K = (0.01, 0.03), mean over the valid region, channels and batch.
-  PARITY UNPINNED for the SSIM half (published algorithm restated); the L1 / blend half is the reference's own code.
+  PARITY UNPINNED for the SSIM half (published algorithm restated; cross-checked against the window-by-window
+  definition in tests/test_loss.py); the L1 / blend half is the reference's own code.
 """
 
 from __future__ import annotations

@@ -26,6 +26,31 @@ def test_oracle_ssim_properties():
     assert abs(float(w.sum()) - 1) < 1e-6 and w.argmax() == 5
 
 
+def test_oracle_ssim_matches_the_windowed_definition():
+    """SSIM as defined by Wang et al. with the 11x11 Gaussian window (sigma 1.5) evaluated window by window over the valid
+    region in plain float64 loops, against the oracle's separable-convolution form (what pytorch_msssim implements)."""
+    import math
+
+    import numpy as np
+
+    g = torch.Generator().manual_seed(4)
+    X, Y = torch.rand(1, 2, 15, 18, generator=g).double(), torch.rand(1, 2, 15, 18, generator=g).double()
+    w1 = np.array([math.exp(-((i - 5) ** 2) / (2 * 1.5 ** 2)) for i in range(11)])
+    w1 /= w1.sum()
+    w2 = np.outer(w1, w1)
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    vals = []
+    for c in range(2):
+        x, y = X[0, c].numpy(), Y[0, c].numpy()
+        for i in range(15 - 10):
+            for j in range(18 - 10):
+                px, py = x[i:i + 11, j:j + 11], y[i:i + 11, j:j + 11]
+                mx, my = (w2 * px).sum(), (w2 * py).sum()
+                vx, vy, cxy = (w2 * px * px).sum() - mx * mx, (w2 * py * py).sum() - my * my, (w2 * px * py).sum() - mx * my
+                vals.append((2 * mx * my + C1) * (2 * cxy + C2) / ((mx * mx + my * my + C1) * (vx + vy + C2)))
+    assert abs(float(OL.ssim(X, Y)) - float(np.mean(vals))) < 1e-12
+
+
 def test_oracle_loss_gradcheck():
     render, alpha, bg, gt = _inputs(14, 15, 1)
     r, a = render.double().requires_grad_(True), alpha.double().requires_grad_(True)
