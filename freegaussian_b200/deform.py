@@ -353,6 +353,9 @@ class DeformNetwork(nn.Module):
 
     def _time_row(self, t: Tensor) -> Tensor:
         """One time value per call (freegaussian_model.py:836 expands ``camera.times``); returns t_emb [t_ch]."""
+        if t.numel() > 1 and not (t.dim() == 2 and t.stride(0) == 0):
+            raise ValueError("DeformNetwork evaluates ONE time value per call, as the reference does with "
+                             "`camera.times.expand(N, -1)`: pass a [1,1] tensor or an expanded view, not per-row times")
         t0 = t.reshape(-1)[:1].reshape(1, 1).to(torch.float32)
         t_emb = _embed(t0, self.t_multires)
         if self.is_blender:
