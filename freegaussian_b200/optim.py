@@ -14,7 +14,8 @@ consumes is ``cat(features_dc[:,None], features_rest)`` (``freegaussian_model.py
 
 Multi-GPU: ``step(shard=(rank, world))`` updates only this rank's contiguous slice of every group
 (the flat gradient arena after a reduce-scatter, SURVEY 8(e) "better variant"); the caller
-all-gathers the parameters afterwards (``dist.sharded_adam_step``).
+all-gathers the parameters afterwards.  The kernel side is tested (``tests/test_optim.py::test_sharded_step_equals_full_step``);
+the reduce-scatter / all-gather plumbing around it is not built yet ("Not widened yet").
 """
 
 from __future__ import annotations
