@@ -380,13 +380,13 @@ def run_ours(args):
             "kernels": kernels,
             "stage_ms": stage_ms,
         }
-        if world == 1 and not args.no_train_iter:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only
+            out["cpu_baseline"] = cpu_arm(args, steps=args.cpu_steps, warmup=0)["cpu_baseline"]
+        if world == 1 and not args.no_train_iter:  # last: nothing after it needs the device
             try:
                 out["train_iter"] = train_iter_section(d, dev, W, H, dev_vm[0], dev_K[0])
             except Exception as exc:  # the headline line must survive a failure of this additional section
                 out["train_iter"] = {"error": f"{type(exc).__name__}: {exc}"}
-        if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only
-            out["cpu_baseline"] = cpu_arm(args, steps=args.cpu_steps, warmup=0)["cpu_baseline"]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
