@@ -1,0 +1,292 @@
+// (5) View-sharded multi-GPU gradient exchange over NVLink peer memory / NVSwitch multicast
+// (BASELINE.json north_star item 5).  The reference has no multi-GPU code; what is
+// exchanged is defined by the single-process semantics: every rank must end the backward pass holding
+// the gradient a single process rendering ALL views would have computed.
+//
+// Design.  The dense parameter gradient is 236 B per Gaussian, 81 % of it the
+// spherical-harmonics rows.  An SH row's gradient is rank one per (view, Gaussian):
+//     v_sh[n, k, :] = sum over views c of  basis_k(dir(n, c)) * v_rgb[c, n, :]
+// so instead of all-reducing 192 B per Gaussian, every rank PUBLISHES the 12-byte colour gradient of its
+// own views (clamp mask applied, plus a 1-bit-per-Gaussian visibility mask) in symmetric memory, and
+// `sh_bwd_views_kernel` on every rank reads all ranks' published rows straight over NVLink (peer loads,
+// rows of invisible splats are never fetched), evaluates the basis for every view and writes the summed
+// rows once: the transfer overlaps the math row by row, the sum order is fixed (rank, view), hence the
+// result is bit-identical on every rank.  Only the geometry part (means, quats, scales, opacity, frame
+// t+1 means: 56 B per Gaussian) needs a reduction: `allreduce_kernel` is a two-shot all-reduce that
+// runs in the switch -- each rank `multimem.ld_reduce`s its 1/G slice (NVSwitch sums the G copies in
+// flight) and `multimem.st`s the result to all ranks -- with the cross-rank barriers inside the kernel
+// (release/acquire flags in symmetric memory).  Without multicast the same kernel falls back to peer
+// loads + peer stores.
+#include "common.cuh"
+#include "splat_math.h"
+
+namespace fg {
+
+constexpr int XB = 512;              // threads per block of the all-reduce kernel
+constexpr int XCHG_SLOT_WORDS = 16;  // one flag word per source rank (FG_XCHG_MAX_RANKS)
+
+struct Peers {
+    int world, rank;
+    char* buf[FG_XCHG_MAX_RANKS];
+    char* mc;
+    uint32_t* flags[FG_XCHG_MAX_RANKS];
+};
+
+__device__ __forceinline__ void flag_store_release(uint32_t* addr, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t flag_load_acquire(const uint32_t* addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Barrier among the blocks with the same index on every rank.  Thread r (< world) tells rank r "block
+// `slot` of rank `me` reached epoch e" and waits for the same word from rank r.  Epochs only grow, so
+// the flags are never reset.  Bounded: a peer that never arrives traps after ~20 s instead of hanging.
+__device__ __forceinline__ void block_barrier(const Peers& p, int slot, uint32_t epoch) {
+    __syncthreads();
+    if (threadIdx.x < p.world) {
+        __threadfence_system();
+        const int r = threadIdx.x;
+        flag_store_release(p.flags[r] + slot * XCHG_SLOT_WORDS + p.rank, epoch);
+        const uint32_t* mine = p.flags[p.rank] + slot * XCHG_SLOT_WORDS + r;
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int32_t)(flag_load_acquire(mine) - epoch) < 0) {
+            if (globaltimer_ns() - t0 > 20000000000ull) {
+                printf("fg exchange: rank %d timed out waiting for rank %d (slot %d, epoch %u)\n", p.rank, r, slot, epoch);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(32) xchg_barrier_kernel(Peers p, uint32_t epoch) {
+    pdl_wait();
+    block_barrier(p, 0, epoch);
+}
+
+__device__ __forceinline__ float4 mc_ld_reduce(const float4* a) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(a)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float4* a, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+// In-place SUM over ranks of n4 float4 at byte offset `off` of the symmetric buffer.  Two-shot: rank r
+// owns the r-th slice.  Slots 1..grid: start barrier (optional), grid+1..2*grid: end barrier.
+template <bool MC>
+__global__ void __launch_bounds__(XB) allreduce_kernel(Peers p, long long off, long long n4, uint32_t epoch,
+                                                       int start_barrier) {
+    pdl_wait();
+    if (start_barrier) block_barrier(p, 1 + blockIdx.x, epoch);
+    const long long per = (n4 + p.world - 1) / p.world;
+    const long long lo = per * p.rank, hi = min(n4, lo + per);
+    const long long stride = (long long)gridDim.x * XB;
+    constexpr int U = 4;
+    if (MC) {
+        float4* mc = reinterpret_cast<float4*>(p.mc + off);
+        long long i = lo + (long long)blockIdx.x * XB + threadIdx.x;
+        for (; i + (U - 1) * stride < hi; i += U * stride) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = mc_ld_reduce(mc + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < U; ++u) mc_st(mc + i + u * stride, v[u]);
+        }
+        for (; i < hi; i += stride) mc_st(mc + i, mc_ld_reduce(mc + i));
+    } else {
+        for (long long i = lo + (long long)blockIdx.x * XB + threadIdx.x; i < hi; i += stride) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < p.world; ++r) {  // fixed order: the sum is the same on every rank
+                const float4 v = *(reinterpret_cast<const float4*>(p.buf[r] + off) + i);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            for (int r = 0; r < p.world; ++r) *(reinterpret_cast<float4*>(p.buf[r] + off) + i) = s;
+        }
+    }
+    block_barrier(p, 1 + gridDim.x + blockIdx.x, epoch);
+}
+
+// ------------------------------------------------------------------------------ SH rows from all views
+// Published block of one rank (byte offset `pub_off` of its symmetric buffer), V views per rank:
+//   float    campos[V][4]                      camera centres (world)
+//   uint32_t mask[V][words]   words = ceil(N/32) rounded up to 4: bit n = splat n is visible in the view
+//   float    rgb[V][N][3]                      d loss / d rgb with the clamp mask applied (garbage where invisible)
+struct PubLayout {
+    long long mask_off, rgb_off;  // byte offsets inside the block
+    int words;
+};
+__host__ __device__ inline PubLayout pub_layout(int V, int N) {
+    PubLayout L;
+    L.words = ((N + 31) / 32 + 3) & ~3;
+    L.mask_off = (long long)((V * 16 + 255) / 256) * 256;
+    L.rgb_off = L.mask_off + (long long)V * L.words * 4;
+    L.rgb_off = (L.rgb_off + 255) / 256 * 256;
+    return L;
+}
+
+constexpr int VB = 128;  // Gaussians per block
+
+template <int DEG>
+__global__ void __launch_bounds__(VB) sh_bwd_views_kernel(Peers p, long long pub_off, int V, int N,
+                                                          const float* __restrict__ means, float* __restrict__ v_sh,
+                                                          int sh_row_floats) {
+    pdl_wait();
+    extern __shared__ __align__(16) float smem[];
+    constexpr int K = (DEG + 1) * (DEG + 1);
+    constexpr int NG = (K + 3) / 4;
+    constexpr int NV3 = NG * 3;
+    constexpr int ROW = 13;  // odd float4 stride: conflict-free own-row access
+    float4* acc = reinterpret_cast<float4*>(smem) + threadIdx.x * ROW;
+    float* campos = smem + VB * ROW * 4;  // [world*V][4]
+    const PubLayout L = pub_layout(V, N);
+    const int n0 = blockIdx.x * VB, n = n0 + threadIdx.x;
+    const bool in_range = n < N;
+    for (int i = threadIdx.x; i < p.world * V * 4; i += VB) {
+        const int r = i / (V * 4);
+        campos[i] = reinterpret_cast<const float*>(p.buf[r] + pub_off)[i - r * V * 4];
+    }
+#pragma unroll
+    for (int j = 0; j < NV3; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (in_range) {
+        float m[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) m[i] = __ldg(means + 3 * (size_t)n + i);
+        for (int r = 0; r < p.world; ++r) {
+            const char* base = p.buf[r] + pub_off;
+            const uint32_t* mask = reinterpret_cast<const uint32_t*>(base + L.mask_off);
+            const float* rgb = reinterpret_cast<const float*>(base + L.rgb_off);
+            for (int v = 0; v < V; ++v) {
+                const uint32_t w = mask[(size_t)v * L.words + (n >> 5)];
+                if (!((w >> (n & 31)) & 1u)) continue;
+                const float* src = rgb + ((size_t)v * N + n) * 3;
+                const float vr0 = src[0], vr1 = src[1], vr2 = src[2];
+                if (vr0 == 0.f && vr1 == 0.f && vr2 == 0.f) continue;
+                const float* cp = campos + (r * V + v) * 4;
+                const float dx = m[0] - cp[0], dy = m[1] - cp[1], dz = m[2] - cp[2];
+                const float inorm = rsqrt_f(dx * dx + dy * dy + dz * dz);
+                float B[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) B[k] = 0.f;
+                sh_basis(DEG, dx * inorm, dy * inorm, dz * inorm, B);
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    float a[12];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float4 t = acc[3 * g + j];
+                        a[4 * j] = t.x; a[4 * j + 1] = t.y; a[4 * j + 2] = t.z; a[4 * j + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int k = 4 * g + b;
+                        a[3 * b] = fmaf(B[k], vr0, a[3 * b]);
+                        a[3 * b + 1] = fmaf(B[k], vr1, a[3 * b + 1]);
+                        a[3 * b + 2] = fmaf(B[k], vr2, a[3 * b + 2]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) acc[3 * g + j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int gv = sh_row_floats >> 2;
+    const int rows = min(VB, N - n0);
+    float4* dst = reinterpret_cast<float4*>(v_sh);
+    const float4* src = reinterpret_cast<const float4*>(smem);
+    for (int qd = threadIdx.x; qd < rows * gv; qd += VB) {
+        const int g = qd / gv, j = qd - g * gv;
+        dst[(size_t)(n0 + g) * gv + j] = (j < NV3) ? src[g * ROW + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int DEG>
+static int launch_views(const Peers& p, long long pub_off, int V, int N, const float* means, float* v_sh,
+                        int sh_row_floats, cudaStream_t st) {
+    const size_t smem = (size_t)VB * 13 * 16 + (size_t)p.world * V * 16;
+    FG_CUDA(cudaFuncSetAttribute(sh_bwd_views_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FG_LAUNCH((sh_bwd_views_kernel<DEG>), ceil_div(N, VB), VB, smem, st, p, pub_off, V, N, means, v_sh, sh_row_floats);
+    return FG_OK;
+}
+
+static int make_peers(const fg_xchg_peers* in, Peers& p) {
+    FG_REQUIRE(in != nullptr, "peers must not be NULL");
+    FG_REQUIRE(in->world >= 1 && in->world <= FG_XCHG_MAX_RANKS, "world must be in 1..FG_XCHG_MAX_RANKS");
+    FG_REQUIRE(in->rank >= 0 && in->rank < in->world, "rank out of range");
+    p.world = in->world; p.rank = in->rank; p.mc = (char*)in->mc;
+    for (int r = 0; r < in->world; ++r) {
+        FG_REQUIRE(in->buf[r] && in->flags[r], "peer buffer / flag pointers must not be NULL");
+        p.buf[r] = (char*)in->buf[r];
+        p.flags[r] = (uint32_t*)in->flags[r];
+    }
+    return FG_OK;
+}
+
+}  // namespace fg
+
+using namespace fg;
+
+extern "C" int64_t fg_xchg_pub_bytes(int V, int N) {
+    const PubLayout L = pub_layout(V, N);
+    return (L.rgb_off + (long long)V * N * 12 + 255) / 256 * 256;
+}
+
+extern "C" int fg_xchg_barrier(const fg_xchg_peers* peers, uint32_t epoch, void* stream) {
+    Peers p = {};
+    if (int e = make_peers(peers, p)) return e;
+    FG_LAUNCH(xchg_barrier_kernel, 1, 32, 0, (cudaStream_t)stream, p, epoch);
+    return FG_OK;
+}
+
+extern "C" int fg_xchg_allreduce_f32(const fg_xchg_peers* peers, int64_t offset_bytes, int64_t n_floats, uint32_t epoch,
+                                     int start_barrier, void* stream) {
+    Peers p = {};
+    if (int e = make_peers(peers, p)) return e;
+    FG_REQUIRE(offset_bytes >= 0 && offset_bytes % 16 == 0, "offset_bytes must be a multiple of 16");
+    FG_REQUIRE(n_floats >= 0 && n_floats % 4 == 0, "n_floats must be a multiple of 4");
+    if (n_floats == 0 && !start_barrier) return FG_OK;
+    const long long n4 = n_floats / 4;
+    // every rank derives the same grid from the same n: the barriers pair block b with block b
+    const long long per = (n4 + p.world - 1) / p.world;
+    int grid = (int)std::min<long long>(kNumSMs, std::max<long long>(1, (per + XB * 4 - 1) / (XB * 4)));
+    FG_REQUIRE(1 + 2 * grid <= FG_XCHG_FLAG_BYTES / (XCHG_SLOT_WORDS * 4), "flag area too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.mc) FG_LAUNCH((allreduce_kernel<true>), grid, XB, 0, st, p, (long long)offset_bytes, n4, epoch, start_barrier);
+    else FG_LAUNCH((allreduce_kernel<false>), grid, XB, 0, st, p, (long long)offset_bytes, n4, epoch, start_barrier);
+    return FG_OK;
+}
+
+extern "C" int fg_xchg_sh_bwd_views(const fg_xchg_peers* peers, int64_t pub_offset_bytes, int V, int N, int sh_degree,
+                                    int sh_bases, const float* means, float* v_sh, void* stream) {
+    Peers p = {};
+    if (int e = make_peers(peers, p)) return e;
+    FG_REQUIRE(V >= 1 && N >= 0 && p.world * V <= 256, "views per rank must be >= 1 and world*V <= 256");
+    FG_REQUIRE(sh_degree >= 0 && sh_degree <= 3 && sh_bases >= (sh_degree + 1) * (sh_degree + 1), "bad sh_degree / sh_bases");
+    FG_REQUIRE(sh_bases % 4 == 0 && (uintptr_t)v_sh % 16 == 0, "v_sh rows must be float4-sized and 16-byte aligned");
+    FG_REQUIRE(pub_offset_bytes % 256 == 0, "pub_offset_bytes must be a multiple of 256");
+    if (N == 0) return FG_OK;
+    FG_REQUIRE(means && v_sh, "means / v_sh must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (sh_degree) {
+        case 0: return launch_views<0>(p, pub_offset_bytes, V, N, means, v_sh, sh_bases * 3, st);
+        case 1: return launch_views<1>(p, pub_offset_bytes, V, N, means, v_sh, sh_bases * 3, st);
+        case 2: return launch_views<2>(p, pub_offset_bytes, V, N, means, v_sh, sh_bases * 3, st);
+        default: return launch_views<3>(p, pub_offset_bytes, V, N, means, v_sh, sh_bases * 3, st);
+    }
+}

@@ -64,6 +64,12 @@ struct ProjParams {
     float* v_means_next;
     float* v_quats_next;
     float* v_scales_next;
+    // multi-GPU exchange (csrc/exchange.cu): the SH kernel publishes the clamp-masked colour gradient of every visible
+    // (view, Gaussian), a visibility bit mask and the camera centres instead of writing v_sh rows
+    float* pub_campos;    // [C,4]
+    uint32_t* pub_mask;   // [C,pub_words]
+    float* pub_rgb;       // [C,N,3]
+    int pub_words;
 };
 
 template <int DEG>
@@ -488,8 +494,19 @@ __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
 #pragma unroll
     for (int j = 0; j < NV3; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     bool vis_any = false;
-    if (in_range && p.v_feat)
-        for (int c = 0; c < p.C; ++c) vis_any |= p.radii_in[(size_t)c * p.N + n] > 0;
+    const bool want_sh = p.v_sh != nullptr;
+    for (int c = 0; c < p.C; ++c) {
+        const bool vis = in_range && p.v_feat && p.radii_in[(size_t)c * p.N + n] > 0;
+        vis_any |= vis;
+        if (p.pub_mask) {  // n0 is a multiple of 128: every warp owns whole mask words
+            const uint32_t bits = __ballot_sync(0xffffffffu, vis);
+            if ((threadIdx.x & 31) == 0 && n < p.N) p.pub_mask[(size_t)c * p.pub_words + (n >> 5)] = bits;
+        }
+    }
+    if (p.pub_campos && blockIdx.x == 0 && threadIdx.x < p.C) {
+        const Camera cam = load_camera(p.viewmats + 16 * threadIdx.x, p.Ks + 9 * threadIdx.x);
+        reinterpret_cast<float4*>(p.pub_campos)[threadIdx.x] = make_float4(cam.pos[0], cam.pos[1], cam.pos[2], 0.f);
+    }
     const int nvis = __syncthreads_count(vis_any);
     const bool staged = SH_BWD_STAGE && nvis * 2 >= PB;
     if (staged) {
@@ -524,6 +541,10 @@ __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
             float vr[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) vr[ch] = (ff[ch] > 0.f) ? vf[ch] : 0.f;
+            if (p.pub_rgb) {
+                float* d = p.pub_rgb + i * 3;
+                d[0] = vr[0]; d[1] = vr[1]; d[2] = vr[2];
+            }
             float sk[16];
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -533,22 +554,25 @@ __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
                     const float4 v = staged ? crow[3 * g + j] : __ldg(crow + 3 * g + j);
                     f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
                 }
-                float a[12];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const float4 v = acc[3 * g + j];
-                    a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
+                for (int b = 0; b < 4; ++b) sk[4 * g + b] = f[3 * b] * vr[0] + f[3 * b + 1] * vr[1] + f[3 * b + 2] * vr[2];
+                if (want_sh) {
+                    float a[12];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float4 v = acc[3 * g + j];
+                        a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int k = 4 * g + b;
+                        a[3 * b] = fmaf(B[k], vr[0], a[3 * b]);
+                        a[3 * b + 1] = fmaf(B[k], vr[1], a[3 * b + 1]);
+                        a[3 * b + 2] = fmaf(B[k], vr[2], a[3 * b + 2]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) acc[3 * g + j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
                 }
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int k = 4 * g + b;
-                    sk[k] = f[3 * b] * vr[0] + f[3 * b + 1] * vr[1] + f[3 * b + 2] * vr[2];
-                    a[3 * b] = fmaf(B[k], vr[0], a[3 * b]);
-                    a[3 * b + 1] = fmaf(B[k], vr[1], a[3 * b + 1]);
-                    a[3 * b + 2] = fmaf(B[k], vr[2], a[3 * b + 2]);
-                }
-#pragma unroll
-                for (int j = 0; j < 3; ++j) acc[3 * g + j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
             }
             float vd[3];
             sh_basis_vjp(DEG, x, y, z, sk, vd);
@@ -562,6 +586,7 @@ __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) p.v_means[3 * (size_t)n + i] = v_md[i];
     }
+    if (!want_sh) return;  // exchange mode: the rows are summed over ALL ranks' views by sh_bwd_views_kernel
     __syncthreads();
     // coalesced write of full rows (zeros beyond the evaluated bases)
     const int rows = min(PB, p.N - n0);
@@ -662,12 +687,12 @@ extern "C" int fg_project_bwd(int C, int N, const float* means, const float* qua
                               const float* feat, int feat_stride, int rgb_off, int depth_off, int flow_off,
                               const float* v_flow_affine, float* v_means, float* v_quats, float* v_scales,
                               float* v_sh, float* v_means_next, float* v_quats_next, float* v_scales_next,
-                              void* stream) {
+                              const fg_project_bwd_pub* pub, void* stream) {
     if (C >= 1 && N == 0) return FG_OK;
     if (int e = check_common(C, N, means, quats, scales, viewmats, Ks, sh_degree, sh_bases, sh_coeffs)) return e;
     FG_REQUIRE(!flow_cov || means_next, "covariance flow mode needs means_next");
     FG_REQUIRE(radii && v_means && v_quats && v_scales, "radii and v_means/v_quats/v_scales must not be NULL");
-    FG_REQUIRE(sh_degree < 0 || v_sh, "v_sh must not be NULL when sh_degree >= 0");
+    FG_REQUIRE(sh_degree < 0 || v_sh || pub, "v_sh must not be NULL when sh_degree >= 0 (unless the colour gradients are published)");
     FG_REQUIRE((quats_next != nullptr) == (v_quats_next != nullptr) || !flow_cov, "v_quats_next must mirror quats_next");
     FG_REQUIRE((scales_next != nullptr) == (v_scales_next != nullptr) || !flow_cov, "v_scales_next must mirror scales_next");
     if (N == 0) return FG_OK;
@@ -684,6 +709,12 @@ extern "C" int fg_project_bwd(int C, int N, const float* means, const float* qua
     p.v_means = v_means; p.v_quats = v_quats; p.v_scales = v_scales; p.v_sh = v_sh; p.v_means_next = v_means_next;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec4 = (p.sh_row_floats % 4 == 0) && ((uintptr_t)sh_coeffs % 16 == 0) && ((uintptr_t)v_sh % 16 == 0);
+    if (pub) {
+        FG_REQUIRE(sh_degree >= 0 && vec4 && sh_bases % 4 == 0 && feat != nullptr && v_feat != nullptr,
+                   "publishing needs the streaming SH kernel: sh_degree >= 0, 16-byte rows of 4k bases, feat and v_feat");
+        FG_REQUIRE(pub->campos && pub->mask && pub->rgb && C <= PB && pub->words >= (N + 31) / 32, "bad fg_project_bwd_pub");
+        p.pub_campos = pub->campos; p.pub_mask = pub->mask; p.pub_rgb = pub->rgb; p.pub_words = pub->words;
+    }
     if (sh_degree >= 0 && vec4 && sh_bases % 4 == 0 && feat != nullptr) {
         // two kernels: streaming SH backward (writes v_sh and the direction term into v_means), then
         // the geometry VJP, which adds that term to its own v_means

@@ -270,6 +270,22 @@ def isect_offset_encode(isect_ids: Tensor, C: int, tile_w: int, tile_h: int) -> 
 
 
 # --------------------------------------------------------------------------- A.6
+class _AbsGradTap(torch.autograd.Function):
+    """Identity on a per-pixel copy ``[G,P]`` of one coordinate of the tile's 2-D means.  Its backward sees
+    d(loss)/d(mu) pixel by pixel and adds ``sum_p |.|`` into ``sink[g, col]`` -- gsplat's ``absgrad``
+    (``meta["means2d"].absgrad``, read at ``freegaussian_model.py:377``), which plain autograd cannot give."""
+
+    @staticmethod
+    def forward(ctx, x, g, sink, col):
+        ctx.g, ctx.sink, ctx.col = g, sink, col
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        ctx.sink[:, ctx.col].index_add_(0, ctx.g, grad.detach().abs().sum(1))
+        return grad, None, None, None
+
+
 def rasterize_to_pixels(
     means2d: Tensor,  # [C,N,2]
     conics: Tensor,  # [C,N,3]
@@ -284,6 +300,7 @@ def rasterize_to_pixels(
     flow_affine: Optional[Tensor] = None,  # [C,N,4] row-major 2x2 (covariance flow mode, A.7)
     flow_channels: Optional[Tuple[int, int]] = None,
     chunk: int = 512,
+    absgrad_sink: Optional[Tensor] = None,  # [C*N,2], filled during backward with sum_p |d loss / d means2d|
 ) -> Tuple[Tensor, Tensor, Tensor]:
     """Per-tile front-to-back alpha compositing (Appendix A.6), differentiable.
 
@@ -328,8 +345,12 @@ def rasterize_to_pixels(
                 for b in range(s, e, chunk):
                     g = fid[b : min(b + chunk, e)]
                     G = g.shape[0]
-                    dx = m2[g, 0][:, None] - px[None]
-                    dy = m2[g, 1][:, None] - py[None]
+                    mx, my = m2[g, 0][:, None], m2[g, 1][:, None]
+                    if absgrad_sink is not None:
+                        mx = _AbsGradTap.apply(mx.expand(G, P), g, absgrad_sink, 0)
+                        my = _AbsGradTap.apply(my.expand(G, P), g, absgrad_sink, 1)
+                    dx = mx - px[None]
+                    dy = my - py[None]
                     con = cn[g]
                     sigma = 0.5 * (con[:, 0:1] * dx * dx + con[:, 2:3] * dy * dy) + con[:, 1:2] * dx * dy
                     alpha = torch.clamp(op[g][:, None] * torch.exp(-sigma), max=ALPHA_MAX)
@@ -504,9 +525,10 @@ def rasterization(
     tile_h = math.ceil(height / tile_size)
     tpg, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, tile_w, tile_h)
     isect_offsets = isect_offset_encode(isect_ids, C, tile_w, tile_h)
+    absgrad_sink = torch.zeros(C * N, 2, dtype=means2d.dtype) if absgrad else None
     render, alphas, last_ids = rasterize_to_pixels(
         means2d, conics, cols, opac, width, height, tile_size, isect_offsets, flatten_ids,
-        backgrounds=backgrounds, flow_affine=flow_affine, flow_channels=flow_channels,
+        backgrounds=backgrounds, flow_affine=flow_affine, flow_channels=flow_channels, absgrad_sink=absgrad_sink,
     )
     flow = None
     if means_next is not None:
@@ -524,6 +546,8 @@ def rasterization(
     }
     if flow is not None:
         meta["flow"] = flow
+    if absgrad_sink is not None:  # complete after backward(): gsplat's means2d.absgrad, [C,N,2]
+        meta["absgrad"] = absgrad_sink.view(C, N, 2)
     if packed:
         idx = torch.nonzero(vis.reshape(-1)).squeeze(-1)
         meta["camera_ids"] = (idx // N).to(torch.int64)

@@ -261,3 +261,33 @@ def test_sh_basis_is_the_real_spherical_harmonics():
             assert np.abs(basis[:, k] - want).max() < 1e-14, (l, m)
             k += 1
     assert k == 16 == O.num_sh_bases(3)
+
+
+def test_absgrad_tap_equals_a_pixel_by_pixel_backward():
+    """``meta["absgrad"]`` (gsplat's ``means2d.absgrad``, consumed at ``freegaussian_model.py:377``) is the sum over pixels of
+    |d loss_p / d means2d|: check the autograd tap against one backward per pixel on a tiny frame."""
+    W, H = 12, 9
+    sc = small_scene(40, W, H, views=1, seed=23, scale_mul=1.5)
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(1, H, W, 3, generator=g).double()
+    d = lambda x: x.double()
+    args = (d(sc.means).requires_grad_(True), d(sc.quats), d(sc.scales), d(sc.opacities), d(sc.sh), d(sc.viewmats),
+            d(sc.Ks), W, H)
+    r, a, m = O.rasterization(*args, sh_degree=3, absgrad=True)
+    assert int((m["radii"] > 0).sum()) > 10
+    m["means2d"].retain_grad()
+    (r * w).sum().backward()
+    want = torch.zeros_like(m["absgrad"])
+    for y in range(H):
+        for x in range(W):
+            r2, _, m2 = O.rasterization(*args, sh_degree=3)
+            m2["means2d"].retain_grad()
+            (r2[0, y, x] * w[0, y, x]).sum().backward()
+            want += m2["means2d"].grad.abs()
+    assert float(want.max()) > 0
+    assert rel_err(m["absgrad"], want) < 1e-12
+    # and the tap leaves the ordinary gradient untouched
+    r3, _, m3 = O.rasterization(*args, sh_degree=3)
+    m3["means2d"].retain_grad()
+    (r3 * w).sum().backward()
+    assert torch.allclose(m["means2d"].grad, m3["means2d"].grad, rtol=0, atol=1e-14)
