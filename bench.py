@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--views-per-gpu", type=int, default=1, help="views each rank renders per step (cfg4: 4)")
     ap.add_argument("--no-train-iter", action="store_true", help="skip the stage-1 training-iteration section (train_iter)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: 'peer' = published colour gradients + in-switch all-reduce inside the backward (csrc/exchange.cu); "
+                         "'nccl' = one NCCL all-reduce over the dense 236 B/Gaussian arena (round-1 path, kept for comparison)")
     return ap.parse_args()
 
 
@@ -130,7 +133,7 @@ def run_ours(args):
     import torch.distributed as dist
     from freegaussian_b200 import _lib
     from freegaussian_b200 import rendering
-    from freegaussian_b200.dist import DensificationStats, exchange
+    from freegaussian_b200.dist import DensificationStats, ViewShardedExchange, exchange
     from freegaussian_b200.rendering import rasterization
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -152,6 +155,10 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     L = _lib.lib()
+    xchg = None
+    if world > 1 and args.exchange == "peer":
+        # the exchange runs inside the projection backward over NVLink peer memory (csrc/exchange.cu)
+        xchg = ViewShardedExchange().install()
 
     n, W, H = WORKLOADS[args.workload]
     sc = build_scene(args.workload, args.recipe, dev, N_VIEW_POOL * world)
@@ -223,7 +230,9 @@ def run_ours(args):
         # exchange step: ONE all-reduce over the flat gradient arena (no-op at N=1).  The densification
         # statistics are accumulated per rank by one kernel per step and reduced across ranks when they
         # are consumed (refine_every = 100 steps in the reference configs) -- same numbers.
-        exchange([p.grad for p in params])
+        if xchg is None and world > 1:
+            with rendering._stage("exchange"):
+                exchange([p.grad for p in params])
         state["it"] += 1
         if state["it"] % REFINE_EVERY == 0:
             stats.sync()
@@ -380,6 +389,19 @@ def run_ours(args):
             "kernels": kernels,
             "stage_ms": stage_ms,
         }
+        if world > 1:
+            geo_b = 4 * (n * 14 + 3 * n)  # means 3 + quats 4 + scales 3 + opacity 1 + means_next 3 floats, reduced in the switch
+            if xchg is not None:
+                out["exchange"] = {"mode": "peer: published colour gradients (12 B per visible (view, Gaussian)) read over NVLink by "
+                                           "fg_xchg_sh_bwd_views + in-switch two-shot all-reduce of the geometry gradients",
+                                   "multicast": bool(xchg.multicast), "ms": stage_ms.get("exchange"),
+                                   "allreduce_bytes": geo_b, "published_bytes_per_rank": n_vis * 12 + n // 8,
+                                   "dense_arena_bytes_replaced": 4 * n * 62}
+            else:
+                out["exchange"] = {"mode": "nccl: one all-reduce over the dense gradient arena", "ms": stage_ms.get("exchange"),
+                                   "allreduce_bytes": 4 * n * 62,
+                                   "bus_gbs": (4 * n * 62 * 2 * (world - 1) / world / (stage_ms["exchange"] * 1e-3) / 1e9)
+                                   if stage_ms.get("exchange") else None}
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only
             out["cpu_baseline"] = cpu_arm(args, steps=args.cpu_steps, warmup=0)["cpu_baseline"]
         if world == 1 and not args.no_train_iter:  # last: nothing after it needs the device

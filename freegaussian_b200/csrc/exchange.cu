@@ -17,6 +17,10 @@
 // flight) and `multimem.st`s the result to all ranks -- with the cross-rank barriers inside the kernel
 // (release/acquire flags in symmetric memory).  Without multicast the same kernel falls back to peer
 // loads + peer stores.
+#include <stdio.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "splat_math.h"
 

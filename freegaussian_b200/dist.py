@@ -17,6 +17,7 @@ single process rendering all views would accumulate.
 
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -118,6 +119,142 @@ class DensificationStats:
     reduce = sync  # per-step use
 
 
+class ViewShardedExchange:
+    """The exchange step of a view-sharded run, executed INSIDE the projection backward over NVLink peer memory
+    (``csrc/exchange.cu``).  After :meth:`install`, ``loss.backward()`` on every rank returns, for
+    every Gaussian parameter of the ``rasterization`` call, the gradient summed over ALL ranks' views -- what a single
+    process rendering every view would have computed.  Every rank must make the same sequence of
+    ``rasterization(...)``/``backward()`` calls with the same N, views per rank and kwargs.
+
+    What travels: the 12-byte colour gradient of every visible (view, Gaussian) is published in symmetric memory and
+    every rank rebuilds the 192-byte SH rows from all views itself (``fg_xchg_sh_bwd_views``: peer loads over NVLink,
+    fixed summation order, bit-identical on every rank); the geometry gradients (56 B per Gaussian: means, quats,
+    scales, opacity, frame t+1 means) are summed in place by a two-shot all-reduce that runs in the NVSwitch
+    (``fg_xchg_allreduce_f32``: ``multimem.ld_reduce`` + ``multimem.st``, barriers inside the kernel).  torch is used for
+    the plumbing only: ``torch.distributed._symmetric_memory`` allocates and peer-maps the buffers.
+
+    The gradient tensors handed to autograd are views of that symmetric buffer: they are overwritten by the next
+    backward (set ``p.grad = None`` before every step, as the reference trainer's ``zero_grad(set_to_none=True)`` does).
+    """
+
+    def __init__(self, group=None, use_multicast: bool = True):
+        assert dist.is_available() and dist.is_initialized(), "init_process_group first"
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.use_multicast = use_multicast and not os.environ.get("FG_XCHG_NO_MULTICAST")
+        self.epoch = 0
+        self.parity = 0
+        self._buf = None       # uint8 tensor over this rank's symmetric block
+        self._peers = None     # _lib.XchgPeers
+        self._layout = None    # (pub_bytes, arena_bytes)
+        self._old = []         # previous blocks are kept alive: a peer may still be reading them
+        self.multicast = False
+
+    # -- lifecycle
+    def active(self) -> bool:
+        return self.world > 1
+
+    def install(self) -> "ViewShardedExchange":
+        from . import rendering
+        rendering._exchange_hook = self
+        return self
+
+    def uninstall(self) -> None:
+        from . import rendering
+        if rendering._exchange_hook is self:
+            rendering._exchange_hook = None
+
+    # -- symmetric memory
+    def _ensure(self, pub_bytes: int, arena_bytes: int, device) -> None:
+        """(Re)allocate the symmetric block: flags | publish block x 2 (double-buffered by step parity) | arena.
+        Collective: every rank computes the same sizes from the same N, so all ranks get here together."""
+        from . import _lib
+        import torch.distributed._symmetric_memory as symm
+        cur = self._layout
+        if cur is not None and pub_bytes <= cur[0] and arena_bytes <= cur[1]:
+            return
+        pub_bytes = max(pub_bytes, cur[0] if cur else 0)
+        arena_bytes = max(arena_bytes, cur[1] if cur else 0)
+        rnd = lambda b: (int(b) + 4095) // 4096 * 4096  # noqa: E731
+        pub_bytes, arena_bytes = rnd(pub_bytes), rnd(arena_bytes)
+        total = _lib.XCHG_FLAG_BYTES + 2 * pub_bytes + arena_bytes
+        if self._buf is not None:
+            torch.cuda.synchronize(device)
+            self._old.append((self._buf, self._hdl))
+        buf = symm.empty(total, dtype=torch.uint8, device=device)
+        hdl = symm.rendezvous(buf, self.group.group_name)
+        buf[:_lib.XCHG_FLAG_BYTES].zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)  # every rank's flags are zero before anyone signals
+        off = buf.data_ptr() - int(hdl.buffer_ptrs[hdl.rank])
+        peers = _lib.XchgPeers()
+        peers.world, peers.rank = self.world, self.rank
+        for r in range(self.world):
+            peers.buf[r] = int(hdl.buffer_ptrs[r]) + off
+            peers.flags[r] = int(hdl.buffer_ptrs[r]) + off  # the flag area is the head of the block
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        self.multicast = bool(mc) and self.use_multicast
+        peers.mc = (mc + off) if self.multicast else None
+        self._buf, self._hdl, self._peers = buf, hdl, peers
+        self._layout = (pub_bytes, arena_bytes)
+        self.pub_off = [_lib.XCHG_FLAG_BYTES, _lib.XCHG_FLAG_BYTES + pub_bytes]
+        self.arena_off = _lib.XCHG_FLAG_BYTES + 2 * pub_bytes
+
+    def prepare(self, n_floats: int, C: int, N: int, device) -> None:
+        """Size the symmetric block for a backward with an ``n_floats`` arena and C published views of N Gaussians
+        (collective the first time and whenever it has to grow)."""
+        from . import _lib
+        pub = int(_lib.lib().fg_xchg_pub_bytes(C, N)) if C else 0
+        self._ensure(pub, (n_floats + 3) // 4 * 16, device)
+
+    def arena(self, n_floats: int, device) -> Tensor:
+        """The flat gradient buffer of one backward: ``n_floats`` fp32 of symmetric memory."""
+        self._ensure(0, (n_floats + 3) // 4 * 16, device)
+        return self._buf[self.arena_off:self.arena_off + 4 * n_floats].view(torch.float32)
+
+    def publish_block(self, C: int, N: int):
+        """``fg_project_bwd_pub`` pointing at this step's publish block (camera centres | mask | colour gradients)."""
+        from . import _lib
+        assert self._layout is not None and int(_lib.lib().fg_xchg_pub_bytes(C, N)) <= self._layout[0], "prepare() first"
+        words = ((N + 31) // 32 + 3) & ~3
+        mask_off = (C * 16 + 255) // 256 * 256
+        rgb_off = (mask_off + C * words * 4 + 255) // 256 * 256
+        base = self._buf.data_ptr() + self.pub_off[self.parity]
+        pub = _lib.ProjectBwdPub()
+        pub.campos, pub.mask, pub.rgb, pub.words = base, base + mask_off, base + rgb_off, words
+        return pub
+
+    def reduce(self, n_floats: int, sh_from_views: bool, C: int, N: int, sh_degree, sh_bases: int, means: Tensor,
+               v_sh: Optional[Tensor]) -> None:
+        """All-reduce the first ``n_floats`` of the arena in place; with ``sh_from_views`` then rebuild the SH rows
+        from every rank's published colour gradients.  Enqueued on the current stream; no host synchronisation."""
+        from . import _lib
+        L = _lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        self.epoch += 1
+        n4 = (n_floats + 3) // 4 * 4
+        _lib.check(L.fg_xchg_allreduce_f32(self._peers, self.arena_off, n4, self.epoch, 1, st))
+        if sh_from_views:
+            _lib.check(L.fg_xchg_sh_bwd_views(self._peers, self.pub_off[self.parity], C, N, int(sh_degree), sh_bases,
+                                              _lib.ptr(means), _lib.ptr(v_sh), st))
+            self.parity ^= 1
+
+    def all_reduce_(self, t: Tensor) -> Tensor:
+        """In-place SUM of any fp32 CUDA tensor over the ranks through the same NVLS kernel (staged through the arena):
+        network weight gradients, densification statistics."""
+        from . import _lib
+        flat = t.reshape(-1)
+        n = flat.numel()
+        a = self.arena(n, t.device)
+        a[:n].copy_(flat)
+        self.epoch += 1
+        _lib.check(_lib.lib().fg_xchg_allreduce_f32(self._peers, self.arena_off, (n + 3) // 4 * 4, self.epoch, 1,
+                                                   torch.cuda.current_stream().cuda_stream))
+        flat.copy_(a[:n])
+        return t
+
+
 def exchange(grads: Sequence[Tensor], group=None) -> None:
     """THE exchange step of a view-sharded training step: all-reduce(SUM) of every
     parameter gradient.  (The densification statistics are reduced by ``DensificationStats.sync``.)
@@ -131,6 +268,13 @@ def exchange(grads: Sequence[Tensor], group=None) -> None:
         return
     from . import rendering
     grads = [g for g in grads if g is not None]
+    hook = rendering._exchange_hook
+    if hook is not None and hook.active() and hook._buf is not None:
+        # gradients that came out of a backward with ViewShardedExchange installed are already summed over the ranks
+        base = hook._buf.untyped_storage().data_ptr()
+        grads = [g for g in grads if g.untyped_storage().data_ptr() != base]
+        if not grads:
+            return
     info = rendering.last_grad_arena() if grads and grads[0].is_cuda else None
     loose = grads
     if info is not None:

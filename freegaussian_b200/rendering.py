@@ -63,6 +63,16 @@ def last_grad_arena():
     return _grad_arena.get("last")
 
 
+# Installed by freegaussian_b200.dist.ViewShardedExchange.install(): when set (and world size > 1) the projection
+# backward writes into symmetric memory and ends with the cross-rank exchange, so the gradients autograd hands to the
+# parameters are already the sums over every rank's views.
+_exchange_hook = None
+
+
+def _align4(n: int) -> int:
+    return (n + 3) & ~3
+
+
 class StageTimer:
     """Optional CUDA-event timing of each C-ABI stage (bench.py's per-kernel roofline).
     Disabled by default: ``with _stage(name)`` then costs one attribute test."""
@@ -120,7 +130,8 @@ class _Project(torch.autograd.Function):
     """fg_project_fwd / fg_project_bwd.  Outputs: radii, means2d, depths, conics, comps, feat, tiles."""
 
     @staticmethod
-    def forward(ctx, means, quats, scales, colors, means_next, quats_next, scales_next, viewmats, Ks, cfg):
+    def forward(ctx, means, quats, scales, colors, means_next, quats_next, scales_next, viewmats, Ks, cfg,
+                opacities=None):
         L = _lib.lib()
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
@@ -214,10 +225,15 @@ class _Project(torch.autograd.Function):
         if flow_affine is None:
             flow_affine = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(flow_affine)
-        return radii, means2d, depths, conics, comps, feat, tiles, flow_affine
+        # the opacities pass through unchanged: their gradient then arrives in THIS node's backward together with every
+        # other parameter gradient of the call, which is where a view-sharded run sums them across ranks
+        opac_out = torch.empty(0, device=dev) if opacities is None else opacities.view(opacities.shape)
+        if opacities is None:
+            ctx.mark_non_differentiable(opac_out)
+        return radii, means2d, depths, conics, comps, feat, tiles, flow_affine, opac_out
 
     @staticmethod
-    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_feat, _v_tiles, v_flow_affine):
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_feat, _v_tiles, v_flow_affine, v_opac):
         L = _lib.lib()
         means, quats, scales, sh, means_next, quats_next, scales_next, viewmats, Ks, radii, feat_fwd = ctx.saved_tensors
         cfg = ctx.cfg
@@ -230,36 +246,63 @@ class _Project(torch.autograd.Function):
 
         v_means2d, v_depths, v_conics, v_feat = c(v_means2d), c(v_depths), c(v_conics), c(v_feat)
         v_comps = c(v_comps) if cfg["antialiased"] else None
-        # All parameter gradients of this call live in ONE flat buffer (plus 3N spare floats), so a
-        # view-sharded trainer can all-reduce them with a single collective (dist.exchange).
-        sizes = [3 * N, 4 * N, 3 * N, sh_bases * 3 * N if use_sh else 0, 3 * N if means_next is not None else 0,
-                 4 * N if quats_next is not None else 0, 3 * N if scales_next is not None else 0]
-        used = sum(sizes)
-        arena = torch.empty(used + 3 * N, device=dev)
-        parts = torch.split(arena[:used], sizes)
-        v_means, v_quats, v_scales = parts[0].view(N, 3), parts[1].view(N, 4), parts[2].view(N, 3)
-        v_sh = parts[3].view(N, sh_bases, 3) if use_sh else None
-        v_means_next = parts[4].view(N, 3) if means_next is not None else None
-        v_quats_next = parts[5].view(N, 4) if quats_next is not None else None
-        v_scales_next = parts[6].view(N, 3) if scales_next is not None else None
+        xc = _exchange_hook if (_exchange_hook is not None and _exchange_hook.active()) else None
+        v_opac = v_opac if ctx.needs_input_grad[10] else None
+        v_col2d = None  # colours given per Gaussian ([N,D], shared by the cameras) instead of SH coefficients
+        if not use_sh and col_dim == 2 and v_feat is not None:
+            v_col2d = v_feat[..., :n_col].sum(0)
+        # All parameter gradients of this call live in ONE flat buffer: the geometry segments first (each padded to
+        # 16 bytes; in a view-sharded run also the gradients that only pass through this node), the SH rows last.
+        # Single GPU: a fresh allocation.  View-sharded: symmetric memory, reduced in place below.
+        geo = [3 * N, 4 * N, 3 * N, 3 * N if means_next is not None else 0, 4 * N if quats_next is not None else 0,
+               3 * N if scales_next is not None else 0,
+               v_opac.numel() if (xc is not None and v_opac is not None) else 0,
+               v_col2d.numel() if (xc is not None and v_col2d is not None) else 0]
+        offs, o = [], 0
+        for n_ in geo:
+            offs.append(o)
+            o += _align4(n_)
+        geo_floats = o
+        sh_floats = sh_bases * 3 * N if use_sh else 0
+        used = geo_floats + sh_floats
+        # view-sharded with SH colours: publish the 12-byte colour gradients instead of writing 192-byte SH rows; the rows
+        # are then summed over every rank's views by fg_xchg_sh_bwd_views and only the geometry segments are all-reduced
+        want_pub = xc is not None and use_sh and sh_bases % 4 == 0 and v_feat is not None and C <= 128 and N > 0
+        if xc is not None:
+            xc.prepare(used, C if want_pub else 0, N, dev)
+        arena = xc.arena(used, dev) if xc is not None else torch.empty(used + 3 * N + 4, device=dev)
+        seg = lambda k, shape: arena[offs[k]:offs[k] + geo[k]].view(shape) if geo[k] else None  # noqa: E731
+        v_means, v_quats, v_scales = seg(0, (N, 3)), seg(1, (N, 4)), seg(2, (N, 3))
+        v_means_next, v_quats_next, v_scales_next = seg(3, (N, 3)), seg(4, (N, 4)), seg(5, (N, 3))
+        v_sh = arena[geo_floats:used].view(N, sh_bases, 3) if use_sh else None
         _grad_arena["last"] = (arena, used)
         v_flow_affine = c(v_flow_affine) if flow_cov else None
+        pub = xc.publish_block(C, N) if want_pub else None
         with _stage("project_bwd"):
           check(L.fg_project_bwd(
             C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
             cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"],
             cfg["sh_degree"] if use_sh else -1, sh_bases, ptr(sh), ptr(means_next), ptr(quats_next), ptr(scales_next),
             int(flow_cov), ptr(radii), ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_feat),
-            ptr(feat_fwd), CH, rgb_off, depth_off, flow_off, ptr(v_flow_affine), ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_sh),
-            ptr(v_means_next), ptr(v_quats_next), ptr(v_scales_next), _stream()))
+            ptr(feat_fwd), CH, rgb_off, depth_off, flow_off, ptr(v_flow_affine), ptr(v_means), ptr(v_quats), ptr(v_scales),
+            None if pub is not None else ptr(v_sh), ptr(v_means_next), ptr(v_quats_next), ptr(v_scales_next),
+            None if pub is None else ctypes.byref(pub), _stream()))
+        if xc is not None:
+            if geo[6]:
+                seg(6, v_opac.shape).copy_(v_opac)
+                v_opac = seg(6, v_opac.shape)
+            if geo[7]:
+                seg(7, v_col2d.shape).copy_(v_col2d)
+                v_col2d = seg(7, v_col2d.shape)
+            with _stage("exchange"):
+                xc.reduce(geo_floats if pub is not None else used, pub is not None, C, N, cfg["sh_degree"], sh_bases, means, v_sh)
         v_colors = None
         if use_sh:
             v_colors = v_sh
         elif col_dim is not None and v_feat is not None:
-            v_colors = v_feat[..., :n_col]
-            if col_dim == 2:
-                v_colors = v_colors.sum(0)
-        return v_means, v_quats, v_scales, v_colors, v_means_next, v_quats_next, v_scales_next, None, None, None
+            v_colors = v_col2d if col_dim == 2 else v_feat[..., :n_col]
+        return (v_means, v_quats, v_scales, v_colors, v_means_next, v_quats_next, v_scales_next, None, None, None,
+                v_opac)
 
 
 # --------------------------------------------------------------------------- tile intersection
@@ -602,8 +645,8 @@ def rasterization(
     cfg["fused"] = bool(FUSED_CALLS and SORT_MODE == "binned" and not stage_timer.enabled and not packed
                         and n_feat <= MAX_CH)
     proj_colors = None if only_depth else colors
-    radii, means2d, depths, conics, comps, feat, tiles, flow_affine = _Project.apply(
-        means, quats, scales, proj_colors, means_next, quats_next, scales_next, viewmats, Ks, cfg)
+    radii, means2d, depths, conics, comps, feat, tiles, flow_affine, opacities = _Project.apply(
+        means, quats, scales, proj_colors, means_next, quats_next, scales_next, viewmats, Ks, cfg, opacities)
     if not cfg["flow_cov"]:
         flow_affine = None
     n_user = feat.shape[-1] - (2 if means_next is not None else 0)

@@ -68,6 +68,18 @@ int fg_project_fwd(int C, int N, const float* means, const float* quats, const f
                    int feat_stride, int rgb_off, int depth_off, int flow_off, float* flow_affine,
                    int32_t* tiles_per_gauss, void* stream);
 
+/* Optional output of fg_project_bwd for the view-sharded multi-GPU exchange (section (5) below): instead of writing
+ * v_sh rows (pass v_sh = NULL), the SH kernel PUBLISHES, for its own C views, the camera centres campos[C,4], a
+ * visibility bit mask mask[C,words] (bit n of view c = radii[c,n] > 0; words >= ceil(N/32)) and the colour gradient
+ * rgb[C,N,3] with the max(rgb+0.5,0) clamp mask applied (rows of invisible splats are not written).  The three
+ * pointers normally point into the rank's block of symmetric memory (fg_xchg_pub_bytes gives the layout). */
+typedef struct {
+    float* campos;
+    uint32_t* mask;
+    float* rgb;
+    int32_t words;
+} fg_project_bwd_pub;
+
 /* VJP of fg_project_fwd (gsplat `fully_fused_projection_bwd` + `spherical_harmonics` bwd).
  * Any of v_means2d / v_depths / v_conics / v_compensations / v_feat / v_flow_affine may be
  * NULL (= zero).  Outputs are fully overwritten (no pre-zeroing needed):
@@ -87,7 +99,7 @@ int fg_project_bwd(int C, int N, const float* means, const float* quats, const f
                    const float* feat, int feat_stride, int rgb_off, int depth_off, int flow_off,
                    const float* v_flow_affine, float* v_means, float* v_quats, float* v_scales,
                    float* v_sh, float* v_means_next, float* v_quats_next, float* v_scales_next,
-                   void* stream);
+                   const fg_project_bwd_pub* pub, void* stream);
 
 /* ---- (2) tile intersection: scan, emission, sort, offsets ------------------------------
  * Replaces gsplat `isect_tiles` (+cumsum), `cub::DeviceRadixSort::SortPairs`, and
@@ -411,6 +423,41 @@ int fg_deform_apply_fwd(int64_t N, const float* head, const float* means, const 
 int fg_deform_apply_bwd(int64_t N, const float* head, const float* means, const float* scales_log, const float* quats,
                         const float* v_means_out, const float* v_scales_out, const float* v_quats_out, float* v_head,
                         float* v_means, float* v_scales_log, float* v_quats, void* stream);
+
+
+/* ---- (5) view-sharded multi-GPU exchange over NVLink peer memory / NVSwitch multicast ------------------
+ * BASELINE.json north_star item 5; the reference itself is single-GPU, so these have no reference
+ * counterpart: they make `loss.backward()` on every rank return the gradient one process rendering all views would.
+ * One process per GPU; every rank owns a block of SYMMETRIC memory (same size on every rank, peer-mapped into every
+ * rank's address space, optionally also mapped through an NVSwitch multicast object).  `buf[r]` / `flags[r]` are rank
+ * r's block and flag area as seen from THIS rank; `mc` is the multicast alias of `buf` (NULL: no NVLS, the kernels use
+ * peer loads / stores instead).  The flag area is FG_XCHG_FLAG_BYTES bytes, zeroed once before first use.  `epoch`
+ * must grow by one per call (all ranks pass the same value); calls must be issued in the same order on every rank. */
+#define FG_XCHG_MAX_RANKS 16
+#define FG_XCHG_FLAG_BYTES 32768
+typedef struct {
+    int32_t world, rank;
+    void* buf[FG_XCHG_MAX_RANKS];
+    void* mc;
+    void* flags[FG_XCHG_MAX_RANKS];
+} fg_xchg_peers;
+
+/* Bytes of one rank's published block for V views of N Gaussians: campos | mask | rgb (see fg_project_bwd_pub). */
+int64_t fg_xchg_pub_bytes(int V, int N);
+/* Cross-rank barrier on the stream: returns (on the device) once every rank's stream has reached it. */
+int fg_xchg_barrier(const fg_xchg_peers* peers_host, uint32_t epoch, void* stream);
+/* In-place all-reduce(SUM) of n_floats (multiple of 4) at offset_bytes (multiple of 16) of the symmetric buffer.
+ * Two-shot inside ONE kernel: rank r multimem.ld_reduce's the r-th slice (summed by the switch), multimem.st's it to
+ * every rank; start_barrier != 0 first waits until every rank has reached the call (its inputs are complete), and the
+ * kernel ends with a barrier, so that on return every rank holds the full result.  Same value on every rank. */
+int fg_xchg_allreduce_f32(const fg_xchg_peers* peers_host, int64_t offset_bytes, int64_t n_floats, uint32_t epoch,
+                          int start_barrier, void* stream);
+/* v_sh[N,sh_bases,3] = sum over ALL ranks' views of basis(dir(n, view)) x published colour gradient: reads every
+ * rank's published block (at pub_offset_bytes of its symmetric buffer) over NVLink; rows of invisible splats are never
+ * fetched.  Fixed summation order (rank, view): bit-identical on every rank.  Call after a barrier that follows the
+ * publishing fg_project_bwd on every rank. */
+int fg_xchg_sh_bwd_views(const fg_xchg_peers* peers_host, int64_t pub_offset_bytes, int V, int N, int sh_degree,
+                         int sh_bases, const float* means, float* v_sh, void* stream);
 
 #ifdef __cplusplus
 }
