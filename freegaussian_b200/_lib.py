@@ -107,8 +107,10 @@ SIGNATURES = {
     "fg_densify_stats": (_i32, [_i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
     "fg_assign_masks": (_i32, [_i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "fg_l1_ssim_workspace_floats": (_i64, [_i32, _i32]),
-    "fg_l1_ssim_fwd": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp]),
-    "fg_l1_ssim_bwd": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "fg_l1_ssim_fwd": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp]),
+    "fg_l1_ssim_bwd": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "fg_depth_fixup_fwd": (_i32, [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "fg_depth_fixup_bwd": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "fg_render_front_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "fg_render_front": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _i32,
                                _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -170,6 +172,32 @@ def ptr(t):
         return None
     assert t.is_contiguous(), "internal: non-contiguous tensor handed to the C ABI"
     return t.data_ptr()
+
+
+def on_device_of(arg):
+    """Decorator: run the call with the CUDA device of tensor argument ``arg`` (position or keyword name) current, so
+    the kernels go to that device's current stream even when the caller's current device is another one.  Non-CUDA
+    arguments pass through untouched (the entry points then raise their own "no CPU path" errors)."""
+    import functools
+    import inspect
+
+    def deco(fn):
+        names = list(inspect.signature(fn).parameters)
+        idx = arg if isinstance(arg, int) else names.index(arg)
+        name = names[idx]
+
+        @functools.wraps(fn)
+        def wrapped(*a, **kw):
+            import torch
+            t = a[idx] if idx < len(a) else kw.get(name)
+            if isinstance(t, torch.Tensor) and t.is_cuda and t.device.index != torch.cuda.current_device():
+                with torch.cuda.device(t.device):
+                    return fn(*a, **kw)
+            return fn(*a, **kw)
+
+        return wrapped
+
+    return deco
 
 
 def launch_count() -> int:

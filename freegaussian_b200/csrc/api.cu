@@ -9,6 +9,18 @@ namespace fg {
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launch_count{0};
 
+int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 int set_error(int code, const char* msg, const char* file, int line) {
     const char* base = strrchr(file, '/');
     snprintf(g_err, sizeof(g_err), "%s (%s:%d)", msg, base ? base + 1 : file, line);
@@ -61,7 +73,7 @@ extern "C" int fg_measure_fp32_tflops(double* tflops_host, void* stream) {
     cudaEvent_t e0, e1;
     FG_CUDA(cudaEventCreate(&e0));
     FG_CUDA(cudaEventCreate(&e1));
-    const int iters = 4096, blocks = fg::kNumSMs * 2;
+    const int iters = 4096, blocks = fg::num_sms() * 2;
     double best = 0;
     for (int rep = 0; rep < 4; ++rep) {
         FG_CUDA(cudaEventRecord(e0, st));

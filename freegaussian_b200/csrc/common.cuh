@@ -14,7 +14,9 @@ int set_error(int code, const char* msg, const char* file, int line);
 int set_cuda_error(cudaError_t e, const char* file, int line);
 extern std::atomic<long long> g_launch_count;
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device (148 on a B200), queried once per device: grids of the persistent / grid-stride
+// kernels are sized from it.
+int num_sms();
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -221,7 +221,7 @@ extern "C" int fg_refine_gather(int64_t n_out, int64_t n_keep, const int32_t* sr
         widest = arrays[i].row_floats > widest ? arrays[i].row_floats : widest;
     }
     long long blocks = (n_out * widest + RB - 1) / RB;
-    const long long cap = (long long)kNumSMs * 32;
+    const long long cap = (long long)num_sms() * 32;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)n_arrays);
     FG_LAUNCH(refine_gather_kernel, grid, RB, 0, stream, p);

@@ -268,7 +268,7 @@ extern "C" int fg_xchg_allreduce_f32(const fg_xchg_peers* peers, int64_t offset_
     const long long n4 = n_floats / 4;
     // every rank derives the same grid from the same n: the barriers pair block b with block b
     const long long per = (n4 + p.world - 1) / p.world;
-    int grid = (int)std::min<long long>(kNumSMs, std::max<long long>(1, (per + XB * 4 - 1) / (XB * 4)));
+    int grid = (int)std::min<long long>(num_sms(), std::max<long long>(1, (per + XB * 4 - 1) / (XB * 4)));
     FG_REQUIRE(1 + 2 * grid <= FG_XCHG_FLAG_BYTES / (XCHG_SLOT_WORDS * 4), "flag area too small");
     cudaStream_t st = (cudaStream_t)stream;
     if (p.mc) FG_LAUNCH((allreduce_kernel<true>), grid, XB, 0, st, p, (long long)offset_bytes, n4, epoch, start_barrier);

@@ -230,7 +230,7 @@ extern "C" int fg_knn_f32(int64_t n, const float* points, int k, float* out_dist
     // 1. bounding box (host needs it to size the grid: one small D2H + sync, init-time only)
     unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     FG_CUDA(cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    FG_LAUNCH(knn_bbox_kernel, (int)std::min<long long>((long long)kNumSMs * 8, ((long long)n + 255) / 256), 256, 0, st, (long long)n, points, bbox);
+    FG_LAUNCH(knn_bbox_kernel, (int)std::min<long long>((long long)num_sms() * 8, ((long long)n + 255) / 256), 256, 0, st, (long long)n, points, bbox);
     unsigned hb[6];
     FG_CUDA(cudaMemcpyAsync(hb, bbox, sizeof(hb), cudaMemcpyDeviceToHost, st));
     FG_CUDA(cudaStreamSynchronize(st));

@@ -14,6 +14,8 @@
 // Roofline: HBM.  Forward reads render, alpha, gt once (+halo re-reads through L2) and writes 3 floats per
 // channel per valid pixel; backward reads them back and writes v_render, v_alpha.  ~50 floats of
 // traffic per pixel against ~15 full-image elementwise/conv passes in the torch formulation.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace fg {
@@ -23,9 +25,10 @@ constexpr int LTX = 32, LTY = 16;        // output block
 constexpr int LHX = LTX + LW - 1, LHY = LTY + LW - 1;  // halo block 42 x 26
 constexpr float SSIM_C1 = 0.01f * 0.01f, SSIM_C2 = 0.03f * 0.03f;
 
-__constant__ float c_win[LW];
-
 struct LossParams {
+    float win[LW];         // the 11 normalised Gaussian taps, by value (kernel parameters live in the constant bank of
+                           // whichever device the launch goes to: no per-device __constant__ symbol to initialise)
+    const float* mask;     // [H,W] or NULL: gt and pred are both multiplied by it (freegaussian_model.py:957-963)
     int W, H, rstride;     // rstride: floats per pixel of `render` (3 or 4 ...)
     const float* render;   // [H,W,rstride]
     const float* alpha;    // [H,W]
@@ -45,6 +48,9 @@ __device__ __forceinline__ float pred_at(const LossParams& p, int x, int y, int 
     raw = p.render[pix * p.rstride + ch] + (1.f - p.alpha[pix]) * p.bg[ch];
     return fminf(fmaxf(raw, 0.f), 1.f);
 }
+__device__ __forceinline__ float mask_at(const LossParams& p, int x, int y) {
+    return p.mask ? p.mask[(size_t)y * p.W + x] : 1.f;
+}
 
 __global__ void __launch_bounds__(256) l1_ssim_fwd_kernel(LossParams p) {
     pdl_wait();
@@ -63,8 +69,9 @@ __global__ void __launch_bounds__(256) l1_ssim_fwd_kernel(LossParams p) {
         float xv = 0.f, yv = 0.f;
         if (x < p.W && y < p.H) {
             float raw;
-            yv = pred_at(p, x, y, ch, raw);
-            xv = p.gt[((size_t)y * p.W + x) * 3 + ch];
+            const float mk = mask_at(p, x, y);
+            yv = pred_at(p, x, y, ch, raw) * mk;
+            xv = p.gt[((size_t)y * p.W + x) * 3 + ch] * mk;
             if (i < LTX && j < LTY) l1 += fabsf(xv - yv);  // every pixel is the interior of exactly one block
         }
         sx[j][i] = xv;
@@ -76,7 +83,7 @@ __global__ void __launch_bounds__(256) l1_ssim_fwd_kernel(LossParams p) {
         float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
 #pragma unroll
         for (int k = 0; k < LW; ++k) {
-            const float w = c_win[k], xv = sx[j][i + k], yv = sy[j][i + k];
+            const float w = p.win[k], xv = sx[j][i + k], yv = sy[j][i + k];
             a = fmaf(w, xv, a); b = fmaf(w, yv, b);
             aa = fmaf(w * xv, xv, aa); bb = fmaf(w * yv, yv, bb); ab = fmaf(w * xv, yv, ab);
         }
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(256) l1_ssim_fwd_kernel(LossParams p) {
         float mu1 = 0.f, mu2 = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
 #pragma unroll
         for (int k = 0; k < LW; ++k) {
-            const float w = c_win[k];
+            const float w = p.win[k];
             mu1 = fmaf(w, hm[0][j + k][i], mu1); mu2 = fmaf(w, hm[1][j + k][i], mu2);
             exx = fmaf(w, hm[2][j + k][i], exx); eyy = fmaf(w, hm[3][j + k][i], eyy);
             exy = fmaf(w, hm[4][j + k][i], exy);
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(256) l1_ssim_bwd_kernel(LossParams p) {
             for (int m = 0; m < 3; ++m) {
                 float a = 0.f;
 #pragma unroll
-                for (int k = 0; k < LW; ++k) a = fmaf(c_win[k], sg[m][j][i + (LW - 1) - k], a);
+                for (int k = 0; k < LW; ++k) a = fmaf(p.win[k], sg[m][j][i + (LW - 1) - k], a);
                 hg[m][j][i] = a;
             }
         }
@@ -179,16 +186,17 @@ __global__ void __launch_bounds__(256) l1_ssim_bwd_kernel(LossParams p) {
             for (int m = 0; m < 3; ++m) {
                 float a = 0.f;
 #pragma unroll
-                for (int k = 0; k < LW; ++k) a = fmaf(c_win[k], hg[m][j + (LW - 1) - k][i], a);
+                for (int k = 0; k < LW; ++k) a = fmaf(p.win[k], hg[m][j + (LW - 1) - k][i], a);
                 t[m] = a;
             }
             float raw;
-            const float pr = pred_at(p, x, y, ch, raw);
-            const float g = p.gt[((size_t)y * p.W + x) * 3 + ch];
+            const float mk = mask_at(p, x, y);
+            const float pr = pred_at(p, x, y, ch, raw) * mk;
+            const float g = p.gt[((size_t)y * p.W + x) * 3 + ch] * mk;
             // d loss / d pred: SSIM part through mu2, E[yy] (2 pred), E[xy] (gt) + L1 part
             float d = t[0] + 2.f * pr * t[1] + g * t[2];
             d += p.l1_scale * ((pr > g) ? 1.f : ((pr < g) ? -1.f : 0.f));
-            d *= vl;
+            d *= vl * mk;
             if (!(raw >= 0.f && raw <= 1.f)) d = 0.f;  // clamp backward
             const size_t pix = (size_t)y * p.W + x;
             p.v_render[pix * p.rstride + ch] = d;
@@ -207,20 +215,45 @@ __global__ void __launch_bounds__(256) l1_ssim_bwd_kernel(LossParams p) {
     }
 }
 
-static int set_window() {
-    static bool done = false;
-    if (done) return FG_OK;
+static void set_window(LossParams& p) {
     float w[LW];
-    double s = 0;
-    for (int i = 0; i < LW; ++i) { double c = i - LR; w[i] = (float)exp(-(c * c) / (2.0 * 1.5 * 1.5)); s += w[i]; }
+    for (int i = 0; i < LW; ++i) { double c = i - LR; w[i] = (float)exp(-(c * c) / (2.0 * 1.5 * 1.5)); }
     // normalise in float like torch: g / g.sum()
     float fs = 0.f;
     for (int i = 0; i < LW; ++i) fs += w[i];
-    for (int i = 0; i < LW; ++i) w[i] = w[i] / fs;
-    (void)s;
-    FG_CUDA(cudaMemcpyToSymbol(c_win, w, sizeof(w)));
-    done = true;
-    return FG_OK;
+    for (int i = 0; i < LW; ++i) p.win[i] = w[i] / fs;
+}
+
+// ---- depth fix-up of freegaussian_model.py:884-886: depth = where(alpha > 0, ED, max over the image of ED) ----
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {  // order-preserving map float -> uint32
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__global__ void __launch_bounds__(256) depth_max_kernel(long long n, const float* render, int stride, int ch, uint32_t* out) {
+    pdl_wait();
+    uint32_t m = 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        m = max(m, float_to_ordered(render[i * stride + ch]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+__global__ void __launch_bounds__(256) depth_fixup_kernel(long long n, const float* render, int stride, int ch,
+                                                          const float* alpha, const uint32_t* mx, float* depth) {
+    pdl_wait();
+    const float big = ordered_to_float(*mx);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        depth[i] = alpha[i] > 0.f ? render[i * stride + ch] : big;
+}
+__global__ void __launch_bounds__(256) depth_fixup_bwd_kernel(long long n, const float* alpha, const float* v_depth,
+                                                              int stride, int ch, float* v_render) {
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        for (int c = 0; c < stride; ++c) v_render[i * stride + c] = (c == ch && alpha[i] > 0.f) ? v_depth[i] : 0.f;
+    }
 }
 
 }  // namespace fg
@@ -233,14 +266,15 @@ extern "C" int64_t fg_l1_ssim_workspace_floats(int width, int height) {
 }
 
 extern "C" int fg_l1_ssim_fwd(int width, int height, int render_stride, const float* render, const float* alpha,
-                              const float* background, const float* gt, float ssim_lambda, float* partial,
-                              double* sums /*[2], zeroed inside*/, void* stream) {
+                              const float* background, const float* gt, const float* mask, float ssim_lambda,
+                              float* partial, double* sums /*[2], zeroed inside*/, void* stream) {
     FG_REQUIRE(width >= LW && height >= LW, "image smaller than the 11x11 SSIM window");
     FG_REQUIRE(render_stride >= 3 && render && alpha && background && gt && partial && sums, "bad arguments");
-    if (int e = set_window()) return e;
     cudaStream_t st = (cudaStream_t)stream;
     FG_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
     LossParams p = {};
+    set_window(p);
+    p.mask = mask;
     p.W = width; p.H = height; p.rstride = render_stride; p.render = render; p.alpha = alpha; p.bg = background; p.gt = gt;
     p.l1_scale = (1.f - ssim_lambda) / (3.f * width * height);
     p.ssim_scale = ssim_lambda / (3.f * (float)(width - (LW - 1)) * (float)(height - (LW - 1)));
@@ -251,18 +285,43 @@ extern "C" int fg_l1_ssim_fwd(int width, int height, int render_stride, const fl
 }
 
 extern "C" int fg_l1_ssim_bwd(int width, int height, int render_stride, const float* render, const float* alpha,
-                              const float* background, const float* gt, float ssim_lambda, const float* partial,
-                              const float* v_loss, float* v_render, float* v_alpha, void* stream) {
+                              const float* background, const float* gt, const float* mask, float ssim_lambda,
+                              const float* partial, const float* v_loss, float* v_render, float* v_alpha, void* stream) {
     FG_REQUIRE(width >= LW && height >= LW, "image smaller than the 11x11 SSIM window");
     FG_REQUIRE(render_stride >= 3 && render && alpha && background && gt && partial && v_loss && v_render && v_alpha,
                "bad arguments");
-    if (int e = set_window()) return e;
     LossParams p = {};
+    set_window(p);
+    p.mask = mask;
     p.W = width; p.H = height; p.rstride = render_stride; p.render = render; p.alpha = alpha; p.bg = background; p.gt = gt;
     p.l1_scale = (1.f - ssim_lambda) / (3.f * width * height);
     p.ssim_scale = ssim_lambda / (3.f * (float)(width - (LW - 1)) * (float)(height - (LW - 1)));
     p.partial = const_cast<float*>(partial); p.v_loss = v_loss; p.v_render = v_render; p.v_alpha = v_alpha;
     dim3 grid((width + LTX - 1) / LTX, (height + LTY - 1) / LTY, 1);
     FG_LAUNCH(l1_ssim_bwd_kernel, grid, 256, 0, stream, p);
+    return FG_OK;
+}
+
+extern "C" int fg_depth_fixup_fwd(int64_t n_pixels, const float* render, int render_stride, int channel, const float* alpha,
+                                  float* depth, uint32_t* max_ws /*[1]*/, void* stream) {
+    FG_REQUIRE(n_pixels >= 0 && render_stride >= 1 && channel >= 0 && channel < render_stride, "bad shape");
+    if (n_pixels == 0) return FG_OK;
+    FG_REQUIRE(render && alpha && depth && max_ws, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    FG_CUDA(cudaMemsetAsync(max_ws, 0, 4, st));
+    const int grid = (int)std::min<long long>((n_pixels + 255) / 256, num_sms() * 8);
+    FG_LAUNCH(depth_max_kernel, grid, 256, 0, st, (long long)n_pixels, render, render_stride, channel, max_ws);
+    FG_LAUNCH(depth_fixup_kernel, grid, 256, 0, st, (long long)n_pixels, render, render_stride, channel, alpha, max_ws, depth);
+    return FG_OK;
+}
+
+extern "C" int fg_depth_fixup_bwd(int64_t n_pixels, const float* alpha, const float* v_depth, int render_stride,
+                                  int channel, float* v_render, void* stream) {
+    FG_REQUIRE(n_pixels >= 0 && render_stride >= 1 && channel >= 0 && channel < render_stride, "bad shape");
+    if (n_pixels == 0) return FG_OK;
+    FG_REQUIRE(alpha && v_depth && v_render, "NULL pointer");
+    const int grid = (int)std::min<long long>((n_pixels + 255) / 256, num_sms() * 8);
+    FG_LAUNCH(depth_fixup_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, (long long)n_pixels, alpha, v_depth, render_stride,
+              channel, v_render);
     return FG_OK;
 }

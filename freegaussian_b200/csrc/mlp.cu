@@ -411,7 +411,7 @@ static int launch_linear(long long M, const float* a0, int k0, const float* a1, 
     auto kern = mlp_linear_kernel<BN, NA, NW, EPI>;
     FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const long long n_tiles = (M + BM - 1) / BM;
-    const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+    const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
     FG_LAUNCH(kern, grid, kLinThreads, SMEM, st, mA0, mA1, mWh, mWl, args);
     return FG_OK;
 }
@@ -652,7 +652,7 @@ static int launch_wgrad(long long N, const float* dz, const float* a, const Wgra
     FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const long long n_blocks = (N + WG_ROWS - 1) / WG_ROWS;
     const long long want = (n_blocks + 63) / 64;  // at least 64 row blocks (1024 rows) per CTA
-    const int grid = (int)(want < 1 ? 1 : (want < kNumSMs ? want : kNumSMs));
+    const int grid = (int)(want < 1 ? 1 : (want < num_sms() ? want : num_sms()));
     FG_LAUNCH(kern, grid, kThreads, SMEM, st, mDz, mA, args);
     return FG_OK;
 }

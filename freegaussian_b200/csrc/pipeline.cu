@@ -51,9 +51,11 @@ static BackLayout back_layout(int C, int tile_w, int tile_h, int64_t Mc) {
     return L;
 }
 
+// One pinned slot per host thread (portable: valid under every device's context): a call synchronises its own stream
+// before it reads the slot, so two threads / devices rendering concurrently never share one.
 static int64_t* pinned_counts() {
-    static int64_t* p = nullptr;
-    if (!p && cudaHostAlloc((void**)&p, 2 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+    static thread_local int64_t* p = nullptr;
+    if (!p && cudaHostAlloc((void**)&p, 2 * sizeof(int64_t), cudaHostAllocPortable) != cudaSuccess) p = nullptr;
     return p;
 }
 

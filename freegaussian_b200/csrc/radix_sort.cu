@@ -284,7 +284,7 @@ static int radix_sort_pairs(long long n, KeyT* keys_in, uint32_t* vals_in, KeyT*
     int* counters = (int*)(ws + L.off_counters);
     uint32_t* status = (uint32_t*)(ws + L.off_status);
     FG_CUDA(cudaMemsetAsync(ws, 0, L.total, st));
-    int hist_blocks = (int)min((long long)kNumSMs * 4, (n + RS_THREADS - 1) / RS_THREADS);  // 1 per SM measured slower
+    int hist_blocks = (int)min((long long)num_sms() * 4, (n + RS_THREADS - 1) / RS_THREADS);  // 1 per SM measured slower
     FG_LAUNCH((rs_histogram_kernel<KeyT>), hist_blocks, RS_THREADS, 0, st, n, keys_in, passes, end_bit, hist);
     FG_LAUNCH(rs_scan_hist_kernel, passes, RS_RADIX, 0, st, hist);
     const size_t smem = sizeof(RsSmem<KeyT>);

@@ -362,6 +362,7 @@ class DeformNetwork(nn.Module):
             t_emb = self.timenet(t_emb)
         return t_emb.reshape(-1)
 
+    @_lib.on_device_of("x")
     def head(self, x: Tensor, t: Tensor) -> Tensor:
         """[N, 32]: branch_w (3) | branch_v (3) | gaussian_rotation (4) | gaussian_scaling (3) | zero padding."""
         if not x.is_cuda:
@@ -379,6 +380,7 @@ class DeformNetwork(nn.Module):
         d_xyz = exp_se3(torch.cat([w, v], -1), theta)
         return d_xyz, h[:, 6:10], h[:, 10:13]
 
+    @_lib.on_device_of("means")
     def deform_gaussians(self, means: Tensor, scales_log: Tensor, quats: Tensor, t: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         """freegaussian_model.py:836-845 in one call: returns the (means, scales, quats) passed to ``rasterization``."""
         return _Apply.apply(self.head(means, t), means, scales_log, quats)
@@ -417,6 +419,7 @@ class ControlNetwork(nn.Module):
             ps += [lin.weight, lin.bias]
         return ps
 
+    @_lib.on_device_of("x")
     def forward(self, x: Tensor, value: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         """(d_xyz [N,3], d_rot [N,4], d_scale [N,3]) -- the reference's return order (:1144-1145)."""
         if not x.is_cuda:

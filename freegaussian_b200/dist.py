@@ -101,10 +101,11 @@ class DensificationStats:
         self._local_size = torch.maximum(self._local_size, size.max(0).values)
 
     @torch.no_grad()
-    def sync(self, group=None) -> None:
+    def sync(self, group=None, reduce: bool = True) -> None:
         """SUM, SUM, MAX across ranks of everything accumulated since the last sync, folded into the
-        running statistics.  Call right before the statistics are read (refinement), or every step."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        running statistics.  Call right before the statistics are read (refinement), or every step.
+        ``reduce=False`` folds the local accumulators in without a collective (a rank that rendered every view)."""
+        if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             packed = torch.stack([self._local_grad, self._local_vis])
             dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
             self._local_grad, self._local_vis = packed[0], packed[1]
@@ -231,13 +232,16 @@ class ViewShardedExchange:
         from every rank's published colour gradients.  Enqueued on the current stream; no host synchronisation."""
         from . import _lib
         L = _lib.lib()
+        from .rendering import _stage
         st = torch.cuda.current_stream().cuda_stream
         self.epoch += 1
         n4 = (n_floats + 3) // 4 * 4
-        _lib.check(L.fg_xchg_allreduce_f32(self._peers, self.arena_off, n4, self.epoch, 1, st))
+        with _stage("xchg_allreduce"):
+            _lib.check(L.fg_xchg_allreduce_f32(self._peers, self.arena_off, n4, self.epoch, 1, st))
         if sh_from_views:
-            _lib.check(L.fg_xchg_sh_bwd_views(self._peers, self.pub_off[self.parity], C, N, int(sh_degree), sh_bases,
-                                              _lib.ptr(means), _lib.ptr(v_sh), st))
+            with _stage("xchg_sh_views"):
+                _lib.check(L.fg_xchg_sh_bwd_views(self._peers, self.pub_off[self.parity], C, N, int(sh_degree), sh_bases,
+                                                  _lib.ptr(means), _lib.ptr(v_sh), st))
             self.parity ^= 1
 
     def all_reduce_(self, t: Tensor) -> Tensor:

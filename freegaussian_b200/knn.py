@@ -18,6 +18,7 @@ from . import _lib
 from ._lib import check, ptr
 
 
+@_lib.on_device_of("x")
 def k_nearest(x: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     """x [N,3] float32 CUDA -> (distances [N,k] float32, indices [N,k] int32), ascending."""
     assert x.dim() == 2 and x.shape[1] == 3, x.shape

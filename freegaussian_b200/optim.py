@@ -68,12 +68,13 @@ class Group:
 class GaussianAdam:
     """``torch.optim.Adam``-equivalent over named groups, one launch per step."""
 
-    def __init__(self, groups: Dict[str, Group], betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-15):
+    def __init__(self, groups: Dict[str, Group], betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-15,
+                 t: int = 0):
         assert len(groups) <= _lib.ADAM_MAX_SEGMENTS, "too many groups for one launch"
         self.groups = groups
         self.betas = betas
         self.eps = eps
-        self.t = 0
+        self.t = int(t)  # steps taken so far (bias correction); survives rebind()
         for name, g in groups.items():
             if not g.param.is_cuda:
                 raise RuntimeError(f"GaussianAdam: group `{name}` is not a CUDA tensor (no CPU path)")
@@ -94,6 +95,24 @@ class GaussianAdam:
             "quats": Group(quats, R["quats"]),
         })
 
+    def rebind(self, params: Dict[str, Tensor], state: Optional[Dict[str, Tuple[Tensor, Tensor]]] = None) -> None:
+        """Swap in the tensors a refinement returned (``densify.refine(...).params`` / ``.state``: rows were split,
+        duplicated or culled, so every tensor is a new allocation) WITHOUT restarting the bias correction: the
+        reference keeps ``step`` inside the surviving ``param_state`` (``freegaussian_model.py:313-367``,
+        ``dup_in_optim`` / ``remove_from_optim``), so ``t`` carries on.  Groups missing from ``state`` get zero moments."""
+        for name, g in self.groups.items():
+            if name not in params:
+                continue
+            p = params[name]
+            assert p.is_cuda and p.dtype == torch.float32 and p.is_contiguous(), name
+            g.param = p
+            if state is not None and name in state:
+                m, v = state[name]
+                assert m.shape == p.shape and v.shape == p.shape, name
+                g.exp_avg, g.exp_avg_sq = m, v
+            else:
+                g.exp_avg, g.exp_avg_sq = torch.zeros_like(p), torch.zeros_like(p)
+
     def set_lr(self, name: str, lr: float, lr_rest: Optional[float] = None) -> None:
         self.groups[name].lr = lr
         if lr_rest is not None:
@@ -101,7 +120,13 @@ class GaussianAdam:
 
     @torch.no_grad()
     def step(self, grads: Optional[Dict[str, Tensor]] = None, shard: Optional[Tuple[int, int]] = None) -> None:
-        """``grads[name]`` defaults to ``param.grad``.  Groups without a gradient are skipped (as torch does)."""
+        """``grads[name]`` defaults to ``param.grad``.  Groups without a gradient are skipped (as torch does).
+        One step counter serves every group (the reference steps all of its Gaussian optimizers every iteration, so
+        their per-parameter ``step`` values coincide)."""
+        dev = next(iter(self.groups.values())).param.device
+        if dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                return self.step(grads, shard)
         self.t += 1
         segs = (_lib.AdamSegment * _lib.ADAM_MAX_SEGMENTS)()
         k = 0

@@ -18,6 +18,7 @@ from ._lib import check, ptr
 
 
 @torch.no_grad()
+@_lib.on_device_of("render")
 def assign_gaussian_masks(render: Tensor, info: dict, atrb_masks: Tensor, gaussian_masks: Tensor,
                           mask_valids: Tensor | None = None) -> Tensor:
     """render [1,H,W,1] expected depth; info: packed meta (means2d [nnz,2], depths [nnz], gaussian_ids [nnz]);

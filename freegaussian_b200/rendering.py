@@ -562,6 +562,7 @@ def rasterize_to_pixels(means2d, conics, colors, opacities, image_width, image_h
 
 
 # --------------------------------------------------------------------------- boundary
+@_lib.on_device_of("means")
 def rasterization(
     means: Tensor,  # [N, 3]
     quats: Tensor,  # [N, 4]

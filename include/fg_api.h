@@ -273,14 +273,25 @@ int fg_assign_masks(int64_t nnz, const float* means2d, const float* depths, cons
  * pytorch_msssim: 11-tap Gaussian, sigma 1.5, valid separable convolution).
  * fwd: sums[0] = (1-l) mean|gt-pred|, sums[1] = l * mean SSIM (doubles, device); `partial` =
  * fg_l1_ssim_workspace_floats(W,H) floats kept for the backward.  bwd: v_render[H,W,render_stride]
- * (channels >= 3 zeroed), v_alpha[H,W], scaled by the device scalar *v_loss. */
+ * (channels >= 3 zeroed), v_alpha[H,W], scaled by the device scalar *v_loss.
+ * mask[H,W] (float, or NULL): gt and pred are both multiplied by it before the loss (freegaussian_model.py:957-963). */
 int64_t fg_l1_ssim_workspace_floats(int width, int height);
 int fg_l1_ssim_fwd(int width, int height, int render_stride, const float* render, const float* alpha,
-                   const float* background, const float* gt, float ssim_lambda, float* partial,
+                   const float* background, const float* gt, const float* mask, float ssim_lambda, float* partial,
                    double* sums, void* stream);
 int fg_l1_ssim_bwd(int width, int height, int render_stride, const float* render, const float* alpha,
-                   const float* background, const float* gt, float ssim_lambda, const float* partial,
+                   const float* background, const float* gt, const float* mask, float ssim_lambda, const float* partial,
                    const float* v_loss, float* v_render, float* v_alpha, void* stream);
+
+/* Depth fix-up of freegaussian_model.py:884-886:
+ *   depth[i] = alpha[i] > 0 ? render[i, channel] : max over ALL pixels of render[:, channel]
+ * (the expected-depth channel of an "RGB+ED" render; the maximum is a constant for the backward, as the reference
+ * detaches it).  max_ws: one uint32 of scratch.  bwd writes the full v_render[n_pixels, render_stride]
+ * (zero outside `channel` and where alpha == 0). */
+int fg_depth_fixup_fwd(int64_t n_pixels, const float* render, int render_stride, int channel, const float* alpha,
+                       float* depth, uint32_t* max_ws, void* stream);
+int fg_depth_fixup_bwd(int64_t n_pixels, const float* alpha, const float* v_depth, int render_stride, int channel,
+                       float* v_render, void* stream);
 
 /* ---- (7) "next" row: optimizer step and refinement -----------------------
  * fg_adam_step: one launch steps every Gaussian parameter group the reference gives its own

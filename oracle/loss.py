@@ -50,9 +50,20 @@ def ssim(X: Tensor, Y: Tensor, data_range: float = 1.0, K=(0.01, 0.03)) -> Tenso
     return ssim_map.flatten(2).mean(-1).mean()
 
 
-def blend_l1_ssim_loss(render: Tensor, alpha: Tensor, background: Tensor, gt: Tensor, ssim_lambda: float = 0.2) -> Tensor:
-    """render [H,W,>=3] (premultiplied, first three channels RGB), alpha [H,W,1], background [3], gt [H,W,3]."""
+def blend_l1_ssim_loss(render: Tensor, alpha: Tensor, background: Tensor, gt: Tensor, ssim_lambda: float = 0.2,
+                       mask: Tensor = None) -> Tensor:
+    """render [H,W,>=3] (premultiplied, first three channels RGB), alpha [H,W,1], background [3], gt [H,W,3],
+    mask [H,W,1] (optional)."""
     pred = torch.clamp(render[..., :3] + (1 - alpha) * background, 0.0, 1.0)  # model.py:876-877
+    if mask is not None:  # model.py:957-963
+        gt = gt * mask
+        pred = pred * mask
     l1 = torch.abs(gt - pred).mean()  # :965
     sim = 1 - ssim(gt.permute(2, 0, 1)[None], pred.permute(2, 0, 1)[None])  # :966
     return (1 - ssim_lambda) * l1 + ssim_lambda * sim  # :981
+
+
+def depth_fixup(render: Tensor, alpha: Tensor) -> Tensor:
+    """``freegaussian_model.py:884-886`` verbatim (before the ``squeeze(0)``): render [1,H,W,4] "RGB+ED", alpha [1,H,W,1]."""
+    depth_im = render[:, ..., 3:4]
+    return torch.where(alpha > 0, depth_im, depth_im.detach().max())

@@ -51,7 +51,7 @@ def main():
         ((r * w_r[views]).sum() + (a * w_a[views]).sum() + (m["flow"] * w_f[views]).sum()).backward()
         st = DensificationStats(N, dev)
         st.accumulate_local(m["radii"], m["means2d"].absgrad, H, W)
-        st.sync()
+        st.sync(reduce=exch is not None)
         grads = {n: p[n].grad.clone() for n in names}
         return grads, st
 

@@ -75,3 +75,50 @@ def test_fused_loss_matches_oracle(built_lib, H, W, rs):
         assert (rg.grad[..., 3:] == 0).all()
     assert grad_rel_err(rg.grad, want_r) < 1e-3
     assert grad_rel_err(ag.grad, ao.grad * 1.7) < 1e-3
+
+
+@pytest.mark.gpu
+def test_fused_loss_with_a_mask_matches_the_reference_lines(built_lib):
+    """get_loss_dict multiplies gt and pred by batch["mask"] before L1 and SSIM (freegaussian_model.py:957-963)."""
+    from freegaussian_b200.losses import blend_l1_ssim_loss
+    H, W = 90, 131
+    render, alpha, bg, gt = _inputs(H, W, 77, 4)
+    g = torch.Generator().manual_seed(5)
+    mask = (torch.rand(H, W, 1, generator=g) > 0.35)
+    ro, ao = render.clone().double().requires_grad_(True), alpha.clone().double().requires_grad_(True)
+    ref = OL.blend_l1_ssim_loss(ro[0], ao[0], bg.double(), gt.double(), mask=mask.double())
+    ref.backward()
+    rg, ag = render.cuda().requires_grad_(True), alpha.cuda().requires_grad_(True)
+    out = blend_l1_ssim_loss(rg, ag, bg.cuda(), gt.cuda(), mask=mask.cuda())
+    out.backward()
+    assert abs(float(out.detach()) - float(ref.detach())) < 1e-5
+    assert grad_rel_err(rg.grad, ro.grad) < 1e-3 and grad_rel_err(ag.grad, ao.grad) < 1e-3
+    unmasked = blend_l1_ssim_loss(render.cuda(), alpha.cuda(), bg.cuda(), gt.cuda())
+    assert abs(float(unmasked) - float(out.detach())) > 1e-3
+
+
+@pytest.mark.gpu
+def test_depth_fixup_matches_the_reference_lines(built_lib):
+    """depth = where(alpha > 0, ED, ED.detach().max()) (freegaussian_model.py:884-886), forward bit-exact and backward."""
+    from freegaussian_b200.losses import depth_fixup
+    from freegaussian_b200.rendering import rasterization
+    from util import small_scene
+    W, H = 160, 96
+    sc = small_scene(400, W, H, views=1, seed=6, scale_mul=0.5).to("cuda")  # sparse: many pixels with alpha == 0
+    means = sc.means.clone().requires_grad_(True)
+    render, alpha, _ = rasterization(means, sc.quats, sc.scales, sc.opacities, sc.sh, sc.viewmats, sc.Ks, W, H, packed=False,
+                                     render_mode="RGB+ED", sh_degree=3)
+    assert 0.05 < float((alpha == 0).float().mean()) < 0.95
+    got = depth_fixup(render, alpha)
+    want = OL.depth_fixup(render.detach().cpu(), alpha.detach().cpu())
+    assert got.shape == want.shape == (1, H, W, 1) and torch.equal(got.detach().cpu(), want)
+    # backward: gradient passes where alpha > 0 only, the maximum is a constant
+    r2 = render.detach().clone().requires_grad_(True)
+    w = torch.randn(1, H, W, 1, device="cuda")
+    (depth_fixup(r2, alpha.detach()) * w).sum().backward()
+    r3 = render.detach().cpu().clone().requires_grad_(True)
+    (OL.depth_fixup(r3, alpha.detach().cpu()) * w.cpu()).sum().backward()
+    assert torch.equal(r2.grad.cpu(), r3.grad)
+    # and it chains into the renderer
+    (got * w).sum().backward()
+    assert means.grad is not None and float(means.grad.abs().max()) > 0

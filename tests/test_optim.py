@@ -112,3 +112,26 @@ def test_sharded_step_equals_full_step(built_lib):
     for k in full.groups:
         assert torch.equal(full.groups[k].param, parts.groups[k].param), k
         assert torch.equal(full.groups[k].exp_avg_sq, parts.groups[k].exp_avg_sq), k
+
+
+@pytest.mark.gpu
+def test_rebind_after_refinement_keeps_the_step_count(built_lib):
+    """After refine() every tensor is a new allocation: rebind() swaps them in and the bias correction carries on
+    (the reference keeps `step` inside the surviving param_state, freegaussian_model.py:313-367)."""
+    from freegaussian_b200.optim import GaussianAdam
+    params, grads = _groups(300, 3)
+    dev = "cuda"
+    mk = lambda: GaussianAdam({"means": __import__("freegaussian_b200.optim", fromlist=["Group"]).Group(params["means"].to(dev).contiguous(), LRS["means"])})  # noqa: E731
+    a, b = mk(), mk()
+    for g in grads[:5]:
+        a.step({"means": g["means"].to(dev)})
+        b.step({"means": g["means"].to(dev)})
+    keep = torch.arange(0, 300, 2, device=dev)  # a cull: half of the rows survive, moments travel with them
+    st = b.state()["means"]
+    b.rebind({"means": b.groups["means"].param[keep].contiguous()}, {"means": (st[0][keep].contiguous(), st[1][keep].contiguous())})
+    assert b.t == 5
+    for g in grads[5:9]:
+        a.step({"means": g["means"].to(dev)})
+        b.step({"means": g["means"].to(dev)[keep].contiguous()})
+    assert torch.equal(a.groups["means"].param[keep], b.groups["means"].param)
+    assert torch.equal(a.groups["means"].exp_avg[keep], b.groups["means"].exp_avg)
