@@ -41,11 +41,11 @@ class MlpPackSegment(C.Structure):  # fg_mlp_pack_segment
 
 
 class ProjectBwdPub(C.Structure):  # fg_project_bwd_pub
-    _fields_ = [("campos", _vp), ("mask", _vp), ("rgb", _vp), ("words", C.c_int32)]
+    _fields_ = [("campos", _vp), ("mask", _vp), ("rgb", _vp), ("words", C.c_int32), ("phase", C.c_int32)]
 
 
 XCHG_MAX_RANKS = 16
-XCHG_FLAG_BYTES = 32768
+XCHG_FLAG_BYTES = 65536
 
 
 class XchgPeers(C.Structure):  # fg_xchg_peers

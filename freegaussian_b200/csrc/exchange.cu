@@ -93,7 +93,7 @@ __device__ __forceinline__ void mc_st(float4* a, float4 v) {
 // In-place SUM over ranks of n4 float4 at byte offset `off` of the symmetric buffer.  Two-shot: rank r
 // owns the r-th slice.  Slots 1..grid: start barrier (optional), grid+1..2*grid: end barrier.
 template <bool MC>
-__global__ void __launch_bounds__(XB) allreduce_kernel(Peers p, long long off, long long n4, uint32_t epoch,
+__global__ void __launch_bounds__(XB, 2) allreduce_kernel(Peers p, long long off, long long n4, uint32_t epoch,
                                                        int start_barrier) {
     pdl_wait();
     if (start_barrier) block_barrier(p, 1 + blockIdx.x, epoch);
@@ -268,7 +268,8 @@ extern "C" int fg_xchg_allreduce_f32(const fg_xchg_peers* peers, int64_t offset_
     const long long n4 = n_floats / 4;
     // every rank derives the same grid from the same n: the barriers pair block b with block b
     const long long per = (n4 + p.world - 1) / p.world;
-    int grid = (int)std::min<long long>(num_sms(), std::max<long long>(1, (per + XB * 4 - 1) / (XB * 4)));
+    // two resident blocks per SM: a switch round trip is several microseconds, the links are only kept full with ~10 MB in flight
+    int grid = (int)std::min<long long>(2 * num_sms(), std::max<long long>(1, (per + XB * 4 - 1) / (XB * 4)));
     FG_REQUIRE(1 + 2 * grid <= FG_XCHG_FLAG_BYTES / (XCHG_SLOT_WORDS * 4), "flag area too small");
     cudaStream_t st = (cudaStream_t)stream;
     if (p.mc) FG_LAUNCH((allreduce_kernel<true>), grid, XB, 0, st, p, (long long)offset_bytes, n4, epoch, start_barrier);

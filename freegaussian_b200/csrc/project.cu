@@ -719,14 +719,17 @@ extern "C" int fg_project_bwd(int C, int N, const float* means, const float* qua
         // two kernels: streaming SH backward (writes v_sh and the direction term into v_means), then
         // the geometry VJP, which adds that term to its own v_means
         p.feat_fwd = feat;
-        int e;
-        switch (sh_degree) {
-            case 0: e = launch_sh_bwd<0>(p, st); break;
-            case 1: e = launch_sh_bwd<1>(p, st); break;
-            case 2: e = launch_sh_bwd<2>(p, st); break;
-            default: e = launch_sh_bwd<3>(p, st); break;
+        const int phase = pub ? pub->phase : 0;  // 1: SH kernel only, 2: geometry kernel only (after a phase-1 call)
+        int e = FG_OK;
+        if (phase != 2) {
+            switch (sh_degree) {
+                case 0: e = launch_sh_bwd<0>(p, st); break;
+                case 1: e = launch_sh_bwd<1>(p, st); break;
+                case 2: e = launch_sh_bwd<2>(p, st); break;
+                default: e = launch_sh_bwd<3>(p, st); break;
+            }
         }
-        if (e) return e;
+        if (e || phase == 1) return e;
         p.v_mean_extra = v_means;
         p.rgb_off = -1;
         return launch_bwd<-1, true>(p, st);

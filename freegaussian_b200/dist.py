@@ -150,6 +150,7 @@ class ViewShardedExchange:
         self._peers = None     # _lib.XchgPeers
         self._layout = None    # (pub_bytes, arena_bytes)
         self._old = []         # previous blocks are kept alive: a peer may still be reading them
+        self._side = None      # side stream of the SH-row summation
         self.multicast = False
 
     # -- lifecycle
@@ -226,23 +227,39 @@ class ViewShardedExchange:
         pub.campos, pub.mask, pub.rgb, pub.words = base, base + mask_off, base + rgb_off, words
         return pub
 
-    def reduce(self, n_floats: int, sh_from_views: bool, C: int, N: int, sh_degree, sh_bases: int, means: Tensor,
-               v_sh: Optional[Tensor]) -> None:
-        """All-reduce the first ``n_floats`` of the arena in place; with ``sh_from_views`` then rebuild the SH rows
-        from every rank's published colour gradients.  Enqueued on the current stream; no host synchronisation."""
+    def sh_rows_async(self, C: int, N: int, sh_degree, sh_bases: int, means: Tensor, v_sh: Tensor) -> None:
+        """After the publishing SH kernel of this step: cross-rank barrier on the current stream (every rank has
+        published), then, on a side stream, ``fg_xchg_sh_bwd_views`` rebuilds the SH rows from every rank's views while the
+        current stream goes on with the geometry kernel and its all-reduce.  :meth:`join` makes the current stream wait."""
         from . import _lib
-        L = _lib.lib()
         from .rendering import _stage
-        st = torch.cuda.current_stream().cuda_stream
+        L = _lib.lib()
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=means.device)
+        self.epoch += 1
+        _lib.check(L.fg_xchg_barrier(self._peers, self.epoch, cur.cuda_stream))
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            with _stage("xchg_sh_views"):
+                _lib.check(L.fg_xchg_sh_bwd_views(self._peers, self.pub_off[self.parity], C, N, int(sh_degree), sh_bases,
+                                                  _lib.ptr(means), _lib.ptr(v_sh), self._side.cuda_stream))
+        self.parity ^= 1
+
+    def join(self) -> None:
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+
+    def reduce(self, n_floats: int) -> None:
+        """In-place all-reduce(SUM) of the first ``n_floats`` of the arena (two-shot, in the switch when multicast is
+        available).  Enqueued on the current stream; no host synchronisation."""
+        from . import _lib
+        from .rendering import _stage
         self.epoch += 1
         n4 = (n_floats + 3) // 4 * 4
         with _stage("xchg_allreduce"):
-            _lib.check(L.fg_xchg_allreduce_f32(self._peers, self.arena_off, n4, self.epoch, 1, st))
-        if sh_from_views:
-            with _stage("xchg_sh_views"):
-                _lib.check(L.fg_xchg_sh_bwd_views(self._peers, self.pub_off[self.parity], C, N, int(sh_degree), sh_bases,
-                                                  _lib.ptr(means), _lib.ptr(v_sh), st))
-            self.parity ^= 1
+            _lib.check(_lib.lib().fg_xchg_allreduce_f32(self._peers, self.arena_off, n4, self.epoch, 1,
+                                                       torch.cuda.current_stream().cuda_stream))
 
     def all_reduce_(self, t: Tensor) -> Tensor:
         """In-place SUM of any fp32 CUDA tensor over the ranks through the same NVLS kernel (staged through the arena):

@@ -278,15 +278,22 @@ class _Project(torch.autograd.Function):
         _grad_arena["last"] = (arena, used)
         v_flow_affine = c(v_flow_affine) if flow_cov else None
         pub = xc.publish_block(C, N) if want_pub else None
-        with _stage("project_bwd"):
-          check(L.fg_project_bwd(
-            C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
-            cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"],
-            cfg["sh_degree"] if use_sh else -1, sh_bases, ptr(sh), ptr(means_next), ptr(quats_next), ptr(scales_next),
-            int(flow_cov), ptr(radii), ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_feat),
-            ptr(feat_fwd), CH, rgb_off, depth_off, flow_off, ptr(v_flow_affine), ptr(v_means), ptr(v_quats), ptr(v_scales),
-            None if pub is not None else ptr(v_sh), ptr(v_means_next), ptr(v_quats_next), ptr(v_scales_next),
-            None if pub is None else ctypes.byref(pub), _stream()))
+
+        def project_bwd(phase):
+            if pub is not None:
+                pub.phase = phase
+            check(L.fg_project_bwd(
+                C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
+                cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"],
+                cfg["sh_degree"] if use_sh else -1, sh_bases, ptr(sh), ptr(means_next), ptr(quats_next), ptr(scales_next),
+                int(flow_cov), ptr(radii), ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comps), ptr(v_feat),
+                ptr(feat_fwd), CH, rgb_off, depth_off, flow_off, ptr(v_flow_affine), ptr(v_means), ptr(v_quats), ptr(v_scales),
+                None if pub is not None else ptr(v_sh), ptr(v_means_next), ptr(v_quats_next), ptr(v_scales_next),
+                None if pub is None else ctypes.byref(pub), _stream()))
+
+        if pub is None:
+            with _stage("project_bwd"):
+                project_bwd(0)
         if xc is not None:
             if geo[6]:
                 seg(6, v_opac.shape).copy_(v_opac)
@@ -294,8 +301,20 @@ class _Project(torch.autograd.Function):
             if geo[7]:
                 seg(7, v_col2d.shape).copy_(v_col2d)
                 v_col2d = seg(7, v_col2d.shape)
-            with _stage("exchange"):
-                xc.reduce(geo_floats if pub is not None else used, pub is not None, C, N, cfg["sh_degree"], sh_bases, means, v_sh)
+            if pub is not None:
+                # SH kernel (publishes) -> barrier -> [side stream: SH rows from every rank's views] || [geometry kernel ->
+                # in-switch all-reduce]; the side stream is joined before the gradients are handed to autograd
+                with _stage("project_bwd"):
+                    project_bwd(1)
+                with _stage("exchange"):
+                    xc.sh_rows_async(C, N, cfg["sh_degree"], sh_bases, means, v_sh)
+                    with _stage("project_bwd_geo"):
+                        project_bwd(2)
+                    xc.reduce(geo_floats)
+                    xc.join()
+            else:
+                with _stage("exchange"):
+                    xc.reduce(used)
         v_colors = None
         if use_sh:
             v_colors = v_sh

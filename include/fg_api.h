@@ -78,6 +78,9 @@ typedef struct {
     uint32_t* mask;
     float* rgb;
     int32_t words;
+    int32_t phase; /* 0: the whole backward; 1: only the SH kernel (publishes, writes the direction term into v_means);
+                      2: only the geometry kernel (adds to the v_means a phase-1 call left) -- lets the caller start the
+                      cross-rank SH summation on another stream while the geometry kernel runs */
 } fg_project_bwd_pub;
 
 /* VJP of fg_project_fwd (gsplat `fully_fused_projection_bwd` + `spherical_harmonics` bwd).
@@ -445,7 +448,7 @@ int fg_deform_apply_bwd(int64_t N, const float* head, const float* means, const 
  * peer loads / stores instead).  The flag area is FG_XCHG_FLAG_BYTES bytes, zeroed once before first use.  `epoch`
  * must grow by one per call (all ranks pass the same value); calls must be issued in the same order on every rank. */
 #define FG_XCHG_MAX_RANKS 16
-#define FG_XCHG_FLAG_BYTES 32768
+#define FG_XCHG_FLAG_BYTES 65536
 typedef struct {
     int32_t world, rank;
     void* buf[FG_XCHG_MAX_RANKS];

@@ -104,7 +104,7 @@ def test_depth_fixup_matches_the_reference_lines(built_lib):
     from freegaussian_b200.rendering import rasterization
     from util import small_scene
     W, H = 160, 96
-    sc = small_scene(400, W, H, views=1, seed=6, scale_mul=0.5).to("cuda")  # sparse: many pixels with alpha == 0
+    sc = small_scene(60, W, H, views=1, seed=6, scale_mul=0.1).to("cuda")  # sparse: ~40 % of the pixels have alpha == 0
     means = sc.means.clone().requires_grad_(True)
     render, alpha, _ = rasterization(means, sc.quats, sc.scales, sc.opacities, sc.sh, sc.viewmats, sc.Ks, W, H, packed=False,
                                      render_mode="RGB+ED", sh_degree=3)
