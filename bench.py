@@ -675,6 +675,26 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
     ms_plain, _, _, q_plain = timed(False)
     l0 = _lib.launch_count()
     ms_full, ms_deform_fwd, ms_deform_bwd, q_full = timed(True)
+    if os.environ.get("FG_BENCH_TIMELINE"):  # device timeline of one iteration (kernel, duration, idle gap before it) on stderr
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                iteration(True)
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        starts = [i for i, e in enumerate(evs) if "deform_embed" in e.name]
+        if len(starts) >= 2:
+            one = evs[starts[-2]:starts[-1]]
+            t_prev, busy = one[0].time_range.start, 0.0
+            print("# device timeline of one training iteration (us): gap-before  duration  kernel", file=sys.stderr)
+            for e in one:
+                gap, dur = e.time_range.start - t_prev, e.time_range.end - e.time_range.start
+                busy += dur
+                if gap > 5 or dur > 50:
+                    print(f"{gap:9.1f} {dur:9.1f}  {e.name[:100]}", file=sys.stderr)
+                t_prev = max(t_prev, e.time_range.end)
+            span = t_prev - one[0].time_range.start
+            print(f"# {len(one)} kernels, span {span:.1f} us, busy {busy:.1f} us, idle {span - busy:.1f} us", file=sys.stderr)
     host_ms = {k: round(v * 1e3 / steps, 3) for k, v in cpu_phase.items()}
     launches = (_lib.launch_count() - l0) / (steps + warmup)
     n_vis = int((last["radii"] > 0).sum())

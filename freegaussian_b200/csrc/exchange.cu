@@ -113,9 +113,28 @@ __global__ void __launch_bounds__(XB, 2) allreduce_kernel(Peers p, long long off
         }
         for (; i < hi; i += stride) mc_st(mc + i, mc_ld_reduce(mc + i));
     } else {
-        for (long long i = lo + (long long)blockIdx.x * XB + threadIdx.x; i < hi; i += stride) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        long long i = lo + (long long)blockIdx.x * XB + threadIdx.x;
+        for (; i + (U - 1) * stride < hi; i += U * stride) {
+            float4 s[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int r = 0; r < p.world; ++r) {  // fixed order: the sum is the same on every rank
+                const float4* src = reinterpret_cast<const float4*>(p.buf[r] + off);
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = src[i + u * stride];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { s[u].x += v[u].x; s[u].y += v[u].y; s[u].z += v[u].z; s[u].w += v[u].w; }
+            }
+            for (int r = 0; r < p.world; ++r) {
+                float4* dst = reinterpret_cast<float4*>(p.buf[r] + off);
+#pragma unroll
+                for (int u = 0; u < U; ++u) dst[i + u * stride] = s[u];
+            }
+        }
+        for (; i < hi; i += stride) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < p.world; ++r) {
                 const float4 v = *(reinterpret_cast<const float4*>(p.buf[r] + off) + i);
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             }

@@ -326,11 +326,14 @@ __device__ __forceinline__ void bwd_init_pixel(const RasterBwdParams& p, int cam
     bin_final = inside ? p.last_ids[pix] : -1;
 }
 
-// partials of one pixel for one Gaussian, written (INIT) or added to val[]
-template <int CH, bool INIT, int NF>
+// partials of one pixel (half J of the thread's pixel pair) for one Gaussian, written (INIT) or added to val[]
+template <int CH, bool INIT, int J, int NF>
 __device__ __forceinline__ void bwd_pixel(bool valid, float alpha, float vis, float raw, float dx, float dy, float u,
-                                          float v, const float (&f)[NF], const float (&v_out)[CH], float& T, float& S,
-                                          float G, float (&val)[16]) {
+                                          float v, const float (&f)[NF], const float2 (&V)[CH], float2& T2, float2& S2,
+                                          float2 G2, float (&val)[16]) {
+    float& T = J ? T2.y : T2.x;
+    float& S = J ? S2.y : S2.x;
+    const float G = J ? G2.y : G2.x;
     if (!valid) { alpha = 0.f; vis = 0.f; }
     float ra;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.f - alpha));
@@ -339,8 +342,9 @@ __device__ __forceinline__ void bwd_pixel(bool valid, float alpha, float vis, fl
     float A = 0.f;
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
-        A = fmaf(f[k], v_out[k], A);
-        val[k] = INIT ? fac * v_out[k] : fmaf(fac, v_out[k], val[k]);
+        const float vo = J ? V[k].y : V[k].x;
+        A = fmaf(f[k], vo, A);
+        val[k] = INIT ? fac * vo : fmaf(fac, vo, val[k]);
     }
     const float v_alpha = fmaf(T, A, (G - S) * ra);
     S = fmaf(fac, A, S);
@@ -357,6 +361,68 @@ __device__ __forceinline__ void bwd_pixel(bool valid, float alpha, float vis, fl
         val[CH + 3] = fmaf(v_sigma, u, val[CH + 3]); val[CH + 4] = fmaf(v_sigma, v, val[CH + 4]);
         val[CH + 5] += fabsf(hx); val[CH + 6] += fabsf(hy); val[CH + 7] += vop;
     }
+}
+
+// ---- packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2): both pixels of the thread in one instruction --------------
+// The kernel is issue-bound (ncu r1: issue slots 76 % busy, FMA pipe 38 %): when both halves of the pixel pair can be
+// reached, the per-pixel arithmetic runs on float2 = (pixel 0, pixel 1) operands.  A scalar operand is broadcast by the
+// instruction itself (`R.F32` operand form), so per-Gaussian values need no duplication.
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+
+// alpha of both pixels; the same operations in the same order as eval_alpha, so forward and backward agree bit for bit
+__device__ __forceinline__ void eval_alpha_pair(const GeomA& a, const GeomB& b, float px, float2 npy, float& dx, float2& dy,
+                                                float2& u, float2& v, float2& vis, float2& raw, float2& alpha, bool& ok0,
+                                                bool& ok1) {
+    dx = a.x - px;
+    dy = __fadd2_rn(bc2(a.y), npy);
+    u = __ffma2_rn(bc2(a.a1), bc2(dx), __fmul2_rn(bc2(b.b1), dy));
+    v = __ffma2_rn(bc2(b.c1), dy, bc2(b.b1 * dx));
+    const float2 pw = __ffma2_rn(u, bc2(dx), __fmul2_rn(v, dy));
+    vis = make_float2(ex2_approx(-pw.x), ex2_approx(-pw.y));
+    raw = __fmul2_rn(bc2(a.opac), vis);
+    alpha = make_float2(fminf(ALPHA_MAX, raw.x), fminf(ALPHA_MAX, raw.y));
+    ok0 = (pw.x >= 0.f) && (alpha.x >= ALPHA_MIN);
+    ok1 = (pw.y >= 0.f) && (alpha.y >= ALPHA_MIN);
+}
+
+template <int CH, int NF>
+__device__ __forceinline__ void bwd_pixel_pair(bool valid0, bool valid1, float2 alpha, float2 vis, float2 raw, float dx,
+                                               float2 dy, float2 u, float2 v, const float (&f)[NF], const float2 (&V)[CH],
+                                               float2& T, float2& S, float2 G, float (&val)[16]) {
+    if (!valid0) { alpha.x = 0.f; vis.x = 0.f; }
+    if (!valid1) { alpha.y = 0.f; vis.y = 0.f; }
+    const float2 om = __ffma2_rn(alpha, bc2(-1.f), bc2(1.f));  // 1 - alpha
+    float2 ra;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra.x) : "f"(om.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra.y) : "f"(om.y));
+    T = __fmul2_rn(T, ra);
+    const float2 fac = __fmul2_rn(alpha, T);
+    float2 A = __fmul2_rn(bc2(f[0]), V[0]);
+#pragma unroll
+    for (int k = 1; k < CH; ++k) A = __ffma2_rn(bc2(f[k]), V[k], A);
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const float2 pr = __fmul2_rn(fac, V[k]);
+        val[k] = pr.x + pr.y;
+    }
+    const float2 gs = __ffma2_rn(S, bc2(-1.f), G);  // G - S
+    const float2 v_alpha = __ffma2_rn(T, A, __fmul2_rn(gs, ra));
+    S = __ffma2_rn(fac, A, S);
+    const float2 nav = __fmul2_rn(alpha, v_alpha), vv = __fmul2_rn(vis, v_alpha);
+    const bool g0 = raw.x <= ALPHA_MAX, g1 = raw.y <= ALPHA_MAX;
+    const float2 v_sigma = make_float2(g0 ? -nav.x : 0.f, g1 ? -nav.y : 0.f);
+    const float2 vop = make_float2(g0 ? vv.x : 0.f, g1 ? vv.y : 0.f);
+    const float2 t2 = __fmul2_rn(v_sigma, dy);
+    const float2 hx = __fmul2_rn(v_sigma, u), hy = __fmul2_rn(v_sigma, v);
+    const float2 t2dy = __fmul2_rn(t2, dy);
+    val[CH] = ((v_sigma.x + v_sigma.y) * dx) * dx;
+    val[CH + 1] = (t2.x + t2.y) * dx;
+    val[CH + 2] = t2dy.x + t2dy.y;
+    val[CH + 3] = hx.x + hx.y;
+    val[CH + 4] = hy.x + hy.y;
+    val[CH + 5] = fabsf(hx.x) + fabsf(hx.y);
+    val[CH + 6] = fabsf(hy.x) + fabsf(hy.y);
+    val[CH + 7] = vop.x + vop.y;
 }
 
 template <int CH>
@@ -402,11 +468,17 @@ __global__ void __launch_bounds__(BWD2_THREADS, 6) rasterize_bwd2_kernel(RasterB
         else if (slot < CH + 8) { out_base = p.v_opacities; out_stride = 4; out_is_opac = true; }
     }
 
-    float v_out0[CH], v_out1[CH];
-    float T0, T1, G0, G1, S0 = 0.f, S1 = 0.f;
+    float2 V[CH];  // upstream gradients of the two pixels, channel by channel: (pixel 0, pixel 1)
+    float2 T, G, S = make_float2(0.f, 0.f);
     int bin0, bin1;
-    bwd_init_pixel<CH>(p, cam, ix, iy0, ix < p.width && iy0 < p.height, v_out0, T0, G0, bin0);
-    bwd_init_pixel<CH>(p, cam, ix, iy1, ix < p.width && iy1 < p.height, v_out1, T1, G1, bin1);
+    {
+        float v_out0[CH], v_out1[CH];
+        bwd_init_pixel<CH>(p, cam, ix, iy0, ix < p.width && iy0 < p.height, v_out0, T.x, G.x, bin0);
+        bwd_init_pixel<CH>(p, cam, ix, iy1, ix < p.width && iy1 < p.height, v_out1, T.y, G.y, bin1);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) V[k] = make_float2(v_out0[k], v_out1[k]);
+    }
+    const float2 npy = make_float2(-py0, -(py0 + 4.f));
     const int warp_bin_final = __reduce_max_sync(0xffffffffu, max(bin0, bin1));
     const int nb_all = (range_end - range_start + BATCH - 1) / BATCH;
 
@@ -469,28 +541,43 @@ __global__ void __launch_bounds__(BWD2_THREADS, 6) rasterize_bwd2_kernel(RasterB
             const GeomA ga = {a4.x, a4.y, a4.z, a4.w};
             const GeomB gb = {b4.x, b4.y, 0, 0.f};
             const bool h0 = e & 0x100, h1 = e & 0x200;  // warp-uniform
-            float dx, dy0 = 0.f, dy1 = 0.f, u0 = 0.f, v0 = 0.f, u1 = 0.f, v1 = 0.f;
-            float vis0 = 0.f, raw0 = 0.f, alpha0 = 0.f, vis1 = 0.f, raw1 = 0.f, alpha1 = 0.f;
-            bool valid0 = false, valid1 = false;
-            if (h0) valid0 = eval_alpha(ga, gb, px, py0, dx, dy0, u0, v0, vis0, raw0, alpha0) && (t >= t_lim0);
-            if (h1) valid1 = eval_alpha(ga, gb, px, py0 + 4.f, dx, dy1, u1, v1, vis1, raw1, alpha1) && (t >= t_lim1);
-            if (!__any_sync(0xffffffffu, valid0 || valid1)) continue;
-            dx = a4.x - px;
-            float f[FV * 4];
-            {
-                const float4 q = lds128<OFF_F>(rec);
-                f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
-            }
-            if (FV > 1) {
-                const float4 q = lds128<OFF_F + REC_STRIDE>(rec);
-                f[4 * (FV - 1)] = q.x; f[4 * (FV - 1) + 1] = q.y; f[4 * (FV - 1) + 2] = q.z; f[4 * (FV - 1) + 3] = q.w;
-            }
             float val[16];
-            if (h0) {
-                bwd_pixel<CH, true>(valid0, alpha0, vis0, raw0, dx, dy0, u0, v0, f, v_out0, T0, S0, G0, val);
-                if (h1) bwd_pixel<CH, false>(valid1, alpha1, vis1, raw1, dx, dy1, u1, v1, f, v_out1, T1, S1, G1, val);
+            if (h0 && h1) {
+                // both halves reachable: packed arithmetic over the pixel pair
+                float dx;
+                float2 dy, u, v, vis, raw, alpha;
+                bool valid0, valid1;
+                eval_alpha_pair(ga, gb, px, npy, dx, dy, u, v, vis, raw, alpha, valid0, valid1);
+                valid0 = valid0 && (t >= t_lim0);
+                valid1 = valid1 && (t >= t_lim1);
+                if (!__any_sync(0xffffffffu, valid0 || valid1)) continue;
+                float f[FV * 4];
+                {
+                    const float4 q = lds128<OFF_F>(rec);
+                    f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+                }
+                if (FV > 1) {
+                    const float4 q = lds128<OFF_F + REC_STRIDE>(rec);
+                    f[4 * (FV - 1)] = q.x; f[4 * (FV - 1) + 1] = q.y; f[4 * (FV - 1) + 2] = q.z; f[4 * (FV - 1) + 3] = q.w;
+                }
+                bwd_pixel_pair<CH>(valid0, valid1, alpha, vis, raw, dx, dy, u, v, f, V, T, S, G, val);
             } else {
-                bwd_pixel<CH, true>(valid1, alpha1, vis1, raw1, dx, dy1, u1, v1, f, v_out1, T1, S1, G1, val);
+                float dx, dy = 0.f, u = 0.f, v = 0.f, vis = 0.f, raw = 0.f, alpha = 0.f;
+                bool valid;
+                if (h0) valid = eval_alpha(ga, gb, px, py0, dx, dy, u, v, vis, raw, alpha) && (t >= t_lim0);
+                else valid = eval_alpha(ga, gb, px, py0 + 4.f, dx, dy, u, v, vis, raw, alpha) && (t >= t_lim1);
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                float f[FV * 4];
+                {
+                    const float4 q = lds128<OFF_F>(rec);
+                    f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+                }
+                if (FV > 1) {
+                    const float4 q = lds128<OFF_F + REC_STRIDE>(rec);
+                    f[4 * (FV - 1)] = q.x; f[4 * (FV - 1) + 1] = q.y; f[4 * (FV - 1) + 2] = q.z; f[4 * (FV - 1) + 3] = q.w;
+                }
+                if (h0) bwd_pixel<CH, true, 0>(valid, alpha, vis, raw, dx, dy, u, v, f, V, T, S, G, val);
+                else bwd_pixel<CH, true, 1>(valid, alpha, vis, raw, dx, dy, u, v, f, V, T, S, G, val);
             }
 #pragma unroll
             for (int k = NVAL; k < 16; ++k) val[k] = 0.f;

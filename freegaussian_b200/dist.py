@@ -196,7 +196,11 @@ class ViewShardedExchange:
             peers.buf[r] = int(hdl.buffer_ptrs[r]) + off
             peers.flags[r] = int(hdl.buffer_ptrs[r]) + off  # the flag area is the head of the block
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
-        self.multicast = bool(mc) and self.use_multicast
+        # Bytes per link direction of the two-shot all-reduce of B bytes over G ranks: in the switch (multimem) every
+        # rank's whole buffer is read once and every rank receives the whole result, (G+1)/G x B -- its own slice loops
+        # through the switch too; with peer loads + peer stores 2(G-1)/G x B.  The switch wins from G = 4 on (G = 2: 1.5 B
+        # against 1.0 B; measured 0.185 ms against the peer path for 68 MB).
+        self.multicast = bool(mc) and self.use_multicast and (self.world >= 4 or bool(os.environ.get("FG_XCHG_FORCE_MULTICAST")))
         peers.mc = (mc + off) if self.multicast else None
         self._buf, self._hdl, self._peers = buf, hdl, peers
         self._layout = (pub_bytes, arena_bytes)

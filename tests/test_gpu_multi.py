@@ -15,7 +15,8 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def _run(world, views, mc=True, port=29631):
-    env = dict(os.environ, FG_TEST_VIEWS_PER_RANK=str(views), FG_XCHG_NO_MULTICAST="" if mc else "1")
+    env = dict(os.environ, FG_TEST_VIEWS_PER_RANK=str(views), FG_XCHG_NO_MULTICAST="" if mc else "1",
+               FG_XCHG_FORCE_MULTICAST="1" if mc else "")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(ROOT / "tests" / "multi" / "worker_exchange.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
@@ -31,5 +32,6 @@ def test_two_ranks_equal_one_process(built_lib, views):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_ranks_without_multicast(built_lib):
-    """The peer load / store fallback of the all-reduce kernel (no NVSwitch multicast object)."""
+    """The peer load / store form of the all-reduce kernel (the default below 4 ranks, and without an NVSwitch multicast
+    object); the two tests above force the in-switch (multimem) form."""
     _run(2, 1, mc=False, port=29641)
