@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfreegaussian_b200.so"
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pi = C.POINTER(C.c_int)
@@ -126,6 +126,11 @@ SIGNATURES = {
     "fg_deform_embed_bwd": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "fg_deform_apply_fwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_deform_apply_bwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_rows_workspace_bytes": (_i64, [_i64]),
+    "fg_rows_active": (_i32, [_i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "fg_rows_gather": (_i32, [_i64, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "fg_time_branch_fwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_time_branch_bwd": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_knn_workspace_bytes": (_i64, [_i64]),
     "fg_knn_f32": (_i32, [_i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
 }

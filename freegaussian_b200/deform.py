@@ -34,7 +34,15 @@ _HEADS = (("branch_w", 3), ("branch_v", 3), ("gaussian_rotation", 4), ("gaussian
 # backward over the rows with a non-zero incoming gradient only, when they are fewer than this fraction of all rows
 SPARSE_BACKWARD = True
 SPARSE_BACKWARD_MAX_FRACTION = 0.75
-_ROW_QUANT = 65536  # granule of the backward's row buffers (rows)
+_CAP_SLACK, _CAP_EXTRA = 1.12, 1024  # head-room of the guessed capacity over the previous count
+_ACTIVE_ROWS: dict = {}   # (device, rows, embedding width) -> active rows of the previous backward of that shape
+_PINNED: dict = {}
+
+
+def _pinned_slot(key) -> Tensor:
+    if key not in _PINNED:
+        _PINNED[key] = torch.zeros(1, dtype=torch.int64).pin_memory()
+    return _PINNED[key]
 
 
 def _embed(x: Tensor, multires: int) -> Tensor:
@@ -177,38 +185,85 @@ class _Trunk(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_head):
+        spec = ctx.spec
+        ld = spec.emb_ld
+        N_all = ctx.saved_tensors[0].shape[0]
+        dev = g_head.device
+        g_head = g_head.contiguous()
+        L = _lib.lib()
+        # Rows whose incoming gradient is exactly zero (Gaussians that were culled or never reached a pixel in this
+        # step's views) contribute exactly nothing to any gradient: run the backward on the other rows only.
+        # Their indices are compacted on the device (fg_rows_active) and the COUNT stays there: the row buffers get a
+        # capacity guessed from the previous backward of this shape, fg_rows_gather zero-fills the rows past the count
+        # (zero rows add nothing to any product below), and the count is only read back AFTER everything has been
+        # enqueued -- if it exceeded the capacity (never in steady state: the capacity carries 12 % head-room) the
+        # backward is redone densely.  No host synchronisation sits in front of the tensor-core kernels any more.
+        if SPARSE_BACKWARD and N_all > 0:
+            key = (str(dev), N_all, ld)
+            ws = torch.empty(int(L.fg_rows_workspace_bytes(N_all)), device=dev, dtype=torch.uint8)
+            idx_buf = torch.empty(N_all, device=dev, dtype=torch.int32)
+            count_dev = torch.empty(1, device=dev, dtype=torch.int64)
+            check(L.fg_rows_active(N_all, ptr(g_head), g_head.shape[1], ptr(idx_buf), ptr(count_dev), ptr(ws), ws.numel(),
+                                   _stream()))
+            guess = _ACTIVE_ROWS.get(key)
+            pending = None
+            if guess is None:  # first backward of this shape: one host read, exact capacity
+                cap = int(count_dev.item())
+            else:
+                cap = min(N_all, -(-int(guess * _CAP_SLACK + _CAP_EXTRA) // 128) * 128)
+                if dev.type == "cuda":
+                    pinned = _pinned_slot(key)
+                    pinned.copy_(count_dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    pending = (pinned, ev)
+                else:
+                    pending = (count_dev, None)
+            if cap < SPARSE_BACKWARD_MAX_FRACTION * N_all:
+                grads_out = _Trunk._backward_rows(ctx, g_head, (idx_buf, count_dev), cap)
+            else:
+                grads_out = _Trunk._backward_rows(ctx, g_head, None, N_all)
+                cap = N_all
+            if pending is not None:
+                if pending[1] is not None:
+                    pending[1].synchronize()
+                count = int(pending[0].item())
+                if count > cap:  # the guess was too small: redo on every row (exact, just slower)
+                    grads_out = _Trunk._backward_rows(ctx, g_head, None, N_all)
+            else:
+                count = cap
+            _ACTIVE_ROWS[key] = count
+            return grads_out
+        return _Trunk._backward_rows(ctx, g_head, None, N_all)
+
+    @staticmethod
+    def _backward_rows(ctx, g_head, active, N):
+        """The backward over N rows: every row (``active is None``) or the ``N``-row capacity buffer of the active rows
+        ``active = (idx, count_dev)`` (rows past the count are zero)."""
         spec, pk, t_ch = ctx.spec, ctx.pk, ctx.t_ch
         ld, emb_ch = spec.emb_ld, spec.emb_ch
         saved = ctx.saved_tensors
         x, e, masks, hs, params = saved[0], saved[1], saved[2], saved[3:3 + _D], saved[3 + _D:]
-        N_all = N = x.shape[0]
+        N_all = x.shape[0]
         dev = g_head.device
-        g_head = g_head.contiguous()
         grads: List[Tensor] = [None] * len(params)
         L = _lib.lib()
-        # Rows whose incoming gradient is exactly zero (Gaussians that were culled or never reached a pixel in this
-        # step's views) contribute exactly nothing to any gradient: run the backward on the other rows only.
-        # One host read (the number of such rows); the saved activations are gathered layer by layer as they are needed.
-        idx = None
-        if SPARSE_BACKWARD and N > 0:
-            act = (g_head != 0).any(1).nonzero().squeeze(1)  # the one host read (nonzero sizes its result)
-            if act.numel() < SPARSE_BACKWARD_MAX_FRACTION * N:
-                idx, N = act, act.numel()
-        # Row buffers are carved from allocations whose size is rounded up to _ROW_QUANT rows: the number of active rows
-        # changes every step, and a fresh size every step would send the caching allocator to cudaMalloc every step.
-        cap = N if idx is None else -(-N // _ROW_QUANT) * _ROW_QUANT
+        idx = active[0] if active is not None else None
 
         def rows(width, dtype=torch.float32):
-            return torch.empty(cap, width, device=dev, dtype=dtype)[:N]
+            return torch.empty(N, width, device=dev, dtype=dtype)
 
         new = lambda n_, w_: rows(w_)  # noqa: E731  (every [N, w] temporary of the backward)
         if idx is None:
             sel = lambda t: t  # noqa: E731
             m_in = lambda i: masks[i]  # noqa: E731
         else:
-            sel = lambda t: torch.index_select(t, 0, idx, out=rows(t.shape[1], t.dtype))  # noqa: E731
-            mask_rows = torch.empty(_D, cap, _W // 32, device=dev, dtype=torch.int32)
-            m_in = lambda i: torch.index_select(masks[i], 0, idx, out=mask_rows[i, :N])  # noqa: E731
+            def sel(t):
+                out = rows(t.shape[1], t.dtype)
+                check(L.fg_rows_gather(N, ptr(idx), ptr(active[1]), ptr(t), t.shape[1] * t.element_size(), ptr(out), _stream()))
+                return out
+
+            m_in = lambda i: sel(masks[i])  # noqa: E731
             g_head = sel(g_head)
         e = sel(e)
         h_in = lambda i: sel(hs[i])  # noqa: E731  activations of layer i (input of layer i + 1)
@@ -265,9 +320,50 @@ class _Trunk(torch.autograd.Function):
             de = new(N, ld)
             _linear(_lib.MLP_LINEAR, N, ld, dz, _W, dz_skip, _W, pk.wt_emb, torch.zeros(ld, device=dev), None, de, None)
             dx = new(N, 3)
-            check(L.fg_deform_embed_bwd(N, ptr(sel(x)), ptr(de), spec.multires, ld, ptr(dx), st))
-            g_x = dx if idx is None else torch.zeros(N_all, 3, device=dev).index_copy_(0, idx, dx)
+            x_rows = x if idx is None else x.index_select(0, idx[:N].long())  # 12-byte rows: not a 16-byte multiple
+            check(L.fg_deform_embed_bwd(N, ptr(x_rows), ptr(de), spec.multires, ld, ptr(dx), st))
+            # rows past the count are zero and point at row 0: adding them changes nothing
+            g_x = dx if idx is None else torch.zeros(N_all, 3, device=dev).index_add_(0, idx[:N].long(), dx)
         return (g_x, None, g_t, None, *grads)
+
+
+class _TimeBranch(torch.autograd.Function):
+    """t [1] (one time value) [, timenet W1, b1, W2, b2] -> t_emb: positional embedding (utils.py:27-56) and, for the
+    blender variant, ``timenet`` (freegaussian_model.py:1066-1071) in ONE launch forward and one backward
+    (``fg_time_branch_fwd/bwd``) instead of ~60 single-row torch kernels per training iteration."""
+
+    @staticmethod
+    def forward(ctx, t0, multires, *net):
+        L = _lib.lib()
+        dev = t0.device
+        in_ch = 1 + 2 * multires
+        emb = torch.empty(in_ch, device=dev, dtype=torch.float32)
+        if not net:
+            check(L.fg_time_branch_fwd(ptr(t0), multires, in_ch, 0, 0, None, None, None, None, ptr(emb), None, None, _stream()))
+            return emb
+        w1, b1, w2, b2 = (p.contiguous() for p in net)
+        hidden, out_ch = w1.shape[0], w2.shape[0]
+        assert w1.shape == (hidden, in_ch) and w2.shape == (out_ch, hidden)
+        h = torch.empty(hidden, device=dev, dtype=torch.float32)
+        out = torch.empty(out_ch, device=dev, dtype=torch.float32)
+        check(L.fg_time_branch_fwd(ptr(t0), multires, in_ch, hidden, out_ch, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(emb), ptr(h),
+                                   ptr(out), _stream()))
+        ctx.save_for_backward(emb, h, w2)
+        ctx.dims = (in_ch, hidden, out_ch)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        emb, h, w2 = ctx.saved_tensors
+        in_ch, hidden, out_ch = ctx.dims
+        dev = g.device
+        dw1 = torch.empty(hidden, in_ch, device=dev)
+        db1 = torch.empty(hidden, device=dev)
+        dw2 = torch.empty(out_ch, hidden, device=dev)
+        db2 = torch.empty(out_ch, device=dev)
+        check(_lib.lib().fg_time_branch_bwd(in_ch, hidden, out_ch, ptr(emb), ptr(h), ptr(w2), ptr(g.contiguous()), ptr(dw1),
+                                            ptr(db1), ptr(dw2), ptr(db2), _stream()))
+        return None, None, dw1, db1, dw2, db2
 
 
 class _Apply(torch.autograd.Function):
@@ -356,11 +452,13 @@ class DeformNetwork(nn.Module):
         if t.numel() > 1 and not (t.dim() == 2 and t.stride(0) == 0):
             raise ValueError("DeformNetwork evaluates ONE time value per call, as the reference does with "
                              "`camera.times.expand(N, -1)`: pass a [1,1] tensor or an expanded view, not per-row times")
-        t0 = t.reshape(-1)[:1].reshape(1, 1).to(torch.float32)
-        t_emb = _embed(t0, self.t_multires)
+        if not t.is_cuda and not getattr(_lib.lib(), "host_memory_model", False):  # (tests/fake_mlp_lib.py runs on host memory)
+            raise RuntimeError("DeformNetwork: `t` is not a CUDA tensor (there is no CPU path)")
+        t0 = t.reshape(-1)[:1].to(torch.float32).contiguous()
         if self.is_blender:
-            t_emb = self.timenet(t_emb)
-        return t_emb.reshape(-1)
+            return _TimeBranch.apply(t0, self.t_multires, self.timenet[0].weight, self.timenet[0].bias,
+                                     self.timenet[2].weight, self.timenet[2].bias)
+        return _TimeBranch.apply(t0, self.t_multires)
 
     @_lib.on_device_of("x")
     def head(self, x: Tensor, t: Tensor) -> Tensor:

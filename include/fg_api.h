@@ -439,6 +439,23 @@ int fg_deform_apply_bwd(int64_t N, const float* head, const float* means, const 
                         float* v_means, float* v_scales_log, float* v_quats, void* stream);
 
 
+/* Host-sync-free sparse backward of the networks (csrc/rows.cu).  fg_rows_active: idx[0 .. count) = indices (ascending) of
+ * the rows of g[N, ld] with a non-zero element, idx[count .. N) = 0, *count_dev = count (int64, device).  fg_rows_gather:
+ * dst[r] = r < *count_dev ? src[idx[r]] : 0 for r < M, rows of row_bytes (a multiple of 16): M is a capacity the host chose
+ * without knowing the count; zero rows contribute nothing to the products of the backward. */
+int64_t fg_rows_workspace_bytes(int64_t N);
+int fg_rows_active(int64_t N, const float* g, int ld, int32_t* idx, int64_t* count_dev, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+int fg_rows_gather(int64_t M, const int32_t* idx, const int64_t* count_dev, const void* src, int row_bytes, void* dst,
+                   void* stream);
+/* Time branch of FreeGaussianDeformableModel (freegaussian_model.py:1066-1071, 1094-1096) for the ONE time value of a call:
+ * emb[in_ch] = [t, sin(2^k t), cos(2^k t)]_k (utils.py:27-56); with w1 != NULL: h[hidden] = relu(W1 emb + b1),
+ * out[out_ch] = W2 h + b2 (`timenet`).  bwd: gradients of the four timenet tensors from g_out[out_ch]. */
+int fg_time_branch_fwd(const float* t, int multires, int in_ch, int hidden, int out_ch, const float* w1, const float* b1,
+                       const float* w2, const float* b2, float* emb, float* h, float* out, void* stream);
+int fg_time_branch_bwd(int in_ch, int hidden, int out_ch, const float* emb, const float* h, const float* w2,
+                       const float* g_out, float* dw1, float* db1, float* dw2, float* db2, void* stream);
+
 /* ---- (5) view-sharded multi-GPU exchange over NVLink peer memory / NVSwitch multicast ------------------
  * BASELINE.json north_star item 5; the reference itself is single-GPU, so these have no reference
  * counterpart: they make `loss.backward()` on every rank return the gradient one process rendering all views would.

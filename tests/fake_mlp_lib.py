@@ -34,6 +34,8 @@ def _tf32_hi(x):
 
 
 class FakeMlpLib:
+    host_memory_model = True  # lets deform.py's "CUDA tensors only" guard of the time branch through
+
     def __init__(self):
         self.calls = []
 
@@ -157,6 +159,59 @@ class FakeMlpLib:
             sum((o * g).sum() for o, g in zip(outs, (t(g_m, 3), t(g_s, 3), t(g_q, 4)))).backward()
         for dst, w_, i in zip((v_head, v_m, v_s, v_q), (HEAD_LD, 3, 3, 4), ins):
             _arr(dst, (N, w_))[:] = i.grad.float().numpy()
+        return 0
+
+    # ---- fg_rows_active / fg_rows_gather (csrc/rows.cu)
+    def fg_rows_workspace_bytes(self, N):
+        return 16
+
+    def fg_rows_active(self, N, g, ld, idx, count_dev, ws, ws_bytes, stream):
+        self.calls.append("rows_active")
+        out = _arr(idx, (N,), np.int32)
+        out[:] = 0
+        act = np.nonzero((_arr(g, (N, ld)) != 0).any(1))[0].astype(np.int32)
+        out[:act.size] = act
+        ctypes.c_int64.from_address(int(count_dev)).value = int(act.size)
+        return 0
+
+    def fg_rows_gather(self, M, idx, count_dev, src, row_bytes, dst, stream):
+        self.calls.append("rows_gather")
+        if M == 0:
+            return 0
+        n = ctypes.c_int64.from_address(int(count_dev)).value
+        w = row_bytes // 4
+        rows = _arr(idx, (M,), np.int32)[:min(n, M)]
+        big = int(rows.max()) + 1 if rows.size else 1
+        s_ = _arr(src, (big, w), np.uint32)
+        d = _arr(dst, (M, w), np.uint32)
+        d[:] = 0
+        d[:rows.size] = s_[rows]
+        return 0
+
+    # ---- time branch
+    def fg_time_branch_fwd(self, t, multires, in_ch, hidden, out_ch, w1, b1, w2, b2, emb, h, out, stream):
+        self.calls.append("time_fwd")
+        tv = _arr(t, (1,)).astype(np.float64)
+        e = [tv]
+        for k in range(multires):
+            e += [np.sin(tv * 2.0 ** k), np.cos(tv * 2.0 ** k)]
+        e = np.concatenate(e)
+        _arr(emb, (in_ch,))[:] = e.astype(np.float32)
+        if not w1:
+            return 0
+        hv = np.maximum(_arr(w1, (hidden, in_ch)).astype(np.float64) @ e + _arr(b1, (hidden,)), 0)
+        _arr(h, (hidden,))[:] = hv.astype(np.float32)
+        _arr(out, (out_ch,))[:] = (_arr(w2, (out_ch, hidden)).astype(np.float64) @ hv + _arr(b2, (out_ch,))).astype(np.float32)
+        return 0
+
+    def fg_time_branch_bwd(self, in_ch, hidden, out_ch, emb, h, w2, g_out, dw1, db1, dw2, db2, stream):
+        self.calls.append("time_bwd")
+        e, hv, g = _arr(emb, (in_ch,)).astype(np.float64), _arr(h, (hidden,)).astype(np.float64), _arr(g_out, (out_ch,)).astype(np.float64)
+        _arr(db2, (out_ch,))[:] = g.astype(np.float32)
+        _arr(dw2, (out_ch, hidden))[:] = np.outer(g, hv).astype(np.float32)
+        dh = (_arr(w2, (out_ch, hidden)).astype(np.float64).T @ g) * (hv > 0)
+        _arr(db1, (hidden,))[:] = dh.astype(np.float32)
+        _arr(dw1, (hidden, in_ch))[:] = np.outer(dh, e).astype(np.float32)
         return 0
 
     def fg_last_error(self):

@@ -94,7 +94,8 @@ def test_module_mirrors_reference_state_dict():
         DeformNetwork(is_blender=True).head(torch.zeros(4, 3), torch.zeros(4, 1))  # no CPU path
     with pytest.raises(ValueError, match="ONE time value"):
         DeformNetwork(is_blender=True)._time_row(torch.rand(4, 1))  # per-row times are not the reference's call
-    assert DeformNetwork(is_blender=True)._time_row(torch.tensor([[0.5]]).expand(4, -1)).shape == (30,)
+    with pytest.raises(RuntimeError):  # the time branch is a kernel too (fg_time_branch_fwd): no CPU path
+        DeformNetwork(is_blender=True)._time_row(torch.tensor([[0.5]]).expand(4, -1))
     from freegaussian_b200.deform import ControlNetwork
 
     net = ControlNetwork()

@@ -22,6 +22,7 @@ def D(monkeypatch):
     monkeypatch.setattr(deform._lib, "lib", lambda: fake)
     monkeypatch.setattr(deform, "_stream", lambda: 0)
     deform._fake = fake
+    deform._ACTIVE_ROWS.clear()
     return deform
 
 
@@ -103,3 +104,42 @@ def test_no_active_rows_gives_zero_gradients(D):
     (head * 0).sum().backward()
     assert all(float(p.grad.abs().max()) == 0.0 for p in net.parameters() if p.grad is not None)
     assert np.isfinite(head.detach().numpy()).all()
+
+
+def test_sparse_backward_capacity_guess_and_overflow(D, monkeypatch):
+    """The second backward of a shape sizes its row buffers from the FIRST one's count (no host read in front of the
+    kernels), zero-filling the rows past the real count; a count that overflows the guess is redone densely.  All exact."""
+    monkeypatch.setattr(D, "_CAP_EXTRA", 0)
+    n = 400
+    params = OD.init_params(is_blender=True, seed=21)
+    net = D.DeformNetwork(is_blender=True)
+    net.load_state_dict(params)
+    means, scales_log, quats, ws0 = _scene(n, 9)
+    t = torch.tensor([[0.6]])
+    spec = D._Spec(D.MLP_EMBED_LD, net.input_ch, net.multires, D._HEADS, input_grad=False)
+
+    def run(active_mod):
+        keep = (torch.arange(n) % 10 < active_mod).float()[:, None]
+        ws = [w * keep for w in ws0]
+        P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        lo = [x.clone().requires_grad_(True) for x in (means, scales_log, quats)]
+        want = OD.deform_gaussians(P, *lo, t.expand(n, -1), True)
+        sum((o * w).sum() for o, w in zip(want, ws)).backward()
+        for p in net.parameters():
+            p.grad = None
+        lp = [x.clone().requires_grad_(True) for x in (means, scales_log, quats)]
+        D._fake.calls.clear()
+        head = D._Trunk.apply(lp[0].detach().contiguous(), None, net._time_row(t).contiguous(), spec, *net._params())
+        got = D._Apply.apply(head, *lp)
+        sum((o * w).sum() for o, w in zip(got, ws)).backward()
+        for a, b in zip(lp, lo):
+            assert grad_rel_err(a.grad, b.grad) < 1e-5
+        for k, v in net.named_parameters():
+            assert grad_rel_err(v.grad, P[k].grad) < 1e-4, k
+        return [c[2] for c in D._fake.calls if isinstance(c, tuple) and c[0] == "linear" and c[1] == 2]
+
+    assert run(4) == [160] * 8                    # first backward: exact count (one host read)
+    assert run(3) == [256] * 8                    # 120 active rows in a 256-row capacity guessed from 160 * 1.12
+    rows = run(9)                                 # 360 active rows overflow the 256-row guess: redone on every row
+    assert rows[:8] == [256] * 8 and rows[8:] == [n] * 8
+    assert run(9) == [n] * 8                      # 360 * 1.12 > 0.75 n: dense from the start
