@@ -670,7 +670,7 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         # iteration i: from its first event to the first event of iteration i+1 (back-to-back, includes every gap)
         per = sorted(marks[i][0].elapsed_time(marks[i + 1][0]) for i in range(steps - 1))
         q = lambda f: per[min(len(per) - 1, int(f * len(per)))]  # noqa: E731
-        return a.elapsed_time(b) / steps, fwd, bwd, {"p10": q(0.1), "p50": q(0.5), "p90": q(0.9)}
+        return a.elapsed_time(b) / steps, fwd, bwd, {"p10": q(0.1), "p50": q(0.5), "p90": q(0.9), "max": per[-1]}
 
     ms_plain, _, _, q_plain = timed(False)
     l0 = _lib.launch_count()

@@ -25,7 +25,7 @@ def _run(world, views, mc=True, port=29631):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("views", [1, 2])
+@pytest.mark.parametrize("views", [1, 2, 5])  # 5 views x 2 ranks: more than one eight-view chunk of fg_xchg_sh_bwd_views
 def test_two_ranks_equal_one_process(built_lib, views):
     _run(2, views, port=29631 + views)
 
