@@ -155,7 +155,8 @@ class ViewShardedExchange:
 
     # -- lifecycle
     def active(self) -> bool:
-        return self.world > 1
+        # FG_XCHG_SOLO: run the exchange kernels in a single-rank group too (single-GPU tests and ncu captures of them)
+        return self.world > 1 or bool(os.environ.get("FG_XCHG_SOLO"))
 
     def install(self) -> "ViewShardedExchange":
         from . import rendering
