@@ -71,6 +71,7 @@ SIGNATURES = {
     "fg_last_error": (C.c_char_p, []),
     "fg_abi_version": (_i32, []),
     "fg_launch_count": (C.c_longlong, []),
+    "fg_set_option": (_i32, [C.c_char_p, _i32]),
     "fg_measure_fp32_tflops": (_i32, [C.POINTER(C.c_double), _vp]),
     "fg_project_fwd": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _i32,
                               _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,

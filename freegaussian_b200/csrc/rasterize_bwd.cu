@@ -363,28 +363,7 @@ __device__ __forceinline__ void bwd_pixel(bool valid, float alpha, float vis, fl
     }
 }
 
-// ---- packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2): both pixels of the thread in one instruction --------------
-// The kernel is issue-bound (ncu r1: issue slots 76 % busy, FMA pipe 38 %): when both halves of the pixel pair can be
-// reached, the per-pixel arithmetic runs on float2 = (pixel 0, pixel 1) operands.  A scalar operand is broadcast by the
-// instruction itself (`R.F32` operand form), so per-Gaussian values need no duplication.
-__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
-
-// alpha of both pixels; the same operations in the same order as eval_alpha, so forward and backward agree bit for bit
-__device__ __forceinline__ void eval_alpha_pair(const GeomA& a, const GeomB& b, float px, float2 npy, float& dx, float2& dy,
-                                                float2& u, float2& v, float2& vis, float2& raw, float2& alpha, bool& ok0,
-                                                bool& ok1) {
-    dx = a.x - px;
-    dy = __fadd2_rn(bc2(a.y), npy);
-    u = __ffma2_rn(bc2(a.a1), bc2(dx), __fmul2_rn(bc2(b.b1), dy));
-    v = __ffma2_rn(bc2(b.c1), dy, bc2(b.b1 * dx));
-    const float2 pw = __ffma2_rn(u, bc2(dx), __fmul2_rn(v, dy));
-    vis = make_float2(ex2_approx(-pw.x), ex2_approx(-pw.y));
-    raw = __fmul2_rn(bc2(a.opac), vis);
-    alpha = make_float2(fminf(ALPHA_MAX, raw.x), fminf(ALPHA_MAX, raw.y));
-    ok0 = (pw.x >= 0.f) && (alpha.x >= ALPHA_MIN);
-    ok1 = (pw.y >= 0.f) && (alpha.y >= ALPHA_MIN);
-}
-
+// ---- packed FP32: both pixels of the thread in one instruction (bc2 / eval_alpha_pair: rasterize_common.cuh) ----------
 template <int CH, int NF>
 __device__ __forceinline__ void bwd_pixel_pair(bool valid0, bool valid1, float2 alpha, float2 vis, float2 raw, float dx,
                                                float2 dy, float2 u, float2 v, const float (&f)[NF], const float2 (&V)[CH],

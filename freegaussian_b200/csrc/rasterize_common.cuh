@@ -57,6 +57,30 @@ __device__ __forceinline__ bool eval_alpha(const GeomA& a, const GeomB& b, float
     return (p >= 0.f) && (alpha >= ALPHA_MIN);
 }
 
+// ---- packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2): both pixels of a thread in one instruction --------------------
+// The compositing kernels are issue-bound (ncu r1: issue slots 76-85 % busy, FMA pipe ~40 %): with two pixels per thread
+// (four rows apart, the two 8x4 patches of the culling mask) the per-pixel arithmetic runs on float2 = (pixel 0, pixel 1)
+// operands.  A scalar operand is broadcast by the instruction itself (`R.F32` operand form in SASS), so per-Gaussian
+// values need no duplication.  tools/ubench/f32x2.cu: FFMA2 sustains the FFMA flop rate with half the issue slots.
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+
+// alpha of both pixels; the same operations in the same order as eval_alpha, so the one- and two-pixel kernels and the
+// forward and backward passes agree bit for bit.  npy = (-py0, -py1).
+__device__ __forceinline__ void eval_alpha_pair(const GeomA& a, const GeomB& b, float px, float2 npy, float& dx, float2& dy,
+                                                float2& u, float2& v, float2& vis, float2& raw, float2& alpha, bool& ok0,
+                                                bool& ok1) {
+    dx = a.x - px;
+    dy = __fadd2_rn(bc2(a.y), npy);
+    u = __ffma2_rn(bc2(a.a1), bc2(dx), __fmul2_rn(bc2(b.b1), dy));
+    v = __ffma2_rn(bc2(b.c1), dy, bc2(b.b1 * dx));
+    const float2 pw = __ffma2_rn(u, bc2(dx), __fmul2_rn(v, dy));
+    vis = make_float2(ex2_approx(-pw.x), ex2_approx(-pw.y));
+    raw = __fmul2_rn(bc2(a.opac), vis);
+    alpha = make_float2(fminf(ALPHA_MAX, raw.x), fminf(ALPHA_MAX, raw.y));
+    ok0 = (pw.x >= 0.f) && (alpha.x >= ALPHA_MIN);
+    ok1 = (pw.y >= 0.f) && (alpha.y >= ALPHA_MIN);
+}
+
 // ---- shared memory by explicit 32-bit address --------------------------------------------------
 // The staged Gaussian records live at fixed offsets from one base (slot t at base + 16 t + k * 4096),
 // so the hot loops form ONE address per Gaussian and use immediate offsets; through C++ arrays the

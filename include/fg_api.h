@@ -38,6 +38,10 @@ int fg_abi_version(void);
 /* Number of kernels launched by this library in this process so far (bench.py `gpu_launches`). */
 long long fg_launch_count(void);
 
+/* Run-time switches for A/B measurements: "fwd_two_pixels" = 1 (default: two pixels per thread, packed FP32) | 0 (the
+ * one-pixel forward kernel).  Both produce the same images.  FG_ERR_INVALID for an unknown name. */
+int fg_set_option(const char* name, int value);
+
 /* Measured FP32 FMA peak of this GPU in TFLOP/s (a short FFMA microbenchmark; synchronises).
  * Denominator for the FP32-pipe-bound compositing kernels' roofline in bench.py. */
 int fg_measure_fp32_tflops(double* tflops_host, void* stream);

@@ -236,3 +236,29 @@ def test_mask_assignment_matches_reference_logic(built_lib):
                                     info["gaussian_ids"].cpu(), mask, acc_ref)
     assert acc_ref.sum() > 50
     assert torch.equal(acc_gpu.cpu(), acc_ref)
+
+
+def test_two_pixel_forward_kernel_equals_the_one_pixel_kernel(built_lib):
+    """rasterize_fwd2_kernel (two pixels per thread, packed FFMA2 arithmetic when both 8x4 patches are reachable) performs
+    the same operations in the same order per pixel as rasterize_fwd_kernel: images, alphas and last_ids bit for bit."""
+    from freegaussian_b200 import _lib
+    from freegaussian_b200.rendering import rasterization
+    L = _lib.lib()
+    outs = {}
+    try:
+        for W, H, n, seed in ((200, 136, 6000, 21), (97, 50, 900, 22)):  # the second frame has partial tiles on both edges
+            sc = small_scene(n, W, H, views=2, seed=seed).to("cuda")
+            for opt in (0, 1):
+                _lib.check(L.fg_set_option(b"fwd_two_pixels", opt))
+                with torch.no_grad():
+                    r, a, m = rasterization(sc.means, sc.quats, sc.scales, sc.opacities, sc.sh, sc.viewmats, sc.Ks, W, H,
+                                            packed=False, render_mode="RGB+ED", sh_degree=3, means_next=sc.means_next,
+                                            backgrounds=torch.rand(2, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(1)))
+                outs[opt] = (r, a, m["flow"], m["last_ids"])
+            for x, y in zip(outs[0], outs[1]):
+                assert torch.equal(x, y)
+            assert float(outs[1][1].max()) > 0.5
+    finally:
+        _lib.check(L.fg_set_option(b"fwd_two_pixels", 1))
+    with pytest.raises(AssertionError):
+        _lib.check(L.fg_set_option(b"no_such_option", 1))
