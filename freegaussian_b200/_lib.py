@@ -127,6 +127,11 @@ SIGNATURES = {
     "fg_deform_embed_bwd": (_i32, [_i64, _vp, _vp, _i32, _i32, _vp, _vp]),
     "fg_deform_apply_fwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_deform_apply_bwd": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fg_pack_workspace_bytes": (_i64, [_i64]),
+    "fg_pack_plan": (_i32, [_i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "fg_pack_gather": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _vp, _vp, _vp, _vp]),
+    "fg_pack_remap": (_i32, [_i64, _vp, _vp, _vp]),
     "fg_rows_workspace_bytes": (_i64, [_i64]),
     "fg_rows_active": (_i32, [_i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "fg_rows_gather": (_i32, [_i64, _vp, _vp, _vp, _i32, _vp, _vp]),

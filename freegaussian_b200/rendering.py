@@ -710,20 +710,48 @@ def rasterization(
         meta["isect_ids"] = isect_ids
     if packed:
         # compact per-Gaussian tensors to the visible (c,n) pairs in ascending order (Appendix A.8)
-        vis = (radii > 0).reshape(-1)
-        idx = torch.nonzero(vis).squeeze(-1)
-        remap = (torch.cumsum(vis, 0, dtype=torch.int32) - 1).to(torch.int32)
-        flatten_ids = remap[flatten_ids.long()].contiguous()
-        means2d = means2d.reshape(C * N, 2)[idx]
-        depths = depths.reshape(C * N)[idx]
-        conics = conics.reshape(C * N, 3)[idx]
-        feat = feat.reshape(C * N, -1)[idx]
-        opac = (opac if opac.dim() == 2 else opac[None].expand(C, N)).reshape(C * N)[idx]
-        if flow_affine is not None:
-            flow_affine = flow_affine.reshape(C * N, 4)[idx]
-        radii = radii.reshape(C * N)[idx]
-        meta["camera_ids"] = idx // N
-        meta["gaussian_ids"] = idx % N
+        needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (means2d, depths, conics, feat, opac))
+        if not needs_grad and C * N > 0:
+            # the preprocess callers (no gradients): three kernels -- flags + scan, one gather of every tensor, list remap
+            L = _lib.lib()
+            dev, st = means.device, _stream()
+            total = C * N
+            offs = torch.empty(total, dtype=torch.int32, device=dev)
+            nnz_dev = torch.empty(1, dtype=torch.int64, device=dev)
+            ws = _ws.get("pack", L.fg_pack_workspace_bytes(total), dev)
+            check(L.fg_pack_plan(total, ptr(radii), ptr(offs), ptr(nnz_dev), ptr(ws), ws.numel(), st))
+            nnz = int(nnz_dev.item())  # sizes the packed tensors (gsplat's packed projection has the same host read)
+            CHf = feat.shape[-1]
+            opac_c = opac.contiguous()
+            new = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype, device=dev)  # noqa: E731
+            radii_p, means2d_p, depths_p, conics_p = new(nnz, dtype=torch.int32), new(nnz, 2), new(nnz), new(nnz, 3)
+            feat_p, opac_p = new(nnz, CHf), new(nnz)
+            aff_p = new(nnz, 4) if flow_affine is not None else None
+            cam_ids, gauss_ids = new(nnz, dtype=torch.int64), new(nnz, dtype=torch.int64)
+            check(L.fg_pack_gather(C, N, CHf, ptr(radii), ptr(offs), ptr(means2d.detach().contiguous()),
+                                   ptr(depths.detach().contiguous()), ptr(conics.detach().contiguous()),
+                                   ptr(feat.detach().contiguous()), ptr(opac_c.detach()), int(opac_c.dim() == 1),
+                                   ptr(flow_affine), ptr(radii_p), ptr(means2d_p), ptr(depths_p), ptr(conics_p), ptr(feat_p),
+                                   ptr(opac_p), ptr(aff_p), ptr(cam_ids), ptr(gauss_ids), st))
+            flatten_ids = flatten_ids.clone()
+            check(L.fg_pack_remap(flatten_ids.numel(), ptr(offs), ptr(flatten_ids), st))
+            radii, means2d, depths, conics, feat, opac, flow_affine = radii_p, means2d_p, depths_p, conics_p, feat_p, opac_p, aff_p
+            meta["camera_ids"], meta["gaussian_ids"] = cam_ids, gauss_ids
+        else:  # differentiable form (torch indexing): gradients flow back to the unpacked projection outputs
+            vis = (radii > 0).reshape(-1)
+            idx = torch.nonzero(vis).squeeze(-1)
+            remap = (torch.cumsum(vis, 0, dtype=torch.int32) - 1).to(torch.int32)
+            flatten_ids = remap[flatten_ids.long()].contiguous()
+            means2d = means2d.reshape(C * N, 2)[idx]
+            depths = depths.reshape(C * N)[idx]
+            conics = conics.reshape(C * N, 3)[idx]
+            feat = feat.reshape(C * N, -1)[idx]
+            opac = (opac if opac.dim() == 2 else opac[None].expand(C, N)).reshape(C * N)[idx]
+            if flow_affine is not None:
+                flow_affine = flow_affine.reshape(C * N, 4)[idx]
+            radii = radii.reshape(C * N)[idx]
+            meta["camera_ids"] = idx // N
+            meta["gaussian_ids"] = idx % N
 
     CH = feat.shape[-1]
     ed_channel = n_user - 1 if render_mode in ("ED", "RGB+ED") else -1

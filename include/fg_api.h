@@ -443,6 +443,21 @@ int fg_deform_apply_bwd(int64_t N, const float* head, const float* means, const 
                         float* v_means, float* v_scales_log, float* v_quats, void* stream);
 
 
+/* packed=True layout of the render call (preprocess/knn_gaussian.py:93-113 and the other preprocess
+ * scripts): compact every per-(camera, Gaussian) tensor to the visible pairs in ascending c*N+n order.
+ * fg_pack_plan: offsets[C*N] = exclusive scan of (radii > 0), *nnz_dev = number of visible pairs (int64, device).
+ * fg_pack_gather: row offsets[i] of every *_p output = row i of the input for each visible i = c*N+n; camera_ids /
+ * gaussian_ids (int64) = c / n.  fg_pack_remap: flatten_ids[m] = offsets[flatten_ids[m]] in place. */
+int64_t fg_pack_workspace_bytes(int64_t total);
+int fg_pack_plan(int64_t total, const int32_t* radii, int32_t* offsets, int64_t* nnz_dev, void* workspace,
+                 int64_t workspace_bytes, void* stream);
+int fg_pack_gather(int C, int N, int CH, const int32_t* radii, const int32_t* offsets, const float* means2d,
+                   const float* depths, const float* conics, const float* feat, const float* opacities, int opac_shared,
+                   const float* flow_affine, int32_t* radii_p, float* means2d_p, float* depths_p, float* conics_p,
+                   float* feat_p, float* opac_p, float* flow_affine_p, int64_t* camera_ids, int64_t* gaussian_ids,
+                   void* stream);
+int fg_pack_remap(int64_t M, const int32_t* offsets, int32_t* flatten_ids, void* stream);
+
 /* Host-sync-free sparse backward of the networks (csrc/rows.cu).  fg_rows_active: idx[0 .. count) = indices (ascending) of
  * the rows of g[N, ld] with a non-zero element, idx[count .. N) = 0, *count_dev = count (int64, device).  fg_rows_gather:
  * dst[r] = r < *count_dev ? src[idx[r]] : 0 for r < M, rows of row_bytes (a multiple of 16): M is a capacity the host chose

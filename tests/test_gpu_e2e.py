@@ -262,3 +262,26 @@ def test_two_pixel_forward_kernel_equals_the_one_pixel_kernel(built_lib):
         _lib.check(L.fg_set_option(b"fwd_two_pixels", 1))
     with pytest.raises(AssertionError):
         _lib.check(L.fg_set_option(b"no_such_option", 1))
+
+
+def test_packed_kernel_path_and_differentiable_path_agree(built_lib):
+    """packed=True without gradients runs fg_pack_plan / fg_pack_gather / fg_pack_remap (the preprocess callers); with
+    gradients it keeps the torch-indexing form.  Same packed tensors either way, and gradients equal the unpacked call's."""
+    from freegaussian_b200.rendering import rasterization
+    W, H = 112, 80
+    sc = small_scene(2500, W, H, views=3, seed=19).to("cuda")
+    args = (sc.quats, sc.scales, sc.opacities, sc.sh, sc.viewmats, sc.Ks, W, H)
+    kw = dict(render_mode="RGB+ED", sh_degree=3, rasterize_mode="antialiased")
+    with torch.no_grad():
+        r0, a0, m0 = rasterization(sc.means, *args, packed=True, **kw)          # kernel path
+    mp = sc.means.clone().requires_grad_(True)
+    r1, a1, m1 = rasterization(mp, *args, packed=True, **kw)                     # differentiable path
+    assert torch.equal(r0, r1) and torch.equal(a0, a1)
+    for k in ("radii", "means2d", "depths", "conics", "opacities", "camera_ids", "gaussian_ids", "flatten_ids"):
+        assert m0[k].dtype == m1[k].dtype and torch.equal(m0[k], m1[k].detach()), k
+    mu = sc.means.clone().requires_grad_(True)
+    r2, a2, _ = rasterization(mu, *args, packed=False, **kw)
+    w = torch.randn_like(r1)
+    (r1 * w).sum().backward()
+    (r2 * w).sum().backward()
+    assert grad_rel_err(mp.grad, mu.grad) < 1e-5
