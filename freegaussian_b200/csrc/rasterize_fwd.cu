@@ -36,8 +36,12 @@ struct RasterFwdParams {
     int32_t* last_ids;
 };
 
-// which forward kernel fg_rasterize_fwd launches (fg_set_option("fwd_two_pixels", 0 / 1)); both give the same images
-static int g_fwd_two_pixels = 1;
+// which forward kernel fg_rasterize_fwd launches (fg_set_option("fwd_two_pixels", 0 / 1)); both give the same images.
+// Default: the one-pixel kernel.  Measured on cfg3 (profiles/r2_rasterize_fwd2_kernel.txt): the two-pixel packed kernel
+// executes 5 % fewer instructions but its per-pixel predication (validity, stop test, selects of w / T / last id: FSETP,
+// FSEL, FMNMX) lands on the half-rate ALU pipe -- 71 % busy, math-pipe-throttle stalls -- and it runs 0.296 ms against
+// 0.270 ms.  (The backward kernel has no such per-pixel control flow and gains 8.6 % from the same packing.)
+static int g_fwd_two_pixels = 0;
 
 template <int CH, bool AFF>
 __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdParams p) {

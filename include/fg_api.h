@@ -38,8 +38,9 @@ int fg_abi_version(void);
 /* Number of kernels launched by this library in this process so far (bench.py `gpu_launches`). */
 long long fg_launch_count(void);
 
-/* Run-time switches for A/B measurements: "fwd_two_pixels" = 1 (default: two pixels per thread, packed FP32) | 0 (the
- * one-pixel forward kernel).  Both produce the same images.  FG_ERR_INVALID for an unknown name. */
+/* Run-time switches for A/B measurements: "fwd_two_pixels" = 0 (default: the one-pixel forward kernel) | 1 (two pixels
+ * per thread, packed FP32; measured slower, kept as the documented experiment).  Both produce the same images.
+ * FG_ERR_INVALID for an unknown name. */
 int fg_set_option(const char* name, int value);
 
 /* Measured FP32 FMA peak of this GPU in TFLOP/s (a short FFMA microbenchmark; synchronises).

@@ -259,7 +259,7 @@ def test_two_pixel_forward_kernel_equals_the_one_pixel_kernel(built_lib):
                 assert torch.equal(x, y)
             assert float(outs[1][1].max()) > 0.5
     finally:
-        _lib.check(L.fg_set_option(b"fwd_two_pixels", 1))
+        _lib.check(L.fg_set_option(b"fwd_two_pixels", 0))
     with pytest.raises(AssertionError):
         _lib.check(L.fg_set_option(b"no_such_option", 1))
 
