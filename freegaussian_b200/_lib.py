@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfreegaussian_b200.so"
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pi = C.POINTER(C.c_int)
@@ -41,7 +41,8 @@ class MlpPackSegment(C.Structure):  # fg_mlp_pack_segment
 
 
 class ProjectBwdPub(C.Structure):  # fg_project_bwd_pub
-    _fields_ = [("campos", _vp), ("mask", _vp), ("rgb", _vp), ("words", C.c_int32), ("phase", C.c_int32)]
+    _fields_ = [("campos", _vp), ("mask", _vp), ("prefix", _vp), ("rgb", _vp), ("offsets", _vp), ("nnz", _vp),
+                ("words", C.c_int32), ("phase", C.c_int32)]
 
 
 XCHG_MAX_RANKS = 16
@@ -80,9 +81,11 @@ SIGNATURES = {
                               _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ProjectBwdPub), _vp]),
     "fg_xchg_pub_bytes": (_i64, [_i32, _i32]),
+    "fg_xchg_pub_layout": (_i32, [_i32, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
+                                  C.POINTER(C.c_int32)]),
     "fg_xchg_barrier": (_i32, [C.POINTER(XchgPeers), C.c_uint32, _vp]),
     "fg_xchg_allreduce_f32": (_i32, [C.POINTER(XchgPeers), _i64, _i64, C.c_uint32, _i32, _vp]),
-    "fg_xchg_sh_bwd_views": (_i32, [C.POINTER(XchgPeers), _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fg_xchg_sh_bwd_views": (_i32, [C.POINTER(XchgPeers), _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "fg_scan_workspace_bytes": (_i64, [_i64]),
     "fg_exclusive_scan_i32": (_i32, [_i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "fg_isect_emit": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),

@@ -39,7 +39,7 @@ int set_cuda_error(cudaError_t e, const char* file, int line) {
 extern "C" {
 
 const char* fg_last_error(void) { return fg::g_err; }
-int fg_abi_version(void) { return 9; }
+int fg_abi_version(void) { return 10; }
 long long fg_launch_count(void) { return fg::g_launch_count.load(); }
 
 }  // extern "C"

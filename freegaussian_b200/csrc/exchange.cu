@@ -145,27 +145,62 @@ __global__ void __launch_bounds__(XB, 2) allreduce_kernel(Peers p, long long off
 }
 
 // ------------------------------------------------------------------------------ SH rows from all views
-// Published block of one rank (byte offset `pub_off` of its symmetric buffer), V views per rank:
-//   float    campos[V][4]                      camera centres (world)
-//   uint32_t mask[V][words]   words = ceil(N/32) rounded up to 4: bit n = splat n is visible in the view
-//   float    rgb[V][N][3]                      d loss / d rgb with the clamp mask applied (garbage where invisible)
+// Published block of one rank (byte offset `pub_off` of its symmetric buffer), V views per rank, `words` = ceil(N/32)
+// rounded up to 4:
+//   float    campos[V][4]            camera centres (world); then one uint32: nnz = visible (view, Gaussian) pairs
+//   uint32_t mask[V][words]          bit n of view v = splat n is visible in the view
+//   uint32_t prefix[V][words]        compact row of the first visible splat of that word (exclusive scan over v*N+n)
+//   float    rgb[nnz][3]             d loss / d rgb of the visible pairs (clamp mask applied), in ascending v*N+n order
+// Everything a peer needs is one contiguous range of fixed_bytes + 12 nnz bytes: fine-grained remote loads are latency
+// bound (8 views x 2 round trips per Gaussian cost 0.23 ms at 8 ranks), so peers PULL that range with coalesced
+// 16-byte loads (xchg_pull_kernel) and the SH rows are then rebuilt from local memory.
 struct PubLayout {
-    long long mask_off, rgb_off;  // byte offsets inside the block
+    long long nnz_off, mask_off, prefix_off, rgb_off;  // byte offsets inside the block
     int words;
 };
 __host__ __device__ inline PubLayout pub_layout(int V, int N) {
     PubLayout L;
     L.words = ((N + 31) / 32 + 3) & ~3;
-    L.mask_off = (long long)((V * 16 + 255) / 256) * 256;
-    L.rgb_off = L.mask_off + (long long)V * L.words * 4;
-    L.rgb_off = (L.rgb_off + 255) / 256 * 256;
+    L.nnz_off = (long long)V * 16;
+    L.mask_off = (L.nnz_off + 16 + 255) / 256 * 256;
+    L.prefix_off = L.mask_off + (long long)V * L.words * 4;
+    L.rgb_off = (L.prefix_off + (long long)V * L.words * 4 + 255) / 256 * 256;
     return L;
+}
+
+struct ViewSrc {
+    const char* base[FG_XCHG_MAX_RANKS];  // published block of every rank as THIS rank reads it (own block / pulled copy)
+};
+
+// Copy every peer's published range into local staging memory.  grid = (blocks per peer, world).
+__global__ void __launch_bounds__(512) xchg_pull_kernel(Peers p, long long pub_off, long long nnz_off, long long fixed_bytes,
+                                                         char* staging, long long staging_stride) {
+    pdl_wait();
+    const int r = blockIdx.y;
+    if (r == p.rank) return;
+    const char* src = p.buf[r] + pub_off;
+    char* dst = staging + (long long)r * staging_stride;
+    const unsigned nnz = *reinterpret_cast<const unsigned*>(src + nnz_off);
+    const long long n16 = (fixed_bytes + (long long)nnz * 12 + 15) / 16;
+    const uint4* s16 = reinterpret_cast<const uint4*>(src);
+    uint4* d16 = reinterpret_cast<uint4*>(dst);
+    const long long stride = (long long)gridDim.x * 512;
+    long long i = (long long)blockIdx.x * 512 + threadIdx.x;
+    constexpr int U = 4;
+    for (; i + (U - 1) * stride < n16; i += U * stride) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = s16[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < U; ++u) d16[i + u * stride] = v[u];
+    }
+    for (; i < n16; i += stride) d16[i] = s16[i];
 }
 
 constexpr int VB = 128;  // Gaussians per block
 
 template <int DEG>
-__global__ void __launch_bounds__(VB) sh_bwd_views_kernel(Peers p, long long pub_off, int V, int N,
+__global__ void __launch_bounds__(VB) sh_bwd_views_kernel(ViewSrc vs, int world, int V, int N,
                                                           const float* __restrict__ means, float* __restrict__ v_sh,
                                                           int sh_row_floats) {
     pdl_wait();
@@ -179,9 +214,9 @@ __global__ void __launch_bounds__(VB) sh_bwd_views_kernel(Peers p, long long pub
     const PubLayout L = pub_layout(V, N);
     const int n0 = blockIdx.x * VB, n = n0 + threadIdx.x;
     const bool in_range = n < N;
-    for (int i = threadIdx.x; i < p.world * V * 4; i += VB) {
+    for (int i = threadIdx.x; i < world * V * 4; i += VB) {
         const int r = i / (V * 4);
-        campos[i] = reinterpret_cast<const float*>(p.buf[r] + pub_off)[i - r * V * 4];
+        campos[i] = reinterpret_cast<const float*>(vs.base[r])[i - r * V * 4];
     }
 #pragma unroll
     for (int j = 0; j < NV3; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -190,11 +225,10 @@ __global__ void __launch_bounds__(VB) sh_bwd_views_kernel(Peers p, long long pub
         float m[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) m[i] = __ldg(means + 3 * (size_t)n + i);
-        // Views are taken eight at a time: first the eight visibility words (one per view, most of them a round trip over
-        // NVLink), then the colour gradients of the views that see this splat -- all loads of a stage are in flight
-        // together, so a thread pays two remote latencies per eight views instead of sixteen.  The accumulation order
-        // stays (rank, view).
-        const int T = p.world * V;
+        // Views are taken eight at a time: first the eight visibility words and prefixes, then the colour gradients of
+        // the views that see this splat -- all loads of a stage are in flight together.  The accumulation order stays
+        // (rank, view).
+        const int T = world * V;
         constexpr int VC = 8;
         for (int base = 0; base < T; base += VC) {
             uint32_t bits = 0;
@@ -205,11 +239,14 @@ __global__ void __launch_bounds__(VB) sh_bwd_views_kernel(Peers p, long long pub
                 src[j] = nullptr;
                 if (view < T) {
                     const int r = view / V, v = view - r * V;
-                    const char* blk = p.buf[r] + pub_off;
-                    const uint32_t w = reinterpret_cast<const uint32_t*>(blk + L.mask_off)[(size_t)v * L.words + (n >> 5)];
+                    const char* blk = vs.base[r];
+                    const size_t wi = (size_t)v * L.words + (n >> 5);
+                    const uint32_t w = reinterpret_cast<const uint32_t*>(blk + L.mask_off)[wi];
                     if ((w >> (n & 31)) & 1u) {
                         bits |= 1u << j;
-                        src[j] = reinterpret_cast<const float*>(blk + L.rgb_off) + ((size_t)v * N + n) * 3;
+                        const uint32_t row = reinterpret_cast<const uint32_t*>(blk + L.prefix_off)[wi] +
+                                             __popc(w & ((1u << (n & 31)) - 1u));
+                        src[j] = reinterpret_cast<const float*>(blk + L.rgb_off) + (size_t)row * 3;
                     }
                 }
             }
@@ -264,11 +301,11 @@ __global__ void __launch_bounds__(VB) sh_bwd_views_kernel(Peers p, long long pub
 }
 
 template <int DEG>
-static int launch_views(const Peers& p, long long pub_off, int V, int N, const float* means, float* v_sh,
-                        int sh_row_floats, cudaStream_t st) {
-    const size_t smem = (size_t)VB * 13 * 16 + (size_t)p.world * V * 16;
+static int launch_views(const ViewSrc& vs, int world, int V, int N, const float* means, float* v_sh, int sh_row_floats,
+                        cudaStream_t st) {
+    const size_t smem = (size_t)VB * 13 * 16 + (size_t)world * V * 16;
     FG_CUDA(cudaFuncSetAttribute(sh_bwd_views_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FG_LAUNCH((sh_bwd_views_kernel<DEG>), ceil_div(N, VB), VB, smem, st, p, pub_off, V, N, means, v_sh, sh_row_floats);
+    FG_LAUNCH((sh_bwd_views_kernel<DEG>), ceil_div(N, VB), VB, smem, st, vs, world, V, N, means, v_sh, sh_row_floats);
     return FG_OK;
 }
 
@@ -292,6 +329,14 @@ using namespace fg;
 extern "C" int64_t fg_xchg_pub_bytes(int V, int N) {
     const PubLayout L = pub_layout(V, N);
     return (L.rgb_off + (long long)V * N * 12 + 255) / 256 * 256;
+}
+
+extern "C" int fg_xchg_pub_layout(int V, int N, int64_t* nnz_off, int64_t* mask_off, int64_t* prefix_off, int64_t* rgb_off,
+                                  int32_t* words) {
+    FG_REQUIRE(nnz_off && mask_off && prefix_off && rgb_off && words, "NULL pointer");
+    const PubLayout L = pub_layout(V, N);
+    *nnz_off = L.nnz_off; *mask_off = L.mask_off; *prefix_off = L.prefix_off; *rgb_off = L.rgb_off; *words = L.words;
+    return FG_OK;
 }
 
 extern "C" int fg_xchg_barrier(const fg_xchg_peers* peers, uint32_t epoch, void* stream) {
@@ -321,7 +366,8 @@ extern "C" int fg_xchg_allreduce_f32(const fg_xchg_peers* peers, int64_t offset_
 }
 
 extern "C" int fg_xchg_sh_bwd_views(const fg_xchg_peers* peers, int64_t pub_offset_bytes, int V, int N, int sh_degree,
-                                    int sh_bases, const float* means, float* v_sh, void* stream) {
+                                    int sh_bases, const float* means, float* v_sh, void* staging, int64_t staging_stride,
+                                    void* stream) {
     Peers p = {};
     if (int e = make_peers(peers, p)) return e;
     FG_REQUIRE(V >= 1 && N >= 0 && p.world * V <= 256, "views per rank must be >= 1 and world*V <= 256");
@@ -330,11 +376,24 @@ extern "C" int fg_xchg_sh_bwd_views(const fg_xchg_peers* peers, int64_t pub_offs
     FG_REQUIRE(pub_offset_bytes % 256 == 0, "pub_offset_bytes must be a multiple of 256");
     if (N == 0) return FG_OK;
     FG_REQUIRE(means && v_sh, "means / v_sh must not be NULL");
+    FG_REQUIRE(p.world == 1 || (staging && staging_stride >= fg_xchg_pub_bytes(V, N) && staging_stride % 16 == 0 &&
+                                (uintptr_t)staging % 16 == 0),
+               "staging must hold world blocks of fg_xchg_pub_bytes(V, N) bytes");
     cudaStream_t st = (cudaStream_t)stream;
+    const PubLayout L = pub_layout(V, N);
+    ViewSrc vs = {};
+    for (int r = 0; r < p.world; ++r)
+        vs.base[r] = (r == p.rank) ? p.buf[r] + pub_offset_bytes : (const char*)staging + (long long)r * staging_stride;
+    if (p.world > 1) {
+        // enough blocks per peer to keep the links busy: ~3.5 MB per peer on the bench scene
+        const int bpp = std::max(8, 2 * num_sms() / (p.world - 1));
+        FG_LAUNCH(xchg_pull_kernel, dim3(bpp, p.world), 512, 0, st, p, (long long)pub_offset_bytes, L.nnz_off, L.rgb_off,
+                  (char*)staging, (long long)staging_stride);
+    }
     switch (sh_degree) {
-        case 0: return launch_views<0>(p, pub_offset_bytes, V, N, means, v_sh, sh_bases * 3, st);
-        case 1: return launch_views<1>(p, pub_offset_bytes, V, N, means, v_sh, sh_bases * 3, st);
-        case 2: return launch_views<2>(p, pub_offset_bytes, V, N, means, v_sh, sh_bases * 3, st);
-        default: return launch_views<3>(p, pub_offset_bytes, V, N, means, v_sh, sh_bases * 3, st);
+        case 0: return launch_views<0>(vs, p.world, V, N, means, v_sh, sh_bases * 3, st);
+        case 1: return launch_views<1>(vs, p.world, V, N, means, v_sh, sh_bases * 3, st);
+        case 2: return launch_views<2>(vs, p.world, V, N, means, v_sh, sh_bases * 3, st);
+        default: return launch_views<3>(vs, p.world, V, N, means, v_sh, sh_bases * 3, st);
     }
 }

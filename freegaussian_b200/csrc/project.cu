@@ -66,9 +66,12 @@ struct ProjParams {
     float* v_scales_next;
     // multi-GPU exchange (csrc/exchange.cu): the SH kernel publishes the clamp-masked colour gradient of every visible
     // (view, Gaussian), a visibility bit mask and the camera centres instead of writing v_sh rows
-    float* pub_campos;    // [C,4]
+    float* pub_campos;    // [C,4], followed by one uint32: nnz
     uint32_t* pub_mask;   // [C,pub_words]
-    float* pub_rgb;       // [C,N,3]
+    uint32_t* pub_prefix; // [C,pub_words]: compact row of the first visible splat of each mask word
+    float* pub_rgb;       // [nnz,3] compact, ascending c*N+n
+    const int32_t* pub_offs;     // [C*N] exclusive scan of (radii > 0)
+    const long long* pub_nnz;    // its total (device)
     int pub_words;
 };
 
@@ -500,12 +503,18 @@ __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
         vis_any |= vis;
         if (p.pub_mask) {  // n0 is a multiple of 128: every warp owns whole mask words
             const uint32_t bits = __ballot_sync(0xffffffffu, vis);
-            if ((threadIdx.x & 31) == 0 && n < p.N) p.pub_mask[(size_t)c * p.pub_words + (n >> 5)] = bits;
+            if ((threadIdx.x & 31) == 0 && n < p.N) {
+                p.pub_mask[(size_t)c * p.pub_words + (n >> 5)] = bits;
+                p.pub_prefix[(size_t)c * p.pub_words + (n >> 5)] = (uint32_t)p.pub_offs[(size_t)c * p.N + n];
+            }
         }
     }
-    if (p.pub_campos && blockIdx.x == 0 && threadIdx.x < p.C) {
-        const Camera cam = load_camera(p.viewmats + 16 * threadIdx.x, p.Ks + 9 * threadIdx.x);
-        reinterpret_cast<float4*>(p.pub_campos)[threadIdx.x] = make_float4(cam.pos[0], cam.pos[1], cam.pos[2], 0.f);
+    if (p.pub_campos && blockIdx.x == 0) {
+        if (threadIdx.x < p.C) {
+            const Camera cam = load_camera(p.viewmats + 16 * threadIdx.x, p.Ks + 9 * threadIdx.x);
+            reinterpret_cast<float4*>(p.pub_campos)[threadIdx.x] = make_float4(cam.pos[0], cam.pos[1], cam.pos[2], 0.f);
+        }
+        if (threadIdx.x == 0) reinterpret_cast<uint32_t*>(p.pub_campos + 4 * p.C)[0] = (uint32_t)*p.pub_nnz;
     }
     const int nvis = __syncthreads_count(vis_any);
     const bool staged = SH_BWD_STAGE && nvis * 2 >= PB;
@@ -542,7 +551,7 @@ __global__ void __launch_bounds__(PB) sh_bwd_kernel(ProjParams p) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) vr[ch] = (ff[ch] > 0.f) ? vf[ch] : 0.f;
             if (p.pub_rgb) {
-                float* d = p.pub_rgb + i * 3;
+                float* d = p.pub_rgb + (size_t)p.pub_offs[i] * 3;
                 d[0] = vr[0]; d[1] = vr[1]; d[2] = vr[2];
             }
             float sk[16];
@@ -712,8 +721,11 @@ extern "C" int fg_project_bwd(int C, int N, const float* means, const float* qua
     if (pub) {
         FG_REQUIRE(sh_degree >= 0 && vec4 && sh_bases % 4 == 0 && feat != nullptr && v_feat != nullptr,
                    "publishing needs the streaming SH kernel: sh_degree >= 0, 16-byte rows of 4k bases, feat and v_feat");
-        FG_REQUIRE(pub->campos && pub->mask && pub->rgb && C <= PB && pub->words >= (N + 31) / 32, "bad fg_project_bwd_pub");
-        p.pub_campos = pub->campos; p.pub_mask = pub->mask; p.pub_rgb = pub->rgb; p.pub_words = pub->words;
+        FG_REQUIRE(pub->campos && pub->mask && pub->prefix && pub->rgb && pub->offsets && pub->nnz && C <= PB &&
+                       pub->words >= (N + 31) / 32,
+                   "bad fg_project_bwd_pub");
+        p.pub_campos = pub->campos; p.pub_mask = pub->mask; p.pub_prefix = pub->prefix; p.pub_rgb = pub->rgb;
+        p.pub_offs = pub->offsets; p.pub_nnz = (const long long*)pub->nnz; p.pub_words = pub->words;
     }
     if (sh_degree >= 0 && vec4 && sh_bases % 4 == 0 && feat != nullptr) {
         // two kernels: streaming SH backward (writes v_sh and the direction term into v_means), then

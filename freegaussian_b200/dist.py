@@ -127,9 +127,10 @@ class ViewShardedExchange:
     process rendering every view would have computed.  Every rank must make the same sequence of
     ``rasterization(...)``/``backward()`` calls with the same N, views per rank and kwargs.
 
-    What travels: the 12-byte colour gradient of every visible (view, Gaussian) is published in symmetric memory and
-    every rank rebuilds the 192-byte SH rows from all views itself (``fg_xchg_sh_bwd_views``: peer loads over NVLink,
-    fixed summation order, bit-identical on every rank); the geometry gradients (56 B per Gaussian: means, quats,
+    What travels: the 12-byte colour gradient of every visible (view, Gaussian) is published in compact form in symmetric
+    memory, every rank pulls the peers' published ranges over NVLink (coalesced 16-byte loads, ~3.5 MB per peer at 1 M
+    Gaussians) and rebuilds the 192-byte SH rows of all views itself (``fg_xchg_sh_bwd_views``: fixed summation order,
+    bit-identical on every rank); the geometry gradients (56 B per Gaussian: means, quats,
     scales, opacity, frame t+1 means) are summed in place by a two-shot all-reduce that runs in the NVSwitch
     (``fg_xchg_allreduce_f32``: ``multimem.ld_reduce`` + ``multimem.st``, barriers inside the kernel).  torch is used for
     the plumbing only: ``torch.distributed._symmetric_memory`` allocates and peer-maps the buffers.
@@ -151,6 +152,8 @@ class ViewShardedExchange:
         self._layout = None    # (pub_bytes, arena_bytes)
         self._old = []         # previous blocks are kept alive: a peer may still be reading them
         self._side = None      # side stream of the SH-row summation
+        self._staging = None   # local copies of the peers' published blocks
+        self._keep = None
         self.multicast = False
 
     # -- lifecycle
@@ -220,16 +223,21 @@ class ViewShardedExchange:
         self._ensure(0, (n_floats + 3) // 4 * 16, device)
         return self._buf[self.arena_off:self.arena_off + 4 * n_floats].view(torch.float32)
 
-    def publish_block(self, C: int, N: int):
-        """``fg_project_bwd_pub`` pointing at this step's publish block (camera centres | mask | colour gradients)."""
+    def publish_block(self, C: int, N: int, offsets: Tensor, nnz_dev: Tensor):
+        """``fg_project_bwd_pub`` pointing at this step's publish block (camera centres + nnz | mask | prefix | compact
+        colour gradients); ``offsets`` / ``nnz_dev`` = the exclusive scan of the visibility (``fg_pack_plan``)."""
+        import ctypes as C_
         from . import _lib
-        assert self._layout is not None and int(_lib.lib().fg_xchg_pub_bytes(C, N)) <= self._layout[0], "prepare() first"
-        words = ((N + 31) // 32 + 3) & ~3
-        mask_off = (C * 16 + 255) // 256 * 256
-        rgb_off = (mask_off + C * words * 4 + 255) // 256 * 256
+        L = _lib.lib()
+        assert self._layout is not None and int(L.fg_xchg_pub_bytes(C, N)) <= self._layout[0], "prepare() first"
+        o = [C_.c_int64() for _ in range(4)]
+        words = C_.c_int32()
+        _lib.check(L.fg_xchg_pub_layout(C, N, *[C_.byref(x) for x in o], C_.byref(words)))
         base = self._buf.data_ptr() + self.pub_off[self.parity]
         pub = _lib.ProjectBwdPub()
-        pub.campos, pub.mask, pub.rgb, pub.words = base, base + mask_off, base + rgb_off, words
+        pub.campos, pub.mask, pub.prefix, pub.rgb = base, base + o[1].value, base + o[2].value, base + o[3].value
+        pub.offsets, pub.nnz, pub.words = offsets.data_ptr(), nnz_dev.data_ptr(), words.value
+        self._keep = (offsets, nnz_dev)  # alive until the kernels that read them have been enqueued behind them
         return pub
 
     def sh_rows_async(self, C: int, N: int, sh_degree, sh_bases: int, means: Tensor, v_sh: Tensor) -> None:
@@ -242,13 +250,18 @@ class ViewShardedExchange:
         cur = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream(device=means.device)
+        stride = int(L.fg_xchg_pub_bytes(C, N))
+        need = stride * self.world if self.world > 1 else 0
+        if self._staging is None or self._staging.numel() < need:
+            self._staging = torch.empty(max(need, 16), dtype=torch.uint8, device=means.device)  # pulled copies: local memory
         self.epoch += 1
         _lib.check(L.fg_xchg_barrier(self._peers, self.epoch, cur.cuda_stream))
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             with _stage("xchg_sh_views"):
                 _lib.check(L.fg_xchg_sh_bwd_views(self._peers, self.pub_off[self.parity], C, N, int(sh_degree), sh_bases,
-                                                  _lib.ptr(means), _lib.ptr(v_sh), self._side.cuda_stream))
+                                                  _lib.ptr(means), _lib.ptr(v_sh), _lib.ptr(self._staging) if need else None,
+                                                  stride, self._side.cuda_stream))
         self.parity ^= 1
 
     def join(self) -> None:

@@ -213,6 +213,16 @@ class _Project(torch.autograd.Function):
                     ptr(tiles), _stream()))
         if not use_sh and colors is not None:
             feat[..., :n_col] = colors if colors.dim() == 3 else colors[None]
+        # view-sharded run: the backward publishes the colour gradients of the visible (view, Gaussian) pairs in compact
+        # form; their rows come from an exclusive scan of the visibility, done here where the radii are produced
+        ctx.pub_scan = None
+        xc = _exchange_hook
+        if xc is not None and xc.active() and use_sh and sh_bases % 4 == 0 and 0 < N and C <= 128:
+            offs = torch.empty(C * N, dtype=torch.int32, device=dev)
+            nnz_dev = torch.empty(1, dtype=torch.int64, device=dev)
+            ws_scan = _ws.get("pub_scan", L.fg_pack_workspace_bytes(C * N), dev)
+            check(L.fg_pack_plan(C * N, ptr(radii), ptr(offs), ptr(nnz_dev), ptr(ws_scan), ws_scan.numel(), _stream()))
+            ctx.pub_scan = (offs, nnz_dev)
         ctx.save_for_backward(means, quats, scales, colors if use_sh else None, means_next, quats_next, scales_next,
                               viewmats, Ks, radii, feat if use_sh else None)
         ctx.cfg = cfg
@@ -267,7 +277,7 @@ class _Project(torch.autograd.Function):
         used = geo_floats + sh_floats
         # view-sharded with SH colours: publish the 12-byte colour gradients instead of writing 192-byte SH rows; the rows
         # are then summed over every rank's views by fg_xchg_sh_bwd_views and only the geometry segments are all-reduced
-        want_pub = xc is not None and use_sh and sh_bases % 4 == 0 and v_feat is not None and C <= 128 and N > 0
+        want_pub = xc is not None and ctx.pub_scan is not None and v_feat is not None
         if xc is not None:
             xc.prepare(used, C if want_pub else 0, N, dev)
         arena = xc.arena(used, dev) if xc is not None else torch.empty(used + 3 * N + 4, device=dev)
@@ -277,7 +287,7 @@ class _Project(torch.autograd.Function):
         v_sh = arena[geo_floats:used].view(N, sh_bases, 3) if use_sh else None
         _grad_arena["last"] = (arena, used)
         v_flow_affine = c(v_flow_affine) if flow_cov else None
-        pub = xc.publish_block(C, N) if want_pub else None
+        pub = xc.publish_block(C, N, *ctx.pub_scan) if want_pub else None
 
         def project_bwd(phase):
             if pub is not None:

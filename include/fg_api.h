@@ -74,14 +74,19 @@ int fg_project_fwd(int C, int N, const float* means, const float* quats, const f
                    int32_t* tiles_per_gauss, void* stream);
 
 /* Optional output of fg_project_bwd for the view-sharded multi-GPU exchange (section (5) below): instead of writing
- * v_sh rows (pass v_sh = NULL), the SH kernel PUBLISHES, for its own C views, the camera centres campos[C,4], a
- * visibility bit mask mask[C,words] (bit n of view c = radii[c,n] > 0; words >= ceil(N/32)) and the colour gradient
- * rgb[C,N,3] with the max(rgb+0.5,0) clamp mask applied (rows of invisible splats are not written).  The three
- * pointers normally point into the rank's block of symmetric memory (fg_xchg_pub_bytes gives the layout). */
+ * v_sh rows (pass v_sh = NULL), the SH kernel PUBLISHES, for its own C views: the camera centres campos[C,4] followed by
+ * one uint32 nnz; a visibility bit mask mask[C,words] (bit n of view c = radii[c,n] > 0; words >= ceil(N/32)); per mask
+ * word the compact row of its first visible splat, prefix[C,words]; and the colour gradient rgb[nnz,3] of the visible
+ * (view, Gaussian) pairs with the max(rgb+0.5,0) clamp mask applied, compact, in ascending c*N+n order.  `offsets` /
+ * `nnz` are the exclusive scan of (radii > 0) over c*N+n and its total (fg_pack_plan).  The four output pointers
+ * normally point into the rank's block of symmetric memory (fg_xchg_pub_layout gives the byte offsets). */
 typedef struct {
     float* campos;
     uint32_t* mask;
+    uint32_t* prefix;
     float* rgb;
+    const int32_t* offsets;
+    const int64_t* nnz;
     int32_t words;
     int32_t phase; /* 0: the whole backward; 1: only the SH kernel (publishes, writes the direction term into v_means);
                       2: only the geometry kernel (adds to the v_means a phase-1 call left) -- lets the caller start the
@@ -493,8 +498,11 @@ typedef struct {
     void* flags[FG_XCHG_MAX_RANKS];
 } fg_xchg_peers;
 
-/* Bytes of one rank's published block for V views of N Gaussians: campos | mask | rgb (see fg_project_bwd_pub). */
+/* Capacity in bytes of one rank's published block for V views of N Gaussians (campos + nnz | mask | prefix | rgb, see
+ * fg_project_bwd_pub), and the byte offsets of its parts. */
 int64_t fg_xchg_pub_bytes(int V, int N);
+int fg_xchg_pub_layout(int V, int N, int64_t* nnz_off, int64_t* mask_off, int64_t* prefix_off, int64_t* rgb_off,
+                       int32_t* words);
 /* Cross-rank barrier on the stream: returns (on the device) once every rank's stream has reached it. */
 int fg_xchg_barrier(const fg_xchg_peers* peers_host, uint32_t epoch, void* stream);
 /* In-place all-reduce(SUM) of n_floats (multiple of 4) at offset_bytes (multiple of 16) of the symmetric buffer.
@@ -503,12 +511,14 @@ int fg_xchg_barrier(const fg_xchg_peers* peers_host, uint32_t epoch, void* strea
  * kernel ends with a barrier, so that on return every rank holds the full result.  Same value on every rank. */
 int fg_xchg_allreduce_f32(const fg_xchg_peers* peers_host, int64_t offset_bytes, int64_t n_floats, uint32_t epoch,
                           int start_barrier, void* stream);
-/* v_sh[N,sh_bases,3] = sum over ALL ranks' views of basis(dir(n, view)) x published colour gradient: reads every
- * rank's published block (at pub_offset_bytes of its symmetric buffer) over NVLink; rows of invisible splats are never
- * fetched.  Fixed summation order (rank, view): bit-identical on every rank.  Call after a barrier that follows the
- * publishing fg_project_bwd on every rank. */
+/* v_sh[N,sh_bases,3] = sum over ALL ranks' views of basis(dir(n, view)) x published colour gradient.  First PULLS every
+ * peer's published range (fixed part + 12 nnz bytes, at pub_offset_bytes of its symmetric buffer) over NVLink with coalesced
+ * 16-byte loads into `staging` (world blocks of staging_stride >= fg_xchg_pub_bytes(V, N) bytes, ordinary device memory),
+ * then rebuilds the rows from local memory; rows of invisible splats never travel.  Fixed summation order (rank, view):
+ * bit-identical on every rank.  Call after a barrier that follows the publishing fg_project_bwd on every rank. */
 int fg_xchg_sh_bwd_views(const fg_xchg_peers* peers_host, int64_t pub_offset_bytes, int V, int N, int sh_degree,
-                         int sh_bases, const float* means, float* v_sh, void* stream);
+                         int sh_bases, const float* means, float* v_sh, void* staging, int64_t staging_stride,
+                         void* stream);
 
 #ifdef __cplusplus
 }
