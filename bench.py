@@ -149,17 +149,17 @@ def build_scene(workload: str, recipe: str, device, n_views: int):
 
 def loss_weights(h: int, w: int, seed: int):
     """The per-step "ground truth" planes of the scalar loss, in the formats a dataloader holds them in on the host:
-    rgb uint8 [h,w,3] (nerfstudio caches images as uint8), depth float32 [h,w,1], flow float16 [h,w,2]."""
+    rgb uint8 [h,w,3] (nerfstudio caches images as uint8), depth float16 [h,w,1] (16-bit depth maps), flow float16 [h,w,2]."""
     g = torch.Generator().manual_seed(seed)
     rgb = torch.randint(0, 256, (1, h, w, 3), generator=g, dtype=torch.uint8)
-    depth = torch.rand(1, h, w, 1, generator=g)
+    depth = torch.rand(1, h, w, 1, generator=g).to(torch.float16)
     flow = (torch.rand(1, h, w, 2, generator=g) * 0.1).to(torch.float16)
     return rgb, depth, flow
 
 
 def decode_weights(rgb_u8, depth, flow_h):
     """uint8 / fp16 host formats -> the float32 weight images of the loss (device-side, as a trainer decodes a batch)."""
-    w_rgbd = torch.cat([rgb_u8.to(torch.float32) * (1.0 / 255.0), depth], -1)
+    w_rgbd = torch.cat([rgb_u8.to(torch.float32) * (1.0 / 255.0), depth.to(torch.float32)], -1)
     return w_rgbd, flow_h.to(torch.float32)
 
 
@@ -446,7 +446,7 @@ def run_ours(args):
             "e2e": {"value": pix * args.steps / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s",
                     "h2d_bytes_per_step": job.h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                     "ms_per_step_quantiles": job.quantiles.get("e2e"),
-                    "host_formats": "cameras f32; target planes as a dataloader holds them: rgb uint8, depth f32, flow f16; copied "
+                    "host_formats": "cameras f32; target planes as a dataloader holds them: rgb uint8, depth f16, flow f16; copied "
                                     "from pinned memory and decoded to f32 on a copy stream, all inside the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -139,7 +139,7 @@ struct BestList {
 };
 
 template <int KCAP>
-__global__ void __launch_bounds__(128, (KCAP <= 17 ? 4 : 1))
+__global__ void __launch_bounds__(128, (KCAP <= 4 ? 12 : KCAP <= 17 ? 4 : 1))
     knn_query_kernel(long long n, const float4* __restrict__ sorted, const int32_t* __restrict__ cell_start,
                      KnnGrid g, int k, float* __restrict__ out_dist, int32_t* __restrict__ out_idx) {
     pdl_wait();
