@@ -36,6 +36,20 @@ int set_cuda_error(cudaError_t e, const char* file, int line) {
 
 }  // namespace fg
 
+namespace fg {
+int g_xchg_ar_blocks = 32;
+int g_xchg_pull_blocks = 4;
+}  // namespace fg
+
+/* Run-time switches for A/B measurements (bench.py, tests). */
+extern "C" int fg_set_option(const char* name, int value) {
+    FG_REQUIRE(name != nullptr, "name must not be NULL");
+    if (strcmp(name, "fwd_two_pixels") == 0) { fg::g_fwd_two_pixels = value != 0; return FG_OK; }
+    if (strcmp(name, "xchg_ar_blocks") == 0) { FG_REQUIRE(value >= 1 && value <= 255, "1..255"); fg::g_xchg_ar_blocks = value; return FG_OK; }
+    if (strcmp(name, "xchg_pull_blocks") == 0) { FG_REQUIRE(value >= 1 && value <= 64, "1..64"); fg::g_xchg_pull_blocks = value; return FG_OK; }
+    FG_REQUIRE(false, "unknown option");
+}
+
 extern "C" {
 
 const char* fg_last_error(void) { return fg::g_err; }

@@ -18,6 +18,11 @@ extern std::atomic<long long> g_launch_count;
 // kernels are sized from it.
 int num_sms();
 
+// run-time switches (fg_set_option, api.cu)
+extern int g_fwd_two_pixels;   // rasterize_fwd.cu: 1 = two-pixel packed forward kernel
+extern int g_xchg_ar_blocks;    // exchange.cu: CTAs of the all-reduce kernel
+extern int g_xchg_pull_blocks;  // exchange.cu: CTAs per peer of the pull kernel
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // first statement of every kernel (see FG_LAUNCH); a no-op under a plain launch

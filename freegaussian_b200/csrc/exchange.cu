@@ -26,7 +26,7 @@
 
 namespace fg {
 
-constexpr int XB = 512;              // threads per block of the all-reduce kernel
+constexpr int XB = 1024;             // threads per block of the all-reduce kernel (one CTA fills an SM)
 constexpr int XCHG_SLOT_WORDS = 16;  // one flag word per source rank (FG_XCHG_MAX_RANKS)
 
 struct Peers {
@@ -92,15 +92,18 @@ __device__ __forceinline__ void mc_st(float4* a, float4 v) {
 
 // In-place SUM over ranks of n4 float4 at byte offset `off` of the symmetric buffer.  Two-shot: rank r
 // owns the r-th slice.  Slots 1..grid: start barrier (optional), grid+1..2*grid: end barrier.
+// Few, fat CTAs (default 32 x 1024 threads, eight 16-byte requests per thread = 4 MB in flight: enough for the switch round
+// trip at link rate) so that the rest of the GPU stays free for the kernels that run beside it -- a first version
+// with two CTAs on every SM measured 0.17 ms alone but starved the SH-row kernel of registers: no overlap at all.
 template <bool MC>
-__global__ void __launch_bounds__(XB, 2) allreduce_kernel(Peers p, long long off, long long n4, uint32_t epoch,
+__global__ void __launch_bounds__(XB, 1) allreduce_kernel(Peers p, long long off, long long n4, uint32_t epoch,
                                                        int start_barrier) {
     pdl_wait();
     if (start_barrier) block_barrier(p, 1 + blockIdx.x, epoch);
     const long long per = (n4 + p.world - 1) / p.world;
     const long long lo = per * p.rank, hi = min(n4, lo + per);
     const long long stride = (long long)gridDim.x * XB;
-    constexpr int U = 4;
+    constexpr int U = MC ? 8 : 4;
     if (MC) {
         float4* mc = reinterpret_cast<float4*>(p.mc + off);
         long long i = lo + (long long)blockIdx.x * XB + threadIdx.x;
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(512) xchg_pull_kernel(Peers p, long long pub_o
     uint4* d16 = reinterpret_cast<uint4*>(dst);
     const long long stride = (long long)gridDim.x * 512;
     long long i = (long long)blockIdx.x * 512 + threadIdx.x;
-    constexpr int U = 4;
+    constexpr int U = 8;
     for (; i + (U - 1) * stride < n16; i += U * stride) {
         uint4 v[U];
 #pragma unroll
@@ -356,8 +359,7 @@ extern "C" int fg_xchg_allreduce_f32(const fg_xchg_peers* peers, int64_t offset_
     const long long n4 = n_floats / 4;
     // every rank derives the same grid from the same n: the barriers pair block b with block b
     const long long per = (n4 + p.world - 1) / p.world;
-    // two resident blocks per SM: a switch round trip is several microseconds, the links are only kept full with ~10 MB in flight
-    int grid = (int)std::min<long long>(2 * num_sms(), std::max<long long>(1, (per + XB * 4 - 1) / (XB * 4)));
+    int grid = (int)std::min<long long>(g_xchg_ar_blocks, std::max<long long>(1, (per + XB * 4 - 1) / (XB * 4)));
     FG_REQUIRE(1 + 2 * grid <= FG_XCHG_FLAG_BYTES / (XCHG_SLOT_WORDS * 4), "flag area too small");
     cudaStream_t st = (cudaStream_t)stream;
     if (p.mc) FG_LAUNCH((allreduce_kernel<true>), grid, XB, 0, st, p, (long long)offset_bytes, n4, epoch, start_barrier);
@@ -385,8 +387,8 @@ extern "C" int fg_xchg_sh_bwd_views(const fg_xchg_peers* peers, int64_t pub_offs
     for (int r = 0; r < p.world; ++r)
         vs.base[r] = (r == p.rank) ? p.buf[r] + pub_offset_bytes : (const char*)staging + (long long)r * staging_stride;
     if (p.world > 1) {
-        // enough blocks per peer to keep the links busy: ~3.5 MB per peer on the bench scene
-        const int bpp = std::max(8, 2 * num_sms() / (p.world - 1));
+        // a few CTAs per peer (~3.5 MB per peer on the bench scene), leaving the SMs to the kernels running beside it
+        const int bpp = g_xchg_pull_blocks;
         FG_LAUNCH(xchg_pull_kernel, dim3(bpp, p.world), 512, 0, st, p, (long long)pub_offset_bytes, L.nnz_off, L.rgb_off,
                   (char*)staging, (long long)staging_stride);
     }

@@ -41,7 +41,7 @@ struct RasterFwdParams {
 // executes 5 % fewer instructions but its per-pixel predication (validity, stop test, selects of w / T / last id: FSETP,
 // FSEL, FMNMX) lands on the half-rate ALU pipe -- 71 % busy, math-pipe-throttle stalls -- and it runs 0.296 ms against
 // 0.270 ms.  (The backward kernel has no such per-pixel control flow and gains 8.6 % from the same packing.)
-static int g_fwd_two_pixels = 0;
+int g_fwd_two_pixels = 0;
 
 template <int CH, bool AFF>
 __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdParams p) {
@@ -377,12 +377,4 @@ extern "C" int fg_rasterize_fwd(int C, int N, int CH, int width, int height, int
         case 7: return launch_raster_fwd<7>(p, st);
         default: return launch_raster_fwd<8>(p, st);
     }
-}
-
-/* Run-time switches for A/B measurements (bench.py, tests): "fwd_two_pixels" = 0 | 1.  Returns FG_ERR_INVALID for an
- * unknown name. */
-extern "C" int fg_set_option(const char* name, int value) {
-    FG_REQUIRE(name != nullptr, "name must not be NULL");
-    if (strcmp(name, "fwd_two_pixels") == 0) { fg::g_fwd_two_pixels = value != 0; return FG_OK; }
-    FG_REQUIRE(false, "unknown option");
 }
