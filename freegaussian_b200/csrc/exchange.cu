@@ -26,7 +26,7 @@
 
 namespace fg {
 
-constexpr int XB = 1024;             // threads per block of the all-reduce kernel (one CTA fills an SM)
+constexpr int XB = 1024;             // most threads per block of the all-reduce kernel (one such CTA fills an SM)
 constexpr int XCHG_SLOT_WORDS = 16;  // one flag word per source rank (FG_XCHG_MAX_RANKS)
 
 struct Peers {
@@ -102,11 +102,11 @@ __global__ void __launch_bounds__(XB, 1) allreduce_kernel(Peers p, long long off
     if (start_barrier) block_barrier(p, 1 + blockIdx.x, epoch);
     const long long per = (n4 + p.world - 1) / p.world;
     const long long lo = per * p.rank, hi = min(n4, lo + per);
-    const long long stride = (long long)gridDim.x * XB;
+    const long long stride = (long long)gridDim.x * blockDim.x;
     constexpr int U = MC ? 8 : 4;
     if (MC) {
         float4* mc = reinterpret_cast<float4*>(p.mc + off);
-        long long i = lo + (long long)blockIdx.x * XB + threadIdx.x;
+        long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
         for (; i + (U - 1) * stride < hi; i += U * stride) {
             float4 v[U];
 #pragma unroll
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(XB, 1) allreduce_kernel(Peers p, long long off
         }
         for (; i < hi; i += stride) mc_st(mc + i, mc_ld_reduce(mc + i));
     } else {
-        long long i = lo + (long long)blockIdx.x * XB + threadIdx.x;
+        long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
         for (; i + (U - 1) * stride < hi; i += U * stride) {
             float4 s[U];
 #pragma unroll
@@ -359,11 +359,15 @@ extern "C" int fg_xchg_allreduce_f32(const fg_xchg_peers* peers, int64_t offset_
     const long long n4 = n_floats / 4;
     // every rank derives the same grid from the same n: the barriers pair block b with block b
     const long long per = (n4 + p.world - 1) / p.world;
-    int grid = (int)std::min<long long>(g_xchg_ar_blocks, std::max<long long>(1, (per + XB * 4 - 1) / (XB * 4)));
+    // in the switch: few fat CTAs (see the kernel); peer loads / stores (2-3 ranks) need the whole GPU's load slots to
+    // fill one link: two 512-thread CTAs per SM (measured at 2 ranks, 68 MB: 0.114 ms against 0.205 ms with 32 x 1024)
+    const int threads = p.mc ? XB : 512;
+    const int cap = p.mc ? g_xchg_ar_blocks : 2 * num_sms();
+    int grid = (int)std::min<long long>(cap, std::max<long long>(1, (per + threads * 4 - 1) / (threads * 4)));
     FG_REQUIRE(1 + 2 * grid <= FG_XCHG_FLAG_BYTES / (XCHG_SLOT_WORDS * 4), "flag area too small");
     cudaStream_t st = (cudaStream_t)stream;
-    if (p.mc) FG_LAUNCH((allreduce_kernel<true>), grid, XB, 0, st, p, (long long)offset_bytes, n4, epoch, start_barrier);
-    else FG_LAUNCH((allreduce_kernel<false>), grid, XB, 0, st, p, (long long)offset_bytes, n4, epoch, start_barrier);
+    if (p.mc) FG_LAUNCH((allreduce_kernel<true>), grid, threads, 0, st, p, (long long)offset_bytes, n4, epoch, start_barrier);
+    else FG_LAUNCH((allreduce_kernel<false>), grid, threads, 0, st, p, (long long)offset_bytes, n4, epoch, start_barrier);
     return FG_OK;
 }
 
