@@ -92,7 +92,7 @@ __device__ __forceinline__ void mc_st(float4* a, float4 v) {
 
 // In-place SUM over ranks of n4 float4 at byte offset `off` of the symmetric buffer.  Two-shot: rank r
 // owns the r-th slice.  Slots 1..grid: start barrier (optional), grid+1..2*grid: end barrier.
-// Few, fat CTAs (default 32 x 1024 threads, eight 16-byte requests per thread = 4 MB in flight: enough for the switch round
+// Few, fat CTAs (default 64 x 1024 threads, eight 16-byte requests per thread = 8 MB in flight: enough for the switch round
 // trip at link rate) so that the rest of the GPU stays free for the kernels that run beside it -- a first version
 // with two CTAs on every SM measured 0.17 ms alone but starved the SH-row kernel of registers: no overlap at all.
 template <bool MC>

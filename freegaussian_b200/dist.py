@@ -164,7 +164,7 @@ class ViewShardedExchange:
     def install(self) -> "ViewShardedExchange":
         from . import _lib, rendering
         for env, opt in (("FG_XCHG_AR_BLOCKS", b"xchg_ar_blocks"), ("FG_XCHG_PULL_BLOCKS", b"xchg_pull_blocks")):
-            if os.environ.get(env):  # CTA counts of the communication kernels (sweeps; defaults 32 / 4)
+            if os.environ.get(env):  # CTA counts of the communication kernels (sweeps; defaults 64 / 4)
                 _lib.check(_lib.lib().fg_set_option(opt, int(os.environ[env])))
         rendering._exchange_hook = self
         return self

@@ -40,7 +40,7 @@ long long fg_launch_count(void);
 
 /* Run-time switches for A/B measurements: "fwd_two_pixels" = 0 (default: the one-pixel forward kernel) | 1 (two pixels
  * per thread, packed FP32; measured slower, kept as the documented experiment; both produce the same images);
- * "xchg_ar_blocks" (default 32) / "xchg_pull_blocks" (default 4): CTAs of the all-reduce kernel / per peer of the
+ * "xchg_ar_blocks" (default 64) / "xchg_pull_blocks" (default 4): CTAs of the all-reduce kernel / per peer of the
  * pull kernel of the multi-GPU exchange.  FG_ERR_INVALID for an unknown name. */
 int fg_set_option(const char* name, int value);
 
