@@ -334,10 +334,22 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     L = _lib.lib()
-    xchg = None
+    xchg, xchg_note = None, None
     if world > 1 and args.exchange == "peer":
-        # the exchange runs inside the projection backward over NVLink peer memory (csrc/exchange.cu)
-        xchg = ViewShardedExchange().install()
+        # the exchange runs inside the projection backward over NVLink peer memory (csrc/exchange.cu); a box without peer
+        # access / symmetric memory falls back -- on every rank together -- to the NCCL all-reduce of the dense arena
+        ok = 1
+        try:
+            xchg = ViewShardedExchange()
+            xchg.prepare(1 << 20, 0, 0, dev)
+        except Exception as exc:  # noqa: BLE001
+            ok, xchg_note = 0, f"{type(exc).__name__}: {exc}"
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            xchg.install()
+        else:
+            xchg, xchg_note = None, xchg_note or "symmetric memory unavailable on another rank"
 
     V = args.views_per_gpu
     job = Job(args, args.workload, args.recipe, V, dev, rank, world, xchg)
@@ -470,7 +482,8 @@ def run_ours(args):
                                    "published_bytes_per_rank": n_vis * 12 + V * n // 8,
                                    "dense_arena_bytes_replaced": 4 * n * 62}
             else:
-                out["exchange"] = {"mode": "nccl: one all-reduce over the dense gradient arena", "ms": stage_ms.get("exchange"),
+                out["exchange"] = {"mode": "nccl: one all-reduce over the dense gradient arena", "fallback_reason": xchg_note,
+                                   "ms": stage_ms.get("exchange"),
                                    "allreduce_bytes": 4 * n * 62,
                                    "bus_gbs": (4 * n * 62 * 2 * (world - 1) / world / (stage_ms["exchange"] * 1e-3) / 1e9)
                                    if stage_ms.get("exchange") else None}
@@ -787,7 +800,7 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         "stage2_ms": ms_stage2, "stage2_quantiles": {"p10": q2_(0.1), "p50": q2_(0.5), "p90": q2_(0.9)},
         "stage2_controlled_gaussians": int(part.numel()),
         "gaussians": n, "visible": n_vis, "launches_per_iter": launches, "steps": steps, "warmup": warmup,
-        "host_enqueue_ms_per_iter": host_ms,
+        "host_enqueue_ms_per_iter": host_ms, "network_backward_paths": dict(__import__("freegaussian_b200.deform", fromlist=["STATS"]).STATS),
         "config": "stage-1 step: DeformNetwork(is_blender=True) -> RGB+ED render -> blend+L1+SSIM -> backward -> Adam; "
                   "stage2_ms: ControlNetwork on the controlled subset -> the same render / loss / backward / Adam",
         "library_kernels": "torch.optim.Adam(fused=True) for the 0.6 M network weights, torch ops for the one-row time branch "

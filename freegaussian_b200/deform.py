@@ -37,6 +37,7 @@ SPARSE_BACKWARD_MAX_FRACTION = 0.75
 _CAP_SLACK, _CAP_EXTRA = 1.12, 1024  # head-room of the guessed capacity over the previous count
 _ACTIVE_ROWS: dict = {}   # (device, rows, embedding width) -> active rows of the previous backward of that shape
 _PINNED: dict = {}
+STATS = {"sparse_backward": 0, "dense_backward": 0, "overflow_redo": 0}  # counters (bench.py reports them)
 
 
 def _pinned_slot(key) -> Tensor:
@@ -205,12 +206,17 @@ class _Trunk(torch.autograd.Function):
             count_dev = torch.empty(1, device=dev, dtype=torch.int64)
             check(L.fg_rows_active(N_all, ptr(g_head), g_head.shape[1], ptr(idx_buf), ptr(count_dev), ptr(ws), ws.numel(),
                                    _stream()))
-            guess = _ACTIVE_ROWS.get(key)
+            guess, prev_cap = _ACTIVE_ROWS.get(key, (None, 0))
             pending = None
             if guess is None:  # first backward of this shape: one host read, exact capacity
                 cap = int(count_dev.item())
             else:
                 cap = min(N_all, -(-int(guess * _CAP_SLACK + _CAP_EXTRA) // 128) * 128)
+                # hysteresis: keep the previous capacity unless the need grows beyond it or falls below 70 % of it, so
+                # that the row buffers have the SAME sizes step after step and the caching allocator reuses them (a
+                # capacity that follows the count row by row made it go to cudaMalloc now and then: 30 ms outliers)
+                if prev_cap and 0.7 * prev_cap <= cap <= prev_cap:
+                    cap = prev_cap
                 if dev.type == "cuda":
                     pinned = _pinned_slot(key)
                     pinned.copy_(count_dev, non_blocking=True)
@@ -220,8 +226,10 @@ class _Trunk(torch.autograd.Function):
                 else:
                     pending = (count_dev, None)
             if cap < SPARSE_BACKWARD_MAX_FRACTION * N_all:
+                STATS["sparse_backward"] += 1
                 grads_out = _Trunk._backward_rows(ctx, g_head, (idx_buf, count_dev), cap)
             else:
+                STATS["dense_backward"] += 1
                 grads_out = _Trunk._backward_rows(ctx, g_head, None, N_all)
                 cap = N_all
             if pending is not None:
@@ -229,10 +237,11 @@ class _Trunk(torch.autograd.Function):
                     pending[1].synchronize()
                 count = int(pending[0].item())
                 if count > cap:  # the guess was too small: redo on every row (exact, just slower)
+                    STATS["overflow_redo"] += 1
                     grads_out = _Trunk._backward_rows(ctx, g_head, None, N_all)
             else:
                 count = cap
-            _ACTIVE_ROWS[key] = count
+            _ACTIVE_ROWS[key] = (count, cap)
             return grads_out
         return _Trunk._backward_rows(ctx, g_head, None, N_all)
 
