@@ -57,6 +57,7 @@ _ws = _Workspace()
 # (tensor, floats in use).  Read by freegaussian_b200.dist.exchange.
 _grad_arena: Dict[str, tuple] = {}
 _list_guess: Dict[tuple, tuple] = {}  # (C, N, W, H, device) -> (capacity of flatten_ids, of the coarse pairs)
+_list_small: Dict[tuple, int] = {}    # consecutive calls that needed less than half of that capacity
 
 
 def last_grad_arena():
@@ -190,7 +191,15 @@ class _Project(torch.autograd.Function):
                 ptr(isect_offsets), ptr(coarse_off), counts, ptr(ws), ws.numel(), ptr(flat_buf), guess_m,
                 ptr(ws2), ws2.numel() if ws2 is not None else 0, _stream()))
             M, Mc = int(counts[0]), int(counts[1])
-            _list_guess[key] = (max(guess_m, int(1.25 * M) + 1024), max(guess_mc, int(1.25 * Mc) + 1024))
+            # capacity for the next call: 1.25 x the largest need seen (stable sizes: the allocator reuses the buffers
+            # call after call); after 64 consecutive calls that needed less than half of it the capacity is re-derived
+            # from the current need (a scene that shrank -- culling after densification -- gives its buffers back)
+            need_m, need_mc = int(1.25 * M) + 1024, int(1.25 * Mc) + 1024
+            small = _list_small.get(key, 0) + 1 if (2 * need_m < guess_m) else 0
+            if small >= 64:
+                guess_m, guess_mc, small = 0, 0, 0
+            _list_small[key] = small
+            _list_guess[key] = (max(guess_m, need_m), max(guess_mc, need_mc))
             if counts[2]:
                 flatten_ids = flat_buf[:M]
             else:
