@@ -122,6 +122,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def quiesce_gc() -> None:
+    """Before a timed region: collect once, then move everything alive (torch / numpy / sklearn module state, the scene) to the
+    permanent generation, so that a generation-2 collection walking ~10^6 long-lived objects (tens of ms of host time, seen as
+    one 37 ms iteration among thirty 10 ms ones) cannot land inside the region.  Garbage produced inside the region is still
+    collected."""
+    import gc
+    gc.collect()
+    gc.freeze()
+
+
 def bind_to_gpu_numa_node(local_rank: int) -> None:
     """Pin this rank's host threads to the CPUs next to its GPU (nvidia-smi topo's "CPU Affinity"), so the pinned staging
     buffers are first-touched on the GPU's NUMA node: at 8 ranks the per-step host->device copies otherwise cross sockets."""
@@ -269,6 +279,7 @@ class Job:
     def timed(self, k: int, e2e: bool) -> float:
         import torch.distributed as dist
         world, dev = self.world, self.dev
+        quiesce_gc()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -679,6 +690,7 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         for _ in range(warmup):
             iteration(with_deform)
         torch.cuda.synchronize()
+        quiesce_gc()
         cpu_phase.clear()
         a, b = ev(), ev()
         a.record()
@@ -690,7 +702,9 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         # iteration i: from its first event to the first event of iteration i+1 (back-to-back, includes every gap)
         per = sorted(marks[i][0].elapsed_time(marks[i + 1][0]) for i in range(steps - 1))
         q = lambda f: per[min(len(per) - 1, int(f * len(per)))]  # noqa: E731
-        return a.elapsed_time(b) / steps, fwd, bwd, {"p10": q(0.1), "p50": q(0.5), "p90": q(0.9), "max": per[-1]}
+        raw = [marks[i][0].elapsed_time(marks[i + 1][0]) for i in range(steps - 1)]
+        return a.elapsed_time(b) / steps, fwd, bwd, {"p10": q(0.1), "p50": q(0.5), "p90": q(0.9), "max": per[-1],
+                                                      "max_at_iteration": raw.index(per[-1])}
 
     ms_plain, _, _, q_plain = timed(False)
     l0 = _lib.launch_count()

@@ -243,6 +243,11 @@ class ViewShardedExchange:
         self._keep = (offsets, nnz_dev)  # alive until the kernels that read them have been enqueued behind them
         return pub
 
+    def side_stream(self, device):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
     def sh_rows_async(self, C: int, N: int, sh_degree, sh_bases: int, means: Tensor, v_sh: Tensor) -> None:
         """After the publishing SH kernel of this step: cross-rank barrier on the current stream (every rank has
         published), then, on a side stream, ``fg_xchg_sh_bwd_views`` rebuilds the SH rows from every rank's views while the
@@ -251,8 +256,7 @@ class ViewShardedExchange:
         from .rendering import _stage
         L = _lib.lib()
         cur = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=means.device)
+        self.side_stream(means.device)
         stride = int(L.fg_xchg_pub_bytes(C, N))
         need = stride * self.world if self.world > 1 else 0
         if self._staging is None or self._staging.numel() < need:

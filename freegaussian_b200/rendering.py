@@ -230,8 +230,13 @@ class _Project(torch.autograd.Function):
             offs = torch.empty(C * N, dtype=torch.int32, device=dev)
             nnz_dev = torch.empty(1, dtype=torch.int64, device=dev)
             ws_scan = _ws.get("pub_scan", L.fg_pack_workspace_bytes(C * N), dev)
-            check(L.fg_pack_plan(C * N, ptr(radii), ptr(offs), ptr(nnz_dev), ptr(ws_scan), ws_scan.numel(), _stream()))
-            ctx.pub_scan = (offs, nnz_dev)
+            # on the exchange's side stream: nothing of the forward pass waits for it, the backward does
+            side = xc.side_stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            check(L.fg_pack_plan(C * N, ptr(radii), ptr(offs), ptr(nnz_dev), ptr(ws_scan), ws_scan.numel(), side.cuda_stream))
+            done = torch.cuda.Event()
+            done.record(side)
+            ctx.pub_scan = (offs, nnz_dev, done)
         ctx.save_for_backward(means, quats, scales, colors if use_sh else None, means_next, quats_next, scales_next,
                               viewmats, Ks, radii, feat if use_sh else None)
         ctx.cfg = cfg
@@ -296,7 +301,10 @@ class _Project(torch.autograd.Function):
         v_sh = arena[geo_floats:used].view(N, sh_bases, 3) if use_sh else None
         _grad_arena["last"] = (arena, used)
         v_flow_affine = c(v_flow_affine) if flow_cov else None
-        pub = xc.publish_block(C, N, *ctx.pub_scan) if want_pub else None
+        pub = None
+        if want_pub:
+            torch.cuda.current_stream().wait_event(ctx.pub_scan[2])  # the visibility scan of the forward pass
+            pub = xc.publish_block(C, N, ctx.pub_scan[0], ctx.pub_scan[1])
 
         def project_bwd(phase):
             if pub is not None:
