@@ -621,8 +621,9 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
     backward -> Adam step of the Gaussian groups and of the network (freegaussian_config.py:48-85).  `deform_fwd_ms` /
     `deform_bwd_ms` are CUDA-event brackets around the network's forward and around its part of `loss.backward()`.  Everything on
     the device is this repo's kernels except the network's Adam (torch.optim.Adam(fused=True), 0.6 M weights), the time
-    branch (one row) and a few scalar glue ops.  Per-iteration times are CUDA-event brackets; p10 / p50 / p90 over `steps`
-    iterations after `warmup`.  The same network in plain torch fp32 (what the reference executes) is timed beside it."""
+    branch (one row) and a few scalar glue ops.  Per-iteration times are CUDA-event brackets (first event of an iteration to
+    the first event of the next: every gap included); `ms` = mean of the steady-state iterations, p10 / p50 / p90 / max over the
+    same, after `warmup` untimed iterations; the first iteration after the synchronize is reported apart.  The same network in plain torch fp32 (what the reference executes) is timed beside it."""
     from freegaussian_b200 import _lib
     from freegaussian_b200.deform import ControlNetwork, DeformNetwork
     from freegaussian_b200.losses import blend_l1_ssim_loss
@@ -700,11 +701,21 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         fwd = statistics.median(m[0].elapsed_time(m[1]) for m in marks)
         bwd = statistics.median(m[2].elapsed_time(m[3]) for m in marks) if with_deform else 0.0
         # iteration i: from its first event to the first event of iteration i+1 (back-to-back, includes every gap)
-        per = sorted(marks[i][0].elapsed_time(marks[i + 1][0]) for i in range(steps - 1))
-        q = lambda f: per[min(len(per) - 1, int(f * len(per)))]  # noqa: E731
         raw = [marks[i][0].elapsed_time(marks[i + 1][0]) for i in range(steps - 1)]
-        return a.elapsed_time(b) / steps, fwd, bwd, {"p10": q(0.1), "p50": q(0.5), "p90": q(0.9), "max": per[-1],
-                                                      "max_at_iteration": raw.index(per[-1])}
+        if os.environ.get("FG_BENCH_PHASES"):
+            for i in (0, 1, steps // 2):
+                m = marks[i]
+                print(f"iteration {i}: deform_fwd {m[0].elapsed_time(m[1]):.2f} render+loss+render_bwd {m[1].elapsed_time(m[2]) if with_deform else -1:.2f} "
+                      f"net_bwd {m[2].elapsed_time(m[3]) if with_deform else -1:.2f} adam {m[3].elapsed_time(m[4]):.2f} total {raw[i]:.2f}", file=sys.stderr)
+        # The first iteration after the synchronize starts from a drained queue (and now and then absorbs a host-side
+        # hiccup of tens of ms: seen at iteration 0 only); `ms` is the mean of the steady-state iterations 1 .. K-2, the
+        # first one is reported separately.
+        steady = raw[1:]
+        per = sorted(steady)
+        q = lambda f: per[min(len(per) - 1, int(f * len(per)))]  # noqa: E731
+        return (sum(steady) / len(steady), fwd, bwd,
+                {"p10": q(0.1), "p50": q(0.5), "p90": q(0.9), "max": per[-1], "first_after_sync": raw[0],
+                 "mean_including_first": a.elapsed_time(b) / steps})
 
     ms_plain, _, _, q_plain = timed(False)
     l0 = _lib.launch_count()
@@ -761,13 +772,15 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
     for _ in range(warmup):
         iteration2()
     torch.cuda.synchronize()
+    quiesce_gc()
     a2, b2 = ev(), ev()
     a2.record()
     marks2 = [iteration2() for _ in range(steps)]
     b2.record()
     torch.cuda.synchronize()
-    ms_stage2 = a2.elapsed_time(b2) / steps
-    per2 = sorted(marks2[i].elapsed_time(marks2[i + 1]) for i in range(steps - 1))
+    raw2 = [marks2[i].elapsed_time(marks2[i + 1]) for i in range(steps - 1)]
+    ms_stage2 = sum(raw2[1:]) / len(raw2[1:])  # steady state, like `ms` above
+    per2 = sorted(raw2[1:])
     q2_ = lambda f: per2[min(len(per2) - 1, int(f * len(per2)))]  # noqa: E731
 
     # the reference's own execution of the network: torch fp32 nn.Linear / relu / cat on this GPU, forward + backward
