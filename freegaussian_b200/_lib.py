@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfreegaussian_b200.so"
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pi = C.POINTER(C.c_int)
@@ -94,6 +94,8 @@ SIGNATURES = {
     "fg_radix_sort_pairs_u32_u32": (_i32, [_i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _pi, _vp]),
     "fg_isect_offsets": (_i32, [_i64, _vp, _i32, _i32, _i32, _vp, _vp]),
     "fg_isect_depth_keys": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "fg_depth_sort_workspace_bytes": (_i64, [_i64]),
+    "fg_depth_sort_visible": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "fg_gather_i32": (_i32, [_i64, _vp, _vp, _vp, _vp]),
     "fg_isect_emit_tiles": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fg_isect_offsets_tiles": (_i32, [_i64, _vp, _i32, _i32, _i32, _vp, _vp]),

@@ -34,6 +34,10 @@ __global__ void __launch_bounds__(256)
     const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
     if (slot >= total) return;
     const long long idx = order[slot];
+    if (idx < 0) {  // past the visible splats (fg_depth_sort_visible leaves -1 there)
+        coarse_cnt[slot] = 0;
+        return;
+    }
     const int r = radii[idx];
     int cnt = 0;
     if (r > 0) {
@@ -103,6 +107,7 @@ __global__ void __launch_bounds__(256)
     const long long slot = (long long)blockIdx.x * 256 + threadIdx.x;
     if (slot >= total) return;
     const long long idx = order[slot];
+    if (idx < 0) return;  // past the visible splats
     const int r = radii[idx];
     if (r <= 0) return;
     const float2 m = means2d[idx];

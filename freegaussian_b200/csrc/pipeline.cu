@@ -13,21 +13,18 @@ namespace fg {
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct FrontLayout {
-    size_t dk, dk2, dv2, diff, ccnt, n2, scan, tscan, sort, total;
+    size_t diff, ccnt, n2, scan, tscan, sort, total;
 };
 static FrontLayout front_layout(int C, int N, int tile_w, int tile_h) {
     const size_t total = (size_t)C * N;
     FrontLayout L;
     size_t o = 0;
-    L.dk = o; o += al(total * 4);
-    L.dk2 = o; o += al(total * 4);
-    L.dv2 = o; o += al(total * 4);
     L.diff = o; o += al((size_t)C * (tile_h + 1) * (tile_w + 1) * 4);
     L.ccnt = o; o += al(total * 4);
-    L.n2 = o; o += al(16);
+    L.n2 = o; o += al(32);
     L.scan = o; o += al((size_t)fg_scan_workspace_bytes((int64_t)total));
     L.tscan = o; o += al((size_t)fg_bin_tile_scan_workspace_bytes(C, tile_w, tile_h));
-    L.sort = o; o += al((size_t)fg_radix_sort_workspace_bytes((int64_t)total));
+    L.sort = o; o += al((size_t)fg_depth_sort_workspace_bytes((int64_t)total));
     L.total = o;
     return L;
 }
@@ -92,15 +89,10 @@ extern "C" int fg_render_front(int C, int N, const float* means, const float* qu
                             flow_cov, radii, means2d, depths, conics, compensations, feat, feat_stride, rgb_off,
                             depth_off, flow_off, flow_affine, tiles_per_gauss, stream)))
         return e;
-    uint32_t* dk = (uint32_t*)(ws + L.dk);
-    uint32_t* dk2 = (uint32_t*)(ws + L.dk2);
-    uint32_t* dv2 = (uint32_t*)(ws + L.dv2);
-    if ((e = fg_isect_depth_keys(total, depths, tiles_per_gauss, dk, (uint32_t*)order, stream))) return e;
-    int sel = 0;
-    if ((e = fg_radix_sort_pairs_u32_u32(total, dk, (uint32_t*)order, dk2, dv2, 32, ws + L.sort,
-                                         (int64_t)(L.total - L.sort), &sel, stream)))
+    // depth order of the visible splats (culled ones are dropped by the first radix pass); n2[2] = their number
+    int64_t* n_vis = (int64_t*)(ws + L.n2) + 2;
+    if ((e = fg_depth_sort_visible(total, depths, tiles_per_gauss, order, n_vis, ws + L.sort, (int64_t)(L.total - L.sort), stream)))
         return e;
-    if (sel == 1 && total > 0) FG_CUDA(cudaMemcpyAsync(order, dv2, (size_t)total * 4, cudaMemcpyDeviceToDevice, st));
     int64_t* n2 = (int64_t*)(ws + L.n2);
     if ((e = fg_bin_count(C, N, order, means2d, radii, tile_size, tile_w, tile_h, (int32_t*)(ws + L.diff),
                           (int32_t*)(ws + L.ccnt), stream)))

@@ -45,10 +45,15 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid, int bits
     return peers;
 }
 
-template <typename KeyT>
+// DEPTH = true: the keys are produced here as well -- key = float bits of the depth (positive, so integer order = float
+// order), all ones for a splat that touches no tile; vals = the flat index -- and the all-ones keys are left out of the
+// histogram (they are dropped by the first sorting pass).
+template <typename KeyT, bool DEPTH = false>
 __global__ void __launch_bounds__(RS_THREADS)
     rs_histogram_kernel(long long n, const KeyT* __restrict__ keys, int passes, int end_bit,
-                        uint32_t* __restrict__ global_hist /*[passes][256]*/) {
+                        uint32_t* __restrict__ global_hist /*[passes][256]*/, const float* __restrict__ depths = nullptr,
+                        const int32_t* __restrict__ tiles_per_gauss = nullptr, KeyT* __restrict__ keys_out = nullptr,
+                        uint32_t* __restrict__ vals_out = nullptr) {
     pdl_wait();
     __shared__ uint32_t hist[8 * RS_RADIX];
     for (int i = threadIdx.x; i < passes * RS_RADIX; i += RS_THREADS) hist[i] = 0;
@@ -58,8 +63,18 @@ __global__ void __launch_bounds__(RS_THREADS)
     // warp-uniform trip count; lanes past the end vote in a padding group
     for (long long base = (long long)blockIdx.x * RS_THREADS + (threadIdx.x - lane); base < n; base += stride) {
         const long long i = base + lane;
-        const bool valid = i < n;
-        KeyT k = valid ? keys[i] : (KeyT)0;
+        bool valid = i < n;
+        KeyT k = (KeyT)0;
+        if (DEPTH) {
+            if (valid) {
+                k = tiles_per_gauss[i] > 0 ? (KeyT)(uint32_t)__float_as_int(depths[i]) : (KeyT)~(KeyT)0;
+                keys_out[i] = k;
+                vals_out[i] = (uint32_t)i;
+                valid = k != (KeyT)~(KeyT)0;
+            }
+        } else {
+            k = valid ? keys[i] : (KeyT)0;
+        }
         // warp-aggregated: lanes with equal digits elect one lane to add their count, so
         // passes whose digit is (nearly) constant do not serialise on one shared-memory word
         for (int p = 0; p < passes; ++p) {
@@ -76,7 +91,8 @@ __global__ void __launch_bounds__(RS_THREADS)
 }
 
 // exclusive scan of each pass's 256 bins, in place; one block of 256 threads per pass
-__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ global_hist) {
+__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ global_hist,
+                                                                long long* __restrict__ n_sorted = nullptr) {
     __shared__ uint32_t warp_tot[8];
     pdl_wait();
     uint32_t* h = global_hist + blockIdx.x * RS_RADIX;
@@ -92,6 +108,7 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __rest
     uint32_t base = 0;
     for (int w = 0; w < warp; ++w) base += warp_tot[w];
     h[threadIdx.x] = base + incl - v;
+    if (n_sorted && blockIdx.x == 0 && threadIdx.x == RS_RADIX - 1) *n_sorted = base + incl;  // items the passes will move
 }
 
 template <typename KeyT>
@@ -103,18 +120,24 @@ struct RsSmem {
     int32_t scatter_base[RS_RADIX];   // global position of the digit's first key minus digit_start
     uint32_t warp_tot[RS_RADIX / 32];
     int tile_id;
+    int tile_valid;
 };
 
 // LB_WIN = status words a look-back round keeps in flight.  Small inputs (every tile resident at
 // once, so tile t really has to walk back over t predecessors) use 32; large inputs use 8 to keep
 // the register count at 64 (2 CTAs per SM).
-template <typename KeyT, int LB_WIN>
+// DROP: items whose key is all ones are not sorted at all (the depth sort's first pass drops the culled splats, so the
+// remaining passes and everything downstream see the visible ones only).  n_dev != NULL: the item count lives on the device
+// (tiles past it exit at once; no tile with work has such a predecessor).
+template <typename KeyT, int LB_WIN, bool DROP = false>
 __global__ void __launch_bounds__(RS_THREADS)
     rs_onesweep_kernel(long long n, const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                        KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift, int bits,
                        const uint32_t* __restrict__ global_offs /*[256] exclusive*/,
-                       volatile uint32_t* status /*[tiles][256]*/, int* __restrict__ tile_counter) {
+                       volatile uint32_t* status /*[tiles][256]*/, int* __restrict__ tile_counter,
+                       const long long* __restrict__ n_dev = nullptr) {
     pdl_wait();
+    if (n_dev) n = min(n, *n_dev);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem<KeyT>& s = *reinterpret_cast<RsSmem<KeyT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -125,6 +148,7 @@ __global__ void __launch_bounds__(RS_THREADS)
     __syncthreads();
     const int tile = s.tile_id;
     const long long tile_base = (long long)tile * RS_TILE;
+    if (tile_base >= n) return;  // (device-side count) block-uniform
     const int tile_n = (int)min((long long)RS_TILE, n - tile_base);
 
     // ---- load (warp-striped) and rank
@@ -133,11 +157,14 @@ __global__ void __launch_bounds__(RS_THREADS)
     uint32_t rank[RS_ITEMS];
     const int warp_base = warp * (32 * RS_ITEMS);
 #pragma unroll
+    bool ok[RS_ITEMS];
+#pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         int local = warp_base + i * 32 + lane;
         bool valid = local < tile_n;
         key[i] = valid ? keys_in[tile_base + local] : (KeyT)~(KeyT)0;
         val[i] = valid ? vals_in[tile_base + local] : 0u;
+        ok[i] = valid && !(DROP && key[i] == (KeyT)~(KeyT)0);
     }
     uint32_t* wh = s.warp_hist + warp * RS_RADIX;
     const uint32_t lt_mask = (1u << lane) - 1;
@@ -145,13 +172,13 @@ __global__ void __launch_bounds__(RS_THREADS)
     uint32_t peers[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const bool valid = warp_base + i * 32 + lane < tile_n;
+        const bool valid = ok[i];
         const uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
         peers[i] = match_digit(d, valid, bits);  // padding lanes: own group
     }
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const bool valid = warp_base + i * 32 + lane < tile_n;
+        const bool valid = ok[i];
         const uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
         const int leader = __ffs(peers[i]) - 1;
         uint32_t before = 0;
@@ -220,14 +247,15 @@ __global__ void __launch_bounds__(RS_THREADS)
         }
         s.digit_start[tid] = dstart;
         s.scatter_base[tid] = (int32_t)(global_offs[tid] + excl) - (int32_t)dstart;
+        if (tid == RS_RADIX - 1) s.tile_valid = (int)(dstart + tile_count);  // items of this tile that are sorted
     }
     __syncthreads();
+    const int tile_valid = DROP ? s.tile_valid : tile_n;
 
     // ---- stage in tile-sorted order
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        int local = warp_base + i * 32 + lane;
-        if (local < tile_n) {
+        if (ok[i]) {
             uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
             uint32_t pos = s.digit_start[d] + s.warp_hist[warp * RS_RADIX + d] + rank[i];
             s.keys[pos] = key[i];
@@ -239,7 +267,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         int pos = i * RS_THREADS + tid;
-        if (pos < tile_n) {
+        if (pos < tile_valid) {
             KeyT k = s.keys[pos];
             uint32_t d = (uint32_t)(k >> shift) & digit_mask;
             long long g = (long long)s.scatter_base[d] + pos;
@@ -285,8 +313,9 @@ static int radix_sort_pairs(long long n, KeyT* keys_in, uint32_t* vals_in, KeyT*
     uint32_t* status = (uint32_t*)(ws + L.off_status);
     FG_CUDA(cudaMemsetAsync(ws, 0, L.total, st));
     int hist_blocks = (int)min((long long)num_sms() * 4, (n + RS_THREADS - 1) / RS_THREADS);  // 1 per SM measured slower
-    FG_LAUNCH((rs_histogram_kernel<KeyT>), hist_blocks, RS_THREADS, 0, st, n, keys_in, passes, end_bit, hist);
-    FG_LAUNCH(rs_scan_hist_kernel, passes, RS_RADIX, 0, st, hist);
+    FG_LAUNCH((rs_histogram_kernel<KeyT, false>), hist_blocks, RS_THREADS, 0, st, n, (const KeyT*)keys_in, passes, end_bit, hist,
+              (const float*)nullptr, (const int32_t*)nullptr, (KeyT*)nullptr, (uint32_t*)nullptr);
+    FG_LAUNCH(rs_scan_hist_kernel, passes, RS_RADIX, 0, st, hist, (long long*)nullptr);
     const size_t smem = sizeof(RsSmem<KeyT>);
     const bool small = false;  // a 32-word window was measured: no gain on 1 M-item sorts (per-tile latency dominates), more registers
     static const cudaError_t attr_once = [] {
@@ -302,11 +331,13 @@ static int radix_sort_pairs(long long n, KeyT* keys_in, uint32_t* vals_in, KeyT*
         int shift = 8 * p;
         int bits = end_bit - shift < 8 ? end_bit - shift : 8;
         if (small) {
-            FG_LAUNCH((rs_onesweep_kernel<KeyT, 32>), (int)L.tiles, RS_THREADS, smem, st, n, kin, vin, kout, vout, shift,
-                      bits, hist + p * RS_RADIX, status + (size_t)p * L.tiles * RS_RADIX, counters + p);
+            FG_LAUNCH((rs_onesweep_kernel<KeyT, 32>), (int)L.tiles, RS_THREADS, smem, st, n, (const KeyT*)kin, (const uint32_t*)vin, kout, vout, shift,
+                      bits, (const uint32_t*)(hist + p * RS_RADIX), status + (size_t)p * L.tiles * RS_RADIX, counters + p,
+                      (const long long*)nullptr);
         } else {
             FG_LAUNCH((rs_onesweep_kernel<KeyT, 8>), (int)L.tiles, RS_THREADS, smem, st, n, (const KeyT*)kin, (const uint32_t*)vin, kout, vout, shift,
-                          bits, (const uint32_t*)(hist + p * RS_RADIX), status + (size_t)p * L.tiles * RS_RADIX, counters + p);
+                          bits, (const uint32_t*)(hist + p * RS_RADIX), status + (size_t)p * L.tiles * RS_RADIX, counters + p,
+                          (const long long*)nullptr);
         }
         KeyT* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
@@ -318,6 +349,64 @@ static int radix_sort_pairs(long long n, KeyT* keys_in, uint32_t* vals_in, KeyT*
 }  // namespace fg
 
 using namespace fg;
+
+static inline size_t rs_al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int64_t fg_depth_sort_workspace_bytes(int64_t total) {
+    const long long n = total < 1 ? 1 : total;
+    return (int64_t)(4 * rs_al((size_t)n * 4) + rs_layout(n, 4).total);
+}
+
+// Depth order of the VISIBLE splats in one call: keys (+ the four digit histograms) from depths / tiles_per_gauss, a first
+// pass that drops the culled splats while it sorts, three passes over the visible ones only.
+extern "C" int fg_depth_sort_visible(int64_t total, const float* depths, const int32_t* tiles_per_gauss, int32_t* order,
+                                     int64_t* n_visible_dev, void* workspace, int64_t workspace_bytes, void* stream) {
+    FG_REQUIRE(total >= 0 && total < (1ll << 30), "total must be in [0, 2^30)");
+    FG_REQUIRE(n_visible_dev != nullptr, "n_visible_dev must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (total == 0) {
+        FG_CUDA(cudaMemsetAsync(n_visible_dev, 0, 8, st));
+        return FG_OK;
+    }
+    FG_REQUIRE(depths && tiles_per_gauss && order && workspace, "NULL pointer");
+    FG_REQUIRE(workspace_bytes >= fg_depth_sort_workspace_bytes(total), "depth-sort workspace too small");
+    unsigned char* ws = (unsigned char*)workspace;
+    const size_t arr = rs_al((size_t)total * 4);
+    uint32_t* kA = (uint32_t*)ws; uint32_t* vA = (uint32_t*)(ws + arr);
+    uint32_t* kB = (uint32_t*)(ws + 2 * arr); uint32_t* vB = (uint32_t*)(ws + 3 * arr);
+    unsigned char* rs = ws + 4 * arr;
+    const RsLayout L = rs_layout(total, 4);
+    uint32_t* hist = (uint32_t*)(rs + L.off_hist);
+    int* counters = (int*)(rs + L.off_counters);
+    uint32_t* status = (uint32_t*)(rs + L.off_status);
+    FG_CUDA(cudaMemsetAsync(rs, 0, L.total, st));
+    FG_CUDA(cudaMemsetAsync(order, 0xff, (size_t)total * 4, st));  // -1 past the visible splats: the consumers stop there
+    const int hist_blocks = (int)min((long long)num_sms() * 4, ((long long)total + RS_THREADS - 1) / RS_THREADS);
+    FG_LAUNCH((rs_histogram_kernel<uint32_t, true>), hist_blocks, RS_THREADS, 0, st, (long long)total, (const uint32_t*)nullptr, 4, 32,
+              hist, depths, tiles_per_gauss, kA, vA);
+    FG_LAUNCH(rs_scan_hist_kernel, 4, RS_RADIX, 0, st, hist, (long long*)n_visible_dev);
+    const size_t smem = sizeof(RsSmem<uint32_t>);
+    static const cudaError_t attr_once = [] {
+        cudaError_t e = cudaFuncSetAttribute(rs_onesweep_kernel<uint32_t, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(RsSmem<uint32_t>));
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(rs_onesweep_kernel<uint32_t, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(RsSmem<uint32_t>));
+    }();
+    FG_CUDA(attr_once);
+    const long long* nv = (const long long*)n_visible_dev;
+    // pass 0 reads every splat and keeps the visible ones; passes 1-3 are launched for the worst case and read the count on
+    // the device (tiles past it exit at once); the last pass writes its values straight into `order`
+    FG_LAUNCH((rs_onesweep_kernel<uint32_t, 8, true>), (int)L.tiles, RS_THREADS, smem, st, (long long)total, (const uint32_t*)kA,
+              (const uint32_t*)vA, kB, vB, 0, 8, (const uint32_t*)hist, status, counters, (const long long*)nullptr);
+    FG_LAUNCH((rs_onesweep_kernel<uint32_t, 8, false>), (int)L.tiles, RS_THREADS, smem, st, (long long)total, (const uint32_t*)kB,
+              (const uint32_t*)vB, kA, vA, 8, 8, (const uint32_t*)(hist + RS_RADIX), status + (size_t)L.tiles * RS_RADIX, counters + 1, nv);
+    FG_LAUNCH((rs_onesweep_kernel<uint32_t, 8, false>), (int)L.tiles, RS_THREADS, smem, st, (long long)total, (const uint32_t*)kA,
+              (const uint32_t*)vA, kB, vB, 16, 8, (const uint32_t*)(hist + 2 * RS_RADIX), status + (size_t)2 * L.tiles * RS_RADIX, counters + 2, nv);
+    FG_LAUNCH((rs_onesweep_kernel<uint32_t, 8, false>), (int)L.tiles, RS_THREADS, smem, st, (long long)total, (const uint32_t*)kB,
+              (const uint32_t*)vB, kA, (uint32_t*)order, 24, 8, (const uint32_t*)(hist + 3 * RS_RADIX), status + (size_t)3 * L.tiles * RS_RADIX, counters + 3, nv);
+    return FG_OK;
+}
 
 extern "C" int64_t fg_radix_sort_workspace_bytes(int64_t n) { return (int64_t)rs_layout(n < 1 ? 1 : n, 8).total; }
 

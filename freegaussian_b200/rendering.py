@@ -411,9 +411,16 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
 
     # ---- both remaining modes start from the splats sorted by depth
     with _stage("depth_sort"):
-        dk, dv = torch.empty(total, **i32), torch.empty(total, **i32)
-        check(L.fg_isect_depth_keys(total, ptr(depths), ptr(tiles_per_gauss), ptr(dk), ptr(dv), st))
-        _, order = _sort_pairs(L, total, dk, dv, torch.empty_like(dk), torch.empty_like(dv), 32, dev, st, False)
+        if mode == "binned":  # visible splats only: keys + histograms in one kernel, culled splats dropped by the first pass
+            order = torch.empty(total, **i32)
+            n_vis_dev = torch.empty(1, dtype=torch.int64, device=dev)
+            wsd = _ws.get("depth_sort", L.fg_depth_sort_workspace_bytes(total), dev)
+            check(L.fg_depth_sort_visible(total, ptr(depths), ptr(tiles_per_gauss), ptr(order), ptr(n_vis_dev), ptr(wsd),
+                                          wsd.numel(), st))
+        else:
+            dk, dv = torch.empty(total, **i32), torch.empty(total, **i32)
+            check(L.fg_isect_depth_keys(total, ptr(depths), ptr(tiles_per_gauss), ptr(dk), ptr(dv), st))
+            _, order = _sort_pairs(L, total, dk, dv, torch.empty_like(dk), torch.empty_like(dv), 32, dev, st, False)
 
     if mode == "binned":
         cw_, ch_ = ctypes.c_int(0), ctypes.c_int(0)

@@ -160,6 +160,14 @@ int fg_isect_offsets(int64_t n_isects, const int64_t* sorted_isect_ids, int C, i
  * depth) keep ascending c*N+n, exactly like the stable 64-bit sort. */
 int fg_isect_depth_keys(int64_t total, const float* depths, const int32_t* tiles_per_gauss,
                         uint32_t* keys, uint32_t* vals, void* stream);
+/* The same order for the VISIBLE splats only, in one call (the default `binned` path): order[0 .. n_visible) = flat ids
+ * (c*N+n) of the splats with tiles_per_gauss > 0, stably sorted by depth bits; order[n_visible .. total) = -1 (the
+ * binning stages stop there); *n_visible_dev (int64, device) = their number.  Keys and the four digit histograms come
+ * from one kernel, the first radix pass drops the culled splats while it sorts, the other three run over the visible
+ * ones only (their count is read on the device).  workspace: fg_depth_sort_workspace_bytes(total). */
+int64_t fg_depth_sort_workspace_bytes(int64_t total);
+int fg_depth_sort_visible(int64_t total, const float* depths, const int32_t* tiles_per_gauss, int32_t* order,
+                          int64_t* n_visible_dev, void* workspace, int64_t workspace_bytes, void* stream);
 int fg_gather_i32(int64_t n, const int32_t* src, const int32_t* idx, int32_t* dst, void* stream);
 int fg_isect_emit_tiles(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
                         const int32_t* offsets, int tile_size, int tile_w, int tile_h, uint32_t* tile_keys,
