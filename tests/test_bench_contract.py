@@ -46,3 +46,40 @@ def test_multi_gpu_line(name):
     d = _load(name)
     assert d["n_gpus"] == 2 and d["scaling"] == "weak" and BASE <= set(d)
     assert "view-sharded" in d["config"]["parallelism"] and d["config"]["views_per_step"] == 2
+
+
+# ---- round 2 lines -------------------------------------------------------------------------------------------------------
+def test_round2_full_line():
+    d = _load("r2_final_bench1.json")  # `python bench.py --steps 20 --warmup 5`
+    assert BASE <= set(d) and {"clocks", "roofline", "cpu_baseline", "train_iter", "configs"} <= set(d)
+    assert d["unit"] == "MPix/s" and d["n_gpus"] == 1 and d["dtype"] == "f32" and d["vs_baseline"] is None
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+    r = d["roofline"]
+    assert r["kernel"] == "rasterize_bwd" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["frac"] > 0.55
+    c = d["configs"]
+    assert "error" not in c and {"cfg1", "cfg2", "knn"} <= set(c)
+    k = c["knn"]
+    assert k["points"] == 3_000_000 and k["k"] == 16 and k["bit_exact_distances_on_sample"] is True
+    assert {"sklearn_1core", "sklearn_all_cores"} <= set(k["cpu"]) and k["roofline"]["bound"] == "hbm"
+    t = d["train_iter"]
+    assert "error" not in t and {"p10", "p50", "p90", "max"} <= set(t["ms_quantiles"])
+    assert t["ms_quantiles"]["p90"] / t["ms_quantiles"]["p50"] < 1.1  # a reproducible number
+    assert 0 < t["deform_roofline"]["frac_algorithmic"] < t["deform_roofline"]["frac"] < 1
+
+
+def test_round2_reference_arm_is_like_for_like():
+    d, r = _load("r2_final_bench1.json"), _load("r2_final_bench_reference.json")
+    assert r["impl"] == "reference" and r["gpu_launches"] == 0
+    assert r["config"]["workload"] == d["config"]["workload"]          # same workload string on both arms
+    assert r["steps"] == d["steps"] and r["warmup"] == d["warmup"]      # same step / warm-up counts
+    assert "crop-extrapolated" in r["cpu_baseline"]["sample"] and r["cpu_baseline"]["value"] == r["value"]
+    assert r["e2e"] == {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.parametrize("name,n", [("r2_final_bench2.json", 2), ("r2_final_bench8.json", 8)])
+def test_round2_multi_gpu_lines(name, n):
+    d = _load(name)
+    assert d["n_gpus"] == n and d["scaling"] == "weak" and BASE <= set(d) and d["config"]["views_per_step"] == n
+    e = d["exchange"]
+    assert e["mode"].startswith("peer") and e["ms"] > 0 and e["allreduce_bytes"] == 68_000_000
+    assert e["multicast"] is (n >= 4)
