@@ -248,22 +248,30 @@ class ViewShardedExchange:
             self._side = torch.cuda.Stream(device=device)
         return self._side
 
+    def barrier_published(self) -> None:
+        """After the publishing SH kernel of this step, on the current stream: cross-rank barrier (every rank has
+        published); the event recorded behind it is what the side stream waits for."""
+        from . import _lib
+        cur = torch.cuda.current_stream()
+        self.epoch += 1
+        _lib.check(_lib.lib().fg_xchg_barrier(self._peers, self.epoch, cur.cuda_stream))
+        self._published = torch.cuda.Event()
+        self._published.record(cur)
+
     def sh_rows_async(self, C: int, N: int, sh_degree, sh_bases: int, means: Tensor, v_sh: Tensor) -> None:
-        """After the publishing SH kernel of this step: cross-rank barrier on the current stream (every rank has
-        published), then, on a side stream, ``fg_xchg_sh_bwd_views`` rebuilds the SH rows from every rank's views while the
-        current stream goes on with the geometry kernel and its all-reduce.  :meth:`join` makes the current stream wait."""
+        """On a side stream, behind :meth:`barrier_published`: pull the peers' published ranges and rebuild the SH rows
+        from every rank's views (``fg_xchg_sh_bwd_views``) while the current stream runs the geometry kernel and its
+        all-reduce.  Call it AFTER the geometry kernel has been enqueued, so that kernel's blocks -- the critical path -- get
+        the SMs first.  :meth:`join` makes the current stream wait for the rows."""
         from . import _lib
         from .rendering import _stage
         L = _lib.lib()
-        cur = torch.cuda.current_stream()
         self.side_stream(means.device)
         stride = int(L.fg_xchg_pub_bytes(C, N))
         need = stride * self.world if self.world > 1 else 0
         if self._staging is None or self._staging.numel() < need:
             self._staging = torch.empty(max(need, 16), dtype=torch.uint8, device=means.device)  # pulled copies: local memory
-        self.epoch += 1
-        _lib.check(L.fg_xchg_barrier(self._peers, self.epoch, cur.cuda_stream))
-        self._side.wait_stream(cur)
+        self._side.wait_event(self._published)
         with torch.cuda.stream(self._side):
             with _stage("xchg_sh_views"):
                 _lib.check(L.fg_xchg_sh_bwd_views(self._peers, self.pub_off[self.parity], C, N, int(sh_degree), sh_bases,

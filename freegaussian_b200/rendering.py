@@ -334,9 +334,10 @@ class _Project(torch.autograd.Function):
                 with _stage("project_bwd"):
                     project_bwd(1)
                 with _stage("exchange"):
-                    xc.sh_rows_async(C, N, cfg["sh_degree"], sh_bases, means, v_sh)
+                    xc.barrier_published()
                     with _stage("project_bwd_geo"):
                         project_bwd(2)
+                    xc.sh_rows_async(C, N, cfg["sh_degree"], sh_bases, means, v_sh)
                     xc.reduce(geo_floats)
                     xc.join()
             else:
