@@ -92,7 +92,7 @@ __device__ __forceinline__ void mc_st(float4* a, float4 v) {
 
 // In-place SUM over ranks of n4 float4 at byte offset `off` of the symmetric buffer.  Two-shot: rank r
 // owns the r-th slice.  Slots 1..grid: start barrier (optional), grid+1..2*grid: end barrier.
-// A bounded number of CTAs (default 256 x 256 threads, eight 16-byte requests per thread = 8 MB in flight: enough for the switch round
+// Few, fat CTAs (default 64 x 1024 threads, eight 16-byte requests per thread = 8 MB in flight: enough for the switch round
 // trip at link rate) so that the rest of the GPU stays free for the kernels that run beside it -- a first version
 // with two CTAs on every SM measured 0.17 ms alone but starved the SH-row kernel of registers: no overlap at all.
 template <bool MC>
@@ -361,11 +361,11 @@ extern "C" int fg_xchg_allreduce_f32(const fg_xchg_peers* peers, int64_t offset_
     const long long per = (n4 + p.world - 1) / p.world;
     // in the switch: few fat CTAs (see the kernel); peer loads / stores (2-3 ranks) need the whole GPU's load slots to
     // fill one link: two 512-thread CTAs per SM (measured at 2 ranks, 68 MB: 0.114 ms against 0.205 ms with 32 x 1024)
-    // (switch path) 256-thread CTAs: a 1024-thread CTA needs a completely empty SM, and with the SH-row kernel's blocks
-    // streaming through every SM it only got one when that kernel was nearly done -- measured 0.245 ms beside it against
-    // 0.172 ms alone; quarter-SM CTAs slot in as soon as any block retires
-    const int threads = p.mc ? 256 : 512;
-    const int cap = p.mc ? 4 * g_xchg_ar_blocks : 2 * num_sms();
+    // Measured at 8 ranks, 68 MB (tools/bench_xchg_allreduce.py, profiles/r2_allreduce_8gpu.txt): alone, 64 / 128 / 256 CTAs of
+    // 256 threads take 0.187 / 0.200 / 0.219 ms (NCCL: 0.281 ms); inside the step, beside the SH-row kernels, 64 CTAs of
+    // 1024 threads gave the shortest step (1.95 ms against 2.06 ms with 256 quarter-SM CTAs, which slow those kernels down)
+    const int threads = p.mc ? XB : 512;
+    const int cap = p.mc ? g_xchg_ar_blocks : 2 * num_sms();
     int grid = (int)std::min<long long>(cap, std::max<long long>(1, (per + threads * 4 - 1) / (threads * 4)));
     FG_REQUIRE(1 + 2 * grid <= FG_XCHG_FLAG_BYTES / (XCHG_SLOT_WORDS * 4), "flag area too small");
     cudaStream_t st = (cudaStream_t)stream;

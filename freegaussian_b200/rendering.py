@@ -335,9 +335,9 @@ class _Project(torch.autograd.Function):
                     project_bwd(1)
                 with _stage("exchange"):
                     xc.barrier_published()
+                    xc.sh_rows_async(C, N, cfg["sh_degree"], sh_bases, means, v_sh)
                     with _stage("project_bwd_geo"):
                         project_bwd(2)
-                    xc.sh_rows_async(C, N, cfg["sh_degree"], sh_bases, means, v_sh)
                     xc.reduce(geo_floats)
                     xc.join()
             else:
