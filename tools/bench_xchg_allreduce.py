@@ -50,7 +50,7 @@ for floats in (17_000_000, 62_000_000):  # geometry gradients of 1 M Gaussians /
         xc.epoch += 1
         _lib.check(L.fg_xchg_allreduce_f32(xc._peers, xc.arena_off, floats // 4 * 4, xc.epoch, 1, st))
 
-    for blocks in ((16, 32, 64, 128, 255) if xc.multicast else (0,)):
+    for blocks in ((16, 32, 64, 128) if xc.multicast else (0,)):
         if blocks:
             _lib.check(L.fg_set_option(b"xchg_ar_blocks", blocks))
         arena.fill_(1.0)
