@@ -656,6 +656,7 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     last = {}
     cpu_phase = {}  # host time spent enqueueing each phase: is the step launch-bound?
+    diag = {}       # allocator / host diagnostics of the timed regions
 
     def tick(name, t0):
         cpu_phase[name] = cpu_phase.get(name, 0.0) + (time.perf_counter() - t0)
@@ -698,11 +699,20 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         torch.cuda.synchronize()
         quiesce_gc()
         cpu_phase.clear()
+        mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         a, b = ev(), ev()
         a.record()
-        marks = [iteration(with_deform) for _ in range(steps)]
+        host_t = []
+        marks = []
+        for _ in range(steps):
+            t_h = time.perf_counter()
+            marks.append(iteration(with_deform))
+            host_t.append((time.perf_counter() - t_h) * 1e3)
         b.record()
         torch.cuda.synchronize()
+        diag["cuda_mallocs_in_timed_region"] = diag.get("cuda_mallocs_in_timed_region", 0) + (
+            torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0)
+        diag["host_ms_per_iteration_max"] = max(diag.get("host_ms_per_iteration_max", 0.0), max(host_t))
         fwd = statistics.median(m[0].elapsed_time(m[1]) for m in marks)
         bwd = statistics.median(m[2].elapsed_time(m[3]) for m in marks) if with_deform else 0.0
         # iteration i: from its first event to the first event of iteration i+1 (back-to-back, includes every gap)
@@ -832,7 +842,7 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         "stage2_ms": ms_stage2, "stage2_quantiles": {"p10": q2_(0.1), "p50": q2_(0.5), "p90": q2_(0.9)},
         "stage2_controlled_gaussians": int(part.numel()),
         "gaussians": n, "visible": n_vis, "launches_per_iter": launches, "steps": steps, "warmup": warmup,
-        "host_enqueue_ms_per_iter": host_ms, "network_backward_paths": dict(__import__("freegaussian_b200.deform", fromlist=["STATS"]).STATS),
+        "host_enqueue_ms_per_iter": host_ms, "diagnostics": diag, "network_backward_paths": dict(__import__("freegaussian_b200.deform", fromlist=["STATS"]).STATS),
         "config": "stage-1 step: DeformNetwork(is_blender=True) -> RGB+ED render -> blend+L1+SSIM -> backward -> Adam; "
                   "stage2_ms: ControlNetwork on the controlled subset -> the same render / loss / backward / Adam",
         "library_kernels": "torch.optim.Adam(fused=True) for the 0.6 M network weights, torch ops for the one-row time branch "

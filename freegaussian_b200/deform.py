@@ -151,6 +151,49 @@ class _Packed:
         self.bias_head = torch.cat([hb, hb.new_zeros(MLP_HEAD_LD - hb.numel())])
 
 
+class _ActivationPool:
+    """Persistent activation workspaces of the trunk, keyed by (device, rows, embedding width): the embedding [N, ld], the
+    eight hidden activations [8, N, 256] and their ReLU bit masks [8, N, 8] -- 9.6 GB at 1 M rows.  A forward pass leases
+    one (allocating only when none is free), the lease goes back to the pool when the autograd context that saved it
+    dies (after the backward, or when an inference result is dropped).  Without the pool every training iteration
+    allocated and freed these tensors through the caching allocator, whose occasional cudaMalloc / cudaFree of
+    gigabyte blocks showed up as 30-190 ms iterations (bench.py train_iter: `cuda_mallocs_in_timed_region`)."""
+
+    def __init__(self):
+        self.free = {}
+
+    def lease(self, dev, N: int, ld: int):
+        key = (str(dev), N, ld)
+        stack = self.free.setdefault(key, [])
+        if stack:
+            bufs = stack.pop()
+        else:
+            bufs = (torch.empty(N, ld, device=dev, dtype=torch.float32),
+                    torch.empty(_D, N, _W, device=dev, dtype=torch.float32),
+                    torch.empty(_D, N, _W // 32, device=dev, dtype=torch.int32))
+        return _Lease(self, key, bufs)
+
+    def clear(self):
+        self.free.clear()
+
+
+class _Lease:
+    def __init__(self, pool, key, bufs):
+        self.pool, self.key, self.bufs = pool, key, bufs
+
+    def __del__(self):
+        try:
+            stack = self.pool.free.setdefault(self.key, [])
+            if len(stack) < 2:  # at most two idle workspaces per shape are kept
+                stack.append(self.bufs)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+_POOL = _ActivationPool()
+USE_ACTIVATION_POOL = True
+
+
 class _Trunk(torch.autograd.Function):
     """x [N,3], x2 [N,3] or None (embedded like x, no gradient), t_emb [t_ch] or None, spec, parameters -> head [N, 32]."""
 
@@ -163,13 +206,18 @@ class _Trunk(torch.autograd.Function):
         t_ch = t_emb.numel() if t_emb is not None else 0
         pk = _Packed(list(params), spec)
         new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
-        e = new(N, ld)
+        if USE_ACTIVATION_POOL and dev.type == "cuda" and N > 0:
+            lease = _POOL.lease(dev, N, ld)
+            e, h_all, masks = lease.bufs
+        else:
+            lease = None
+            e, h_all = new(N, ld), new(_D, N, _W)
+            masks = torch.empty(_D, N, _W // 32, device=dev, dtype=torch.int32)  # ReLU bit masks of all layers, one tensor
         check(L.fg_deform_embed(N, ptr(x), ptr(x2), ptr(t_emb), t_ch, spec.multires, ld, ptr(e), _stream()))
         hs: List[Tensor] = []
-        masks = torch.empty(_D, N, _W // 32, device=dev, dtype=torch.int32)  # ReLU bit masks of all layers, one tensor
         prev = None
         for i in range(_D):
-            out, bits = new(N, _W), masks[i]
+            out, bits = h_all[i], masks[i]
             if i == 0:
                 _linear(_lib.MLP_RELU, N, _W, e, ld, None, 0, pk.w[0], pk.bias[0], None, out, bits)
             elif i == _SKIP + 1:
@@ -182,6 +230,7 @@ class _Trunk(torch.autograd.Function):
         _linear(_lib.MLP_LINEAR, N, MLP_HEAD_LD, prev, _W, None, 0, pk.w_head, pk.bias_head, None, head, None)
         ctx.save_for_backward(x, e, masks, *hs, *params)
         ctx.pk, ctx.spec, ctx.t_ch = pk, spec, t_ch
+        ctx.lease = lease  # the workspace returns to the pool when this context dies
         return head
 
     @staticmethod
