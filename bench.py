@@ -658,8 +658,14 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
     cpu_phase = {}  # host time spent enqueueing each phase: is the step launch-bound?
     diag = {}       # allocator / host diagnostics of the timed regions
 
+    phase_log = []  # per iteration: host ms of each phase (the slowest iteration is reported)
+
     def tick(name, t0):
-        cpu_phase[name] = cpu_phase.get(name, 0.0) + (time.perf_counter() - t0)
+        dt = time.perf_counter() - t0
+        cpu_phase[name] = cpu_phase.get(name, 0.0) + dt
+        if name == "deform_fwd":
+            phase_log.append({})
+        phase_log[-1][name] = round(dt * 1e3, 3)
         return time.perf_counter()
 
     def iteration(with_deform: bool):
@@ -712,7 +718,14 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         torch.cuda.synchronize()
         diag["cuda_mallocs_in_timed_region"] = diag.get("cuda_mallocs_in_timed_region", 0) + (
             torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0)
-        diag["host_ms_per_iteration_max"] = max(diag.get("host_ms_per_iteration_max", 0.0), max(host_t))
+        if max(host_t) > diag.get("host_ms_per_iteration_max", 0.0):
+            k = host_t.index(max(host_t))
+            m = marks[k]
+            diag["host_ms_per_iteration_max"] = max(host_t)
+            diag["slowest_iteration_host_phases_ms"] = phase_log[len(phase_log) - steps + k]
+            diag["slowest_iteration_device_phases_ms"] = {
+                "deform_fwd": m[0].elapsed_time(m[1]), "render_to_end_of_backward": m[1].elapsed_time(m[3]),
+                "adam": m[3].elapsed_time(m[4]), "index": k}
         fwd = statistics.median(m[0].elapsed_time(m[1]) for m in marks)
         bwd = statistics.median(m[2].elapsed_time(m[3]) for m in marks) if with_deform else 0.0
         # iteration i: from its first event to the first event of iteration i+1 (back-to-back, includes every gap)
@@ -735,7 +748,31 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
     ms_plain, _, _, q_plain = timed(False)
     l0 = _lib.launch_count()
     ms_full, ms_deform_fwd, ms_deform_bwd, q_full = timed(True)
-    if os.environ.get("FG_BENCH_TIMELINE"):  # device timeline of one iteration (kernel, duration, idle gap before it) on stderr
+    if os.environ.get("FG_BENCH_TIMELINE") == "hunt":  # 40 profiled iterations: the longest kernels and the largest idle gaps
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(40):
+                iteration(True)
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        longest = sorted(evs, key=lambda e: e.time_range.end - e.time_range.start, reverse=True)[:6]
+        print("# longest device activities (us):", file=sys.stderr)
+        for e in longest:
+            print(f"{e.time_range.end - e.time_range.start:10.1f}  {e.name[:110]}", file=sys.stderr)
+        gaps, t_prev, prev = [], evs[0].time_range.end, evs[0]
+        for e in evs[1:]:
+            gaps.append((e.time_range.start - t_prev, prev.name[:60], e.name[:60]))
+            if e.time_range.end > t_prev:
+                t_prev, prev = e.time_range.end, e
+        print("# largest idle gaps (us): gap, after, before", file=sys.stderr)
+        for g in sorted(gaps, reverse=True)[:6]:
+            print(f"{g[0]:10.1f}  after {g[1]}  | before {g[2]}", file=sys.stderr)
+        cpu = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU),
+                     key=lambda e: e.time_range.end - e.time_range.start, reverse=True)[:8]
+        print("# longest host-side ops (us):", file=sys.stderr)
+        for e in cpu:
+            print(f"{e.time_range.end - e.time_range.start:10.1f}  {e.name[:110]}", file=sys.stderr)
+    elif os.environ.get("FG_BENCH_TIMELINE"):  # device timeline of one iteration (kernel, duration, idle gap before it) on stderr
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
             for _ in range(3):

@@ -46,9 +46,35 @@ class _Workspace:
         key = (name, torch.device(device).index or 0)
         buf = self.bufs.get(key)
         if buf is None or buf.numel() < nbytes:
+            # a buffer that has to grow grows by a quarter beyond the need: a size that creeps upward call after call
+            # (list lengths of a scene in training) must not turn into a cudaMalloc per call
+            if buf is not None:
+                nbytes = _round_up(nbytes + nbytes // 4, 1 << 20)
+            self.bufs[key] = buf = None  # the old buffer goes back to the allocator before the new one is asked for
             buf = torch.empty(max(nbytes, 1024), dtype=torch.uint8, device=device)
             self.bufs[key] = buf
         return buf
+
+
+def _round_up(x: int, q: int) -> int:
+    return (x + q - 1) // q * q
+
+
+_Counts3 = ctypes.c_int64 * 3  # (M, Mc, lists built) written by fg_render_front
+_LIST_QUANTUM = 1 << 22  # entries (16 MiB of int32): list capacities are multiples of this
+
+
+def _list_capacity(cur: int, need: int) -> int:
+    """Capacity of a guessed-size list buffer for the next call, given the current capacity and the last call's need.
+
+    Stable by construction: the capacity changes only when the need comes within 8 % of it, and then jumps to 1.3 x the
+    need rounded up to 16 MiB, so that a need that drifts (Gaussians move while training) changes the buffer size -- and
+    sends torch's caching allocator to cudaMalloc, 10 - 200 ms with kernels in flight -- once per ~20 % of growth instead
+    of at every new maximum (bench.py's train_iter section, round 2: 20 - 29 cudaMallocs per 90 iterations before this).
+    """
+    if need > cur - cur // 12:
+        return _round_up(need + (3 * need) // 10 + 1024, _LIST_QUANTUM)
+    return cur
 
 
 _ws = _Workspace()
@@ -181,7 +207,7 @@ class _Project(torch.autograd.Function):
             guess_m, guess_mc = _list_guess.get(key, (0, 0))
             flat_buf = torch.empty(guess_m, dtype=torch.int32, device=dev) if guess_m else None
             ws2 = _ws.get("back", L.fg_render_back_workspace_bytes(C, tile_w, tile_h, guess_mc), dev) if guess_m else None
-            counts = (ctypes.c_int64 * 3)()
+            counts = _Counts3()
             check(L.fg_render_front(
                 C, N, ptr(means), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), cfg["width"], cfg["height"],
                 cfg["eps2d"], cfg["near_plane"], cfg["far_plane"], cfg["radius_clip"], cfg["tile_size"],
@@ -191,15 +217,14 @@ class _Project(torch.autograd.Function):
                 ptr(isect_offsets), ptr(coarse_off), counts, ptr(ws), ws.numel(), ptr(flat_buf), guess_m,
                 ptr(ws2), ws2.numel() if ws2 is not None else 0, _stream()))
             M, Mc = int(counts[0]), int(counts[1])
-            # capacity for the next call: 1.25 x the largest need seen (stable sizes: the allocator reuses the buffers
-            # call after call); after 64 consecutive calls that needed less than half of it the capacity is re-derived
+            # capacity for the next call (_list_capacity: stable sizes, so that the allocator hands back the same blocks
+            # call after call); after 64 consecutive calls that needed less than a third of it the capacity is re-derived
             # from the current need (a scene that shrank -- culling after densification -- gives its buffers back)
-            need_m, need_mc = int(1.25 * M) + 1024, int(1.25 * Mc) + 1024
-            small = _list_small.get(key, 0) + 1 if (2 * need_m < guess_m) else 0
+            small = _list_small.get(key, 0) + 1 if (3 * M + 3 * _LIST_QUANTUM < guess_m) else 0
             if small >= 64:
                 guess_m, guess_mc, small = 0, 0, 0
             _list_small[key] = small
-            _list_guess[key] = (max(guess_m, need_m), max(guess_mc, need_mc))
+            _list_guess[key] = (_list_capacity(guess_m, M), _list_capacity(guess_mc, Mc))
             if counts[2]:
                 flatten_ids = flat_buf[:M]
             else:
