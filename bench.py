@@ -648,7 +648,14 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
     quats = d.quats.detach().clone().requires_grad_(True)
     op_logit = torch.logit(d.opacities.detach().clamp(1e-4, 1 - 1e-4)).requires_grad_(True)  # and logit opacities (:851)
     sh = d.sh.detach().clone().requires_grad_(True)
-    gt = torch.rand(H, W, 3, generator=gen).to(dev)
+    # ground truth = the scene's own render with perturbed colours: a training state near its optimum, so the workload is
+    # stationary.  (A noise image as target makes the optimiser blur the scene -- every Gaussian inflates, the tile lists grow
+    # from 33 M to 109 M entries within 50 iterations, r2 measurement -- and the "iteration" timed is a different one each time.)
+    with torch.no_grad():
+        sh_gt = d.sh.detach() + 0.05 * torch.randn(d.sh.shape, generator=gen).to(dev)
+        gt = rasterization(d.means, d.quats, d.scales, d.opacities, sh_gt, vm, K, W, H, packed=False, near_plane=0.01,
+                           far_plane=1e10, render_mode="RGB", sh_degree=3, rasterize_mode="classic")[0][0].clamp(0, 1).contiguous()
+        del sh_gt
     bg = torch.zeros(3, device=dev)
     t = torch.tensor([[0.3]], device=dev).expand(n, -1)
     adam = GaussianAdam.for_reference_groups(means, sh, op_logit, scales_log, quats)
@@ -706,6 +713,9 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         quiesce_gc()
         cpu_phase.clear()
         mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        from freegaussian_b200 import rendering as _R
+        _R.STATS.update(list_len_min=0, list_len_max=0)
+        lists0 = dict(_R.STATS)
         a, b = ev(), ev()
         a.record()
         host_t = []
@@ -718,6 +728,9 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
         torch.cuda.synchronize()
         diag["cuda_mallocs_in_timed_region"] = diag.get("cuda_mallocs_in_timed_region", 0) + (
             torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0)
+        for k_ in ("list_capacity_changes", "list_second_call"):
+            diag[k_] = diag.get(k_, 0) + _R.STATS[k_] - lists0[k_]
+        diag.setdefault("tile_list_lengths", []).append([_R.STATS["list_len_min"], _R.STATS["list_len_max"]])
         if max(host_t) > diag.get("host_ms_per_iteration_max", 0.0):
             k = host_t.index(max(host_t))
             m = marks[k]
@@ -750,6 +763,26 @@ def train_iter_section(d, dev, W, H, vm, K, steps=30, warmup=20):
     ms_full, ms_deform_fwd, ms_deform_bwd, q_full = timed(True)
     if os.environ.get("FG_BENCH_TIMELINE") == "hunt":  # 40 profiled iterations: the longest kernels and the largest idle gaps
         from torch.profiler import ProfilerActivity, profile
+        try:
+            # which allocation goes to cudaMalloc: the allocator's own event trace, with Python stacks
+            torch.cuda.memory._record_memory_history(max_entries=200000, context="alloc", stacks="python")
+            for _ in range(40):
+                iteration(True)
+            torch.cuda.synchronize()
+            snap = torch.cuda.memory._snapshot()
+            torch.cuda.memory._record_memory_history(enabled=None)
+            print("# cudaMalloc calls of 40 iterations (size MiB, innermost repo frames):", file=sys.stderr)
+            for trace in snap.get("device_traces", []):
+                for k, e in enumerate(trace):
+                    if e.get("action") != "segment_alloc":
+                        continue
+                    # the segment is created for the allocation that follows it in the trace
+                    frames = e.get("frames") or (trace[k + 1].get("frames") if k + 1 < len(trace) else []) or []
+                    mine = [f"{os.path.basename(f['filename'])}:{f['line']}" for f in frames
+                            if "/site-packages/" not in f.get("filename", "") and f.get("filename", "").endswith(".py")][:4]
+                    print(f"{e['size'] / 2**20:10.1f}  {' < '.join(mine)}", file=sys.stderr)
+        except Exception as exc:  # a diagnostic: never in the way of the run
+            print(f'# allocator trace unavailable: {exc!r}', file=sys.stderr)
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
             for _ in range(40):
                 iteration(True)

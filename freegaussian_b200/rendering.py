@@ -84,6 +84,7 @@ _ws = _Workspace()
 _grad_arena: Dict[str, tuple] = {}
 _list_guess: Dict[tuple, tuple] = {}  # (C, N, W, H, device) -> (capacity of flatten_ids, of the coarse pairs)
 _list_small: Dict[tuple, int] = {}    # consecutive calls that needed less than half of that capacity
+STATS = {"list_capacity_changes": 0, "list_second_call": 0, "list_len_min": 0, "list_len_max": 0}  # diagnostics (bench.py)
 
 
 def last_grad_arena():
@@ -224,7 +225,12 @@ class _Project(torch.autograd.Function):
             if small >= 64:
                 guess_m, guess_mc, small = 0, 0, 0
             _list_small[key] = small
-            _list_guess[key] = (_list_capacity(guess_m, M), _list_capacity(guess_mc, Mc))
+            new_guess = (_list_capacity(guess_m, M), _list_capacity(guess_mc, Mc))
+            STATS["list_capacity_changes"] += new_guess != _list_guess.get(key)
+            STATS["list_second_call"] += not counts[2]
+            STATS["list_len_min"] = min(STATS["list_len_min"] or M, M)
+            STATS["list_len_max"] = max(STATS["list_len_max"], M)
+            _list_guess[key] = new_guess
             if counts[2]:
                 flatten_ids = flat_buf[:M]
             else:
