@@ -210,7 +210,7 @@ class Job:
         # uint8 / f16 planes as copied, and the float32 weight images they are decoded into on the same stream
         self.stage_bufs = [tuple(torch.empty_like(t, device=dev) for t in (self.host_vm[0], self.host_K[0], *self.host_w))
                            for _ in range(2)]
-        self.decoded = [(torch.empty_like(self.w_rgbd), torch.empty_like(self.w_flow)) for _ in range(2)]
+        self.decoded = [(self.w_rgbd.clone(), self.w_flow.clone()) for _ in range(2)]
         self.consumed = [None, None]  # event: the step that read staging set k has finished with it
         self.h2d_bytes = int(sum(t.numel() * t.element_size() for t in (self.host_vm[0], self.host_K[0], *self.host_w)))
 
@@ -226,8 +226,7 @@ class Job:
                 dst.copy_(src, non_blocking=True)
             # decode behind the copy, still on the copy stream (what a data-loading stream does): uint8 -> [0,1], f16 -> f32
             wr, wf = self.decoded[k]
-            wr[..., :3].copy_(bufs[2])
-            wr[..., :3].mul_(1.0 / 255.0)
+            torch.mul(bufs[2], 1.0 / 255.0, out=wr[..., :3])
             wr[..., 3:].copy_(bufs[3])
             wf.copy_(bufs[4])
             ev = torch.cuda.Event()
@@ -255,7 +254,12 @@ class Job:
                                             sh_degree=3, sparse_grad=False, absgrad=True, rasterize_mode="classic",
                                             means_next=d.means_next)
         meta["means2d"].retain_grad()
-        loss = (render * wr).sum() + (meta["flow"] * wf).sum()
+        # weighted sums as dot products: one reduction kernel each, no 33 MB product tensor in between (the loss only
+        # exists to hand the compositing backward dense, non-trivial upstream gradients: v_render = wr, v_flow = wf)
+        if render.shape[0] == 1:
+            loss = torch.dot(render.reshape(-1), wr.reshape(-1)) + torch.dot(meta["flow"].reshape(-1), wf.reshape(-1))
+        else:  # several views per step share the planes
+            loss = (render * wr).sum() + (meta["flow"] * wf).sum()
         # at N>1 with --exchange peer the cross-rank sum of every parameter gradient happens INSIDE this backward
         loss.backward()
         self.stats.accumulate_local(meta["radii"], meta["means2d"].absgrad, H, W)

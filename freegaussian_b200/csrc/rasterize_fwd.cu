@@ -72,9 +72,12 @@ __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdPar
 
     float T = 1.f;
     int cur_idx = 0;
-    float acc[CH];
+    // the channels accumulate in pairs, one FFMA2 per pair (the weight is the instruction's broadcast operand): the same
+    // IEEE fma per channel as the scalar form, half the issue slots -- the kernel is issue-bound (ncu r2: 80 % of the slots)
+    constexpr int CP = (CH + 1) / 2;
+    float2 acc2[CP];
 #pragma unroll
-    for (int k = 0; k < CH; ++k) acc[k] = 0.f;
+    for (int k = 0; k < CP; ++k) acc2[k] = make_float2(0.f, 0.f);
 
     const unsigned rec0 = smem_addr(&sRec[0][0]);
     const unsigned list0 = smem_addr(&sList[warp][0]);
@@ -134,13 +137,13 @@ __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdPar
                 e1 = M.z * dx + M.w * dy;
             }
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                float fk = f[k];
+            for (int k = 0; k < CP; ++k) {
+                float f0 = f[2 * k], f1 = (2 * k + 1 < CH) ? f[2 * k + 1] : 0.f;
                 if (AFF) {
-                    if (k == p.flow_ch0) fk -= e0;
-                    if (k == p.flow_ch0 + 1) fk -= e1;
+                    f0 -= (2 * k == p.flow_ch0) ? e0 : (2 * k == p.flow_ch0 + 1) ? e1 : 0.f;
+                    f1 -= (2 * k + 1 == p.flow_ch0) ? e0 : (2 * k + 1 == p.flow_ch0 + 1) ? e1 : 0.f;
                 }
-                acc[k] = fmaf(fk, w, acc[k]);
+                acc2[k] = __ffma2_rn(make_float2(f0, f1), bc2(w), acc2[k]);
             }
             cur_idx = batch_start + t;
             T = next_T;
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(TILE_PIX, 6) rasterize_fwd_kernel(RasterFwdPar
         const int n2 = CH - p.split;
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
-            float v = acc[k];
+            float v = (k & 1) ? acc2[k >> 1].y : acc2[k >> 1].x;
             if (p.backgrounds) v = fmaf(T, p.backgrounds[cam * CH + k], v);
             if (k == p.ed_channel) v = v / fmaxf(a_out, 1e-10f);
             if (k < p.split) p.render[pix * p.split + k] = v;
