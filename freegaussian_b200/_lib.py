@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libfreegaussian_b200.so"
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pi = C.POINTER(C.c_int)
@@ -105,6 +105,10 @@ SIGNATURES = {
     "fg_bin_tile_scan_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "fg_bin_tile_scan": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "fg_bin_coarse_emit": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fg_bin_ranked_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "fg_bin_count_cells": (_i32, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "fg_bin_cell_scan": (_i32, [_i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "fg_bin_ranked_emit": (_i32, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "fg_bin_fine": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fg_rasterize_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                 _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -123,7 +127,7 @@ SIGNATURES = {
                                _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp, _i64, _vp,
                                _i64, _vp, _i64, _vp]),
     "fg_render_back_workspace_bytes": (_i64, [_i32, _i32, _i32, _i64]),
-    "fg_render_back": (_i32, [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64,
+    "fg_render_back": (_i32, [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _i64,
                               _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "fg_mlp_linear": (_i32, [_i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fg_mlp_wgrad": (_i32, [_i64, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),

@@ -53,7 +53,7 @@ extern "C" int fg_set_option(const char* name, int value) {
 extern "C" {
 
 const char* fg_last_error(void) { return fg::g_err; }
-int fg_abi_version(void) { return 11; }
+int fg_abi_version(void) { return 12; }
 long long fg_launch_count(void) { return fg::g_launch_count.load(); }
 
 }  // extern "C"

@@ -125,6 +125,202 @@ __global__ void __launch_bounds__(256)
         }
 }
 
+// ---- steps 2 + 4 without a sort: ranked placement of the (splat, cell) pairs -----------------------------------------
+// The pairs only have to end up grouped by cell, in depth order inside a cell.  With at most RK_MAX_CELLS coarse cells
+// (one 1080p view: 510) that position can be COMPUTED instead of sorted for:
+//   bin_count_cells : CTA = chunk of RK_CHUNK consecutive depth-ordered slots; besides the corner increments it counts
+//                     the chunk's pairs per cell (shared-memory histogram) -> mat[chunk][cell]
+//   cell_scan       : per cell, exclusive prefix over the chunks (in place) and the cell totals; the last CTA to finish
+//                     scans the totals -> cell_offsets[n_cells + 1], Mc
+//   ranked_emit     : CTA = chunk again; a bitmap per (cell, warp) of the chunk's splats that touch the cell; position of
+//                     a pair = cell_offsets[cell] + mat[chunk][cell] + (set bits below this splat): depth order, exactly
+//                     what the stable sort by cell produced -- without keys, histogram, two onesweep passes, the scan over
+//                     C*N per-splat counts and the cell-offsets kernel (7 launches, 0.12 ms of 1.56 at cfg3).
+constexpr int RK_CHUNK = 512;
+constexpr int RK_WARPS = RK_CHUNK / 32;
+constexpr int RK_MAX_CELLS = 1024;  // = threads of the totals scan; shared memory of ranked_emit: 128 B per cell
+
+struct RankedLayout {
+    size_t mat, total, counter, bytes;
+    long long n_chunks;
+    int n_cells;
+};
+static RankedLayout ranked_layout(int C, int N, int tile_w, int tile_h) {
+    RankedLayout L;
+    const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
+    const long long cells = (long long)C * cw * chh;
+    L.n_cells = cells <= RK_MAX_CELLS ? (int)cells : 0;
+    L.n_chunks = ((long long)C * N + RK_CHUNK - 1) / RK_CHUNK;
+    size_t o = 0;
+    L.mat = o; o += ((size_t)L.n_chunks * L.n_cells * 4 + 255) & ~(size_t)255;
+    L.total = o; o += ((size_t)L.n_cells * 4 + 255) & ~(size_t)255;
+    L.counter = o; o += 256;
+    L.bytes = L.n_cells ? o : 0;
+    return L;
+}
+
+__global__ void __launch_bounds__(RK_CHUNK)
+    bin_count_cells_kernel(int N, long long total, const int32_t* __restrict__ order, const float2* __restrict__ means2d,
+                           const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
+                           int n_cells, int32_t* __restrict__ diff, int32_t* __restrict__ mat, int32_t* __restrict__ counter) {
+    extern __shared__ int s_cnt[];
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const long long slot0 = (long long)blockIdx.x * RK_CHUNK;
+    if (blockIdx.x == 0 && tid == 0) *counter = 0;  // cell_scan's "last CTA" ticket
+    if (order[slot0] < 0) return;  // the whole chunk lies past the visible splats (fg_depth_sort_visible leaves -1 there)
+    for (int i = tid; i < n_cells; i += RK_CHUNK) s_cnt[i] = 0;
+    __syncthreads();
+    const long long slot = slot0 + tid;
+    const long long idx = slot < total ? order[slot] : -1;
+    if (idx >= 0) {
+        const int r = radii[idx];
+        if (r > 0) {
+            const float2 m = means2d[idx];
+            const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
+            if (t.x1 > t.x0 && t.y1 > t.y0) {
+                const int cam = (int)(idx / N);
+                int32_t* g = diff + cam * (long long)(tile_h + 1) * (tile_w + 1);
+                const int W1 = tile_w + 1;
+                atomicAdd(g + t.y0 * W1 + t.x0, 1);
+                atomicAdd(g + t.y0 * W1 + t.x1, -1);
+                atomicAdd(g + t.y1 * W1 + t.x0, -1);
+                atomicAdd(g + t.y1 * W1 + t.x1, 1);
+                const int cx0 = t.x0 >> CK_SHIFT, cx1 = (t.x1 + CK - 1) >> CK_SHIFT;
+                const int cy0 = t.y0 >> CK_SHIFT, cy1 = (t.y1 + CK - 1) >> CK_SHIFT;
+                int* c = s_cnt + cam * cw * chh;
+                for (int y = cy0; y < cy1; ++y)
+                    for (int x = cx0; x < cx1; ++x) atomicAdd(c + y * cw + x, 1);
+            }
+        }
+    }
+    __syncthreads();
+    int32_t* row = mat + (long long)blockIdx.x * n_cells;
+    for (int i = tid; i < n_cells; i += RK_CHUNK) row[i] = s_cnt[i];
+}
+
+// grid = ceil(n_cells / 32) CTAs of 32 x 32 threads: lane = cell, row = a 1/32 share of the active chunks
+__global__ void __launch_bounds__(1024)
+    cell_scan_kernel(const int64_t* __restrict__ n_visible, int n_cells, int32_t* __restrict__ mat,
+                     int32_t* __restrict__ cell_total, int32_t* __restrict__ counter, int32_t* __restrict__ cell_offsets,
+                     int64_t* __restrict__ n_coarse) {
+    __shared__ int s_part[32][33];
+    __shared__ int s_warp[32];
+    __shared__ bool s_last;
+    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
+    const int cell = blockIdx.x * 32 + lane;
+    const long long n_act = (*n_visible + RK_CHUNK - 1) / RK_CHUNK;
+    const long long per = (n_act + 31) / 32;
+    const long long k0 = min(row * per, n_act), k1 = min(k0 + per, n_act);
+    int sum = 0;
+    if (cell < n_cells)
+        for (long long k = k0; k < k1; ++k) sum += mat[k * n_cells + cell];
+    s_part[row][lane] = sum;
+    __syncthreads();
+    if (row == 0) {
+        int run = 0;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int c = s_part[r][lane];
+            s_part[r][lane] = run;
+            run += c;
+        }
+        if (cell < n_cells) cell_total[cell] = run;
+    }
+    __syncthreads();
+    if (cell < n_cells) {
+        int run = s_part[row][lane];
+        for (long long k = k0; k < k1; ++k) {
+            const int c = mat[k * n_cells + cell];
+            mat[k * n_cells + cell] = run;
+            run += c;
+        }
+    }
+    // the last CTA to get here turns the cell totals into cell offsets
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    int v = tid < n_cells ? ((const volatile int32_t*)cell_total)[tid] : 0;
+    const int mine = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    if (lane == 31) s_warp[row] = v;
+    __syncthreads();
+    if (row == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += o;
+        }
+        s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int excl = v - mine + (row ? s_warp[row - 1] : 0);
+    if (tid < n_cells) cell_offsets[tid] = excl;
+    if (tid == 1023) {
+        cell_offsets[n_cells] = excl + mine;
+        *n_coarse = excl + mine;
+    }
+}
+
+__global__ void __launch_bounds__(RK_CHUNK)
+    ranked_emit_kernel(int N, long long total, const int32_t* __restrict__ order, const float2* __restrict__ means2d,
+                       const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh, int n_cells,
+                       const int32_t* __restrict__ mat, const int32_t* __restrict__ cell_offsets,
+                       int32_t* __restrict__ vals) {
+    extern __shared__ unsigned s_rk[];
+    pdl_wait();
+    unsigned* bm = s_rk;                                   // [RK_WARPS][n_cells]: splats (lanes) of warp w touching the cell
+    int* pre = (int*)(s_rk + (size_t)RK_WARPS * n_cells);  // [RK_WARPS][n_cells]: position of warp w's first pair in the cell
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long slot0 = (long long)blockIdx.x * RK_CHUNK;
+    if (order[slot0] < 0) return;
+    for (int i = tid; i < RK_WARPS * n_cells; i += RK_CHUNK) bm[i] = 0;
+    __syncthreads();
+    const long long slot = slot0 + tid;
+    const long long idx = slot < total ? order[slot] : -1;
+    int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0, cell0 = 0;
+    if (idx >= 0) {
+        const int r = radii[idx];
+        if (r > 0) {
+            const float2 m = means2d[idx];
+            const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
+            if (t.x1 > t.x0 && t.y1 > t.y0) {
+                cx0 = t.x0 >> CK_SHIFT; cx1 = (t.x1 + CK - 1) >> CK_SHIFT;
+                cy0 = t.y0 >> CK_SHIFT; cy1 = (t.y1 + CK - 1) >> CK_SHIFT;
+                cell0 = (int)(idx / N) * cw * chh + warp * n_cells;
+            }
+        }
+    }
+    for (int y = cy0; y < cy1; ++y)
+        for (int x = cx0; x < cx1; ++x) atomicOr(bm + cell0 + y * cw + x, 1u << lane);
+    __syncthreads();
+    const int32_t* row = mat + (long long)blockIdx.x * n_cells;
+    for (int cell = tid; cell < n_cells; cell += RK_CHUNK) {
+        int run = cell_offsets[cell] + row[cell];
+#pragma unroll
+        for (int w = 0; w < RK_WARPS; ++w) {
+            pre[w * n_cells + cell] = run;
+            run += __popc(bm[w * n_cells + cell]);
+        }
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1;
+    for (int y = cy0; y < cy1; ++y)
+        for (int x = cx0; x < cx1; ++x) {
+            const int c = cell0 + y * cw + x;
+            vals[pre[c] + __popc(bm[c] & lt)] = (int32_t)idx;
+        }
+}
+
 // ---- step 5 -------------------------------------------------------------------------------
 // CTA = coarse cell.  Chunks of FB_THREADS list entries (thread = entry); for each of the cell's 16
 // tiles the entries that overlap it are ranked with a ballot + per-warp prefix and appended to
@@ -276,6 +472,65 @@ extern "C" int fg_bin_coarse_emit(int C, int N, const int32_t* order, const floa
     const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
     FG_LAUNCH(coarse_emit_kernel, ceil_div(total, 256), 256, 0, stream, C, N, total, order, (const float2*)means2d,
               radii, coarse_off, tile_size, tile_w, tile_h, cw, chh, coarse_keys, coarse_vals);
+    return FG_OK;
+}
+
+extern "C" int64_t fg_bin_ranked_workspace_bytes(int C, int N, int tile_w, int tile_h) {
+    if (C < 1 || N < 0 || tile_w < 1 || tile_h < 1) return 0;
+    return (int64_t)ranked_layout(C, N, tile_w, tile_h).bytes;
+}
+
+extern "C" int fg_bin_count_cells(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
+                                  int tile_size, int tile_w, int tile_h, int32_t* diff_grid, void* ranked_workspace,
+                                  int64_t ranked_workspace_bytes, void* stream) {
+    FG_REQUIRE(C >= 1 && N >= 0 && (long long)C * N < (1ll << 31), "bad C/N");
+    FG_REQUIRE(diff_grid, "diff_grid must not be NULL");
+    const RankedLayout L = ranked_layout(C, N, tile_w, tile_h);
+    FG_REQUIRE(L.n_cells > 0, "too many coarse cells for the ranked path (fg_bin_ranked_workspace_bytes == 0)");
+    FG_REQUIRE(ranked_workspace && (size_t)ranked_workspace_bytes >= L.bytes, "ranked workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    FG_CUDA(cudaMemsetAsync(diff_grid, 0, sizeof(int32_t) * (size_t)C * (tile_h + 1) * (tile_w + 1), st));
+    unsigned char* ws = (unsigned char*)ranked_workspace;
+    if (N == 0) {
+        FG_CUDA(cudaMemsetAsync(ws + L.counter, 0, 4, st));
+        return FG_OK;
+    }
+    FG_REQUIRE(order && means2d && radii, "NULL pointer");
+    const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
+    FG_LAUNCH(bin_count_cells_kernel, (unsigned)L.n_chunks, RK_CHUNK, (size_t)L.n_cells * 4, st, N, (long long)C * N, order,
+              (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, L.n_cells, diff_grid,
+              (int32_t*)(ws + L.mat), (int32_t*)(ws + L.counter));
+    return FG_OK;
+}
+
+extern "C" int fg_bin_cell_scan(int C, int N, int tile_w, int tile_h, const int64_t* n_visible, void* ranked_workspace,
+                                int64_t ranked_workspace_bytes, int32_t* cell_offsets, int64_t* n_coarse, void* stream) {
+    const RankedLayout L = ranked_layout(C, N, tile_w, tile_h);
+    FG_REQUIRE(L.n_cells > 0, "too many coarse cells for the ranked path");
+    FG_REQUIRE(ranked_workspace && (size_t)ranked_workspace_bytes >= L.bytes, "ranked workspace too small");
+    FG_REQUIRE(n_visible && cell_offsets && n_coarse, "NULL pointer");
+    unsigned char* ws = (unsigned char*)ranked_workspace;
+    FG_LAUNCH(cell_scan_kernel, (L.n_cells + 31) / 32, 1024, 0, stream, n_visible, L.n_cells, (int32_t*)(ws + L.mat),
+              (int32_t*)(ws + L.total), (int32_t*)(ws + L.counter), cell_offsets, n_coarse);
+    return FG_OK;
+}
+
+extern "C" int fg_bin_ranked_emit(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
+                                  int tile_size, int tile_w, int tile_h, const void* ranked_workspace,
+                                  int64_t ranked_workspace_bytes, const int32_t* cell_offsets, int32_t* coarse_vals,
+                                  void* stream) {
+    const RankedLayout L = ranked_layout(C, N, tile_w, tile_h);
+    FG_REQUIRE(L.n_cells > 0, "too many coarse cells for the ranked path");
+    FG_REQUIRE(ranked_workspace && (size_t)ranked_workspace_bytes >= L.bytes, "ranked workspace too small");
+    if (N == 0) return FG_OK;
+    FG_REQUIRE(order && means2d && radii && cell_offsets && coarse_vals, "NULL pointer");
+    const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
+    const size_t smem = (size_t)2 * RK_WARPS * L.n_cells * 4;
+    FG_CUDA(cudaFuncSetAttribute(ranked_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned char* ws = (const unsigned char*)ranked_workspace;
+    FG_LAUNCH(ranked_emit_kernel, (unsigned)L.n_chunks, RK_CHUNK, smem, stream, N, (long long)C * N, order,
+              (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, L.n_cells, (const int32_t*)(ws + L.mat),
+              cell_offsets, coarse_vals);
     return FG_OK;
 }
 

@@ -1,7 +1,8 @@
 // Host-side orchestration of the forward pass in two C calls (the native runtime of the path):
-//   fg_render_front: projection -> depth sort -> bin count -> tile scan -> coarse scan -> the ONE host
+//   fg_render_front: projection -> depth sort -> bin count -> tile scan -> coarse (cell) scan -> the ONE host
 //                    sync (M = tile intersections, Mc = coarse pairs size the list buffers)
-//   fg_render_back : coarse emit -> coarse sort -> cell offsets -> fine binning -> compositing forward
+//   fg_render_back : coarse pairs by cell (ranked placement, or emit -> sort -> cell offsets when there are more than
+//                    1024 coarse cells) -> fine binning -> compositing forward
 // Same kernels as the granular entry points (which stay for tests, the other list-building modes
 // and per-stage timing); what this removes is ~10 Python/ctypes round trips and a dozen temporary
 // allocations per step: on the 10 k-Gaussian cfg1 scene a step is host-bound (1.0 ms against
@@ -13,7 +14,8 @@ namespace fg {
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct FrontLayout {
-    size_t diff, ccnt, n2, scan, tscan, sort, total;
+    size_t diff, ccnt, n2, scan, tscan, sort, rank, coff, total;
+    size_t rank_bytes;  // > 0: the ranked placement of binning.cu applies (few enough coarse cells)
 };
 static FrontLayout front_layout(int C, int N, int tile_w, int tile_h) {
     const size_t total = (size_t)C * N;
@@ -25,8 +27,14 @@ static FrontLayout front_layout(int C, int N, int tile_w, int tile_h) {
     L.scan = o; o += al((size_t)fg_scan_workspace_bytes((int64_t)total));
     L.tscan = o; o += al((size_t)fg_bin_tile_scan_workspace_bytes(C, tile_w, tile_h));
     L.sort = o; o += al((size_t)fg_depth_sort_workspace_bytes((int64_t)total));
+    // read by fg_render_back: the (chunk, cell) prefix matrix and the cell offsets of the ranked placement
+    L.rank_bytes = (size_t)fg_bin_ranked_workspace_bytes(C, N, tile_w, tile_h);
+    L.rank = o; o += al(L.rank_bytes);
+    int cw = 0, chh = 0;
+    fg_bin_coarse_dims(tile_w, tile_h, &cw, &chh);
+    L.coff = o; o += al(L.rank_bytes ? ((size_t)C * cw * chh + 1) * 4 : 0);
     L.total = o;
-    return L;
+        return L;
 }
 
 struct BackLayout {
@@ -134,17 +142,26 @@ extern "C" int fg_render_front(int C, int N, const float* means, const float* qu
         return e;
     // depth order of the visible splats (culled ones are dropped by the first radix pass); n2[2] = their number
     int64_t* n_vis = (int64_t*)(ws + L.n2) + 2;
-    if ((e = fg_depth_sort_visible(total, depths, tiles_per_gauss, order, n_vis, ws + L.sort, (int64_t)(L.total - L.sort), stream)))
+    if ((e = fg_depth_sort_visible(total, depths, tiles_per_gauss, order, n_vis, ws + L.sort, (int64_t)(L.rank - L.sort), stream)))
         return e;
     int64_t* n2 = (int64_t*)(ws + L.n2);
-    if ((e = fg_bin_count(C, N, order, means2d, radii, tile_size, tile_w, tile_h, (int32_t*)(ws + L.diff),
-                          (int32_t*)(ws + L.ccnt), stream)))
+    const bool ranked = L.rank_bytes > 0;
+    if (ranked) {  // few coarse cells: the (splat, cell) pairs are placed by rank, never sorted (binning.cu)
+        if ((e = fg_bin_count_cells(C, N, order, means2d, radii, tile_size, tile_w, tile_h, (int32_t*)(ws + L.diff),
+                                    ws + L.rank, (int64_t)L.rank_bytes, stream)))
+            return e;
+    } else if ((e = fg_bin_count(C, N, order, means2d, radii, tile_size, tile_w, tile_h, (int32_t*)(ws + L.diff),
+                                 (int32_t*)(ws + L.ccnt), stream)))
         return e;
     if ((e = fg_bin_tile_scan(C, tile_w, tile_h, (int32_t*)(ws + L.diff), isect_offsets, n2, ws + L.tscan,
                               (int64_t)(L.sort - L.tscan), stream)))
         return e;
-    if ((e = fg_exclusive_scan_i32(total, (const int32_t*)(ws + L.ccnt), coarse_off, n2 + 1, ws + L.scan,
-                                   (int64_t)(L.tscan - L.scan), stream)))
+    if (ranked) {
+        if ((e = fg_bin_cell_scan(C, N, tile_w, tile_h, n_vis, ws + L.rank, (int64_t)L.rank_bytes, (int32_t*)(ws + L.coff),
+                                  n2 + 1, stream)))
+            return e;
+    } else if ((e = fg_exclusive_scan_i32(total, (const int32_t*)(ws + L.ccnt), coarse_off, n2 + 1, ws + L.scan,
+                                          (int64_t)(L.tscan - L.scan), stream)))
         return e;
     CountSlot* slot = count_slot();
     FG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
@@ -159,8 +176,9 @@ extern "C" int fg_render_front(int C, int N, const float* means, const float* qu
     if (flatten_ids && back_workspace && pin[0] <= flatten_capacity &&
         fg_render_back_workspace_bytes(C, tile_w, tile_h, pin[1]) <= back_workspace_bytes) {
         if ((e = fg_render_back(C, N, pin[0], pin[1], order, coarse_off, means2d, radii, tile_size, isect_offsets,
-                                flatten_ids, back_workspace, back_workspace_bytes, 0, width, height, nullptr, nullptr,
-                                nullptr, nullptr, nullptr, -1, 0, -1, 0, nullptr, nullptr, nullptr, nullptr, stream)))
+                                flatten_ids, back_workspace, back_workspace_bytes, workspace, workspace_bytes, 0, width,
+                                height, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 0, -1, 0, nullptr, nullptr, nullptr,
+                                nullptr, stream)))
             return e;
         counts_host[2] = 1;
     }
@@ -174,7 +192,8 @@ extern "C" int64_t fg_render_back_workspace_bytes(int C, int tile_w, int tile_h,
 extern "C" int fg_render_back(int C, int N, int64_t n_isects, int64_t n_coarse, const int32_t* order,
                               const int32_t* coarse_off, const float* means2d, const int32_t* radii, int tile_size,
                               const int32_t* isect_offsets, int32_t* flatten_ids, void* workspace,
-                              int64_t workspace_bytes, int CH, int width, int height, const float* conics,
+                              int64_t workspace_bytes, const void* front_workspace, int64_t front_workspace_bytes, int CH,
+                              int width, int height, const float* conics,
                               const float* feat, const float* opacities, const float* backgrounds,
                               const float* flow_affine, int flow_ch0, int split, int ed_channel, int opac_shared,
                               float* render, float* render2, float* alphas, int32_t* last_ids, void* stream) {
@@ -192,21 +211,34 @@ extern "C" int fg_render_back(int C, int N, int64_t n_isects, int64_t n_coarse, 
         int32_t* cv = (int32_t*)(ws + L.cv);
         uint32_t* ck2 = (uint32_t*)(ws + L.ck2);
         int32_t* cv2 = (int32_t*)(ws + L.cv2);
-        if ((e = fg_bin_coarse_emit(C, N, order, means2d, radii, coarse_off, tile_size, tile_w, tile_h, ck, cv, stream)))
-            return e;
-        int bits = 1;
-        while ((1ll << bits) < (long long)C * cw * chh) ++bits;
-        int sel = 0;
-        if ((e = fg_radix_sort_pairs_u32_u32(n_coarse, ck, (uint32_t*)cv, ck2, (uint32_t*)cv2, bits, ws + L.sort,
-                                             (int64_t)(L.total - L.sort), &sel, stream)))
-            return e;
-        const uint32_t* ks = sel ? ck2 : ck;
-        const int32_t* vs = sel ? cv2 : cv;
-        int32_t* coff = (int32_t*)(ws + L.coff);
-        if ((e = fg_isect_offsets_tiles(n_coarse, ks, C, cw, chh, coff, stream))) return e;
-        if ((e = fg_bin_fine(C, N, n_coarse, coff, vs, means2d, radii, tile_size, tile_w, tile_h, isect_offsets,
-                             flatten_ids, stream)))
-            return e;
+        const FrontLayout F = front_layout(C, N, tile_w, tile_h);
+        if (F.rank_bytes > 0) {  // ranked placement: the front call left the prefix matrix and the cell offsets in its workspace
+            FG_REQUIRE(front_workspace && (size_t)front_workspace_bytes >= F.total,
+                       "fg_render_back needs the workspace fg_render_front ran with");
+            const unsigned char* fws = (const unsigned char*)front_workspace;
+            if ((e = fg_bin_ranked_emit(C, N, order, means2d, radii, tile_size, tile_w, tile_h, fws + F.rank,
+                                        (int64_t)F.rank_bytes, (const int32_t*)(fws + F.coff), cv, stream)))
+                return e;
+            if ((e = fg_bin_fine(C, N, n_coarse, (const int32_t*)(fws + F.coff), cv, means2d, radii, tile_size, tile_w,
+                                 tile_h, isect_offsets, flatten_ids, stream)))
+                return e;
+        } else {
+            if ((e = fg_bin_coarse_emit(C, N, order, means2d, radii, coarse_off, tile_size, tile_w, tile_h, ck, cv, stream)))
+                return e;
+            int bits = 1;
+            while ((1ll << bits) < (long long)C * cw * chh) ++bits;
+            int sel = 0;
+            if ((e = fg_radix_sort_pairs_u32_u32(n_coarse, ck, (uint32_t*)cv, ck2, (uint32_t*)cv2, bits, ws + L.sort,
+                                                 (int64_t)(L.total - L.sort), &sel, stream)))
+                return e;
+            const uint32_t* ks = sel ? ck2 : ck;
+            const int32_t* vs = sel ? cv2 : cv;
+            int32_t* coff = (int32_t*)(ws + L.coff);
+            if ((e = fg_isect_offsets_tiles(n_coarse, ks, C, cw, chh, coff, stream))) return e;
+            if ((e = fg_bin_fine(C, N, n_coarse, coff, vs, means2d, radii, tile_size, tile_w, tile_h, isect_offsets,
+                                 flatten_ids, stream)))
+                return e;
+        }
     }
     if (CH == 0) return FG_OK;  // lists only: the caller composites later with fg_rasterize_fwd
     return fg_rasterize_fwd(C, N, CH, width, height, tile_size, means2d, conics, feat, opacities, backgrounds,

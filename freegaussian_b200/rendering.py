@@ -30,6 +30,7 @@ from ._lib import check, ptr
 MAX_CH = 8  # FG_MAX_CHANNELS
 FUSED_CALLS = True  # forward pass through fg_render_front / fg_render_back (two C calls) when possible
 SORT_MODE = "binned"  # "binned" | "two_level" | "key64" (the reference's literal 64-bit key sort); same lists
+BIN_RANKED = True  # granular "binned" mode: ranked placement of the coarse pairs when it applies (False: emit + sort, for tests)
 
 
 def _stream() -> int:
@@ -237,7 +238,8 @@ class _Project(torch.autograd.Function):
                 flatten_ids = torch.empty(M, dtype=torch.int32, device=dev)
                 ws2 = _ws.get("back", L.fg_render_back_workspace_bytes(C, tile_w, tile_h, Mc), dev)
                 check(L.fg_render_back(C, N, M, Mc, ptr(order), ptr(coarse_off), ptr(means2d), ptr(radii),
-                                       cfg["tile_size"], ptr(isect_offsets), ptr(flatten_ids), ptr(ws2), ws2.numel(), 0,
+                                       cfg["tile_size"], ptr(isect_offsets), ptr(flatten_ids), ptr(ws2), ws2.numel(),
+                                       ptr(ws), ws.numel(), 0,
                                        cfg["width"], cfg["height"], None, None, None, None, None, -1, 0, -1, 0, None,
                                        None, None, None, _stream()))
             cfg["_front"] = dict(isect_offsets=isect_offsets, flatten_ids=flatten_ids, M=M, Mc=Mc, tile_w=tile_w,
@@ -459,28 +461,45 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
         check(L.fg_bin_coarse_dims(tile_w, tile_h, ctypes.byref(cw_), ctypes.byref(ch_)))
         cw, chh = cw_.value, ch_.value
         n2 = torch.empty(2, dtype=torch.int64, device=dev)
+        # few coarse cells (one or two 1080p views): the (splat, cell) pairs are placed by rank, never sorted
+        rank_bytes = L.fg_bin_ranked_workspace_bytes(C, N, tile_w, tile_h) if BIN_RANKED else 0
         with _stage("bin_count"):
             diff = torch.empty(C * (tile_h + 1) * (tile_w + 1), **i32)
-            coarse_cnt = torch.empty(total, **i32)
-            check(L.fg_bin_count(C, N, ptr(order), ptr(means2d), ptr(radii), tile_size, tile_w, tile_h, ptr(diff),
-                                 ptr(coarse_cnt), st))
+            if rank_bytes:
+                wsr = _ws.get("bin_ranked", rank_bytes, dev)
+                check(L.fg_bin_count_cells(C, N, ptr(order), ptr(means2d), ptr(radii), tile_size, tile_w, tile_h, ptr(diff),
+                                           ptr(wsr), wsr.numel(), st))
+            else:
+                coarse_cnt = torch.empty(total, **i32)
+                check(L.fg_bin_count(C, N, ptr(order), ptr(means2d), ptr(radii), tile_size, tile_w, tile_h, ptr(diff),
+                                     ptr(coarse_cnt), st))
             ws2 = _ws.get("tile_scan", L.fg_bin_tile_scan_workspace_bytes(C, tile_w, tile_h), dev)
             check(L.fg_bin_tile_scan(C, tile_w, tile_h, ptr(diff), ptr(isect_offsets), n2[0:1].data_ptr(), ptr(ws2),
                                      ws2.numel(), st))
-            check(L.fg_exclusive_scan_i32(total, ptr(coarse_cnt), ptr(offsets), n2[1:2].data_ptr(), ptr(ws),
-                                          ws.numel(), st))
+            if rank_bytes:
+                coarse_offsets = torch.empty(C * cw * chh + 1, **i32)
+                check(L.fg_bin_cell_scan(C, N, tile_w, tile_h, ptr(n_vis_dev), ptr(wsr), wsr.numel(), ptr(coarse_offsets),
+                                         n2[1:2].data_ptr(), st))
+            else:
+                check(L.fg_exclusive_scan_i32(total, ptr(coarse_cnt), ptr(offsets), n2[1:2].data_ptr(), ptr(ws),
+                                              ws.numel(), st))
         M, Mc = (int(v) for v in n2.tolist())  # the one host sync: sizes the list buffers
         assert M < 2**31, "too many tile intersections"
         fl = torch.empty(M, **i32)
         if M > 0:
             with _stage("coarse_sort"):
-                ck, cv = torch.empty(Mc, **i32), torch.empty(Mc, **i32)
-                check(L.fg_bin_coarse_emit(C, N, ptr(order), ptr(means2d), ptr(radii), ptr(offsets), tile_size,
-                                           tile_w, tile_h, ptr(ck), ptr(cv), st))
-                bits = max(1, int(math.ceil(math.log2(C * cw * chh))))
-                ck, cv = _sort_pairs(L, Mc, ck, cv, torch.empty_like(ck), torch.empty_like(cv), bits, dev, st, False)
-                coarse_offsets = torch.empty(C * cw * chh, **i32)
-                check(L.fg_isect_offsets_tiles(Mc, ptr(ck), C, cw, chh, ptr(coarse_offsets), st))
+                cv = torch.empty(Mc, **i32)
+                if rank_bytes:
+                    check(L.fg_bin_ranked_emit(C, N, ptr(order), ptr(means2d), ptr(radii), tile_size, tile_w, tile_h,
+                                               ptr(wsr), wsr.numel(), ptr(coarse_offsets), ptr(cv), st))
+                else:
+                    ck = torch.empty(Mc, **i32)
+                    check(L.fg_bin_coarse_emit(C, N, ptr(order), ptr(means2d), ptr(radii), ptr(offsets), tile_size,
+                                               tile_w, tile_h, ptr(ck), ptr(cv), st))
+                    bits = max(1, int(math.ceil(math.log2(C * cw * chh))))
+                    ck, cv = _sort_pairs(L, Mc, ck, cv, torch.empty_like(ck), torch.empty_like(cv), bits, dev, st, False)
+                    coarse_offsets = torch.empty(C * cw * chh, **i32)
+                    check(L.fg_isect_offsets_tiles(Mc, ptr(ck), C, cw, chh, ptr(coarse_offsets), st))
             with _stage("fine_bin"):
                 check(L.fg_bin_fine(C, N, Mc, ptr(coarse_offsets), ptr(cv), ptr(means2d), ptr(radii), tile_size,
                                     tile_w, tile_h, ptr(isect_offsets), ptr(fl), st))

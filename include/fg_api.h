@@ -197,6 +197,22 @@ int fg_bin_tile_scan(int C, int tile_w, int tile_h, int32_t* diff_grid, int32_t*
 int fg_bin_coarse_emit(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii,
                        const int32_t* coarse_off, int tile_size, int tile_w, int tile_h,
                        uint32_t* coarse_keys, int32_t* coarse_vals, void* stream);
+/* Ranked placement of the (splat, cell) pairs: the same cell-grouped, depth-ordered `coarse_vals` as fg_bin_coarse_emit
+ * followed by a stable sort by cell, computed without a sort.  Applies when C * cw * ch <= 1024 coarse cells (one or two
+ * 1080p views); fg_bin_ranked_workspace_bytes returns 0 otherwise and the emit + sort path is the one to use.
+ *   fg_bin_count_cells  fg_bin_count's corner increments + per (chunk of 512 depth-ordered slots, cell) pair counts
+ *   fg_bin_cell_scan    per cell: exclusive prefix over the chunks; cell_offsets[n_cells + 1] (= fg_bin_fine's
+ *                       coarse_offsets), *n_coarse = Mc (device).  n_visible: device count from fg_depth_sort_visible
+ *   fg_bin_ranked_emit  coarse_vals[Mc]: position = cell offset + chunk prefix + rank inside the chunk (bitmaps) */
+int64_t fg_bin_ranked_workspace_bytes(int C, int N, int tile_w, int tile_h);
+int fg_bin_count_cells(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii, int tile_size,
+                       int tile_w, int tile_h, int32_t* diff_grid, void* ranked_workspace, int64_t ranked_workspace_bytes,
+                       void* stream);
+int fg_bin_cell_scan(int C, int N, int tile_w, int tile_h, const int64_t* n_visible, void* ranked_workspace,
+                     int64_t ranked_workspace_bytes, int32_t* cell_offsets, int64_t* n_coarse, void* stream);
+int fg_bin_ranked_emit(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii, int tile_size,
+                       int tile_w, int tile_h, const void* ranked_workspace, int64_t ranked_workspace_bytes,
+                       const int32_t* cell_offsets, int32_t* coarse_vals, void* stream);
 int fg_bin_fine(int C, int N, int64_t n_coarse, const int32_t* coarse_offsets,
                 const int32_t* coarse_vals_sorted, const float* means2d, const int32_t* radii, int tile_size,
                 int tile_w, int tile_h, const int32_t* isect_offsets, int32_t* flatten_ids, void* stream);
@@ -247,8 +263,11 @@ int fg_densify_stats(int C, int N, const int32_t* radii, const float* absgrad, f
  * passes a flatten_ids buffer of a guessed capacity >= M (and a back workspace large enough for Mc), the
  * list-building half of fg_render_back is enqueued right here, without a round trip through the host mirror
  * (pass NULL / 0 to opt out).  Otherwise the caller allocates flatten_ids[M] and calls
- * fg_render_back = coarse emit + sort + cell offsets + fg_bin_fine + fg_rasterize_fwd.
- * Arguments are those of the granular entry points; `order`, `coarse_off` are [C*N] int32.  * fg_render_back with CH == 0 builds the tile lists only (flatten_ids) and skips compositing: the host
+ * fg_render_back = coarse pairs grouped by cell (ranked placement when it applies, else emit + sort + cell offsets) +
+ * fg_bin_fine + fg_rasterize_fwd.  `front_workspace` is the workspace fg_render_front ran with, untouched since (the ranked
+ * placement reads its prefix matrix and cell offsets from it).
+ * Arguments are those of the granular entry points; `order`, `coarse_off` are [C*N] int32.
+ * fg_render_back with CH == 0 builds the tile lists only (flatten_ids) and skips compositing: the host
  * mirror calls it right after the sync so the GPU is busy again while Python assembles the compositing call.
  */
 int64_t fg_render_front_workspace_bytes(int C, int N, int tile_w, int tile_h);
@@ -266,6 +285,7 @@ int64_t fg_render_back_workspace_bytes(int C, int tile_w, int tile_h, int64_t n_
 int fg_render_back(int C, int N, int64_t n_isects, int64_t n_coarse, const int32_t* order,
                    const int32_t* coarse_off, const float* means2d, const int32_t* radii, int tile_size,
                    const int32_t* isect_offsets, int32_t* flatten_ids, void* workspace, int64_t workspace_bytes,
+                   const void* front_workspace, int64_t front_workspace_bytes,
                    int CH, int width, int height, const float* conics, const float* feat, const float* opacities,
                    const float* backgrounds, const float* flow_affine, int flow_ch0, int split, int ed_channel,
                    int opac_shared, float* render, float* render2, float* alphas, int32_t* last_ids, void* stream);

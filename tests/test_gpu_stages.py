@@ -59,6 +59,19 @@ def test_projection_matches_oracle(L, sh_degree, recipe):
     assert torch.equal(tiles, ((x1 - x0) * (y1 - y0)).to(torch.int32))
 
 
+def _isect(mode, *args):
+    """isect_tiles in one of its list-building modes; "binned" places the coarse (splat, cell) pairs by rank when the call
+    has few enough coarse cells, "binned_sorted" forces the emit + stable-sort variant (what larger calls use)."""
+    from freegaussian_b200 import rendering
+    if mode != "binned_sorted":
+        return rendering.isect_tiles(*args, mode=mode)
+    rendering.BIN_RANKED = False
+    try:
+        return rendering.isect_tiles(*args, mode="binned")
+    finally:
+        rendering.BIN_RANKED = True
+
+
 def test_isect_sort_offsets_bit_exact(L):
     """Same projected tensors into both implementations: keys, order and tile ranges must be identical."""
     from freegaussian_b200.rendering import isect_tiles, isect_ids_from_tiles
@@ -71,8 +84,8 @@ def test_isect_sort_offsets_bit_exact(L):
         r_offs = O.isect_offset_encode(r_ids, views, tw, th)
         assert torch.equal(tpg, tiles)
         assert r_ids.numel() > 1000
-        for mode in ("key64", "two_level", "binned"):
-            ids, flat, offs, tk = isect_tiles(m2d.cuda(), radii.cuda(), dep.cuda(), tiles.cuda(), 16, tw, th, mode=mode)
+        for mode in ("key64", "two_level", "binned", "binned_sorted"):
+            ids, flat, offs, tk = _isect(mode, m2d.cuda(), radii.cuda(), dep.cuda(), tiles.cuda(), 16, tw, th)
             if ids is None and tk is not None:
                 ids = isect_ids_from_tiles(tk, flat, dep.cuda(), tw, th)
             if ids is not None:
@@ -189,7 +202,8 @@ def test_densify_stats_kernel_matches_reference_formula(L):
     assert torch.allclose(a.max_2Dsize.cpu(), b.max_2Dsize, rtol=1e-6)
 
 
-@pytest.mark.parametrize("seed,C,W,H,n", [(0, 1, 50, 33, 3000), (1, 3, 333, 190, 20000), (2, 5, 1000, 37, 8000)])
+@pytest.mark.parametrize("seed,C,W,H,n", [(0, 1, 50, 33, 3000), (1, 3, 333, 190, 20000), (2, 5, 1000, 37, 8000),
+                                          (3, 2, 1920, 1080, 6000)])  # the last: 1020 coarse cells, the ranked path's limit
 def test_tile_lists_adversarial(L, seed, C, W, H, n):
     """All three list builders against the oracle on hand-made splats: radii from 1 px to larger than the
     image, centres far outside, exact depth ties (tie-break = ascending c*N+n), ragged image sizes."""
@@ -209,8 +223,8 @@ def test_tile_lists_adversarial(L, seed, C, W, H, n):
     tpg, r_ids, r_flat = O.isect_tiles(m2d, radii, dep, 16, tw, th)
     r_offs = O.isect_offset_encode(r_ids, C, tw, th)
     assert torch.equal(tpg, tiles) and r_ids.numel() > 0
-    for mode in ("key64", "two_level", "binned"):
-        ids, flat, offs, tk = isect_tiles(m2d.cuda(), radii.cuda(), dep.cuda(), tiles.cuda(), 16, tw, th, mode=mode)
+    for mode in ("key64", "two_level", "binned", "binned_sorted"):
+        ids, flat, offs, tk = _isect(mode, m2d.cuda(), radii.cuda(), dep.cuda(), tiles.cuda(), 16, tw, th)
         assert torch.equal(flat.cpu(), r_flat), f"{mode}: list order differs"
         assert torch.equal(offs.cpu(), r_offs), f"{mode}: tile ranges differ"
         if ids is None and tk is not None:
