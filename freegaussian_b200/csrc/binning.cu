@@ -139,6 +139,23 @@ __global__ void __launch_bounds__(256)
 constexpr int RK_CHUNK = 512;
 constexpr int RK_WARPS = RK_CHUNK / 32;
 constexpr int RK_MAX_CELLS = 1024;  // = threads of the totals scan; shared memory of ranked_emit: 128 B per cell
+constexpr int FB_SEG = 1024;  // pairs per CTA of fine_bin_seg_kernel (= its threads)
+constexpr int RK_BIG = 8;  // a splat over more cells than this is walked by its whole warp (a full-screen splat touches every
+                           // cell: one thread looping over 510 of them would hold up the CTA's barriers)
+
+// cells [x0, x0 + w) x [y0, ..) of a cell rectangle with n cells, as the warp sees the rectangle of lane `src`
+struct WarpRect {
+    int x0, y0, w, n, base;
+};
+__device__ __forceinline__ WarpRect warp_rect(int src, int x0, int y0, int w, int n, int base) {
+    WarpRect r;
+    r.x0 = __shfl_sync(0xffffffffu, x0, src);
+    r.y0 = __shfl_sync(0xffffffffu, y0, src);
+    r.w = __shfl_sync(0xffffffffu, w, src);
+    r.n = __shfl_sync(0xffffffffu, n, src);
+    r.base = __shfl_sync(0xffffffffu, base, src);
+    return r;
+}
 
 struct RankedLayout {
     size_t mat, total, counter, bytes;
@@ -171,8 +188,10 @@ __global__ void __launch_bounds__(RK_CHUNK)
     if (order[slot0] < 0) return;  // the whole chunk lies past the visible splats (fg_depth_sort_visible leaves -1 there)
     for (int i = tid; i < n_cells; i += RK_CHUNK) s_cnt[i] = 0;
     __syncthreads();
+    const int lane = tid & 31;
     const long long slot = slot0 + tid;
     const long long idx = slot < total ? order[slot] : -1;
+    int cx0 = 0, cy0 = 0, cwid = 0, n_my = 0, base = 0;
     if (idx >= 0) {
         const int r = radii[idx];
         if (r > 0) {
@@ -186,13 +205,20 @@ __global__ void __launch_bounds__(RK_CHUNK)
                 atomicAdd(g + t.y0 * W1 + t.x1, -1);
                 atomicAdd(g + t.y1 * W1 + t.x0, -1);
                 atomicAdd(g + t.y1 * W1 + t.x1, 1);
-                const int cx0 = t.x0 >> CK_SHIFT, cx1 = (t.x1 + CK - 1) >> CK_SHIFT;
-                const int cy0 = t.y0 >> CK_SHIFT, cy1 = (t.y1 + CK - 1) >> CK_SHIFT;
-                int* c = s_cnt + cam * cw * chh;
-                for (int y = cy0; y < cy1; ++y)
-                    for (int x = cx0; x < cx1; ++x) atomicAdd(c + y * cw + x, 1);
+                cx0 = t.x0 >> CK_SHIFT;
+                cy0 = t.y0 >> CK_SHIFT;
+                cwid = ((t.x1 + CK - 1) >> CK_SHIFT) - cx0;
+                n_my = cwid * (((t.y1 + CK - 1) >> CK_SHIFT) - cy0);
+                base = cam * cw * chh;
             }
         }
+    }
+    const bool big = n_my > RK_BIG;
+    if (!big)
+        for (int i = 0; i < n_my; ++i) atomicAdd(s_cnt + base + (cy0 + i / cwid) * cw + cx0 + i % cwid, 1);
+    for (unsigned todo = __ballot_sync(0xffffffffu, big); todo; todo &= todo - 1) {
+        const WarpRect R = warp_rect(__ffs(todo) - 1, cx0, cy0, cwid, n_my, base);
+        for (int i = lane; i < R.n; i += 32) atomicAdd(s_cnt + R.base + (R.y0 + i / R.w) * cw + R.x0 + i % R.w, 1);
     }
     __syncthreads();
     int32_t* row = mat + (long long)blockIdx.x * n_cells;
@@ -269,6 +295,31 @@ __global__ void __launch_bounds__(1024)
         cell_offsets[n_cells] = excl + mine;
         *n_coarse = excl + mine;
     }
+    // second table, behind the first: where each cell's segments of FB_SEG pairs start in fine_bin_seg_kernel's grid
+    __syncthreads();
+    int sv = (mine + FB_SEG - 1) / FB_SEG;
+    const int smine = sv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, sv, d);
+        if (lane >= d) sv += o;
+    }
+    if (lane == 31) s_warp[row] = sv;
+    __syncthreads();
+    if (row == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += o;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int sexcl = sv - smine + (row ? s_warp[row - 1] : 0);
+    int32_t* seg_offsets = cell_offsets + n_cells + 1;
+    if (tid < n_cells) seg_offsets[tid] = sexcl;
+    if (tid == 1023) seg_offsets[n_cells] = sexcl + smine;
 }
 
 __global__ void __launch_bounds__(RK_CHUNK)
@@ -287,21 +338,30 @@ __global__ void __launch_bounds__(RK_CHUNK)
     __syncthreads();
     const long long slot = slot0 + tid;
     const long long idx = slot < total ? order[slot] : -1;
-    int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0, cell0 = 0;
+    int cx0 = 0, cy0 = 0, cwid = 0, n_my = 0, cell0 = 0;
     if (idx >= 0) {
         const int r = radii[idx];
         if (r > 0) {
             const float2 m = means2d[idx];
             const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
             if (t.x1 > t.x0 && t.y1 > t.y0) {
-                cx0 = t.x0 >> CK_SHIFT; cx1 = (t.x1 + CK - 1) >> CK_SHIFT;
-                cy0 = t.y0 >> CK_SHIFT; cy1 = (t.y1 + CK - 1) >> CK_SHIFT;
+                cx0 = t.x0 >> CK_SHIFT;
+                cy0 = t.y0 >> CK_SHIFT;
+                cwid = ((t.x1 + CK - 1) >> CK_SHIFT) - cx0;
+                n_my = cwid * (((t.y1 + CK - 1) >> CK_SHIFT) - cy0);
                 cell0 = (int)(idx / N) * cw * chh + warp * n_cells;
             }
         }
     }
-    for (int y = cy0; y < cy1; ++y)
-        for (int x = cx0; x < cx1; ++x) atomicOr(bm + cell0 + y * cw + x, 1u << lane);
+    const bool big = n_my > RK_BIG;
+    const unsigned big_lanes = __ballot_sync(0xffffffffu, big);
+    if (!big)
+        for (int i = 0; i < n_my; ++i) atomicOr(bm + cell0 + (cy0 + i / cwid) * cw + cx0 + i % cwid, 1u << lane);
+    for (unsigned todo = big_lanes; todo; todo &= todo - 1) {
+        const int src = __ffs(todo) - 1;
+        const WarpRect R = warp_rect(src, cx0, cy0, cwid, n_my, cell0);
+        for (int i = lane; i < R.n; i += 32) atomicOr(bm + R.base + (R.y0 + i / R.w) * cw + R.x0 + i % R.w, 1u << src);
+    }
     __syncthreads();
     const int32_t* row = mat + (long long)blockIdx.x * n_cells;
     for (int cell = tid; cell < n_cells; cell += RK_CHUNK) {
@@ -314,11 +374,21 @@ __global__ void __launch_bounds__(RK_CHUNK)
     }
     __syncthreads();
     const unsigned lt = (1u << lane) - 1;
-    for (int y = cy0; y < cy1; ++y)
-        for (int x = cx0; x < cx1; ++x) {
-            const int c = cell0 + y * cw + x;
+    if (!big)
+        for (int i = 0; i < n_my; ++i) {
+            const int c = cell0 + (cy0 + i / cwid) * cw + cx0 + i % cwid;
             vals[pre[c] + __popc(bm[c] & lt)] = (int32_t)idx;
         }
+    for (unsigned todo = big_lanes; todo; todo &= todo - 1) {
+        const int src = __ffs(todo) - 1;
+        const WarpRect R = warp_rect(src, cx0, cy0, cwid, n_my, cell0);
+        const int id = __shfl_sync(0xffffffffu, (int)idx, src);
+        const unsigned below = (1u << src) - 1;
+        for (int i = lane; i < R.n; i += 32) {
+            const int c = R.base + (R.y0 + i / R.w) * cw + R.x0 + i % R.w;
+            vals[pre[c] + __popc(bm[c] & below)] = id;
+        }
+    }
 }
 
 // ---- step 5 -------------------------------------------------------------------------------
@@ -414,6 +484,104 @@ __global__ void __launch_bounds__(FB_THREADS)
         }
         __syncthreads();
     }
+}
+
+
+// ---- step 5, one CTA per SEGMENT of a cell's list (ranked path) ------------------------------------------------------
+// fine_bin_kernel walks a cell's list chunk after chunk, so its time is the longest cell's (~25 sequential chunks at cfg3:
+// 0.106 ms for 16 us worth of traffic).  Here every FB_SEG-pair segment of every cell is its own CTA; the tile cursors a
+// segment starts from are the totals of the cell's earlier segments, obtained by decoupled look-back over 16 status words
+// per segment (flag in the top two bits, as in radix_sort.cu).  Segments are numbered cell after cell and a CTA takes the
+// next number from a ticket counter, so every predecessor of a running CTA is itself running or done.
+constexpr uint32_t FS_LOCAL = 1u << 30, FS_INCLUSIVE = 2u << 30, FS_FLAGS = 3u << 30;
+
+__global__ void __launch_bounds__(FB_SEG)
+    fine_bin_seg_kernel(int n_cells, const int32_t* __restrict__ cell_offsets /*[n_cells+1] ++ segment starts [n_cells+1]*/,
+                        const int32_t* __restrict__ coarse_vals, const float2* __restrict__ means2d,
+                        const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
+                        const int32_t* __restrict__ isect_offsets, int32_t* __restrict__ flatten_ids,
+                        int* __restrict__ ticket_counter, volatile uint32_t* status /*[segments][16], zeroed*/) {
+    constexpr int NT = CK * CK;
+    __shared__ int s_warp_cnt[FB_SEG / 32][NT];
+    __shared__ int s_base[NT];
+    __shared__ int s_seg[3];  // ticket, cell, segment inside the cell
+    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t* seg_offsets = cell_offsets + n_cells + 1;
+    if (tid == 0) {
+        const int t = atomicAdd(ticket_counter, 1);
+        int cell = -1;
+        if (t < seg_offsets[n_cells]) {  // last cell whose first segment is <= t (empty cells share their successor's start)
+            int lo = 0, hi = n_cells;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (seg_offsets[mid] <= t) lo = mid; else hi = mid;
+            }
+            cell = lo;
+        }
+        s_seg[0] = t; s_seg[1] = cell; s_seg[2] = cell >= 0 ? t - seg_offsets[cell] : 0;
+    }
+    __syncthreads();
+    const int ticket = s_seg[0], cell = s_seg[1], seg = s_seg[2];
+    if (cell < 0) return;  // the grid is sized from an upper bound of the segment count
+    const int cam = cell / (cw * chh);
+    const int crem = cell - cam * cw * chh;
+    const int cy = crem / cw, cx = crem - cy * cw;
+    const int e = cell_offsets[cell] + seg * FB_SEG + tid;
+    const int end = cell_offsets[cell + 1];
+    if (tid < NT) {
+        const int tx = cx * CK + (tid & (CK - 1)), ty = cy * CK + (tid >> CK_SHIFT);
+        s_base[tid] = (tx < tile_w && ty < tile_h) ? isect_offsets[(cam * tile_h + ty) * tile_w + tx] : 0;
+    }
+    unsigned mask = 0;  // bit (iy*CK + ix) set if the splat overlaps tile (cx*CK+ix, cy*CK+iy)
+    int id = 0;
+    if (e < end) {
+        id = coarse_vals[e];
+        const float2 m = means2d[id];
+        const TileRect t = tile_rect(m.x, m.y, radii[id], tile_size, tile_w, tile_h);
+        const int x0 = max(t.x0 - cx * CK, 0), x1 = min(t.x1 - cx * CK, CK);
+        const int y0 = max(t.y0 - cy * CK, 0), y1 = min(t.y1 - cy * CK, CK);
+        if (x1 > x0 && y1 > y0) {
+            const unsigned cols = ((1u << x1) - 1) & ~((1u << x0) - 1);  // CK bits
+            for (int y = y0; y < y1; ++y) mask |= cols << (y * CK);
+        }
+    }
+    unsigned bal[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        bal[t] = __ballot_sync(0xffffffffu, (mask >> t) & 1u);
+        if (lane == 0) s_warp_cnt[warp][t] = __popc(bal[t]);
+    }
+    __syncthreads();
+    if (tid < NT) {
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < FB_SEG / 32; ++w) {
+            const int c = s_warp_cnt[w][tid];
+            s_warp_cnt[w][tid] = run;
+            run += c;
+        }
+        volatile uint32_t* mine = status + (size_t)ticket * NT + tid;
+        uint32_t excl = 0;
+        if (seg == 0) {
+            *mine = FS_INCLUSIVE | (uint32_t)run;
+        } else {
+            *mine = FS_LOCAL | (uint32_t)run;
+            for (int t = ticket - 1;; --t) {  // t >= ticket - seg: the cell's first segment always publishes INCLUSIVE
+                uint32_t st;
+                do { st = status[(size_t)t * NT + tid]; } while ((st & FS_FLAGS) == 0);
+                excl += st & ~FS_FLAGS;
+                if ((st & FS_FLAGS) == FS_INCLUSIVE) break;
+            }
+            *mine = FS_INCLUSIVE | (excl + (uint32_t)run);
+        }
+        s_base[tid] += (int)excl;
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1;
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+        if ((mask >> t) & 1u) flatten_ids[s_base[t] + s_warp_cnt[warp][t] + __popc(bal[t] & lt)] = id;
 }
 
 }  // namespace fg
@@ -546,5 +714,32 @@ extern "C" int fg_bin_fine(int C, int N, int64_t n_coarse, const int32_t* coarse
     FG_LAUNCH(fine_bin_kernel, n_cells, FB_THREADS, 0, stream, N, coarse_offsets, (long long)n_coarse, n_cells,
               coarse_vals_sorted, (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, isect_offsets,
               flatten_ids);
+    return FG_OK;
+}
+
+extern "C" int64_t fg_bin_fine_segments_workspace_bytes(int C, int tile_w, int tile_h, int64_t n_coarse) {
+    const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
+    const int64_t segs = n_coarse / FB_SEG + (int64_t)C * cw * chh;  // upper bound: one partial segment per cell
+    return 256 + segs * (CK * CK) * 4;
+}
+
+extern "C" int fg_bin_fine_segments(int C, int N, int64_t n_coarse, const int32_t* cell_offsets,
+                                    const int32_t* coarse_vals_sorted, const float* means2d, const int32_t* radii,
+                                    int tile_size, int tile_w, int tile_h, const int32_t* isect_offsets,
+                                    int32_t* flatten_ids, void* workspace, int64_t workspace_bytes, void* stream) {
+    FG_REQUIRE(C >= 1 && n_coarse >= 0 && n_coarse < (1ll << 31), "bad arguments");
+    if (n_coarse == 0) return FG_OK;
+    FG_REQUIRE(cell_offsets && coarse_vals_sorted && means2d && radii && isect_offsets && flatten_ids && workspace,
+               "NULL pointer");
+    const int64_t need = fg_bin_fine_segments_workspace_bytes(C, tile_w, tile_h, n_coarse);
+    FG_REQUIRE(workspace_bytes >= need, "fine-binning workspace too small");
+    const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
+    const int n_cells = C * cw * chh;
+    const int64_t segs = n_coarse / FB_SEG + n_cells;
+    cudaStream_t st = (cudaStream_t)stream;
+    FG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)need, st));  // ticket counter + status words
+    FG_LAUNCH(fine_bin_seg_kernel, (unsigned)segs, FB_SEG, 0, st, n_cells, cell_offsets, coarse_vals_sorted,
+              (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, isect_offsets, flatten_ids,
+              (int*)workspace, (volatile uint32_t*)((unsigned char*)workspace + 256));
     return FG_OK;
 }
