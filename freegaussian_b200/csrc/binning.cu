@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256)
 // The pairs only have to end up grouped by cell, in depth order inside a cell.  With at most RK_MAX_CELLS coarse cells
 // (one 1080p view: 510) that position can be COMPUTED instead of sorted for:
 //   bin_count_cells : CTA = chunk of RK_CHUNK consecutive depth-ordered slots; besides the corner increments it counts
-//                     the chunk's pairs per cell (shared-memory histogram) -> mat[chunk][cell]
+//                     the chunk's pairs per cell (a difference grid in cell space) -> mat[chunk][cell]
 //   cell_scan       : per cell, exclusive prefix over the chunks (in place) and the cell totals; the last CTA to finish
 //                     scans the totals -> cell_offsets[n_cells + 1], Mc
 //   ranked_emit     : CTA = chunk again; a bitmap per (cell, warp) of the chunk's splats that touch the cell; position of
@@ -139,21 +139,25 @@ __global__ void __launch_bounds__(256)
 constexpr int RK_CHUNK = 512;
 constexpr int RK_WARPS = RK_CHUNK / 32;
 constexpr int RK_MAX_CELLS = 1024;  // = threads of the totals scan; shared memory of ranked_emit: 128 B per cell
-constexpr int FB_SEG = 1024;  // pairs per CTA of fine_bin_seg_kernel (= its threads)
-constexpr int RK_BIG = 8;  // a splat over more cells than this is walked by its whole warp (a full-screen splat touches every
+constexpr int FB_SEG = 512;  // pairs per CTA of fine_bin_seg_kernel (= its threads: 16 warps, one per tile of the cell)
+constexpr int RK_BIG = 16;  // a splat over more cells than this is walked by its whole warp (a full-screen splat touches every
                            // cell: one thread looping over 510 of them would hold up the CTA's barriers)
 
 // cells [x0, x0 + w) x [y0, ..) of a cell rectangle with n cells, as the warp sees the rectangle of lane `src`
 struct WarpRect {
-    int x0, y0, w, n, base;
+    int w, n, base;     // width, cells, index of the rectangle's first cell
+    unsigned inv_w;     // ceil(2^20 / w): i / w == (i * inv_w) >> 20 for i, w <= 1024 (i * w < 2^20)
+    __device__ __forceinline__ int cell(int i, int cw) const {  // index of the rectangle's i-th cell (row-major)
+        const int y = (int)(((unsigned)i * inv_w) >> 20);
+        return base + y * cw + (i - y * w);
+    }
 };
-__device__ __forceinline__ WarpRect warp_rect(int src, int x0, int y0, int w, int n, int base) {
+__device__ __forceinline__ WarpRect warp_rect(int src, int w, int n, int base) {
     WarpRect r;
-    r.x0 = __shfl_sync(0xffffffffu, x0, src);
-    r.y0 = __shfl_sync(0xffffffffu, y0, src);
     r.w = __shfl_sync(0xffffffffu, w, src);
     r.n = __shfl_sync(0xffffffffu, n, src);
     r.base = __shfl_sync(0xffffffffu, base, src);
+    r.inv_w = ((1u << 20) + (unsigned)r.w - 1) / (unsigned)r.w;
     return r;
 }
 
@@ -176,22 +180,26 @@ static RankedLayout ranked_layout(int C, int N, int tile_w, int tile_h) {
     return L;
 }
 
+// Pair counts per cell of one chunk.  A splat covers ~11 cells at cfg3, and one shared-memory atomic per (splat, cell) made
+// this kernel MIO-bound (ncu r2b: 17 mio_throttle stall cycles per issue, 43 us).  The counts come from a difference grid
+// in cell space instead -- four atomics per splat at the corners of its cell rectangle, then a 2-D prefix sum of the
+// (cw+1) x (chh+1) grid of every camera -- the same trick as the tile counts, one level up.
 __global__ void __launch_bounds__(RK_CHUNK)
-    bin_count_cells_kernel(int N, long long total, const int32_t* __restrict__ order, const float2* __restrict__ means2d,
-                           const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
-                           int n_cells, int32_t* __restrict__ diff, int32_t* __restrict__ mat, int32_t* __restrict__ counter) {
-    extern __shared__ int s_cnt[];
+    bin_count_cells_kernel(int C, int N, long long total, const int32_t* __restrict__ order,
+                           const float2* __restrict__ means2d, const int32_t* __restrict__ radii, int tile_size, int tile_w,
+                           int tile_h, int cw, int chh, int n_cells, int32_t* __restrict__ diff, int32_t* __restrict__ mat,
+                           int32_t* __restrict__ counter) {
+    extern __shared__ int s_grid[];  // [C][chh + 1][cw + 1]
     pdl_wait();
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long slot0 = (long long)blockIdx.x * RK_CHUNK;
     if (blockIdx.x == 0 && tid == 0) *counter = 0;  // cell_scan's "last CTA" ticket
     if (order[slot0] < 0) return;  // the whole chunk lies past the visible splats (fg_depth_sort_visible leaves -1 there)
-    for (int i = tid; i < n_cells; i += RK_CHUNK) s_cnt[i] = 0;
+    const int GW = cw + 1, GH = chh + 1;
+    for (int i = tid; i < C * GW * GH; i += RK_CHUNK) s_grid[i] = 0;
     __syncthreads();
-    const int lane = tid & 31;
     const long long slot = slot0 + tid;
     const long long idx = slot < total ? order[slot] : -1;
-    int cx0 = 0, cy0 = 0, cwid = 0, n_my = 0, base = 0;
     if (idx >= 0) {
         const int r = radii[idx];
         if (r > 0) {
@@ -205,24 +213,46 @@ __global__ void __launch_bounds__(RK_CHUNK)
                 atomicAdd(g + t.y0 * W1 + t.x1, -1);
                 atomicAdd(g + t.y1 * W1 + t.x0, -1);
                 atomicAdd(g + t.y1 * W1 + t.x1, 1);
-                cx0 = t.x0 >> CK_SHIFT;
-                cy0 = t.y0 >> CK_SHIFT;
-                cwid = ((t.x1 + CK - 1) >> CK_SHIFT) - cx0;
-                n_my = cwid * (((t.y1 + CK - 1) >> CK_SHIFT) - cy0);
-                base = cam * cw * chh;
+                const int cx0 = t.x0 >> CK_SHIFT, cx1 = (t.x1 + CK - 1) >> CK_SHIFT;
+                const int cy0 = t.y0 >> CK_SHIFT, cy1 = (t.y1 + CK - 1) >> CK_SHIFT;
+                int* c = s_grid + cam * GW * GH;
+                atomicAdd(c + cy0 * GW + cx0, 1);
+                atomicAdd(c + cy0 * GW + cx1, -1);
+                atomicAdd(c + cy1 * GW + cx0, -1);
+                atomicAdd(c + cy1 * GW + cx1, 1);
             }
         }
     }
-    const bool big = n_my > RK_BIG;
-    if (!big)
-        for (int i = 0; i < n_my; ++i) atomicAdd(s_cnt + base + (cy0 + i / cwid) * cw + cx0 + i % cwid, 1);
-    for (unsigned todo = __ballot_sync(0xffffffffu, big); todo; todo &= todo - 1) {
-        const WarpRect R = warp_rect(__ffs(todo) - 1, cx0, cy0, cwid, n_my, base);
-        for (int i = lane; i < R.n; i += 32) atomicAdd(s_cnt + R.base + (R.y0 + i / R.w) * cw + R.x0 + i % R.w, 1);
+    __syncthreads();
+    // rows: a warp per row, 32 columns at a time with a carry
+    for (int row = warp; row < C * GH; row += RK_WARPS) {
+        int* g = s_grid + row * GW;
+        int carry = 0;
+        for (int x0 = 0; x0 < GW; x0 += 32) {
+            const int x = x0 + lane;
+            int v = x < GW ? g[x] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += o;
+            }
+            v += carry;
+            if (x < GW) g[x] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
     }
     __syncthreads();
-    int32_t* row = mat + (long long)blockIdx.x * n_cells;
-    for (int i = tid; i < n_cells; i += RK_CHUNK) row[i] = s_cnt[i];
+    // columns: a thread per (camera, column); the running sum is the cell's count
+    int32_t* out = mat + (long long)blockIdx.x * n_cells;
+    for (int col = tid; col < C * cw; col += RK_CHUNK) {
+        const int cam = col / cw, x = col - cam * cw;
+        const int* g = s_grid + cam * GW * GH + x;
+        int run = 0;
+        for (int y = 0; y < chh; ++y) {
+            run += g[y * GW];
+            out[(cam * chh + y) * cw + x] = run;
+        }
+    }
 }
 
 // grid = ceil(n_cells / 32) CTAs of 32 x 32 threads: lane = cell, row = a 1/32 share of the active chunks
@@ -338,29 +368,30 @@ __global__ void __launch_bounds__(RK_CHUNK)
     __syncthreads();
     const long long slot = slot0 + tid;
     const long long idx = slot < total ? order[slot] : -1;
-    int cx0 = 0, cy0 = 0, cwid = 0, n_my = 0, cell0 = 0;
+    int cwid = 0, chgt = 0, n_my = 0, cell0 = 0;  // the splat's cell rectangle: width, height, cells, first cell (+ warp plane)
     if (idx >= 0) {
         const int r = radii[idx];
         if (r > 0) {
             const float2 m = means2d[idx];
             const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
             if (t.x1 > t.x0 && t.y1 > t.y0) {
-                cx0 = t.x0 >> CK_SHIFT;
-                cy0 = t.y0 >> CK_SHIFT;
+                const int cx0 = t.x0 >> CK_SHIFT, cy0 = t.y0 >> CK_SHIFT;
                 cwid = ((t.x1 + CK - 1) >> CK_SHIFT) - cx0;
-                n_my = cwid * (((t.y1 + CK - 1) >> CK_SHIFT) - cy0);
-                cell0 = (int)(idx / N) * cw * chh + warp * n_cells;
+                chgt = ((t.y1 + CK - 1) >> CK_SHIFT) - cy0;
+                n_my = cwid * chgt;
+                cell0 = (int)(idx / N) * cw * chh + warp * n_cells + cy0 * cw + cx0;
             }
         }
     }
     const bool big = n_my > RK_BIG;
     const unsigned big_lanes = __ballot_sync(0xffffffffu, big);
     if (!big)
-        for (int i = 0; i < n_my; ++i) atomicOr(bm + cell0 + (cy0 + i / cwid) * cw + cx0 + i % cwid, 1u << lane);
+        for (int y = 0, c = cell0; y < chgt; ++y, c += cw)
+            for (int x = 0; x < cwid; ++x) atomicOr(bm + c + x, 1u << lane);
     for (unsigned todo = big_lanes; todo; todo &= todo - 1) {
         const int src = __ffs(todo) - 1;
-        const WarpRect R = warp_rect(src, cx0, cy0, cwid, n_my, cell0);
-        for (int i = lane; i < R.n; i += 32) atomicOr(bm + R.base + (R.y0 + i / R.w) * cw + R.x0 + i % R.w, 1u << src);
+        const WarpRect R = warp_rect(src, cwid, n_my, cell0);
+        for (int i = lane; i < R.n; i += 32) atomicOr(bm + R.cell(i, cw), 1u << src);
     }
     __syncthreads();
     const int32_t* row = mat + (long long)blockIdx.x * n_cells;
@@ -375,17 +406,15 @@ __global__ void __launch_bounds__(RK_CHUNK)
     __syncthreads();
     const unsigned lt = (1u << lane) - 1;
     if (!big)
-        for (int i = 0; i < n_my; ++i) {
-            const int c = cell0 + (cy0 + i / cwid) * cw + cx0 + i % cwid;
-            vals[pre[c] + __popc(bm[c] & lt)] = (int32_t)idx;
-        }
+        for (int y = 0, c = cell0; y < chgt; ++y, c += cw)
+            for (int x = 0; x < cwid; ++x) vals[pre[c + x] + __popc(bm[c + x] & lt)] = (int32_t)idx;
     for (unsigned todo = big_lanes; todo; todo &= todo - 1) {
         const int src = __ffs(todo) - 1;
-        const WarpRect R = warp_rect(src, cx0, cy0, cwid, n_my, cell0);
+        const WarpRect R = warp_rect(src, cwid, n_my, cell0);
         const int id = __shfl_sync(0xffffffffu, (int)idx, src);
         const unsigned below = (1u << src) - 1;
         for (int i = lane; i < R.n; i += 32) {
-            const int c = R.base + (R.y0 + i / R.w) * cw + R.x0 + i % R.w;
+            const int c = R.cell(i, cw);
             vals[pre[c] + __popc(bm[c] & below)] = id;
         }
     }
@@ -491,9 +520,11 @@ __global__ void __launch_bounds__(FB_THREADS)
 // fine_bin_kernel walks a cell's list chunk after chunk, so its time is the longest cell's (~25 sequential chunks at cfg3:
 // 0.106 ms for 16 us worth of traffic).  Here every FB_SEG-pair segment of every cell is its own CTA; the tile cursors a
 // segment starts from are the totals of the cell's earlier segments, obtained by decoupled look-back over 16 status words
-// per segment (flag in the top two bits, as in radix_sort.cu).  Segments are numbered cell after cell and a CTA takes the
+// per segment (flag in the top two bits, as in radix_sort.cu); 512-thread CTAs, four per SM, so that one segment's
+// look-back latency hides behind the others' work (ncu r2b, 1024 threads: 14 barrier-stall cycles per issue).  Segments are numbered cell after cell and a CTA takes the
 // next number from a ticket counter, so every predecessor of a running CTA is itself running or done.
 constexpr uint32_t FS_LOCAL = 1u << 30, FS_INCLUSIVE = 2u << 30, FS_FLAGS = 3u << 30;
+static_assert(FB_SEG / 32 == CK * CK, "fine_bin_seg_kernel: warp t finishes tile t");
 
 __global__ void __launch_bounds__(FB_SEG)
     fine_bin_seg_kernel(int n_cells, const int32_t* __restrict__ cell_offsets /*[n_cells+1] ++ segment starts [n_cells+1]*/,
@@ -501,10 +532,10 @@ __global__ void __launch_bounds__(FB_SEG)
                         const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
                         const int32_t* __restrict__ isect_offsets, int32_t* __restrict__ flatten_ids,
                         int* __restrict__ ticket_counter, volatile uint32_t* status /*[segments][16], zeroed*/) {
-    constexpr int NT = CK * CK;
-    __shared__ int s_warp_cnt[FB_SEG / 32][NT];
-    __shared__ int s_base[NT];
-    __shared__ int s_seg[3];  // ticket, cell, segment inside the cell
+    constexpr int NT = CK * CK, NW = FB_SEG / 32;
+    __shared__ int s_warp_cnt[NW][NT + 1];  // per (warp, tile): entries, then the warp's first position in the segment
+    __shared__ int s_base[NT];              // where the segment's entries of each tile start in flatten_ids
+    __shared__ int s_seg[3];                // ticket, cell, segment inside the cell
     pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t* seg_offsets = cell_offsets + n_cells + 1;
@@ -543,7 +574,8 @@ __global__ void __launch_bounds__(FB_SEG)
         const int y0 = max(t.y0 - cy * CK, 0), y1 = min(t.y1 - cy * CK, CK);
         if (x1 > x0 && y1 > y0) {
             const unsigned cols = ((1u << x1) - 1) & ~((1u << x0) - 1);  // CK bits
-            for (int y = y0; y < y1; ++y) mask |= cols << (y * CK);
+            const unsigned rows = ((1u << (y1 * CK)) - 1) & ~((1u << (y0 * CK)) - 1);
+            mask = (cols * 0x1111u) & rows;  // the column pattern in every row, cut to rows [y0, y1)
         }
     }
     unsigned bal[NT];
@@ -553,35 +585,45 @@ __global__ void __launch_bounds__(FB_SEG)
         if (lane == 0) s_warp_cnt[warp][t] = __popc(bal[t]);
     }
     __syncthreads();
-    if (tid < NT) {
-        int run = 0;
+    // warp t finishes tile t: exclusive prefix of the tile's per-warp counts, then (one lane) the look-back over the
+    // cell's earlier segments -- sixteen tiles side by side instead of sixteen threads looping over the warps
+    {
+        const int tile = warp;
+        const int c = lane < NW ? s_warp_cnt[lane][tile] : 0;
+        int incl = c;
 #pragma unroll
-        for (int w = 0; w < FB_SEG / 32; ++w) {
-            const int c = s_warp_cnt[w][tid];
-            s_warp_cnt[w][tid] = run;
-            run += c;
+        for (int d = 1; d < NW; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
         }
-        volatile uint32_t* mine = status + (size_t)ticket * NT + tid;
-        uint32_t excl = 0;
-        if (seg == 0) {
-            *mine = FS_INCLUSIVE | (uint32_t)run;
-        } else {
-            *mine = FS_LOCAL | (uint32_t)run;
-            for (int t = ticket - 1;; --t) {  // t >= ticket - seg: the cell's first segment always publishes INCLUSIVE
-                uint32_t st;
-                do { st = status[(size_t)t * NT + tid]; } while ((st & FS_FLAGS) == 0);
-                excl += st & ~FS_FLAGS;
-                if ((st & FS_FLAGS) == FS_INCLUSIVE) break;
+        if (lane < NW) s_warp_cnt[lane][tile] = incl - c;
+        if (lane == NW - 1) {
+            const uint32_t run = (uint32_t)incl;
+            volatile uint32_t* mine = status + (size_t)ticket * NT + tile;
+            uint32_t excl = 0;
+            if (seg == 0) {
+                *mine = FS_INCLUSIVE | run;
+            } else {
+                *mine = FS_LOCAL | run;
+                for (int t = ticket - 1;; --t) {  // t >= ticket - seg: the cell's first segment always publishes INCLUSIVE
+                    uint32_t st;
+                    do { st = status[(size_t)t * NT + tile]; } while ((st & FS_FLAGS) == 0);
+                    excl += st & ~FS_FLAGS;
+                    if ((st & FS_FLAGS) == FS_INCLUSIVE) break;
+                }
+                *mine = FS_INCLUSIVE | (excl + run);
             }
-            *mine = FS_INCLUSIVE | (excl + (uint32_t)run);
+            s_base[tile] += (int)excl;
         }
-        s_base[tid] += (int)excl;
     }
     __syncthreads();
     const unsigned lt = (1u << lane) - 1;
+    const int first = lane < NT ? s_base[lane] + s_warp_cnt[warp][lane] : 0;  // lane t: this warp's first position in tile t
 #pragma unroll
-    for (int t = 0; t < NT; ++t)
-        if ((mask >> t) & 1u) flatten_ids[s_base[t] + s_warp_cnt[warp][t] + __popc(bal[t] & lt)] = id;
+    for (int t = 0; t < NT; ++t) {
+        const int pos = __shfl_sync(0xffffffffu, first, t) + __popc(bal[t] & lt);
+        if ((mask >> t) & 1u) flatten_ids[pos] = id;
+    }
 }
 
 }  // namespace fg
@@ -665,8 +707,8 @@ extern "C" int fg_bin_count_cells(int C, int N, const int32_t* order, const floa
     }
     FG_REQUIRE(order && means2d && radii, "NULL pointer");
     const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
-    FG_LAUNCH(bin_count_cells_kernel, (unsigned)L.n_chunks, RK_CHUNK, (size_t)L.n_cells * 4, st, N, (long long)C * N, order,
-              (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, L.n_cells, diff_grid,
+    FG_LAUNCH(bin_count_cells_kernel, (unsigned)L.n_chunks, RK_CHUNK, (size_t)C * (cw + 1) * (chh + 1) * 4, st, C, N,
+              (long long)C * N, order, (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, L.n_cells, diff_grid,
               (int32_t*)(ws + L.mat), (int32_t*)(ws + L.counter));
     return FG_OK;
 }
