@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256)
 constexpr int RK_CHUNK = 512;
 constexpr int RK_WARPS = RK_CHUNK / 32;
 constexpr int RK_MAX_CELLS = 1024;  // = threads of the totals scan; shared memory of ranked_emit: 128 B per cell
-constexpr int FB_SEG = 512;  // pairs per CTA of fine_bin_seg_kernel (= its threads: 16 warps, one per tile of the cell)
+constexpr int FB_SEG = 1024;  // pairs per CTA of fine_bin_seg_kernel
 constexpr int RK_BIG = 16;  // a splat over more cells than this is walked by its whole warp (a full-screen splat touches every
                            // cell: one thread looping over 510 of them would hold up the CTA's barriers)
 
@@ -521,83 +521,91 @@ __global__ void __launch_bounds__(FB_THREADS)
 // 0.106 ms for 16 us worth of traffic).  Here every FB_SEG-pair segment of every cell is its own CTA; the tile cursors a
 // segment starts from are the totals of the cell's earlier segments, obtained by decoupled look-back over 16 status words
 // per segment (flag in the top two bits, as in radix_sort.cu); 512-thread CTAs, four per SM, so that one segment's
-// look-back latency hides behind the others' work (ncu r2b, 1024 threads: 14 barrier-stall cycles per issue).  Segments are numbered cell after cell and a CTA takes the
+// look-back latency hides behind the others' work (ncu r2b, 1024 threads: 14 barrier-stall cycles per issue); a CTA
+// finds its (cell, segment) in shared-memory copies of the two tables (a binary search over global memory cost each CTA
+// ten dependent L2 round trips before its first useful load: 120 us).  Segments are numbered cell after cell and a CTA takes the
 // next number from a ticket counter, so every predecessor of a running CTA is itself running or done.
 constexpr uint32_t FS_LOCAL = 1u << 30, FS_INCLUSIVE = 2u << 30, FS_FLAGS = 3u << 30;
-static_assert(FB_SEG / 32 == CK * CK, "fine_bin_seg_kernel: warp t finishes tile t");
+constexpr int FS_THREADS = 512, FS_ITEMS = FB_SEG / FS_THREADS;  // thread = FS_ITEMS entries, FS_THREADS apart
+constexpr int FS_ROWS = FS_ITEMS * (FS_THREADS / 32);            // (item, warp) groups of 32 consecutive entries
+static_assert(FS_THREADS / 32 == CK * CK, "fine_bin_seg_kernel: warp t finishes tile t");
+static_assert(FS_ROWS <= 32, "one warp scans the groups of a tile");
 
-__global__ void __launch_bounds__(FB_SEG)
+__device__ __forceinline__ unsigned cell_tile_mask(float2 m, int r, int tile_size, int tile_w, int tile_h, int cx, int cy) {
+    const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
+    const int x0 = max(t.x0 - cx * CK, 0), x1 = min(t.x1 - cx * CK, CK);
+    const int y0 = max(t.y0 - cy * CK, 0), y1 = min(t.y1 - cy * CK, CK);
+    if (!(x1 > x0 && y1 > y0)) return 0u;
+    const unsigned cols = ((1u << x1) - 1) & ~((1u << x0) - 1);  // CK bits
+    const unsigned rows = ((1u << (y1 * CK)) - 1) & ~((1u << (y0 * CK)) - 1);
+    return (cols * 0x1111u) & rows;  // the column pattern in every row, cut to rows [y0, y1)
+}
+
+__global__ void __launch_bounds__(FS_THREADS, 4)
     fine_bin_seg_kernel(int n_cells, const int32_t* __restrict__ cell_offsets /*[n_cells+1] ++ segment starts [n_cells+1]*/,
                         const int32_t* __restrict__ coarse_vals, const float2* __restrict__ means2d,
                         const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
                         const int32_t* __restrict__ isect_offsets, int32_t* __restrict__ flatten_ids,
                         int* __restrict__ ticket_counter, volatile uint32_t* status /*[segments][16], zeroed*/) {
-    constexpr int NT = CK * CK, NW = FB_SEG / 32;
-    __shared__ int s_warp_cnt[NW][NT + 1];  // per (warp, tile): entries, then the warp's first position in the segment
-    __shared__ int s_base[NT];              // where the segment's entries of each tile start in flatten_ids
-    __shared__ int s_seg[3];                // ticket, cell, segment inside the cell
+    constexpr int NT = CK * CK;
+    __shared__ int s_tab[2 * (RK_MAX_CELLS + 1)];  // both tables: a CTA finds its (cell, segment) without a chain of global loads
+    __shared__ int s_cnt[FS_ROWS][NT + 1];         // per (group, tile): entries, then the group's first position in the segment
+    __shared__ int s_base[NT];                     // where the segment's entries of each tile start in flatten_ids
+    __shared__ int s_ticket;
     pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int32_t* seg_offsets = cell_offsets + n_cells + 1;
-    if (tid == 0) {
-        const int t = atomicAdd(ticket_counter, 1);
-        int cell = -1;
-        if (t < seg_offsets[n_cells]) {  // last cell whose first segment is <= t (empty cells share their successor's start)
-            int lo = 0, hi = n_cells;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (seg_offsets[mid] <= t) lo = mid; else hi = mid;
-            }
-            cell = lo;
-        }
-        s_seg[0] = t; s_seg[1] = cell; s_seg[2] = cell >= 0 ? t - seg_offsets[cell] : 0;
-    }
+    if (tid == 0) s_ticket = atomicAdd(ticket_counter, 1);
+    for (int i = tid; i < 2 * (n_cells + 1); i += FS_THREADS) s_tab[i] = cell_offsets[i];
     __syncthreads();
-    const int ticket = s_seg[0], cell = s_seg[1], seg = s_seg[2];
-    if (cell < 0) return;  // the grid is sized from an upper bound of the segment count
+    const int* seg_offsets = s_tab + n_cells + 1;
+    const int ticket = s_ticket;
+    if (ticket >= seg_offsets[n_cells]) return;  // the grid is sized from an upper bound of the segment count
+    int cell = 0;
+    {  // last cell whose first segment is <= ticket (empty cells share their successor's start)
+        int hi = n_cells;
+        while (hi - cell > 1) {
+            const int mid = (cell + hi) >> 1;
+            if (seg_offsets[mid] <= ticket) cell = mid; else hi = mid;
+        }
+    }
+    const int seg = ticket - seg_offsets[cell];
     const int cam = cell / (cw * chh);
     const int crem = cell - cam * cw * chh;
     const int cy = crem / cw, cx = crem - cy * cw;
-    const int e = cell_offsets[cell] + seg * FB_SEG + tid;
-    const int end = cell_offsets[cell + 1];
+    const int e0 = s_tab[cell] + seg * FB_SEG + tid;
+    const int end = s_tab[cell + 1];
     if (tid < NT) {
         const int tx = cx * CK + (tid & (CK - 1)), ty = cy * CK + (tid >> CK_SHIFT);
         s_base[tid] = (tx < tile_w && ty < tile_h) ? isect_offsets[(cam * tile_h + ty) * tile_w + tx] : 0;
     }
-    unsigned mask = 0;  // bit (iy*CK + ix) set if the splat overlaps tile (cx*CK+ix, cy*CK+iy)
-    int id = 0;
-    if (e < end) {
-        id = coarse_vals[e];
-        const float2 m = means2d[id];
-        const TileRect t = tile_rect(m.x, m.y, radii[id], tile_size, tile_w, tile_h);
-        const int x0 = max(t.x0 - cx * CK, 0), x1 = min(t.x1 - cx * CK, CK);
-        const int y0 = max(t.y0 - cy * CK, 0), y1 = min(t.y1 - cy * CK, CK);
-        if (x1 > x0 && y1 > y0) {
-            const unsigned cols = ((1u << x1) - 1) & ~((1u << x0) - 1);  // CK bits
-            const unsigned rows = ((1u << (y1 * CK)) - 1) & ~((1u << (y0 * CK)) - 1);
-            mask = (cols * 0x1111u) & rows;  // the column pattern in every row, cut to rows [y0, y1)
-        }
-    }
-    unsigned bal[NT];
+    int id[FS_ITEMS];
+    unsigned mask[FS_ITEMS];  // bit (iy*CK + ix) set if the splat overlaps tile (cx*CK+ix, cy*CK+iy)
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        bal[t] = __ballot_sync(0xffffffffu, (mask >> t) & 1u);
-        if (lane == 0) s_warp_cnt[warp][t] = __popc(bal[t]);
-    }
+    for (int i = 0; i < FS_ITEMS; ++i) id[i] = (e0 + i * FS_THREADS < end) ? coarse_vals[e0 + i * FS_THREADS] : -1;
+#pragma unroll
+    for (int i = 0; i < FS_ITEMS; ++i)
+        mask[i] = id[i] >= 0 ? cell_tile_mask(means2d[id[i]], radii[id[i]], tile_size, tile_w, tile_h, cx, cy) : 0u;
+#pragma unroll
+    for (int i = 0; i < FS_ITEMS; ++i)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const unsigned b = __ballot_sync(0xffffffffu, (mask[i] >> t) & 1u);
+            if (lane == 0) s_cnt[i * (FS_THREADS / 32) + warp][t] = __popc(b);
+        }
     __syncthreads();
-    // warp t finishes tile t: exclusive prefix of the tile's per-warp counts, then (one lane) the look-back over the
-    // cell's earlier segments -- sixteen tiles side by side instead of sixteen threads looping over the warps
+    // warp t finishes tile t: exclusive prefix of the tile's per-group counts, then (one lane) the look-back over the
+    // cell's earlier segments -- sixteen tiles side by side
     {
         const int tile = warp;
-        const int c = lane < NW ? s_warp_cnt[lane][tile] : 0;
+        const int c = lane < FS_ROWS ? s_cnt[lane][tile] : 0;
         int incl = c;
 #pragma unroll
-        for (int d = 1; d < NW; d <<= 1) {
+        for (int d = 1; d < FS_ROWS; d <<= 1) {
             const int o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += o;
         }
-        if (lane < NW) s_warp_cnt[lane][tile] = incl - c;
-        if (lane == NW - 1) {
+        if (lane < FS_ROWS) s_cnt[lane][tile] = incl - c;
+        if (lane == FS_ROWS - 1) {
             const uint32_t run = (uint32_t)incl;
             volatile uint32_t* mine = status + (size_t)ticket * NT + tile;
             uint32_t excl = 0;
@@ -618,11 +626,16 @@ __global__ void __launch_bounds__(FB_SEG)
     }
     __syncthreads();
     const unsigned lt = (1u << lane) - 1;
-    const int first = lane < NT ? s_base[lane] + s_warp_cnt[warp][lane] : 0;  // lane t: this warp's first position in tile t
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        const int pos = __shfl_sync(0xffffffffu, first, t) + __popc(bal[t] & lt);
-        if ((mask >> t) & 1u) flatten_ids[pos] = id;
+    for (int i = 0; i < FS_ITEMS; ++i) {
+        // lane t: this group's first position in tile t
+        const int first = lane < NT ? s_base[lane] + s_cnt[i * (FS_THREADS / 32) + warp][lane] : 0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const unsigned b = __ballot_sync(0xffffffffu, (mask[i] >> t) & 1u);
+            const int pos = __shfl_sync(0xffffffffu, first, t) + __popc(b & lt);
+            if ((mask[i] >> t) & 1u) flatten_ids[pos] = id[i];
+        }
     }
 }
 
@@ -780,7 +793,7 @@ extern "C" int fg_bin_fine_segments(int C, int N, int64_t n_coarse, const int32_
     const int64_t segs = n_coarse / FB_SEG + n_cells;
     cudaStream_t st = (cudaStream_t)stream;
     FG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)need, st));  // ticket counter + status words
-    FG_LAUNCH(fine_bin_seg_kernel, (unsigned)segs, FB_SEG, 0, st, n_cells, cell_offsets, coarse_vals_sorted,
+    FG_LAUNCH(fine_bin_seg_kernel, (unsigned)segs, FS_THREADS, 0, st, n_cells, cell_offsets, coarse_vals_sorted,
               (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, isect_offsets, flatten_ids,
               (int*)workspace, (volatile uint32_t*)((unsigned char*)workspace + 256));
     return FG_OK;

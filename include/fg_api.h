@@ -203,10 +203,10 @@ int fg_bin_coarse_emit(int C, int N, const int32_t* order, const float* means2d,
  *   fg_bin_count_cells  fg_bin_count's corner increments + per (chunk of 512 depth-ordered slots, cell) pair counts
  *   fg_bin_cell_scan    per cell: exclusive prefix over the chunks; cell_offsets[2 * (n_cells + 1)]: the first n_cells + 1
  *                       entries are fg_bin_fine's coarse_offsets (+ the total), the second n_cells + 1 the start of each
- *                       cell's 512-pair segments in fg_bin_fine_segments' grid; *n_coarse = Mc (device).
+ *                       cell's 1024-pair segments in fg_bin_fine_segments' grid; *n_coarse = Mc (device).
  *                       n_visible: device count from fg_depth_sort_visible
  *   fg_bin_ranked_emit  coarse_vals[Mc]: position = cell offset + chunk prefix + rank inside the chunk (bitmaps)
- *   fg_bin_fine_segments  fg_bin_fine with one CTA per 512-pair segment of a cell instead of one per cell (decoupled
+ *   fg_bin_fine_segments  fg_bin_fine with one CTA per 1024-pair segment of a cell instead of one per cell (decoupled
  *                       look-back between the segments of a cell): same lists, no serial walk over the heavy cells */
 int64_t fg_bin_ranked_workspace_bytes(int C, int N, int tile_w, int tile_h);
 int fg_bin_count_cells(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii, int tile_size,
