@@ -526,10 +526,10 @@ __global__ void __launch_bounds__(FB_THREADS)
 // ten dependent L2 round trips before its first useful load: 120 us).  Segments are numbered cell after cell and a CTA takes the
 // next number from a ticket counter, so every predecessor of a running CTA is itself running or done.
 constexpr uint32_t FS_LOCAL = 1u << 30, FS_INCLUSIVE = 2u << 30, FS_FLAGS = 3u << 30;
-constexpr int FS_THREADS = 512, FS_ITEMS = FB_SEG / FS_THREADS;  // thread = FS_ITEMS entries, FS_THREADS apart
-constexpr int FS_ROWS = FS_ITEMS * (FS_THREADS / 32);            // (item, warp) groups of 32 consecutive entries
-static_assert(FS_THREADS / 32 == CK * CK, "fine_bin_seg_kernel: warp t finishes tile t");
-static_assert(FS_ROWS <= 32, "one warp scans the groups of a tile");
+constexpr int FS_THREADS = 512, FS_ITEMS = FB_SEG / FS_THREADS;  // loading: thread = FS_ITEMS entries, FS_THREADS apart
+constexpr int FS_GROUPS = FB_SEG / 32;                           // groups of 32 consecutive entries
+static_assert(FS_THREADS / 32 == CK * CK, "fine_bin_seg_kernel: warp t writes tile t");
+static_assert(FS_GROUPS <= 32, "the ballots of a segment stay in registers");
 
 __device__ __forceinline__ unsigned cell_tile_mask(float2 m, int r, int tile_size, int tile_w, int tile_h, int cx, int cy) {
     const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
@@ -541,16 +541,18 @@ __device__ __forceinline__ unsigned cell_tile_mask(float2 m, int r, int tile_siz
     return (cols * 0x1111u) & rows;  // the column pattern in every row, cut to rows [y0, y1)
 }
 
-__global__ void __launch_bounds__(FS_THREADS, 4)
+// Tile-major: the CTA stages its segment once (id + 16-bit tile mask per entry), then WARP t walks the staged entries for
+// tile t alone -- one ballot per 32 entries, a running position, coalesced stores into one list -- instead of every warp
+// ranking its 32 entries for all 16 tiles (620 instructions per 32 entries, ncu r2b/r2d: issue-bound at 0.10-0.12 ms).
+__global__ void __launch_bounds__(FS_THREADS, 2)
     fine_bin_seg_kernel(int n_cells, const int32_t* __restrict__ cell_offsets /*[n_cells+1] ++ segment starts [n_cells+1]*/,
                         const int32_t* __restrict__ coarse_vals, const float2* __restrict__ means2d,
                         const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
                         const int32_t* __restrict__ isect_offsets, int32_t* __restrict__ flatten_ids,
                         int* __restrict__ ticket_counter, volatile uint32_t* status /*[segments][16], zeroed*/) {
-    constexpr int NT = CK * CK;
     __shared__ int s_tab[2 * (RK_MAX_CELLS + 1)];  // both tables: a CTA finds its (cell, segment) without a chain of global loads
-    __shared__ int s_cnt[FS_ROWS][NT + 1];         // per (group, tile): entries, then the group's first position in the segment
-    __shared__ int s_base[NT];                     // where the segment's entries of each tile start in flatten_ids
+    __shared__ int s_id[FB_SEG];
+    __shared__ unsigned short s_mask[FB_SEG];  // bit (iy*CK + ix): the splat overlaps tile (cx*CK+ix, cy*CK+iy)
     __shared__ int s_ticket;
     pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -572,70 +574,58 @@ __global__ void __launch_bounds__(FS_THREADS, 4)
     const int cam = cell / (cw * chh);
     const int crem = cell - cam * cw * chh;
     const int cy = crem / cw, cx = crem - cy * cw;
-    const int e0 = s_tab[cell] + seg * FB_SEG + tid;
+    const int e0 = s_tab[cell] + seg * FB_SEG;
     const int end = s_tab[cell + 1];
-    if (tid < NT) {
-        const int tx = cx * CK + (tid & (CK - 1)), ty = cy * CK + (tid >> CK_SHIFT);
-        s_base[tid] = (tx < tile_w && ty < tile_h) ? isect_offsets[(cam * tile_h + ty) * tile_w + tx] : 0;
-    }
     int id[FS_ITEMS];
-    unsigned mask[FS_ITEMS];  // bit (iy*CK + ix) set if the splat overlaps tile (cx*CK+ix, cy*CK+iy)
 #pragma unroll
-    for (int i = 0; i < FS_ITEMS; ++i) id[i] = (e0 + i * FS_THREADS < end) ? coarse_vals[e0 + i * FS_THREADS] : -1;
-#pragma unroll
-    for (int i = 0; i < FS_ITEMS; ++i)
-        mask[i] = id[i] >= 0 ? cell_tile_mask(means2d[id[i]], radii[id[i]], tile_size, tile_w, tile_h, cx, cy) : 0u;
-#pragma unroll
-    for (int i = 0; i < FS_ITEMS; ++i)
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const unsigned b = __ballot_sync(0xffffffffu, (mask[i] >> t) & 1u);
-            if (lane == 0) s_cnt[i * (FS_THREADS / 32) + warp][t] = __popc(b);
-        }
-    __syncthreads();
-    // warp t finishes tile t: exclusive prefix of the tile's per-group counts, then (one lane) the look-back over the
-    // cell's earlier segments -- sixteen tiles side by side
-    {
-        const int tile = warp;
-        const int c = lane < FS_ROWS ? s_cnt[lane][tile] : 0;
-        int incl = c;
-#pragma unroll
-        for (int d = 1; d < FS_ROWS; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane < FS_ROWS) s_cnt[lane][tile] = incl - c;
-        if (lane == FS_ROWS - 1) {
-            const uint32_t run = (uint32_t)incl;
-            volatile uint32_t* mine = status + (size_t)ticket * NT + tile;
-            uint32_t excl = 0;
-            if (seg == 0) {
-                *mine = FS_INCLUSIVE | run;
-            } else {
-                *mine = FS_LOCAL | run;
-                for (int t = ticket - 1;; --t) {  // t >= ticket - seg: the cell's first segment always publishes INCLUSIVE
-                    uint32_t st;
-                    do { st = status[(size_t)t * NT + tile]; } while ((st & FS_FLAGS) == 0);
-                    excl += st & ~FS_FLAGS;
-                    if ((st & FS_FLAGS) == FS_INCLUSIVE) break;
-                }
-                *mine = FS_INCLUSIVE | (excl + run);
-            }
-            s_base[tile] += (int)excl;
-        }
-    }
-    __syncthreads();
-    const unsigned lt = (1u << lane) - 1;
+    for (int i = 0; i < FS_ITEMS; ++i) id[i] = (e0 + i * FS_THREADS + tid < end) ? coarse_vals[e0 + i * FS_THREADS + tid] : -1;
 #pragma unroll
     for (int i = 0; i < FS_ITEMS; ++i) {
-        // lane t: this group's first position in tile t
-        const int first = lane < NT ? s_base[lane] + s_cnt[i * (FS_THREADS / 32) + warp][lane] : 0;
+        s_id[i * FS_THREADS + tid] = id[i];
+        s_mask[i * FS_THREADS + tid] = id[i] >= 0
+            ? (unsigned short)cell_tile_mask(means2d[id[i]], radii[id[i]], tile_size, tile_w, tile_h, cx, cy) : (unsigned short)0;
+    }
+    __syncthreads();
+    // from here on the warps are independent: warp = tile
+    const int tx = cx * CK + (warp & (CK - 1)), ty = cy * CK + (warp >> CK_SHIFT);
+    if (tx >= tile_w || ty >= tile_h) return;  // tile outside the image: nothing overlaps it, nobody looks its status up
+    const int n_groups = min(FS_GROUPS, (end - e0 + 31) >> 5);
+    const unsigned bit = 1u << warp;
+    unsigned bal[FS_GROUPS];
+    int count = 0;
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const unsigned b = __ballot_sync(0xffffffffu, (mask[i] >> t) & 1u);
-            const int pos = __shfl_sync(0xffffffffu, first, t) + __popc(b & lt);
-            if ((mask[i] >> t) & 1u) flatten_ids[pos] = id[i];
+    for (int g = 0; g < FS_GROUPS; ++g) {
+        bal[g] = 0;
+        if (g < n_groups) {
+            bal[g] = __ballot_sync(0xffffffffu, (s_mask[g * 32 + lane] & bit) != 0);
+            count += __popc(bal[g]);
         }
+    }
+    int pos = isect_offsets[(cam * tile_h + ty) * tile_w + tx];
+    if (lane == 0) {
+        volatile uint32_t* mine = status + (size_t)ticket * (CK * CK) + warp;
+        uint32_t excl = 0;
+        if (seg == 0) {
+            *mine = FS_INCLUSIVE | (uint32_t)count;
+        } else {
+            *mine = FS_LOCAL | (uint32_t)count;
+            for (int t = ticket - 1;; --t) {  // t >= ticket - seg: the cell's first segment always publishes INCLUSIVE
+                uint32_t st;
+                do { st = status[(size_t)t * (CK * CK) + warp]; } while ((st & FS_FLAGS) == 0);
+                excl += st & ~FS_FLAGS;
+                if ((st & FS_FLAGS) == FS_INCLUSIVE) break;
+            }
+            *mine = FS_INCLUSIVE | (excl + (uint32_t)count);
+        }
+        pos += (int)excl;
+    }
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    const unsigned lt = (1u << lane) - 1;
+#pragma unroll
+    for (int g = 0; g < FS_GROUPS; ++g) {
+        const unsigned b = bal[g];
+        if ((b >> lane) & 1u) flatten_ids[pos + __popc(b & lt)] = s_id[g * 32 + lane];
+        pos += __popc(b);
     }
 }
 

@@ -466,7 +466,13 @@ struct TileRect {
 };
 FG_HD TileRect tile_rect(float mx, float my, int radius, int tile_size, int tile_w, int tile_h) {
     float ts = (float)tile_size;
-    float tr = (float)radius / ts, tx = mx / ts, ty = my / ts;
+    float tr, tx, ty;
+    if ((tile_size & (tile_size - 1)) == 0) {  // power of two (16 in every caller): x * 2^-k == x / 2^k exactly, bit for bit
+        const float inv = 1.0f / ts;
+        tr = (float)radius * inv; tx = mx * inv; ty = my * inv;
+    } else {
+        tr = (float)radius / ts; tx = mx / ts; ty = my / ts;
+    }
     float fx0 = floorf(tx - tr), fx1 = ceilf(tx + tr), fy0 = floorf(ty - tr), fy1 = ceilf(ty + tr);
     TileRect r;
     r.x0 = (int)fminf_(fmaxf_(fx0, 0.f), (float)tile_w);
