@@ -109,8 +109,6 @@ SIGNATURES = {
     "fg_bin_count_cells": (_i32, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "fg_bin_cell_scan": (_i32, [_i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     "fg_bin_ranked_emit": (_i32, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
-    "fg_bin_fine_segments_workspace_bytes": (_i64, [_i32, _i32, _i32, _i64]),
-    "fg_bin_fine_segments": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "fg_bin_fine": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fg_rasterize_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                 _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

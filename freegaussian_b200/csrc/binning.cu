@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(256)
 // in place, then compacted to [tile_h][tile_w]); the exclusive scan over all tiles is the generic
 // scan of isect.cu, so many-camera calls (cfg4: 32 views, ~0.7 M tiles) stay parallel.
 __global__ void __launch_bounds__(1024)
-    tile_count_kernel(int tile_w, int tile_h, int32_t* __restrict__ diff, int32_t* __restrict__ counts) {
+    tile_count_kernel(int tile_w, int tile_h, int32_t* __restrict__ diff, int32_t* __restrict__ counts,
+                      int32_t* __restrict__ offsets_out /*one camera only: the exclusive scan too, or NULL*/,
+                      int64_t* __restrict__ total_out) {
+    __shared__ int s_scan[32];
     pdl_wait();
     const int W1 = tile_w + 1, H1 = tile_h + 1;
     const int c = blockIdx.x;
@@ -95,6 +98,38 @@ __global__ void __launch_bounds__(1024)
             out[y * tile_w + x] = run;
         }
     }
+    if (!offsets_out) return;
+    // single camera: this CTA holds every count, so it finishes the job (three launches of the generic scan otherwise)
+    __syncthreads();
+    const int n = tile_w * tile_h, per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int i0 = min((int)threadIdx.x * per, n), i1 = min(i0 + per, n);
+    int sum = 0;
+    for (int i = i0; i < i1; ++i) sum += out[i];
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane_ >= d) incl += o;
+    }
+    if (lane_ == 31) s_scan[warp_] = incl;
+    __syncthreads();
+    if (warp_ == 0) {
+        int w = lane_ < nwarps ? s_scan[lane_] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane_ >= d) w += o;
+        }
+        s_scan[lane_] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    int run = incl - sum + (warp_ ? s_scan[warp_ - 1] : 0);
+    for (int i = i0; i < i1; ++i) {
+        const int c = out[i];
+        offsets_out[i] = run;
+        run += c;
+    }
+    if (threadIdx.x == blockDim.x - 1) *total_out = run;
 }
 
 // ---- step 4: emit (splat, coarse cell) pairs in depth order --------------------------------
@@ -139,7 +174,6 @@ __global__ void __launch_bounds__(256)
 constexpr int RK_CHUNK = 512;
 constexpr int RK_WARPS = RK_CHUNK / 32;
 constexpr int RK_MAX_CELLS = 1024;  // = threads of the totals scan; shared memory of ranked_emit: 128 B per cell
-constexpr int FB_SEG = 1024;  // pairs per CTA of fine_bin_seg_kernel
 constexpr int RK_BIG = 16;  // a splat over more cells than this is walked by its whole warp (a full-screen splat touches every
                            // cell: one thread looping over 510 of them would hold up the CTA's barriers)
 
@@ -325,31 +359,6 @@ __global__ void __launch_bounds__(1024)
         cell_offsets[n_cells] = excl + mine;
         *n_coarse = excl + mine;
     }
-    // second table, behind the first: where each cell's segments of FB_SEG pairs start in fine_bin_seg_kernel's grid
-    __syncthreads();
-    int sv = (mine + FB_SEG - 1) / FB_SEG;
-    const int smine = sv;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, sv, d);
-        if (lane >= d) sv += o;
-    }
-    if (lane == 31) s_warp[row] = sv;
-    __syncthreads();
-    if (row == 0) {
-        int w = s_warp[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, w, d);
-            if (lane >= d) w += o;
-        }
-        s_warp[lane] = w;
-    }
-    __syncthreads();
-    const int sexcl = sv - smine + (row ? s_warp[row - 1] : 0);
-    int32_t* seg_offsets = cell_offsets + n_cells + 1;
-    if (tid < n_cells) seg_offsets[tid] = sexcl;
-    if (tid == 1023) seg_offsets[n_cells] = sexcl + smine;
 }
 
 __global__ void __launch_bounds__(RK_CHUNK)
@@ -479,9 +488,8 @@ __global__ void __launch_bounds__(FB_THREADS)
             const int y0 = max(t.y0 - cy * CK, 0), y1 = min(t.y1 - cy * CK, CK);
             if (x1 > x0 && y1 > y0) {
                 const unsigned cols = ((1u << x1) - 1) & ~((1u << x0) - 1);  // CK bits
-                unsigned rows = 0;
-                for (int y = y0; y < y1; ++y) rows |= cols << (y * CK);
-                mask = rows;
+                const unsigned rows = ((1u << (y1 * CK)) - 1) & ~((1u << (y0 * CK)) - 1);
+                mask = (cols * 0x1111u) & rows;  // the column pattern in every row, cut to rows [y0, y1)
             }
         }
         // per-warp counts per tile
@@ -504,130 +512,16 @@ __global__ void __launch_bounds__(FB_THREADS)
             s_cursor[tid] = run;
         }
         __syncthreads();
+        const int first = lane < NT ? s_tile_off[lane] + s_warp_cnt[warp][lane] : 0;  // lane t: the warp's first slot in tile t
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            if ((mask >> t) & 1u) {
-                const int pos = s_tile_off[t] + s_warp_cnt[warp][t] + __popc(bal[t] & lt);
-                flatten_ids[pos] = id;
-            }
+            const int pos = __shfl_sync(0xffffffffu, first, t) + __popc(bal[t] & lt);
+            if ((mask >> t) & 1u) flatten_ids[pos] = id;
         }
         __syncthreads();
     }
 }
 
-
-// ---- step 5, one CTA per SEGMENT of a cell's list (ranked path) ------------------------------------------------------
-// fine_bin_kernel walks a cell's list chunk after chunk, so its time is the longest cell's (~25 sequential chunks at cfg3:
-// 0.106 ms for 16 us worth of traffic).  Here every FB_SEG-pair segment of every cell is its own CTA; the tile cursors a
-// segment starts from are the totals of the cell's earlier segments, obtained by decoupled look-back over 16 status words
-// per segment (flag in the top two bits, as in radix_sort.cu); 512-thread CTAs, four per SM, so that one segment's
-// look-back latency hides behind the others' work (ncu r2b, 1024 threads: 14 barrier-stall cycles per issue); a CTA
-// finds its (cell, segment) in shared-memory copies of the two tables (a binary search over global memory cost each CTA
-// ten dependent L2 round trips before its first useful load: 120 us).  Segments are numbered cell after cell and a CTA takes the
-// next number from a ticket counter, so every predecessor of a running CTA is itself running or done.
-constexpr uint32_t FS_LOCAL = 1u << 30, FS_INCLUSIVE = 2u << 30, FS_FLAGS = 3u << 30;
-constexpr int FS_THREADS = 512, FS_ITEMS = FB_SEG / FS_THREADS;  // loading: thread = FS_ITEMS entries, FS_THREADS apart
-constexpr int FS_GROUPS = FB_SEG / 32;                           // groups of 32 consecutive entries
-static_assert(FS_THREADS / 32 == CK * CK, "fine_bin_seg_kernel: warp t writes tile t");
-static_assert(FS_GROUPS <= 32, "the ballots of a segment stay in registers");
-
-__device__ __forceinline__ unsigned cell_tile_mask(float2 m, int r, int tile_size, int tile_w, int tile_h, int cx, int cy) {
-    const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h);
-    const int x0 = max(t.x0 - cx * CK, 0), x1 = min(t.x1 - cx * CK, CK);
-    const int y0 = max(t.y0 - cy * CK, 0), y1 = min(t.y1 - cy * CK, CK);
-    if (!(x1 > x0 && y1 > y0)) return 0u;
-    const unsigned cols = ((1u << x1) - 1) & ~((1u << x0) - 1);  // CK bits
-    const unsigned rows = ((1u << (y1 * CK)) - 1) & ~((1u << (y0 * CK)) - 1);
-    return (cols * 0x1111u) & rows;  // the column pattern in every row, cut to rows [y0, y1)
-}
-
-// Tile-major: the CTA stages its segment once (id + 16-bit tile mask per entry), then WARP t walks the staged entries for
-// tile t alone -- one ballot per 32 entries, a running position, coalesced stores into one list -- instead of every warp
-// ranking its 32 entries for all 16 tiles (620 instructions per 32 entries, ncu r2b/r2d: issue-bound at 0.10-0.12 ms).
-__global__ void __launch_bounds__(FS_THREADS, 2)
-    fine_bin_seg_kernel(int n_cells, const int32_t* __restrict__ cell_offsets /*[n_cells+1] ++ segment starts [n_cells+1]*/,
-                        const int32_t* __restrict__ coarse_vals, const float2* __restrict__ means2d,
-                        const int32_t* __restrict__ radii, int tile_size, int tile_w, int tile_h, int cw, int chh,
-                        const int32_t* __restrict__ isect_offsets, int32_t* __restrict__ flatten_ids,
-                        int* __restrict__ ticket_counter, volatile uint32_t* status /*[segments][16], zeroed*/) {
-    __shared__ int s_tab[2 * (RK_MAX_CELLS + 1)];  // both tables: a CTA finds its (cell, segment) without a chain of global loads
-    __shared__ int s_id[FB_SEG];
-    __shared__ unsigned short s_mask[FB_SEG];  // bit (iy*CK + ix): the splat overlaps tile (cx*CK+ix, cy*CK+iy)
-    __shared__ int s_ticket;
-    pdl_wait();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_ticket = atomicAdd(ticket_counter, 1);
-    for (int i = tid; i < 2 * (n_cells + 1); i += FS_THREADS) s_tab[i] = cell_offsets[i];
-    __syncthreads();
-    const int* seg_offsets = s_tab + n_cells + 1;
-    const int ticket = s_ticket;
-    if (ticket >= seg_offsets[n_cells]) return;  // the grid is sized from an upper bound of the segment count
-    int cell = 0;
-    {  // last cell whose first segment is <= ticket (empty cells share their successor's start)
-        int hi = n_cells;
-        while (hi - cell > 1) {
-            const int mid = (cell + hi) >> 1;
-            if (seg_offsets[mid] <= ticket) cell = mid; else hi = mid;
-        }
-    }
-    const int seg = ticket - seg_offsets[cell];
-    const int cam = cell / (cw * chh);
-    const int crem = cell - cam * cw * chh;
-    const int cy = crem / cw, cx = crem - cy * cw;
-    const int e0 = s_tab[cell] + seg * FB_SEG;
-    const int end = s_tab[cell + 1];
-    int id[FS_ITEMS];
-#pragma unroll
-    for (int i = 0; i < FS_ITEMS; ++i) id[i] = (e0 + i * FS_THREADS + tid < end) ? coarse_vals[e0 + i * FS_THREADS + tid] : -1;
-#pragma unroll
-    for (int i = 0; i < FS_ITEMS; ++i) {
-        s_id[i * FS_THREADS + tid] = id[i];
-        s_mask[i * FS_THREADS + tid] = id[i] >= 0
-            ? (unsigned short)cell_tile_mask(means2d[id[i]], radii[id[i]], tile_size, tile_w, tile_h, cx, cy) : (unsigned short)0;
-    }
-    __syncthreads();
-    // from here on the warps are independent: warp = tile
-    const int tx = cx * CK + (warp & (CK - 1)), ty = cy * CK + (warp >> CK_SHIFT);
-    if (tx >= tile_w || ty >= tile_h) return;  // tile outside the image: nothing overlaps it, nobody looks its status up
-    const int n_groups = min(FS_GROUPS, (end - e0 + 31) >> 5);
-    const unsigned bit = 1u << warp;
-    unsigned bal[FS_GROUPS];
-    int count = 0;
-#pragma unroll
-    for (int g = 0; g < FS_GROUPS; ++g) {
-        bal[g] = 0;
-        if (g < n_groups) {
-            bal[g] = __ballot_sync(0xffffffffu, (s_mask[g * 32 + lane] & bit) != 0);
-            count += __popc(bal[g]);
-        }
-    }
-    int pos = isect_offsets[(cam * tile_h + ty) * tile_w + tx];
-    if (lane == 0) {
-        volatile uint32_t* mine = status + (size_t)ticket * (CK * CK) + warp;
-        uint32_t excl = 0;
-        if (seg == 0) {
-            *mine = FS_INCLUSIVE | (uint32_t)count;
-        } else {
-            *mine = FS_LOCAL | (uint32_t)count;
-            for (int t = ticket - 1;; --t) {  // t >= ticket - seg: the cell's first segment always publishes INCLUSIVE
-                uint32_t st;
-                do { st = status[(size_t)t * (CK * CK) + warp]; } while ((st & FS_FLAGS) == 0);
-                excl += st & ~FS_FLAGS;
-                if ((st & FS_FLAGS) == FS_INCLUSIVE) break;
-            }
-            *mine = FS_INCLUSIVE | (excl + (uint32_t)count);
-        }
-        pos += (int)excl;
-    }
-    pos = __shfl_sync(0xffffffffu, pos, 0);
-    const unsigned lt = (1u << lane) - 1;
-#pragma unroll
-    for (int g = 0; g < FS_GROUPS; ++g) {
-        const unsigned b = bal[g];
-        if ((b >> lane) & 1u) flatten_ids[pos + __popc(b & lt)] = s_id[g * 32 + lane];
-        pos += __popc(b);
-    }
-}
 
 }  // namespace fg
 
@@ -671,7 +565,11 @@ extern "C" int fg_bin_tile_scan(int C, int tile_w, int tile_h, int32_t* diff_gri
     const int64_t n = (int64_t)C * tile_w * tile_h;
     int32_t* counts = (int32_t*)workspace;
     unsigned char* scan_ws = (unsigned char*)workspace + ((n * 4 + 255) & ~(int64_t)255);
-    FG_LAUNCH(tile_count_kernel, C, 1024, 0, stream, tile_w, tile_h, diff_grid, counts);
+    if (C == 1) {  // one camera = one CTA holds all counts: it scans them too
+        FG_LAUNCH(tile_count_kernel, 1, 1024, 0, stream, tile_w, tile_h, diff_grid, counts, isect_offsets, total);
+        return FG_OK;
+    }
+    FG_LAUNCH(tile_count_kernel, C, 1024, 0, stream, tile_w, tile_h, diff_grid, counts, (int32_t*)nullptr, (int64_t*)nullptr);
     return fg_exclusive_scan_i32(n, counts, isect_offsets, total, scan_ws, fg_scan_workspace_bytes(n), stream);
 }
 
@@ -759,32 +657,5 @@ extern "C" int fg_bin_fine(int C, int N, int64_t n_coarse, const int32_t* coarse
     FG_LAUNCH(fine_bin_kernel, n_cells, FB_THREADS, 0, stream, N, coarse_offsets, (long long)n_coarse, n_cells,
               coarse_vals_sorted, (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, isect_offsets,
               flatten_ids);
-    return FG_OK;
-}
-
-extern "C" int64_t fg_bin_fine_segments_workspace_bytes(int C, int tile_w, int tile_h, int64_t n_coarse) {
-    const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
-    const int64_t segs = n_coarse / FB_SEG + (int64_t)C * cw * chh;  // upper bound: one partial segment per cell
-    return 256 + segs * (CK * CK) * 4;
-}
-
-extern "C" int fg_bin_fine_segments(int C, int N, int64_t n_coarse, const int32_t* cell_offsets,
-                                    const int32_t* coarse_vals_sorted, const float* means2d, const int32_t* radii,
-                                    int tile_size, int tile_w, int tile_h, const int32_t* isect_offsets,
-                                    int32_t* flatten_ids, void* workspace, int64_t workspace_bytes, void* stream) {
-    FG_REQUIRE(C >= 1 && n_coarse >= 0 && n_coarse < (1ll << 31), "bad arguments");
-    if (n_coarse == 0) return FG_OK;
-    FG_REQUIRE(cell_offsets && coarse_vals_sorted && means2d && radii && isect_offsets && flatten_ids && workspace,
-               "NULL pointer");
-    const int64_t need = fg_bin_fine_segments_workspace_bytes(C, tile_w, tile_h, n_coarse);
-    FG_REQUIRE(workspace_bytes >= need, "fine-binning workspace too small");
-    const int cw = (tile_w + CK - 1) / CK, chh = (tile_h + CK - 1) / CK;
-    const int n_cells = C * cw * chh;
-    const int64_t segs = n_coarse / FB_SEG + n_cells;
-    cudaStream_t st = (cudaStream_t)stream;
-    FG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)need, st));  // ticket counter + status words
-    FG_LAUNCH(fine_bin_seg_kernel, (unsigned)segs, FS_THREADS, 0, st, n_cells, cell_offsets, coarse_vals_sorted,
-              (const float2*)means2d, radii, tile_size, tile_w, tile_h, cw, chh, isect_offsets, flatten_ids,
-              (int*)workspace, (volatile uint32_t*)((unsigned char*)workspace + 256));
     return FG_OK;
 }

@@ -32,13 +32,13 @@ static FrontLayout front_layout(int C, int N, int tile_w, int tile_h) {
     L.rank = o; o += al(L.rank_bytes);
     int cw = 0, chh = 0;
     fg_bin_coarse_dims(tile_w, tile_h, &cw, &chh);
-    L.coff = o; o += al(L.rank_bytes ? ((size_t)C * cw * chh + 1) * 8 : 0);  // cell offsets ++ segment starts
+    L.coff = o; o += al(L.rank_bytes ? ((size_t)C * cw * chh + 1) * 4 : 0);
     L.total = o;
         return L;
 }
 
 struct BackLayout {
-    size_t ck, cv, ck2, cv2, coff, sort, fseg, total;
+    size_t ck, cv, ck2, cv2, coff, sort, total;
 };
 static BackLayout back_layout(int C, int tile_w, int tile_h, int64_t Mc) {
     int cw = 0, chh = 0;
@@ -52,7 +52,6 @@ static BackLayout back_layout(int C, int tile_w, int tile_h, int64_t Mc) {
     L.cv2 = o; o += al(m * 4);
     L.coff = o; o += al((size_t)C * cw * chh * 4);
     L.sort = o; o += al((size_t)fg_radix_sort_workspace_bytes((int64_t)m));
-    L.fseg = o; o += al((size_t)fg_bin_fine_segments_workspace_bytes(C, tile_w, tile_h, Mc));
     L.total = o;
         return L;
 }
@@ -220,9 +219,8 @@ extern "C" int fg_render_back(int C, int N, int64_t n_isects, int64_t n_coarse, 
             if ((e = fg_bin_ranked_emit(C, N, order, means2d, radii, tile_size, tile_w, tile_h, fws + F.rank,
                                         (int64_t)F.rank_bytes, (const int32_t*)(fws + F.coff), cv, stream)))
                 return e;
-            if ((e = fg_bin_fine_segments(C, N, n_coarse, (const int32_t*)(fws + F.coff), cv, means2d, radii, tile_size,
-                                          tile_w, tile_h, isect_offsets, flatten_ids, ws + L.fseg,
-                                          (int64_t)(L.total - L.fseg), stream)))
+            if ((e = fg_bin_fine(C, N, n_coarse, (const int32_t*)(fws + F.coff), cv, means2d, radii, tile_size, tile_w,
+                                 tile_h, isect_offsets, flatten_ids, stream)))
                 return e;
         } else {
             if ((e = fg_bin_coarse_emit(C, N, order, means2d, radii, coarse_off, tile_size, tile_w, tile_h, ck, cv, stream)))
@@ -231,7 +229,7 @@ extern "C" int fg_render_back(int C, int N, int64_t n_isects, int64_t n_coarse, 
             while ((1ll << bits) < (long long)C * cw * chh) ++bits;
             int sel = 0;
             if ((e = fg_radix_sort_pairs_u32_u32(n_coarse, ck, (uint32_t*)cv, ck2, (uint32_t*)cv2, bits, ws + L.sort,
-                                                 (int64_t)(L.fseg - L.sort), &sel, stream)))
+                                                 (int64_t)(L.total - L.sort), &sel, stream)))
                 return e;
             const uint32_t* ks = sel ? ck2 : ck;
             const int32_t* vs = sel ? cv2 : cv;

@@ -477,7 +477,7 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
             check(L.fg_bin_tile_scan(C, tile_w, tile_h, ptr(diff), ptr(isect_offsets), n2[0:1].data_ptr(), ptr(ws2),
                                      ws2.numel(), st))
             if rank_bytes:
-                coarse_offsets = torch.empty(2 * (C * cw * chh + 1), **i32)  # cell offsets ++ segment starts
+                coarse_offsets = torch.empty(C * cw * chh + 1, **i32)
                 check(L.fg_bin_cell_scan(C, N, tile_w, tile_h, ptr(n_vis_dev), ptr(wsr), wsr.numel(), ptr(coarse_offsets),
                                          n2[1:2].data_ptr(), st))
             else:
@@ -501,13 +501,8 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss:
                     coarse_offsets = torch.empty(C * cw * chh, **i32)
                     check(L.fg_isect_offsets_tiles(Mc, ptr(ck), C, cw, chh, ptr(coarse_offsets), st))
             with _stage("fine_bin"):
-                if rank_bytes:
-                    wsf = _ws.get("fine_seg", L.fg_bin_fine_segments_workspace_bytes(C, tile_w, tile_h, Mc), dev)
-                    check(L.fg_bin_fine_segments(C, N, Mc, ptr(coarse_offsets), ptr(cv), ptr(means2d), ptr(radii), tile_size,
-                                                 tile_w, tile_h, ptr(isect_offsets), ptr(fl), ptr(wsf), wsf.numel(), st))
-                else:
-                    check(L.fg_bin_fine(C, N, Mc, ptr(coarse_offsets), ptr(cv), ptr(means2d), ptr(radii), tile_size,
-                                        tile_w, tile_h, ptr(isect_offsets), ptr(fl), st))
+                check(L.fg_bin_fine(C, N, Mc, ptr(coarse_offsets), ptr(cv), ptr(means2d), ptr(radii), tile_size,
+                                    tile_w, tile_h, ptr(isect_offsets), ptr(fl), st))
         return None, fl, isect_offsets, None
 
     # ---- two-level

@@ -201,13 +201,10 @@ int fg_bin_coarse_emit(int C, int N, const int32_t* order, const float* means2d,
  * followed by a stable sort by cell, computed without a sort.  Applies when C * cw * ch <= 1024 coarse cells (one or two
  * 1080p views); fg_bin_ranked_workspace_bytes returns 0 otherwise and the emit + sort path is the one to use.
  *   fg_bin_count_cells  fg_bin_count's corner increments + per (chunk of 512 depth-ordered slots, cell) pair counts
- *   fg_bin_cell_scan    per cell: exclusive prefix over the chunks; cell_offsets[2 * (n_cells + 1)]: the first n_cells + 1
- *                       entries are fg_bin_fine's coarse_offsets (+ the total), the second n_cells + 1 the start of each
- *                       cell's 1024-pair segments in fg_bin_fine_segments' grid; *n_coarse = Mc (device).
- *                       n_visible: device count from fg_depth_sort_visible
- *   fg_bin_ranked_emit  coarse_vals[Mc]: position = cell offset + chunk prefix + rank inside the chunk (bitmaps)
- *   fg_bin_fine_segments  fg_bin_fine with one CTA per 1024-pair segment of a cell instead of one per cell (decoupled
- *                       look-back between the segments of a cell): same lists, no serial walk over the heavy cells */
+ *   fg_bin_cell_scan    per cell: exclusive prefix over the chunks; cell_offsets[n_cells + 1] (= fg_bin_fine's
+ *                       coarse_offsets, then the total), *n_coarse = Mc (device).  n_visible: device count from
+ *                       fg_depth_sort_visible
+ *   fg_bin_ranked_emit  coarse_vals[Mc]: position = cell offset + chunk prefix + rank inside the chunk (bitmaps) */
 int64_t fg_bin_ranked_workspace_bytes(int C, int N, int tile_w, int tile_h);
 int fg_bin_count_cells(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii, int tile_size,
                        int tile_w, int tile_h, int32_t* diff_grid, void* ranked_workspace, int64_t ranked_workspace_bytes,
@@ -217,11 +214,6 @@ int fg_bin_cell_scan(int C, int N, int tile_w, int tile_h, const int64_t* n_visi
 int fg_bin_ranked_emit(int C, int N, const int32_t* order, const float* means2d, const int32_t* radii, int tile_size,
                        int tile_w, int tile_h, const void* ranked_workspace, int64_t ranked_workspace_bytes,
                        const int32_t* cell_offsets, int32_t* coarse_vals, void* stream);
-int64_t fg_bin_fine_segments_workspace_bytes(int C, int tile_w, int tile_h, int64_t n_coarse);
-int fg_bin_fine_segments(int C, int N, int64_t n_coarse, const int32_t* cell_offsets, const int32_t* coarse_vals_sorted,
-                         const float* means2d, const int32_t* radii, int tile_size, int tile_w, int tile_h,
-                         const int32_t* isect_offsets, int32_t* flatten_ids, void* workspace, int64_t workspace_bytes,
-                         void* stream);
 int fg_bin_fine(int C, int N, int64_t n_coarse, const int32_t* coarse_offsets,
                 const int32_t* coarse_vals_sorted, const float* means2d, const int32_t* radii, int tile_size,
                 int tile_w, int tile_h, const int32_t* isect_offsets, int32_t* flatten_ids, void* stream);
