@@ -9,7 +9,7 @@ mkdir -p $OUT
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --no-train-iter"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv \
     $BENCH > $OUT/${TAG}_launches_bench.log 2>&1
-for k in rasterize_bwd2_kernel rasterize_fwd_kernel project_bwd_kernel sh_bwd_kernel project_fwd_kernel fine_bin_kernel; do
+for k in rasterize_bwd2_kernel rasterize_fwd_kernel project_bwd_kernel sh_bwd_kernel project_fwd_kernel fine_bin_kernel ranked_emit_kernel bin_count_cells_kernel; do
     timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 3 --launch-count 1 \
         -f -o $OUT/${TAG}_$k $BENCH > $OUT/${TAG}_$k.log 2>&1
 done
