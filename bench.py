@@ -6,7 +6,7 @@
 
 Workload (config.workload = "cfg3"): 1 M Gaussians, 1920x1080, SH degree 3, render_mode
 "RGB+ED" + rendered flow (6 composited channels), one view per GPU per step (view-sharded,
-weak scaling), scalar loss = sum(render * w_rgbd) + sum(flow * w_flow), backward to all
+weak scaling), scalar loss = <render, w_rgbd> + <flow, w_flow> (gradient planes w_rgbd / w_flow), backward to all
 Gaussian parameters; at N>1 the exchange of the parameter gradients runs inside the backward
 (freegaussian_b200/dist.py::ViewShardedExchange, csrc/exchange.cu).  Synthetic "trained-like" scene
 (SURVEY.md 8(d)); working set (236 MB of parameters + ~0.5 GB of intersection buffers) is far
@@ -256,12 +256,17 @@ class Job:
         meta["means2d"].retain_grad()
         # weighted sums as dot products: one reduction kernel each, no 33 MB product tensor in between (the loss only
         # exists to hand the compositing backward dense, non-trivial upstream gradients: v_render = wr, v_flow = wf)
+        # at N>1 with --exchange peer the cross-rank sum of every parameter gradient happens INSIDE this backward
         if render.shape[0] == 1:
-            loss = torch.dot(render.reshape(-1), wr.reshape(-1)) + torch.dot(meta["flow"].reshape(-1), wf.reshape(-1))
+            # the loss is linear in the images, so its gradient with respect to them IS (w_rgbd, w_flow): the planes go to
+            # autograd as the upstream gradients directly (what `loss.backward()` computes, minus two 33 MB multiplications
+            # by the scalar 1.0), and the loss value itself is two dot products outside the graph
+            with torch.no_grad():
+                loss = torch.dot(render.reshape(-1), wr.reshape(-1)) + torch.dot(meta["flow"].reshape(-1), wf.reshape(-1))
+            torch.autograd.backward([render, meta["flow"]], [wr.view_as(render), wf.view_as(meta["flow"])])
         else:  # several views per step share the planes
             loss = (render * wr).sum() + (meta["flow"] * wf).sum()
-        # at N>1 with --exchange peer the cross-rank sum of every parameter gradient happens INSIDE this backward
-        loss.backward()
+            loss.backward()
         self.stats.accumulate_local(meta["radii"], meta["means2d"].absgrad, H, W)
         if self.xchg is None and self.world > 1:  # --exchange nccl: one all-reduce over the dense arena
             with rendering._stage("exchange"):
