@@ -570,8 +570,8 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, `ncu --set full` captures under profiles/ (cfg3, trained_like)
-NCU_TRAFFIC = {"rasterize_bwd": 127.1e6, "rasterize_fwd": 24.9e6, "project_bwd": 403.5e6, "project_fwd": 148.0e6,
-               "fine_bin": 103.3e6}
+NCU_TRAFFIC = {"rasterize_bwd": 127.1e6, "rasterize_fwd": 25.9e6, "project_bwd": 403.5e6, "project_fwd": 148.0e6,
+               "fine_bin": 103.0e6}
 
 
 # ------------------------------------------------------------------------------ k-NN (BASELINE cfg5)
