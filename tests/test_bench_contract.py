@@ -76,7 +76,7 @@ def test_round2_reference_arm_is_like_for_like():
     assert r["e2e"] == {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
-@pytest.mark.parametrize("name,n", [("r2_final_bench2.json", 2), ("r2_final_bench8.json", 8)])
+@pytest.mark.parametrize("name,n", [("r2_final_bench2.json", 2), ("r2_final_bench4.json", 4), ("r2_final_bench8.json", 8)])
 def test_round2_multi_gpu_lines(name, n):
     d = _load(name)
     assert d["n_gpus"] == n and d["scaling"] == "weak" and BASE <= set(d) and d["config"]["views_per_step"] == n
