@@ -62,3 +62,18 @@ def test_ranked_binning_applies_up_to_1024_coarse_cells():
                 assert got >= 4 * chunks * cells + 4 * cells + 4
         # the front workspace carries it, plus the cell offsets
         assert int(L.fg_render_front_workspace_bytes(Cn, 1000, tw, th)) >= int(L.fg_bin_ranked_workspace_bytes(Cn, 1000, tw, th))
+
+
+def test_ranked_entry_points_refuse_what_they_cannot_do():
+    """The ranked binning calls validate before they touch the device: too many coarse cells, missing or short workspaces
+    come back as error codes with a message (no GPU needed to see them)."""
+    L = _lib()
+    one = 1  # any non-NULL address: the checks below fail before a pointer is followed
+    assert L.fg_bin_count_cells(1, 10, one, one, one, 16, 200, 200, one, one, 1 << 30, None) != 0
+    assert b"too many coarse cells" in L.fg_last_error()
+    need = int(L.fg_bin_ranked_workspace_bytes(1, 10, 120, 68))
+    assert need > 0
+    assert L.fg_bin_count_cells(1, 10, one, one, one, 16, 120, 68, one, one, need - 1, None) != 0
+    assert b"workspace too small" in L.fg_last_error()
+    assert L.fg_bin_cell_scan(1, 10, 120, 68, None, one, need, one, one, None) != 0
+    assert L.fg_bin_ranked_emit(1, 10, one, one, one, 16, 120, 68, None, need, one, one, None) != 0
