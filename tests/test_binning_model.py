@@ -94,3 +94,28 @@ def test_reciprocal_scaling_is_exact_for_power_of_two_tiles():
     x = x[np.isfinite(x)]
     inv = np.float32(1.0) / np.float32(16.0)
     assert np.array_equal((x * inv).view(np.uint32), (x / np.float32(16.0)).view(np.uint32))
+
+
+def test_compact_row_of_a_published_colour_gradient():
+    """csrc/exchange.cu (sh_bwd_views_kernel) finds the compact row of the visible pair (view c, Gaussian n) as
+    prefix[c][n >> 5] + popcount(mask[c][n >> 5] & ((1 << (n & 31)) - 1)), where prefix[c][w] is the exclusive scan of the
+    visibility at the first bit of word w (project.cu publishes exactly that).  Model: it equals the exclusive scan itself."""
+    rng = np.random.default_rng(2)
+    C, N = 3, 1000
+    vis = rng.random((C, N)) < 0.3
+    flat = vis.reshape(-1)
+    excl = np.cumsum(flat) - flat                     # fg_pack_plan: exclusive scan over c*N+n
+    words = (N + 31) // 32
+    mask = np.zeros((C, words), np.uint64)
+    prefix = np.zeros((C, words), np.int64)
+    for c in range(C):
+        for n in range(N):
+            if vis[c, n]:
+                mask[c, n >> 5] |= np.uint64(1) << np.uint64(n & 31)
+        for w in range(words):
+            prefix[c, w] = excl[c * N + 32 * w]       # what lane 0 of each warp stores
+    for c in range(C):
+        for n in range(N):
+            if vis[c, n]:
+                below = int(mask[c, n >> 5]) & ((1 << (n & 31)) - 1)
+                assert prefix[c, n >> 5] + bin(below).count("1") == excl[c * N + n]
